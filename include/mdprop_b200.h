@@ -1,0 +1,207 @@
+/*
+ * mdprop_b200.h -- C ABI of libmdprop_b200.so: the B200 (sm_100a) implementation of the mdproptools
+ * trajectory post-processing hot path.
+ *
+ * The reference (molmd/mdproptools v0.0.6) is pure Python; it has no FFI.  Its "native" layer is the
+ * set of numba-jitted loops and numpy/FFT correlators listed below.  Each entry point here replaces
+ * one of them; the Python package mdproptools_b200 binds these symbols with ctypes and keeps the
+ * reference's public API on top (INTEGRATION.md shows the binding a maintainer of the reference would
+ * add).  Citations are file:line relative to the reference root.
+ *
+ * Conventions
+ *   - plain C types only; every pointer documented as DEVICE is a CUDA device pointer owned by the
+ *     caller (the Python side uses torch tensors for that), HOST pointers are ordinary memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls enqueue work
+ *     on it and return without synchronising unless stated;
+ *   - return value 0 = success, negative = error; mdp_last_error() returns a thread-local message;
+ *   - outputs documented "accumulate" are added to (caller zeroes), like the reference's kernels
+ *     which receive zeroed arrays and add in place (rdf_cn.py:485-486, 633);
+ *   - scratch memory lives in the context (grown on demand, reused between calls); one context per
+ *     device per host thread.  There is NO CPU fallback anywhere in this library.
+ */
+#ifndef MDPROP_B200_H
+#define MDPROP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDP_VERSION 100
+
+typedef struct mdp_ctx mdp_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int mdp_version(void);
+const char *mdp_last_error(void);
+int mdp_ctx_create(int device, mdp_ctx **out);
+void mdp_ctx_destroy(mdp_ctx *ctx);
+/* bytes of scratch currently held / upper bound the context may grow to (default 8 GiB) */
+int64_t mdp_ctx_scratch_bytes(mdp_ctx *ctx);
+int mdp_ctx_set_scratch_limit(mdp_ctx *ctx, int64_t bytes);
+/* counters: number of kernels this library launched since creation (bench.py's gpu_launches) */
+int64_t mdp_ctx_launch_count(mdp_ctx *ctx);
+/* statistics of the last pair call: [0]=tile-pair items evaluated, [1]=nominal tile pairs,
+ * [2]=pair distance evaluations actually executed (32 x chunk steps), device->host sync. */
+int mdp_ctx_pair_stats(mdp_ctx *ctx, int64_t out[4]);
+
+/* ---- binning ------------------------------------------------------------------------------- */
+/*
+ * Edge table of the reference's bin function  bin(rsq) = (int64)(sqrt(rsq) / ddr)
+ * (rdf_cn.py:68 `np.sqrt(rsq)/ddr`, truncated at :85 `.astype(np.int64)`).
+ * edges[k] (k = 0..nb) = smallest double rsq with bin(rsq) >= k, found by bisection on the bit
+ * pattern with IEEE sqrt and divide, so that  bin(rsq) = #{k >= 1 : edges[k] <= rsq}  exactly.
+ * HOST: edges[nb + 1].
+ */
+int mdp_bin_edges(double ddr, int nb, double *edges);
+
+/* ---- pair kernels ---------------------------------------------------------------------------
+ * Replace _calc_rsq + _remove_outliers + _rdf_loop / _cn_loop / _rdf_mol_loop / _cn_mol_loop
+ * (rdf_cn.py:35-162).  Distances: d = a - b per axis, single-shift orthorhombic minimum image with
+ * strict compares against l/2 (rdf_cn.py:50-55), rsq = (dx*dx + dy*dy) + dz*dz unfused fp64 (:56),
+ * cutoff rsq < rcut2 strict (:66).  Results are integer counts, bit-exact.
+ *
+ * Point sets: SoA coordinates xyz = [nframes][3][n] doubles (DEVICE) with frame stride 3*n, in the
+ * caller's row order (the reference's id order); cls = int32 class id per point in [0, ncls)
+ * (DEVICE; cls_stride = n if it differs per frame, 0 if one array serves all frames).
+ * box = HOST [nframes][3] box lengths as the reference passes them (lattice lengths or bound
+ * extents).
+ *
+ * Set B == NULL  -> symmetric mode: unordered pairs i<j of set A, each counted ONCE in the
+ *                   class-pair histogram (the x2 of rdf_cn.py:85-86 and the two role orders of
+ *                   :89-96 are applied by mdp_hist_reduce weights);
+ *                   hist rows = ncls_a*(ncls_a+1)/2, row(ci<=cj) = ci*ncls_a - ci*(ci-1)/2 + (cj-ci).
+ * Set B != NULL  -> rectangular mode: every a in A against every b in B, no self exclusion
+ *                   (rdf_cn.py:131-140); hist rows = ncls_a*ncls_b, row = ci*ncls_b + cj.
+ *
+ * Binning: edges = HOST [nbins+1] ascending rsq thresholds with edges[0] ignored (treated as 0);
+ * bin(rsq) = #{k>=1 : edges[k] <= rsq}; pairs with bin >= nbins are dropped.  uniform_ddr > 0 tells
+ * the kernel the table came from mdp_bin_edges(uniform_ddr, nbins) so it may locate the bin from an
+ * fp32 estimate and correct it with the table; uniform_ddr = 0 -> the table is searched (use for the
+ * per-relation cutoffs of the coordination-number calls, rdf_cn.py:112).
+ *
+ * hist_out: DEVICE uint64 [nframes][rows][nbins], accumulate.
+ */
+int mdp_pair_hist(mdp_ctx *ctx, int nframes,
+                  int64_t n_a, const double *xyz_a, const int32_t *cls_a, int64_t cls_stride_a, int ncls_a,
+                  int64_t n_b, const double *xyz_b, const int32_t *cls_b, int64_t cls_stride_b, int ncls_b,
+                  const double *box, double rcut2, const double *edges, int nbins, double uniform_ddr,
+                  uint64_t *hist_out, int flags, void *stream);
+#define MDP_PAIR_NO_CULL 1     /* evaluate every tile pair (brute force, for A/B measurements) */
+#define MDP_PAIR_NO_SORT 2     /* keep caller order inside tiles (no spatial sort; implies little culling) */
+
+/*
+ * out[f][r][b] = sum_rows weights[r][row] * hist[f][row][b]     (all integer)
+ * weights: HOST int32 [nout][rows].  For calc_atomic_rdf: row 0 of the output is g_full with weight 2
+ * on every class pair (rdf_cn.py:85-86), relation (a,b) has weight 2 on row(a,a) if a==b else 1 on
+ * row(a,b) (rdf_cn.py:89-96).  With cumulative != 0 the bins are prefix-summed first (coordination
+ * counts: everything below each cutoff).  hist, out: DEVICE uint64; out is overwritten.
+ */
+int mdp_hist_reduce(mdp_ctx *ctx, int nframes, int rows, int nbins, const uint64_t *hist, int nout,
+                    const int32_t *weights, int cumulative, uint64_t *out, void *stream);
+
+/*
+ * Neighbour list (replaces the cutoff searches of get_clusters cluster_analysis.py:150-161,
+ * get_angle hydration_number.py:16-19 and ResidenceTime loop 1 residence_time.py:100-104):
+ * every (a in A, b in B) with  rin2 < rsq <= rout2  (shell_mode 1, residence_time.py:102) or
+ * rsq < rout2 (shell_mode 0, cluster_analysis.py:160), excluding a==b index pairs when
+ * exclude_same_index != 0 (residence_time.py:103-104).  Output entries are (frame, ia, ib) in the
+ * caller's row order, unordered within the list; list_out = DEVICE int32 [capacity][3];
+ * rsq_out = DEVICE double[capacity] or NULL; count_out = DEVICE int64 (total found; if it exceeds
+ * capacity only `capacity` entries were written -- call again with a bigger list).
+ */
+int mdp_pair_list(mdp_ctx *ctx, int nframes,
+                  int64_t n_a, const double *xyz_a, int64_t n_b, const double *xyz_b,
+                  const double *box, double rin2, double rout2, int shell_mode, int exclude_same_index,
+                  int32_t *list_out, double *rsq_out, int64_t capacity, int64_t *count_out, void *stream);
+
+/* ---- segmented (per-molecule) reductions ------------------------------------------------------
+ * calc_com (com_mols.py:5-62) / _define_mol_cols (rdf_cn.py:218-241): for each segment s (molecule;
+ * atoms seg_off[s]..seg_off[s+1]-1 in id order) out[c][s] = sum_a w[a]*attr[c][a] / sum_a w[a],
+ * sequential fp64 accumulation in atom order, unfused.  attr = DEVICE [nframes][ncomp][n],
+ * w = DEVICE [n] (masses), seg_off = DEVICE int32[nseg+1], out = DEVICE [nframes][ncomp][nseg].
+ * wsum_out (DEVICE [nseg], may be NULL) receives sum_a w[a]; extra (DEVICE [n], may be NULL) is summed
+ * unweighted into extra_out [nseg] (molecular charge, com_mols.py:43-46).
+ */
+int mdp_segment_com(mdp_ctx *ctx, int nframes, int ncomp, int64_t n, const double *attr, const double *w,
+                    int64_t nseg, const int32_t *seg_off, double *out, double *wsum_out,
+                    const double *extra, double *extra_out, void *stream);
+
+/* ---- MSD (diffusion.py:207-238) ----------------------------------------------------------------
+ * traj = DEVICE [nframes][3][n], ref = DEVICE [3][n] (the Time==0 frame, diffusion.py:213);
+ * groups are contiguous row ranges: group_off = HOST int64[ngroups+1] (NULL = one group of all rows)
+ * -- molecule types are contiguous in id order (com_mols.py:31-42).
+ * sums_out = DEVICE [nframes][ngroups][4]: per-group SUMS of dx2, dy2, dz2 and (dx2+dy2)+dz2
+ * (diffusion.py:214-215); the caller divides by the group sizes (groupby.mean, :218).
+ * per_atom_out = DEVICE [nframes][4][n] or NULL (msd_all, :216).  scale multiplies coordinates
+ * before differencing (the SI conversion of diffusion.py:201-203 happens before the subtraction).
+ */
+int mdp_msd_single_origin(mdp_ctx *ctx, int nframes, int64_t n, const double *traj, const double *ref,
+                          double scale, const int64_t *group_off, int ngroups, double *sums_out,
+                          double *per_atom_out, void *stream);
+/* msd_int (diffusion.py:225-237): frames 0, stride, 2*stride, ...; per atom the MEAN over the nint-1
+ * squared steps for dx2/dy2/dz2 and SUM/nint for msd (the n vs n-1 quirk of the reference).
+ * out = DEVICE [4][n]. */
+int mdp_msd_interval(mdp_ctx *ctx, int nframes, int64_t n, const double *traj, double scale, int stride,
+                     double *out, void *stream);
+/* Windowed MSD over all time origins (north-star extension, no reference implementation):
+ * sums_out = DEVICE [max_lag][ngroups][4] accumulate: sum over atoms of the group and over all origins
+ * t0 with t0+lag < nframes of the squared displacement; divide by count*(nframes-lag). */
+int mdp_msd_all_origins(mdp_ctx *ctx, int nframes, int64_t n, const double *traj, double scale,
+                        const int64_t *group_off, int ngroups, int max_lag, double *sums_out, void *stream);
+
+/* ---- Green-Kubo ---------------------------------------------------------------------------------
+ * conductivity_loop (_conductivity.py:7-36): per frame, per molecule COM velocity (mass weighted,
+ * sequential) times vel_scale, molecular charge (sum q) times q_scale, J[c][g][frame] = sum over
+ * molecules of type g of q_mol * v_com,c.  vel = DEVICE [nframes][3][n]; mass,q = DEVICE [n];
+ * seg_off = DEVICE int32 [nseg+1]; group_seg_off = HOST int64 [ngroups+1] (molecule types are contiguous
+ * segment ranges); out = DEVICE [3][ngroups][out_stride] written at column frame0 + f. */
+int mdp_charge_flux(mdp_ctx *ctx, int nframes, int64_t n, const double *vel, const double *mass,
+                    const double *q, int64_t nseg, const int32_t *seg_off, const int64_t *group_seg_off,
+                    int ngroups, double vel_scale, double q_scale, double *out, int64_t out_stride,
+                    int64_t frame0, void *stream);
+/* Conductivity.correlate (conductivity.py:97-114) / Viscosity.autocorrelate (viscosity.py:86-120):
+ * out[c][tau] = (sum_{t < T-tau} a[c][t+tau] * b[c][t]) / (T - tau), direct fp64 sum (the reference
+ * uses an FFT; agreement is to its round-off, ~1e-15 max|C|).  a,b,out = DEVICE [nchan][T];
+ * nlags <= T lags are produced (out row stride = nlags). */
+int mdp_xcorr_unbiased(mdp_ctx *ctx, int nchan, int64_t T, const double *a, const double *b, int64_t nlags,
+                       double *out, void *stream);
+/* cumulative trapezoid along rows (conductivity.py:231 with leading zero, viscosity.py:151 without):
+ * in = DEVICE [nrows][T]; out = DEVICE [nrows][T] if leading_zero else [nrows][T-1]; out = scale*integral. */
+int mdp_cumtrapz(mdp_ctx *ctx, int nrows, int64_t T, const double *in, double dx, double scale,
+                 int leading_zero, double *out, void *stream);
+
+/* ---- residence time (residence_time.py:70-148) ---------------------------------------------------
+ * Survival correlation from per-pair time bitmasks.  masks = DEVICE uint64 [npairs][nwords], bit t of
+ * pair p set when the pair is inside the shell in frame t (built by mdp_pair_list + mdp_bitmask_fill).
+ * cnt_out = DEVICE uint64 [T] accumulate: cnt[tau] = sum_p popcount(m_p & (m_p >> tau)). */
+int mdp_bitmask_fill(mdp_ctx *ctx, int64_t nentries, const int32_t *list, int64_t n_b, const int64_t *pair_keys,
+                     int64_t npairs, int nwords, uint64_t *masks, void *stream);
+int mdp_bitmask_autocorr(mdp_ctx *ctx, int64_t npairs, int nwords, int64_t T, const uint64_t *masks,
+                         uint64_t *cnt_out, void *stream);
+
+/* ---- OLS through the origin (diffusion.py:323-329) -------------------------------------------------
+ * out[c] = {sum t*t, sum t*y_c, sum y_c*y_c} over rows i0..i1-1; the host forms slope, bse, R2.
+ * t = DEVICE [T], y = DEVICE [ncol][T], out = DEVICE [ncol][3]. */
+int mdp_ols_sums(mdp_ctx *ctx, int ncol, int64_t T, const double *t, const double *y, int64_t i0, int64_t i1,
+                 double *out, void *stream);
+
+/* ---- LAMMPS dump reader (replaces pymatgen parse_lammps_dumps at rdf_cn.py:176 etc.) ---------------
+ * HOST-side, multi-threaded.  Parses one frame of dump text into SoA doubles scattered by id
+ * (row id-1 <- the reference's sort_values("id"), rdf_cn.py:191-192).
+ *   text,len      : the frame text starting at "ITEM: TIMESTEP"
+ *   want          : array of nwant column names to extract
+ *   out           : HOST [nwant][natoms] doubles (pinned memory recommended)
+ *   header_out    : HOST double[16]: timestep, natoms, xlo,xhi,ylo,yhi,zlo,zhi (after the tilt
+ *                   correction pymatgen applies), xy,xz,yz, triclinic flag, ncols, id_contiguous flag
+ * mdp_dump_scan splits a buffer into frames (offsets of every "ITEM: TIMESTEP"). */
+int64_t mdp_dump_scan(const char *text, int64_t len, int64_t *offsets, int64_t max_frames);
+int mdp_dump_header(const char *text, int64_t len, double *header_out, char *columns_out, int columns_cap);
+int mdp_dump_parse(const char *text, int64_t len, const char *const *want, int nwant, double *out,
+                   int64_t out_stride, double *header_out, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDPROP_B200_H */

@@ -1,0 +1,1129 @@
+// pair.cu -- minimum-image pair-distance engine for sm_100a.
+//
+// Replaces the numba loops of mdproptools/structural/rdf_cn.py:35-162 (_calc_rsq, _remove_outliers,
+// _rdf_loop, _cn_loop, _rdf_mol_loop, _cn_mol_loop) and the cutoff searches that call _calc_rsq
+// (cluster_analysis.py:150-161, hydration_number.py:16-19, residence_time.py:100-104).
+//
+// Design (B200-first, not a translation of the row-by-row reference loop):
+//   1. per frame the point set is binned on a Morton grid by a counting sort and written out as
+//      32-byte AoS records (x, y, z, class|index), padded to 256-point tiles; every 32-point group and
+//      every tile gets an axis-aligned bounding box;
+//   2. tile pairs whose boxes cannot contain a pair inside the cutoff (under the REFERENCE's
+//      single-shift minimum image, evaluated with interval arithmetic that is exact w.r.t. the fp64
+//      operation order) are dropped when the work list is built; inside a tile pair every warp
+//      repeats the test per 32-point chunk.  The set of pairs with rsq < rcut2 is unchanged, each
+//      surviving pair's rsq is computed in the reference's unfused fp64 order, so counts are bit-exact;
+//   3. persistent CTAs (2 per SM) pull tile pairs from a global counter; the j tile is staged in
+//      shared memory, each lane keeps one i point in registers; chunk pairs whose displacement
+//      interval lies inside [-l/2, l/2] on all axes take a path with no minimum-image work at all
+//      (8 fp64 ops / pair), the others the general path (11 fp64 ops + integer compares);
+//   4. in-cutoff pairs are compacted into a per-warp shared-memory queue (ballot + popc) and binned
+//      32 at a time at full lane utilisation: bin index from an fp32 sqrt estimate corrected against
+//      the exact fp64 edge table, then a shared-memory histogram atomic; per-CTA histograms are
+//      flushed to the per-frame uint64 global histogram when the frame changes.
+#include <float.h>
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TS = 256;        // points per tile
+constexpr int GS = 32;         // points per group (one warp's i points / one j chunk)
+constexpr int GPT = TS / GS;   // groups per tile
+constexpr int NWARP = 8;       // warps per CTA of the pair kernel
+constexpr int QCAP = 160;      // queue entries per warp (32 carried + 4 steps x 32)
+constexpr int MAX_CLS = 64;
+
+struct __align__(16) AtomRec {
+    double x, y, z;
+    int32_t cls;
+    int32_t idx;   // row in the caller's order, -1 for padding
+};
+static_assert(sizeof(AtomRec) == 32, "AtomRec must be 32 bytes");
+
+enum { MODE_HIST_UNIFORM = 0, MODE_HIST_TABLE = 1, MODE_LIST = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v)
+{
+    // spread the low 10 bits of v so that there are two zero bits between each
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// Lower bound of |f(d)| over d in [dlo, dhi], f = the reference's single-shift minimum image
+// (rdf_cn.py:50-55): f(d) = d - l if d > h, d + l if d < -h, else d  (h = l/2).  Because fp64
+// subtraction/addition are monotone, evaluating the pieces at the interval end points with the same
+// operations the pair loop uses gives a bound that no pair of the two boxes can undercut.
+// general <- true when some d of the interval needs a shift.
+__device__ __forceinline__ double axis_lower_bound(double alo, double ahi, double blo, double bhi, double l, double h,
+                                                   bool &general)
+{
+    const double dlo = __dsub_rn(alo, bhi), dhi = __dsub_rn(ahi, blo);
+    double best = DBL_MAX;
+    {
+        const double lo = fmax(dlo, -h), hi = fmin(dhi, h);
+        if (lo <= hi) best = (lo <= 0.0 && hi >= 0.0) ? 0.0 : fmin(fabs(lo), fabs(hi));
+    }
+    if (dhi > h) {
+        general = true;
+        const double lo = __dsub_rn(fmax(dlo, h), l), hi = __dsub_rn(dhi, l);
+        best = fmin(best, (lo <= 0.0 && hi >= 0.0) ? 0.0 : fmin(fabs(lo), fabs(hi)));
+    }
+    if (dlo < -h) {
+        general = true;
+        const double lo = __dadd_rn(dlo, l), hi = __dadd_rn(fmin(dhi, -h), l);
+        best = fmin(best, (lo <= 0.0 && hi >= 0.0) ? 0.0 : fmin(fabs(lo), fabs(hi)));
+    }
+    return best;
+}
+
+// box-pair test: returns true when some pair of the two boxes may have rsq < rcut2
+__device__ __forceinline__ bool boxes_may_interact(const double *a, const double *b, double lx, double ly, double lz,
+                                                   double rcut2, bool &general)
+{
+    if (a[0] > a[3] || b[0] > b[3]) return false;   // empty box (padding only)
+    general = false;
+    const double bx = axis_lower_bound(a[0], a[3], b[0], b[3], lx, lx * 0.5, general);
+    const double by = axis_lower_bound(a[1], a[4], b[1], b[4], ly, ly * 0.5, general);
+    const double bz = axis_lower_bound(a[2], a[5], b[2], b[5], lz, lz * 0.5, general);
+    const double lb = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
+    return lb < rcut2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// preparation kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_minmax(const double *__restrict__ xyz, int64_t n, double *__restrict__ mm)
+{
+    const int f = blockIdx.x;
+    const double *p = xyz + (int64_t)f * 3 * n;
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double v = p[c * n + i];
+            lo[c] = fmin(lo[c], v);
+            hi[c] = fmax(hi[c], v);
+        }
+    }
+    __shared__ double s[32][6];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        lo[c] = warp_min(lo[c]);
+        hi[c] = warp_max(hi[c]);
+    }
+    if (lane == 0) {
+        for (int c = 0; c < 3; ++c) {
+            s[w][c] = lo[c];
+            s[w][3 + c] = hi[c];
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int c = 0; c < 3; ++c) {
+            double a = lane < nw ? s[lane][c] : DBL_MAX, b = lane < nw ? s[lane][3 + c] : -DBL_MAX;
+            a = warp_min(a);
+            b = warp_max(b);
+            if (lane == 0) {
+                mm[f * 6 + c] = a;
+                mm[f * 6 + 3 + c] = b;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cell_count(const double *__restrict__ xyz, int64_t n, const double *__restrict__ mm,
+                                                    int bits, uint32_t *__restrict__ code, uint32_t *__restrict__ rank,
+                                                    uint32_t *__restrict__ cnt)
+{
+    const int f = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (bits == 0) {   // MDP_PAIR_NO_SORT (or a tiny set): keep the caller's order, single cell
+        code[(int64_t)f * n + i] = 0u;
+        rank[(int64_t)f * n + i] = (uint32_t)i;
+        return;
+    }
+    uint32_t c = 0;
+    {
+        const double *p = xyz + (int64_t)f * 3 * n;
+        const int nc = 1 << bits;
+        uint32_t q[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double lo = mm[f * 6 + a], hi = mm[f * 6 + 3 + a];
+            const double ext = hi - lo;
+            int v = ext > 0.0 ? (int)((p[a * n + i] - lo) / ext * (double)nc) : 0;
+            v = v < 0 ? 0 : (v >= nc ? nc - 1 : v);
+            q[a] = (uint32_t)v;
+        }
+        c = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+    }
+    const int64_t ncode = (int64_t)1 << (3 * bits);
+    code[(int64_t)f * n + i] = c;
+    rank[(int64_t)f * n + i] = atomicAdd(&cnt[(int64_t)f * ncode + c], 1u);
+}
+
+// exclusive scan of ncode counters per frame, in place (one CTA per frame)
+__global__ void __launch_bounds__(1024) k_cell_scan(uint32_t *__restrict__ cnt, int64_t ncode)
+{
+    uint32_t *c = cnt + (int64_t)blockIdx.x * ncode;
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int64_t per = (ncode + nt - 1) / nt;
+    const int64_t b = (int64_t)t * per, e = b + per < ncode ? b + per : ncode;
+    uint32_t s = 0;
+    for (int64_t k = b; k < e; ++k) s += c[k];
+    __shared__ uint32_t ws[32];
+    const int lane = t & 31, w = t >> 5;
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t v = lane < (nt >> 5) ? ws[lane] : 0u;
+        uint32_t iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += u;
+        }
+        ws[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = ws[w] + inc - s;
+    for (int64_t k = b; k < e; ++k) {
+        const uint32_t v = c[k];
+        c[k] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const double *__restrict__ xyz, const int32_t *__restrict__ cls,
+                                                 int64_t cls_stride, int64_t n, int64_t npad, int bits,
+                                                 const uint32_t *__restrict__ code, const uint32_t *__restrict__ rank,
+                                                 const uint32_t *__restrict__ cnt, double pad_sign, AtomRec *__restrict__ rec)
+{
+    const int f = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    AtomRec r;
+    int64_t pos;
+    if (i < n) {
+        const double *p = xyz + (int64_t)f * 3 * n;
+        const int64_t ncode = (int64_t)1 << (3 * bits);
+        pos = (int64_t)cnt[(int64_t)f * ncode + code[(int64_t)f * n + i]] + rank[(int64_t)f * n + i];
+        r.x = p[i];
+        r.y = p[n + i];
+        r.z = p[2 * n + i];
+        r.cls = cls ? cls[(int64_t)f * cls_stride + i] : 0;
+        r.idx = (int32_t)i;
+    } else {
+        // padding: far away, pairwise distinct, opposite sign for the two sets so that no pad-pad
+        // pair of a rectangular call can coincide
+        pos = i;
+        r.x = pad_sign * (1.0e30 + (double)(i - n) * 1.0e25);
+        r.y = 0.0;
+        r.z = 0.0;
+        r.cls = 0;
+        r.idx = -1;
+    }
+    rec[(int64_t)f * npad + pos] = r;
+}
+
+// group (32 points) and tile (256 points) bounding boxes over the valid points; one CTA per tile
+__global__ void __launch_bounds__(TS) k_aabb(const AtomRec *__restrict__ rec, int64_t npad, int ngroups, int ntiles,
+                                             double *__restrict__ gaabb, double *__restrict__ taabb)
+{
+    const int f = blockIdx.y, t = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const AtomRec r = rec[(int64_t)f * npad + (int64_t)t * TS + threadIdx.x];
+    const bool valid = r.idx >= 0;
+    double lo[3] = {valid ? r.x : DBL_MAX, valid ? r.y : DBL_MAX, valid ? r.z : DBL_MAX};
+    double hi[3] = {valid ? r.x : -DBL_MAX, valid ? r.y : -DBL_MAX, valid ? r.z : -DBL_MAX};
+    __shared__ double s[GPT][6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        lo[c] = warp_min(lo[c]);
+        hi[c] = warp_max(hi[c]);
+    }
+    if (lane == 0) {
+        double *g = gaabb + ((int64_t)f * ngroups + (int64_t)t * GPT + w) * 6;
+        for (int c = 0; c < 3; ++c) {
+            g[c] = lo[c];
+            g[3 + c] = hi[c];
+            s[w][c] = lo[c];
+            s[w][3 + c] = hi[c];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int c = threadIdx.x;
+        double v = s[0][c];
+        for (int k = 1; k < GPT; ++k) v = c < 3 ? fmin(v, s[k][c]) : fmax(v, s[k][c]);
+        taabb[((int64_t)f * ntiles + t) * 6 + c] = v;
+    }
+}
+
+// one warp per (frame, ta) row: count (FILL=false) or emit (FILL=true) the tile pairs that may interact
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_items(const double *__restrict__ taabbA, const double *__restrict__ taabbB, int ntA,
+                                               int ntB, bool symm, bool nocull, const double *__restrict__ box,
+                                               double rcut2, int nframes, uint32_t *__restrict__ rowcnt,
+                                               const uint32_t *__restrict__ rowoff, uint64_t *__restrict__ items)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= (int64_t)nframes * ntA) return;
+    const int f = (int)(row / ntA), ta = (int)(row % ntA);
+    const double lx = box[f * 3 + 0], ly = box[f * 3 + 1], lz = box[f * 3 + 2];
+    double a[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a[c] = taabbA[((int64_t)f * ntA + ta) * 6 + c];
+    uint32_t count = 0;
+    const uint32_t base = FILL ? rowoff[row] : 0u;
+    for (int tb0 = symm ? ta : 0; tb0 < ntB; tb0 += 32) {
+        const int tb = tb0 + lane;
+        bool ok = false;
+        if (tb < ntB) {
+            double b[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) b[c] = taabbB[((int64_t)f * ntB + tb) * 6 + c];
+            bool general;
+            ok = boxes_may_interact(a, b, lx, ly, lz, rcut2, general);
+            if (nocull) ok = !(a[0] > a[3] || b[0] > b[3]);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (FILL && ok) {
+            const uint32_t pos = base + count + __popc(m & ((1u << lane) - 1u));
+            items[pos] = ((uint64_t)f << 44) | ((uint64_t)ta << 22) | (uint64_t)tb;
+        }
+        count += __popc(m);
+    }
+    if (!FILL && lane == 0) rowcnt[row] = count;
+}
+
+// exclusive scan over the rows (single CTA); also resets the work counter and records the totals
+__global__ void __launch_bounds__(1024) k_row_scan(const uint32_t *__restrict__ rowcnt, uint32_t *__restrict__ rowoff,
+                                                   int64_t nrows, unsigned long long *__restrict__ total,
+                                                   unsigned int *__restrict__ counter, unsigned long long *__restrict__ stats,
+                                                   unsigned long long nominal)
+{
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int64_t per = (nrows + nt - 1) / nt;
+    const int64_t b = (int64_t)t * per, e = b + per < nrows ? b + per : nrows;
+    uint32_t s = 0;
+    for (int64_t k = b; k < e; ++k) s += rowcnt[k];
+    __shared__ uint32_t ws[32];
+    const int lane = t & 31, w = t >> 5;
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const uint32_t v = lane < (nt >> 5) ? ws[lane] : 0u;
+        uint32_t iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += u;
+        }
+        ws[lane] = iv - v;
+        if (lane == 31) {
+            *total = (unsigned long long)iv;
+            *counter = 0u;
+            atomicAdd(&stats[0], (unsigned long long)iv);
+            atomicAdd(&stats[1], nominal);
+        }
+    }
+    __syncthreads();
+    uint32_t run = ws[w] + inc - s;
+    for (int64_t k = b; k < e; ++k) {
+        const uint32_t v = rowcnt[k];
+        rowoff[k] = run;
+        run += v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the pair kernel
+// ---------------------------------------------------------------------------------------------
+struct PairParams {
+    const AtomRec *recA, *recB;
+    const double *gaabbA, *gaabbB;
+    int64_t npadA, npadB;
+    int ngA, ngB;
+    const double *box;               // device [F][3]
+    const uint64_t *items;
+    const unsigned long long *total;
+    unsigned int *counter;
+    unsigned long long *stats;
+    double rcut2;                    // pre-filter cutoff (max of all cutoffs)
+    // histogram modes
+    int nbins, nrows, nclsB;
+    const double2 *edges2;           // device [nbins+1]: {e[k], e[k+1]}, e[nbins+1] = +inf
+    const int *cptab;                // device [nclsA*nclsB] -> histogram row
+    float inv_ddr;
+    unsigned long long *hist;        // device [F][nrows][nbins]
+    int edges_in_smem;
+    // list mode
+    double rin2, rout2;
+    int shell_mode, exclude_same;
+    int32_t *list;
+    double *list_rsq;
+    long long capacity;
+    unsigned long long *list_count;
+    int frame0;                      // global index of the first frame of this sub-batch
+    int nocull;                      // MDP_PAIR_NO_CULL: evaluate every chunk pair on the general path
+};
+
+struct Shared {
+    AtomRec *tileB;
+    double *baabb;
+    double *qr;
+    uint2 *qm;
+    const double2 *edges2;
+    const int *cptab;
+    unsigned int *hist;
+};
+
+template <int MODE, bool MULTICLS>
+__device__ __forceinline__ void drain(const PairParams &p, const Shared &sh, int lane, int m, const double *qr,
+                                      const uint2 *qm, int base, int frame)
+{
+    __syncwarp();
+    if (MODE == MODE_LIST) {
+        bool ok = false;
+        double r2 = 0.0;
+        uint2 me = make_uint2(0u, 0u);
+        if (lane < m) {
+            r2 = qr[base + lane];
+            me = qm[base + lane];
+            ok = p.shell_mode ? (r2 > p.rin2 && r2 <= p.rout2) : (r2 < p.rout2);
+            if (p.exclude_same && me.x == me.y) ok = false;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (mask) {
+            unsigned long long b0 = 0;
+            if (lane == 0) b0 = atomicAdd(p.list_count, (unsigned long long)__popc(mask));
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+            if (ok) {
+                const long long pos = (long long)b0 + __popc(mask & ((1u << lane) - 1u));
+                if (pos < p.capacity) {
+                    p.list[pos * 3 + 0] = frame;
+                    p.list[pos * 3 + 1] = (int32_t)me.x;
+                    p.list[pos * 3 + 2] = (int32_t)me.y;
+                    if (p.list_rsq) p.list_rsq[pos] = r2;
+                }
+            }
+        }
+    } else {
+        if (lane < m) {
+            const double r2 = qr[base + lane];
+            if (r2 < p.rcut2) {
+                int k;
+                if (MODE == MODE_HIST_UNIFORM) {
+                    // fp32 estimate of sqrt(rsq)/ddr is within +-1 of the reference bin; the exact fp64
+                    // edge pair {e[k], e[k+1]} settles it (see mdp_bin_edges)
+                    float s;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(__double2float_rz(r2)));
+                    s *= p.inv_ddr;
+                    k = (int)s;
+                    k = k < 0 ? 0 : (k > p.nbins ? p.nbins : k);
+                    const double2 e = sh.edges2[k];
+                    k += (r2 >= e.y) ? 1 : 0;
+                    k -= (r2 < e.x) ? 1 : 0;
+                } else {
+                    k = 0;
+                    for (int j = 1; j <= p.nbins; ++j) k += (sh.edges2[j].x <= r2) ? 1 : 0;
+                }
+                if (k >= 0 && k < p.nbins) {
+                    const int row = MULTICLS ? sh.cptab[qm[base + lane].x] : 0;
+                    atomicAdd(&sh.hist[row * p.nbins + k], 1u);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int MODE, bool MULTICLS, bool GENERAL, bool TRI>
+__device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh, const AtomRec *__restrict__ cb,
+                                           double xi, double yi, double zi, uint32_t mi, double lx, double ly, double lz,
+                                           long long hxb, long long hyb, long long hzb, int rc_hi, int lane, int &qn,
+                                           double *qr, uint2 *qm, int frame)
+{
+    constexpr bool META = MULTICLS || MODE == MODE_LIST;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int j0 = 0; j0 < GS; j0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = j0 + u;
+            const double2 xy = *reinterpret_cast<const double2 *>(&cb[jj]);
+            const double2 zw = *(reinterpret_cast<const double2 *>(&cb[jj]) + 1);
+            double ax = __dsub_rn(xi, xy.x), ay = __dsub_rn(yi, xy.y), az = __dsub_rn(zi, zw.x);
+            if (GENERAL) {
+                // single-shift minimum image (rdf_cn.py:50-55); only the square is used, so
+                // (d - sign(d) l)^2 == (|d| - l)^2 bit for bit
+                ax = fabs(ax);
+                ay = fabs(ay);
+                az = fabs(az);
+                if (__double_as_longlong(ax) > hxb) ax = __dsub_rn(ax, lx);
+                if (__double_as_longlong(ay) > hyb) ay = __dsub_rn(ay, ly);
+                if (__double_as_longlong(az) > hzb) az = __dsub_rn(az, lz);
+            }
+            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+            bool hit = __double2hiint(r2) <= rc_hi;   // superset of rsq < rcut2; settled exactly in drain()
+            if (TRI) hit = hit && (jj > lane);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                if (hit) {
+                    const int pos = qn + __popc(m & lt);
+                    qr[pos] = r2;
+                    if (META) {
+                        if (MODE == MODE_LIST)
+                            qm[pos] = make_uint2(mi, (uint32_t)__double2hiint(zw.y));
+                        else
+                            qm[pos] = make_uint2(mi + (uint32_t)__double2loint(zw.y), 0u);
+                    }
+                }
+                qn += __popc(m);
+            }
+        }
+        while (qn >= 32) {
+            qn -= 32;
+            drain<MODE, MULTICLS>(p, sh, lane, 32, qr, qm, qn, frame);
+        }
+    }
+}
+
+template <int MODE, bool MULTICLS, bool SYMM>
+__global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool META = MULTICLS || MODE == MODE_LIST;
+    Shared sh;
+    unsigned char *sp = smem_raw;
+    sh.tileB = reinterpret_cast<AtomRec *>(sp);
+    sp += TS * sizeof(AtomRec);
+    sh.baabb = reinterpret_cast<double *>(sp);
+    sp += GPT * 6 * sizeof(double);
+    sh.qr = reinterpret_cast<double *>(sp);
+    sp += NWARP * QCAP * sizeof(double);
+    sh.qm = reinterpret_cast<uint2 *>(sp);
+    if (META) sp += NWARP * QCAP * sizeof(uint2);
+    double2 *edges_s = reinterpret_cast<double2 *>(sp);
+    if (MODE != MODE_LIST && p.edges_in_smem) sp += (size_t)(p.nbins + 1) * sizeof(double2);
+    int *cptab_s = reinterpret_cast<int *>(sp);
+    if (MULTICLS) sp += (size_t)((MAX_CLS * MAX_CLS * 4 + 15) & ~15);
+    sh.hist = reinterpret_cast<unsigned int *>(sp);
+    __shared__ unsigned int s_item;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nhist = MODE == MODE_LIST ? 0 : p.nrows * p.nbins;
+
+    if (MODE != MODE_LIST) {
+        if (p.edges_in_smem) {
+            for (int k = tid; k <= p.nbins; k += blockDim.x) edges_s[k] = p.edges2[k];
+            sh.edges2 = edges_s;
+        } else {
+            sh.edges2 = p.edges2;
+        }
+        for (int k = tid; k < nhist; k += blockDim.x) sh.hist[k] = 0u;
+    }
+    if (MULTICLS) {
+        for (int k = tid; k < MAX_CLS * MAX_CLS; k += blockDim.x) cptab_s[k] = p.cptab[k];
+        sh.cptab = cptab_s;
+    }
+    double *qr = sh.qr + w * QCAP;
+    uint2 *qm = sh.qm + w * QCAP;
+    int qn = 0;
+    const int rc_hi = __double2hiint(p.rcut2);
+    const unsigned long long total = *p.total;
+
+    int cur_frame = -1;
+    double lx = 0, ly = 0, lz = 0;
+    long long hxb = 0, hyb = 0, hzb = 0;
+    unsigned long long my_chunks = 0;
+
+    unsigned int nxt = 0;
+    if (tid == 0) nxt = atomicAdd(p.counter, 1u);
+    for (;;) {
+        __syncthreads();   // every warp is done with tileB / s_item of the previous item
+        if (tid == 0) s_item = nxt;
+        __syncthreads();
+        const unsigned int it = s_item;
+        if ((unsigned long long)it >= total) break;
+        if (tid == 0) nxt = atomicAdd(p.counter, 1u);   // prefetch the next work index
+        const uint64_t item = p.items[it];
+        const int f = (int)(item >> 44), ta = (int)((item >> 22) & 0x3fffffu), tb = (int)(item & 0x3fffffu);
+
+        if (f != cur_frame) {
+            if (cur_frame >= 0) {
+                // finish the previous frame: drain the queues, flush the CTA histogram
+                if (qn > 0) {
+                    drain<MODE, MULTICLS>(p, sh, lane, qn, qr, qm, 0, p.frame0 + cur_frame);
+                    qn = 0;
+                }
+                if (MODE != MODE_LIST) {
+                    __syncthreads();
+                    unsigned long long *hg = p.hist + (int64_t)(p.frame0 + cur_frame) * nhist;
+                    for (int k = tid; k < nhist; k += blockDim.x) {
+                        const unsigned int v = sh.hist[k];
+                        if (v) {
+                            atomicAdd(&hg[k], (unsigned long long)v);
+                            sh.hist[k] = 0u;
+                        }
+                    }
+                }
+            }
+            cur_frame = f;
+            lx = p.box[f * 3 + 0];
+            ly = p.box[f * 3 + 1];
+            lz = p.box[f * 3 + 2];
+            hxb = __double_as_longlong(lx * 0.5);
+            hyb = __double_as_longlong(ly * 0.5);
+            hzb = __double_as_longlong(lz * 0.5);
+        }
+
+        // stage the j tile and its chunk boxes
+        {
+            const AtomRec *src = p.recB + (int64_t)f * p.npadB + (int64_t)tb * TS;
+            const double2 *s2 = reinterpret_cast<const double2 *>(src);
+            double2 *d2 = reinterpret_cast<double2 *>(sh.tileB);
+            d2[2 * tid] = s2[2 * tid];
+            d2[2 * tid + 1] = s2[2 * tid + 1];
+            if (tid < GPT * 6) sh.baabb[tid] = p.gaabbB[((int64_t)f * p.ngB + (int64_t)tb * GPT) * 6 + tid];
+        }
+        // my i point and my group's box
+        const AtomRec me = p.recA[(int64_t)f * p.npadA + (int64_t)ta * TS + tid];
+        double ga[6];
+        {
+            const double *g = p.gaabbA + ((int64_t)f * p.ngA + (int64_t)ta * GPT + w) * 6;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) ga[c] = g[c];
+        }
+        __syncthreads();
+
+        const bool diag = SYMM && ta == tb;
+        bool need = false, gen = false;
+        if (lane < GPT) {
+            const int c = lane;
+            if (!(diag && c < w)) {
+                double bb[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) bb[k] = sh.baabb[c * 6 + k];
+                need = boxes_may_interact(ga, bb, lx, ly, lz, p.rcut2, gen);
+                if (p.nocull) {
+                    need = !(ga[0] > ga[3] || bb[0] > bb[3]);
+                    gen = true;
+                }
+            }
+        }
+        unsigned needmask = __ballot_sync(0xffffffffu, need);
+        const unsigned genmask = __ballot_sync(0xffffffffu, gen);
+        const uint32_t mi = MODE == MODE_LIST ? (uint32_t)me.idx : (uint32_t)(me.cls * p.nclsB);
+        const int frame = p.frame0 + f;
+        while (needmask) {
+            const int c = __ffs(needmask) - 1;
+            needmask &= needmask - 1;
+            const AtomRec *cb = sh.tileB + c * GS;
+            const bool g = (genmask >> c) & 1u;
+            const bool tri = diag && c == w;
+            ++my_chunks;
+            if (g) {
+                if (tri)
+                    chunk_loop<MODE, MULTICLS, true, true>(p, sh, cb, me.x, me.y, me.z, mi, lx, ly, lz, hxb, hyb, hzb, rc_hi,
+                                                           lane, qn, qr, qm, frame);
+                else
+                    chunk_loop<MODE, MULTICLS, true, false>(p, sh, cb, me.x, me.y, me.z, mi, lx, ly, lz, hxb, hyb, hzb,
+                                                            rc_hi, lane, qn, qr, qm, frame);
+            } else {
+                if (tri)
+                    chunk_loop<MODE, MULTICLS, false, true>(p, sh, cb, me.x, me.y, me.z, mi, lx, ly, lz, hxb, hyb, hzb,
+                                                            rc_hi, lane, qn, qr, qm, frame);
+                else
+                    chunk_loop<MODE, MULTICLS, false, false>(p, sh, cb, me.x, me.y, me.z, mi, lx, ly, lz, hxb, hyb, hzb,
+                                                             rc_hi, lane, qn, qr, qm, frame);
+            }
+        }
+    }
+
+    // tail: last frame of this CTA
+    if (cur_frame >= 0) {
+        if (qn > 0) {
+            drain<MODE, MULTICLS>(p, sh, lane, qn, qr, qm, 0, p.frame0 + cur_frame);
+            qn = 0;
+        }
+        if (MODE != MODE_LIST) {
+            __syncthreads();
+            unsigned long long *hg = p.hist + (int64_t)(p.frame0 + cur_frame) * nhist;
+            for (int k = tid; k < nhist; k += blockDim.x) {
+                const unsigned int v = sh.hist[k];
+                if (v) atomicAdd(&hg[k], (unsigned long long)v);
+            }
+        }
+    }
+    if (lane == 0 && my_chunks) atomicAdd(&p.stats[2], my_chunks * (unsigned long long)(GS * GS));
+}
+
+// out[f][r][b] = sum_rows w[r][row] * (cumulative ? prefix : value) hist[f][row][b]
+__global__ void __launch_bounds__(256) k_hist_reduce(const unsigned long long *__restrict__ hist, int rows, int nbins,
+                                                     int nout, const int *__restrict__ wts, int cumulative,
+                                                     unsigned long long *__restrict__ out)
+{
+    const int f = blockIdx.y;
+    const int r = blockIdx.x;
+    const unsigned long long *h = hist + (int64_t)f * rows * nbins;
+    unsigned long long *o = out + ((int64_t)f * nout + r) * nbins;
+    if (!cumulative) {
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+            unsigned long long s = 0;
+            for (int q = 0; q < rows; ++q) {
+                const int wv = wts[r * rows + q];
+                if (wv) s += (unsigned long long)wv * h[(int64_t)q * nbins + b];
+            }
+            o[b] = s;
+        }
+    } else if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int b = 0; b < nbins; ++b) {
+            for (int q = 0; q < rows; ++q) {
+                const int wv = wts[r * rows + q];
+                if (wv) run += (unsigned long long)wv * h[(int64_t)q * nbins + b];
+            }
+            o[b] = run;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------
+struct SetPlan {
+    int64_t n = 0, npad = 0;
+    int ntiles = 0, ngroups = 0, bits = 0;
+    int64_t ncode = 1;
+    // device scratch (per sub-batch)
+    AtomRec *rec = nullptr;
+    double *gaabb = nullptr, *taabb = nullptr, *mm = nullptr;
+    uint32_t *code = nullptr, *rank = nullptr, *cnt = nullptr;
+};
+
+static void plan_set(SetPlan &s, int64_t n, bool nosort)
+{
+    s.n = n;
+    s.ntiles = (int)ceil_div<int64_t>(n, TS);
+    s.npad = (int64_t)s.ntiles * TS;
+    s.ngroups = s.ntiles * GPT;
+    // ~4 points per Morton cell
+    int bits = 0;
+    if (!nosort) {
+        while (bits < 7 && ((int64_t)1 << (3 * (bits + 1))) * 4 <= n * 2) ++bits;
+    }
+    s.bits = bits;
+    s.ncode = (int64_t)1 << (3 * bits);
+}
+
+static size_t set_bytes_per_frame(const SetPlan &s)
+{
+    return align256(s.npad * sizeof(AtomRec)) + align256(s.ngroups * 48) + align256(s.ntiles * 48) + align256(48) +
+           2 * align256(s.n * 4) + align256(s.ncode * 4) + 4096;
+}
+
+static int carve_set(mdp_ctx *ctx, SetPlan &s, int F)
+{
+    s.rec = (AtomRec *)ctx->arena_take((size_t)F * s.npad * sizeof(AtomRec));
+    s.gaabb = (double *)ctx->arena_take((size_t)F * s.ngroups * 48);
+    s.taabb = (double *)ctx->arena_take((size_t)F * s.ntiles * 48);
+    s.mm = (double *)ctx->arena_take((size_t)F * 48);
+    s.code = (uint32_t *)ctx->arena_take((size_t)F * s.n * 4);
+    s.rank = (uint32_t *)ctx->arena_take((size_t)F * s.n * 4);
+    s.cnt = (uint32_t *)ctx->arena_take((size_t)F * s.ncode * 4);
+    if (!s.rec || !s.gaabb || !s.taabb || !s.mm || !s.code || !s.rank || !s.cnt) {
+        mdp_set_error("internal: scratch arena exhausted while carving a point set");
+        return MDP_ERR_OOM;
+    }
+    return 0;
+}
+
+static int sort_set(mdp_ctx *ctx, SetPlan &s, int F, const double *xyz, const int32_t *cls, int64_t cls_stride,
+                    double pad_sign, cudaStream_t st)
+{
+    if (s.bits > 0) {
+        k_minmax<<<F, 1024, 0, st>>>(xyz, s.n, s.mm);
+        MDP_LAUNCHED(ctx);
+    }
+    MDP_CUDA(cudaMemsetAsync(s.cnt, 0, (size_t)F * s.ncode * 4, st));
+    dim3 g1((unsigned)ceil_div<int64_t>(s.n, 256), F);
+    k_cell_count<<<g1, 256, 0, st>>>(xyz, s.n, s.mm, s.bits, s.code, s.rank, s.cnt);
+    MDP_LAUNCHED(ctx);
+    k_cell_scan<<<F, 1024, 0, st>>>(s.cnt, s.ncode);
+    MDP_LAUNCHED(ctx);
+    dim3 g2((unsigned)ceil_div<int64_t>(s.npad, 256), F);
+    k_scatter<<<g2, 256, 0, st>>>(xyz, cls, cls_stride, s.n, s.npad, s.bits, s.code, s.rank, s.cnt, pad_sign, s.rec);
+    MDP_LAUNCHED(ctx);
+    dim3 g3(s.ntiles, F);
+    k_aabb<<<g3, TS, 0, st>>>(s.rec, s.npad, s.ngroups, s.ntiles, s.gaabb, s.taabb);
+    MDP_LAUNCHED(ctx);
+    return mdp_check_launch("pair prep");
+}
+
+typedef void (*pair_kernel_t)(const PairParams);
+
+template <int MODE>
+static pair_kernel_t pick_kernel(bool multicls, bool symm)
+{
+    if (multicls) return symm ? k_pair<MODE, true, true> : k_pair<MODE, true, false>;
+    return symm ? k_pair<MODE, false, true> : k_pair<MODE, false, false>;
+}
+
+struct PairCall {
+    int mode = MODE_HIST_UNIFORM;
+    int nframes = 0;
+    int64_t n_a = 0, n_b = 0;
+    const double *xyz_a = nullptr, *xyz_b = nullptr;
+    const int32_t *cls_a = nullptr, *cls_b = nullptr;
+    int64_t cls_stride_a = 0, cls_stride_b = 0;
+    int ncls_a = 1, ncls_b = 1;
+    const double *box = nullptr;   // host
+    double rcut2 = 0;
+    const double *edges = nullptr; // host
+    int nbins = 0;
+    double uniform_ddr = 0;
+    uint64_t *hist_out = nullptr;
+    int flags = 0;
+    // list
+    double rin2 = 0, rout2 = 0;
+    int shell_mode = 0, exclude_same = 0;
+    int32_t *list = nullptr;
+    double *list_rsq = nullptr;
+    int64_t capacity = 0;
+    int64_t *list_count = nullptr;
+};
+
+static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
+{
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    const bool symm = c.xyz_b == nullptr;
+    const bool nosort = (c.flags & MDP_PAIR_NO_SORT) != 0;
+    const bool nocull = (c.flags & MDP_PAIR_NO_CULL) != 0;
+    const bool hist_mode = c.mode != MODE_LIST;
+    const int nclsB = symm ? c.ncls_a : c.ncls_b;
+    const int nrows = symm ? c.ncls_a * (c.ncls_a + 1) / 2 : c.ncls_a * c.ncls_b;
+    const bool multicls = hist_mode && nrows > 1;
+
+    SetPlan A, B;
+    plan_set(A, c.n_a, nosort);
+    if (!symm) plan_set(B, c.n_b, nosort);
+    const SetPlan &Bp = symm ? A : B;
+    MDP_REQUIRE(A.ntiles < (1 << 22) && Bp.ntiles < (1 << 22), "pair: too many tiles");
+
+    // shared memory budget of the pair kernel
+    size_t smem = TS * sizeof(AtomRec) + GPT * 6 * sizeof(double) + NWARP * QCAP * sizeof(double);
+    const bool meta = multicls || !hist_mode;
+    if (meta) smem += NWARP * QCAP * sizeof(uint2);
+    int edges_in_smem = 0;
+    if (hist_mode) {
+        const size_t hist_bytes = (size_t)nrows * c.nbins * 4;
+        const size_t edge_bytes = (size_t)(c.nbins + 1) * sizeof(double2);
+        if (multicls) smem += (MAX_CLS * MAX_CLS * 4 + 15) & ~15;
+        const size_t cap = std::min<size_t>(ctx->smem_optin, 72 * 1024);   // keep 3 CTAs per SM
+        MDP_REQUIRE(smem + hist_bytes <= ctx->smem_optin,
+                    "pair: histogram of %d rows x %d bins does not fit in shared memory (%zu B needed); "
+                    "reduce the number of distinct classes or bins per call",
+                    nrows, c.nbins, smem + hist_bytes);
+        if (smem + hist_bytes + edge_bytes <= cap) {
+            edges_in_smem = 1;
+            smem += edge_bytes;
+        }
+        smem += hist_bytes;
+    }
+
+    // sub-batching over frames so that scratch stays bounded
+    const size_t items_worst = symm ? (size_t)A.ntiles * (A.ntiles + 1) / 2 : (size_t)A.ntiles * Bp.ntiles;
+    const size_t per_frame = set_bytes_per_frame(A) + (symm ? 0 : set_bytes_per_frame(B)) + align256(items_worst * 8) +
+                             2 * align256((size_t)A.ntiles * 4) + 64;
+    const size_t fixed = align256((size_t)(c.nbins + 2) * sizeof(double2)) + align256(MAX_CLS * MAX_CLS * 4) + 8192;
+    const size_t target = std::min<size_t>(ctx->slab_limit, (size_t)3 << 29);   // 1.5 GiB working set
+    int Fsub = (int)std::max<size_t>(1, std::min<size_t>((size_t)c.nframes, (target - std::min(target, fixed)) / per_frame));
+    Fsub = std::min(Fsub, 1 << 19);
+    MDP_REQUIRE((size_t)Fsub * items_worst < ((size_t)1 << 32), "pair: work list too long");
+    int rc = ctx->arena_reserve(fixed + (size_t)Fsub * per_frame + (size_t)Fsub * 24 + 65536);
+    if (rc) return rc;
+
+    // edge pairs / class-pair table (host side staging)
+    std::vector<double2> e2;
+    std::vector<int> cpt(MAX_CLS * MAX_CLS, 0);
+    if (hist_mode) {
+        e2.resize(c.nbins + 2);
+        for (int k = 0; k <= c.nbins; ++k) {
+            const double lo = k == 0 ? 0.0 : c.edges[k];
+            const double hi = k + 1 <= c.nbins ? c.edges[k + 1] : INFINITY;
+            e2[k] = make_double2(lo, hi);
+        }
+        e2[c.nbins + 1] = make_double2(INFINITY, INFINITY);
+        if (symm) {
+            for (int i = 0; i < c.ncls_a; ++i)
+                for (int j = 0; j < c.ncls_a; ++j) {
+                    const int a = std::min(i, j), b = std::max(i, j);
+                    cpt[i * c.ncls_a + j] = a * c.ncls_a - a * (a - 1) / 2 + (b - a);
+                }
+        } else {
+            for (int i = 0; i < c.ncls_a; ++i)
+                for (int j = 0; j < c.ncls_b; ++j) cpt[i * c.ncls_b + j] = i * c.ncls_b + j;
+        }
+    }
+
+    pair_kernel_t kern = c.mode == MODE_HIST_UNIFORM ? pick_kernel<MODE_HIST_UNIFORM>(multicls, symm)
+                         : c.mode == MODE_HIST_TABLE ? pick_kernel<MODE_HIST_TABLE>(multicls, symm)
+                                                     : pick_kernel<MODE_LIST>(false, symm);
+    MDP_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    MDP_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), st));
+
+    for (int f0 = 0; f0 < c.nframes; f0 += Fsub) {
+        const int F = std::min(Fsub, c.nframes - f0);
+        ctx->arena_reset();
+        double2 *d_e2 = (double2 *)ctx->arena_take((size_t)(c.nbins + 2) * sizeof(double2));
+        int *d_cpt = (int *)ctx->arena_take(MAX_CLS * MAX_CLS * 4);
+        double *d_box = (double *)ctx->arena_take((size_t)F * 24);
+        unsigned long long *d_total = (unsigned long long *)ctx->arena_take(16);
+        unsigned int *d_counter = (unsigned int *)(d_total + 1);
+        rc = carve_set(ctx, A, F);
+        if (rc) return rc;
+        if (!symm) {
+            rc = carve_set(ctx, B, F);
+            if (rc) return rc;
+        }
+        uint32_t *rowcnt = (uint32_t *)ctx->arena_take((size_t)F * A.ntiles * 4);
+        uint32_t *rowoff = (uint32_t *)ctx->arena_take((size_t)F * A.ntiles * 4);
+        uint64_t *items = (uint64_t *)ctx->arena_take((size_t)F * items_worst * 8);
+        if (!d_e2 || !d_cpt || !d_box || !d_total || !rowcnt || !rowoff || !items) {
+            mdp_set_error("internal: scratch arena exhausted");
+            return MDP_ERR_OOM;
+        }
+        if (hist_mode) {
+            MDP_CUDA(cudaMemcpyAsync(d_e2, e2.data(), e2.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
+            MDP_CUDA(cudaMemcpyAsync(d_cpt, cpt.data(), cpt.size() * 4, cudaMemcpyHostToDevice, st));
+        }
+        MDP_CUDA(cudaMemcpyAsync(d_box, c.box + (size_t)f0 * 3, (size_t)F * 24, cudaMemcpyHostToDevice, st));
+
+        rc = sort_set(ctx, A, F, c.xyz_a + (size_t)f0 * 3 * c.n_a, c.cls_a ? c.cls_a + (size_t)f0 * c.cls_stride_a : nullptr,
+                      c.cls_stride_a, +1.0, st);
+        if (rc) return rc;
+        if (!symm) {
+            rc = sort_set(ctx, B, F, c.xyz_b + (size_t)f0 * 3 * c.n_b,
+                          c.cls_b ? c.cls_b + (size_t)f0 * c.cls_stride_b : nullptr, c.cls_stride_b, -1.0, st);
+            if (rc) return rc;
+        }
+        const SetPlan &Bs = symm ? A : B;
+        const int64_t nrows_items = (int64_t)F * A.ntiles;
+        const unsigned gi = (unsigned)ceil_div<int64_t>(nrows_items * 32, 256);
+        k_items<false><<<gi, 256, 0, st>>>(A.taabb, Bs.taabb, A.ntiles, Bs.ntiles, symm, nocull, d_box, c.rcut2, F, rowcnt,
+                                           rowoff, items);
+        MDP_LAUNCHED(ctx);
+        k_row_scan<<<1, 1024, 0, st>>>(rowcnt, rowoff, nrows_items, d_total, d_counter, ctx->d_stats,
+                                       (unsigned long long)F * (unsigned long long)items_worst);
+        MDP_LAUNCHED(ctx);
+        k_items<true><<<gi, 256, 0, st>>>(A.taabb, Bs.taabb, A.ntiles, Bs.ntiles, symm, nocull, d_box, c.rcut2, F, rowcnt,
+                                          rowoff, items);
+        MDP_LAUNCHED(ctx);
+
+        PairParams p;
+        memset(&p, 0, sizeof(p));
+        p.recA = A.rec;
+        p.recB = Bs.rec;
+        p.gaabbA = A.gaabb;
+        p.gaabbB = Bs.gaabb;
+        p.npadA = A.npad;
+        p.npadB = Bs.npad;
+        p.ngA = A.ngroups;
+        p.ngB = Bs.ngroups;
+        p.box = d_box;
+        p.items = items;
+        p.total = d_total;
+        p.counter = d_counter;
+        p.stats = ctx->d_stats;
+        p.rcut2 = c.rcut2;
+        p.nbins = c.nbins;
+        p.nrows = nrows;
+        p.nclsB = nclsB;
+        p.edges2 = d_e2;
+        p.cptab = d_cpt;
+        p.inv_ddr = c.uniform_ddr > 0 ? (float)(1.0 / c.uniform_ddr) : 0.f;
+        p.hist = (unsigned long long *)c.hist_out;
+        p.edges_in_smem = edges_in_smem;
+        p.rin2 = c.rin2;
+        p.rout2 = c.rout2;
+        p.shell_mode = c.shell_mode;
+        p.exclude_same = c.exclude_same;
+        p.list = c.list;
+        p.list_rsq = c.list_rsq;
+        p.capacity = c.capacity;
+        p.list_count = (unsigned long long *)c.list_count;
+        p.frame0 = f0;
+        p.nocull = nocull ? 1 : 0;
+        kern<<<ctx->sm_count * 3, NWARP * 32, smem, st>>>(p);
+        MDP_LAUNCHED(ctx);
+        rc = mdp_check_launch("k_pair");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int mdp_bin_edges(double ddr, int nb, double *edges)
+{
+    MDP_REQUIRE(ddr > 0 && nb > 0 && edges, "mdp_bin_edges: bad argument");
+    // bin(rsq) = (int64)(sqrt(rsq)/ddr) is monotone non-decreasing in rsq (IEEE sqrt and divide are
+    // monotone), so the smallest rsq reaching bin k is found by bisection on the (ordered) bit pattern.
+    auto bin_of = [ddr](double rsq) -> long long {
+        volatile double s = sqrt(rsq);
+        volatile double q = s / ddr;
+        return (long long)q;
+    };
+    edges[0] = 0.0;
+    for (int k = 1; k <= nb; ++k) {
+        uint64_t lo = 0;   // bin(lo) < k   (bin(0) = 0 < k)
+        double hi_d = ((double)k * ddr) * ((double)k * ddr) * 1.0000001 + 1e-300;
+        while (bin_of(hi_d) < k) hi_d *= 2.0;
+        uint64_t hi;
+        memcpy(&hi, &hi_d, 8);   // bin(hi) >= k
+        while (hi - lo > 1) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            double md;
+            memcpy(&md, &mid, 8);
+            if (bin_of(md) >= k)
+                hi = mid;
+            else
+                lo = mid;
+        }
+        memcpy(&edges[k], &hi, 8);
+    }
+    return 0;
+}
+
+int mdp_pair_hist(mdp_ctx *ctx, int nframes, int64_t n_a, const double *xyz_a, const int32_t *cls_a, int64_t cls_stride_a,
+                  int ncls_a, int64_t n_b, const double *xyz_b, const int32_t *cls_b, int64_t cls_stride_b, int ncls_b,
+                  const double *box, double rcut2, const double *edges, int nbins, double uniform_ddr, uint64_t *hist_out,
+                  int flags, void *stream)
+{
+    MDP_REQUIRE(ctx && xyz_a && box && edges && hist_out, "mdp_pair_hist: NULL argument");
+    MDP_REQUIRE(nframes > 0 && n_a > 0 && nbins > 0, "mdp_pair_hist: nframes, n_a and nbins must be positive");
+    MDP_REQUIRE(n_a < ((int64_t)1 << 30) && n_b < ((int64_t)1 << 30), "mdp_pair_hist: point sets limited to 2^30 points");
+    MDP_REQUIRE(ncls_a >= 1 && ncls_a <= MAX_CLS && (xyz_b == nullptr || (ncls_b >= 1 && ncls_b <= MAX_CLS)),
+                "mdp_pair_hist: class count must be in [1, %d]", MAX_CLS);
+    MDP_REQUIRE(xyz_b == nullptr || n_b > 0, "mdp_pair_hist: n_b must be positive when set B is given");
+    MDP_REQUIRE(rcut2 > 0, "mdp_pair_hist: rcut2 must be positive");
+    MDP_REQUIRE(uniform_ddr == 0.0 || nbins <= (1 << 18), "mdp_pair_hist: uniform binning limited to 2^18 bins");
+    MDP_REQUIRE(uniform_ddr > 0.0 || nbins <= 64, "mdp_pair_hist: table binning limited to 64 thresholds");
+    PairCall c;
+    c.mode = uniform_ddr > 0 ? MODE_HIST_UNIFORM : MODE_HIST_TABLE;
+    c.nframes = nframes;
+    c.n_a = n_a;
+    c.xyz_a = xyz_a;
+    c.cls_a = cls_a;
+    c.cls_stride_a = cls_stride_a;
+    c.ncls_a = ncls_a;
+    c.n_b = n_b;
+    c.xyz_b = xyz_b;
+    c.cls_b = cls_b;
+    c.cls_stride_b = cls_stride_b;
+    c.ncls_b = ncls_b;
+    c.box = box;
+    c.rcut2 = rcut2;
+    c.edges = edges;
+    c.nbins = nbins;
+    c.uniform_ddr = uniform_ddr;
+    c.hist_out = hist_out;
+    c.flags = flags;
+    return run_pair_call(ctx, c, (cudaStream_t)stream);
+}
+
+int mdp_pair_list(mdp_ctx *ctx, int nframes, int64_t n_a, const double *xyz_a, int64_t n_b, const double *xyz_b,
+                  const double *box, double rin2, double rout2, int shell_mode, int exclude_same_index, int32_t *list_out,
+                  double *rsq_out, int64_t capacity, int64_t *count_out, void *stream)
+{
+    MDP_REQUIRE(ctx && xyz_a && xyz_b && box && list_out && count_out, "mdp_pair_list: NULL argument");
+    MDP_REQUIRE(nframes > 0 && n_a > 0 && n_b > 0 && capacity > 0, "mdp_pair_list: sizes must be positive");
+    MDP_REQUIRE(n_a < ((int64_t)1 << 30) && n_b < ((int64_t)1 << 30), "mdp_pair_list: point sets limited to 2^30 points");
+    MDP_REQUIRE(rout2 > 0, "mdp_pair_list: rout2 must be positive");
+    PairCall c;
+    c.mode = MODE_LIST;
+    c.nframes = nframes;
+    c.n_a = n_a;
+    c.xyz_a = xyz_a;
+    c.n_b = n_b;
+    c.xyz_b = xyz_b;
+    c.box = box;
+    // pre-filter must pass rsq <= rout2 too: use the next double above rout2 as the strict cutoff
+    c.rcut2 = nextafter(rout2, INFINITY);
+    c.rin2 = rin2;
+    c.rout2 = rout2;
+    c.shell_mode = shell_mode;
+    c.exclude_same = exclude_same_index;
+    c.list = list_out;
+    c.list_rsq = rsq_out;
+    c.capacity = capacity;
+    c.list_count = count_out;
+    return run_pair_call(ctx, c, (cudaStream_t)stream);
+}
+
+int mdp_hist_reduce(mdp_ctx *ctx, int nframes, int rows, int nbins, const uint64_t *hist, int nout, const int32_t *weights,
+                    int cumulative, uint64_t *out, void *stream)
+{
+    MDP_REQUIRE(ctx && hist && weights && out, "mdp_hist_reduce: NULL argument");
+    MDP_REQUIRE(nframes > 0 && rows > 0 && nbins > 0 && nout > 0, "mdp_hist_reduce: sizes must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->arena_reserve((size_t)nout * rows * 4 + 4096);
+    if (rc) return rc;
+    ctx->arena_reset();
+    int *d_w = (int *)ctx->arena_take((size_t)nout * rows * 4);
+    MDP_CUDA(cudaMemcpyAsync(d_w, weights, (size_t)nout * rows * 4, cudaMemcpyHostToDevice, st));
+    dim3 g(nout, nframes);
+    k_hist_reduce<<<g, 256, 0, st>>>((const unsigned long long *)hist, rows, nbins, nout, d_w, cumulative,
+                                     (unsigned long long *)out);
+    MDP_LAUNCHED(ctx);
+    return mdp_check_launch("k_hist_reduce");
+}
+
+} // extern "C"

@@ -1,0 +1,444 @@
+// reduce.cu -- streaming fp64 reductions of the dynamical hot path (HBM-bound kernels).
+//
+// Replaces: calc_com (common/com_mols.py:5-62), _define_mol_cols (structural/rdf_cn.py:218-241),
+// the MSD arithmetic of Diffusion.get_msd_from_dump (dynamical/diffusion.py:207-238), conductivity_loop
+// (dynamical/_conductivity.py:7-36) and the OLS sums behind Diffusion.calc_diff (diffusion.py:323-329).
+// All arithmetic is unfused fp64 in the reference's operation order; block partial sums are combined in a
+// fixed order (two-stage, no floating-point atomics) so results are run-to-run deterministic.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int RB = 256;          // threads per block
+constexpr int MSD_APT = 8;       // atoms per thread in the streaming MSD kernel
+
+__device__ __forceinline__ double block_sum(double v, double *sm)
+{
+    // deterministic block reduction (fixed shuffle tree, fixed warp order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = lane < (int)(blockDim.x >> 5) ? sm[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, o));
+    }
+    return r;   // valid in warp 0
+}
+
+__device__ __forceinline__ double2 ld_stream2(const double *p)
+{
+    double2 v;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream1(const double *p)
+{
+    double v;
+    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// ---- MSD, single time origin ----------------------------------------------------------------
+// grid (nchunks, nframes); a chunk is RB*MSD_APT consecutive atoms of [a0, a1).
+template <bool VEC, bool PER_ATOM>
+__global__ void __launch_bounds__(RB) k_msd_single(const double *__restrict__ traj, const double *__restrict__ ref, int64_t n,
+                                                   int64_t a0, int64_t a1, double scale, double *__restrict__ partial,
+                                                   int nchunks, double *__restrict__ per_atom)
+{
+    __shared__ double sm[32];
+    const int f = blockIdx.y;
+    const double *tx = traj + (int64_t)f * 3 * n;
+    const int64_t base = a0 + (int64_t)blockIdx.x * (RB * MSD_APT);
+    double sx = 0, sy = 0, sz = 0, st = 0;
+    if (VEC) {
+#pragma unroll
+        for (int k = 0; k < MSD_APT / 2; ++k) {
+            const int64_t i = base + (int64_t)k * (RB * 2) + threadIdx.x * 2;
+            if (i + 1 < a1) {
+                const double2 x = ld_stream2(tx + i), y = ld_stream2(tx + n + i), z = ld_stream2(tx + 2 * n + i);
+                const double2 rx = *reinterpret_cast<const double2 *>(ref + i);
+                const double2 ry = *reinterpret_cast<const double2 *>(ref + n + i);
+                const double2 rz = *reinterpret_cast<const double2 *>(ref + 2 * n + i);
+                // SI conversion before differencing (diffusion.py:201-203, 214)
+                double dx0 = __dsub_rn(__dmul_rn(x.x, scale), __dmul_rn(rx.x, scale));
+                double dy0 = __dsub_rn(__dmul_rn(y.x, scale), __dmul_rn(ry.x, scale));
+                double dz0 = __dsub_rn(__dmul_rn(z.x, scale), __dmul_rn(rz.x, scale));
+                double dx1 = __dsub_rn(__dmul_rn(x.y, scale), __dmul_rn(rx.y, scale));
+                double dy1 = __dsub_rn(__dmul_rn(y.y, scale), __dmul_rn(ry.y, scale));
+                double dz1 = __dsub_rn(__dmul_rn(z.y, scale), __dmul_rn(rz.y, scale));
+                dx0 = __dmul_rn(dx0, dx0); dy0 = __dmul_rn(dy0, dy0); dz0 = __dmul_rn(dz0, dz0);
+                dx1 = __dmul_rn(dx1, dx1); dy1 = __dmul_rn(dy1, dy1); dz1 = __dmul_rn(dz1, dz1);
+                const double m0 = __dadd_rn(__dadd_rn(dx0, dy0), dz0), m1 = __dadd_rn(__dadd_rn(dx1, dy1), dz1);
+                sx = __dadd_rn(sx, __dadd_rn(dx0, dx1));
+                sy = __dadd_rn(sy, __dadd_rn(dy0, dy1));
+                sz = __dadd_rn(sz, __dadd_rn(dz0, dz1));
+                st = __dadd_rn(st, __dadd_rn(m0, m1));
+                if (PER_ATOM) {
+                    double *o = per_atom + (int64_t)f * 4 * n;
+                    *reinterpret_cast<double2 *>(o + i) = make_double2(dx0, dx1);
+                    *reinterpret_cast<double2 *>(o + n + i) = make_double2(dy0, dy1);
+                    *reinterpret_cast<double2 *>(o + 2 * n + i) = make_double2(dz0, dz1);
+                    *reinterpret_cast<double2 *>(o + 3 * n + i) = make_double2(m0, m1);
+                }
+            } else if (i < a1) {
+                double dx0 = __dsub_rn(__dmul_rn(tx[i], scale), __dmul_rn(ref[i], scale));
+                double dy0 = __dsub_rn(__dmul_rn(tx[n + i], scale), __dmul_rn(ref[n + i], scale));
+                double dz0 = __dsub_rn(__dmul_rn(tx[2 * n + i], scale), __dmul_rn(ref[2 * n + i], scale));
+                dx0 = __dmul_rn(dx0, dx0); dy0 = __dmul_rn(dy0, dy0); dz0 = __dmul_rn(dz0, dz0);
+                const double m0 = __dadd_rn(__dadd_rn(dx0, dy0), dz0);
+                sx = __dadd_rn(sx, dx0); sy = __dadd_rn(sy, dy0); sz = __dadd_rn(sz, dz0); st = __dadd_rn(st, m0);
+                if (PER_ATOM) {
+                    double *o = per_atom + (int64_t)f * 4 * n;
+                    o[i] = dx0; o[n + i] = dy0; o[2 * n + i] = dz0; o[3 * n + i] = m0;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < MSD_APT; ++k) {
+            const int64_t i = base + (int64_t)k * RB + threadIdx.x;
+            if (i < a1) {
+                double dx0 = __dsub_rn(__dmul_rn(ld_stream1(tx + i), scale), __dmul_rn(ref[i], scale));
+                double dy0 = __dsub_rn(__dmul_rn(ld_stream1(tx + n + i), scale), __dmul_rn(ref[n + i], scale));
+                double dz0 = __dsub_rn(__dmul_rn(ld_stream1(tx + 2 * n + i), scale), __dmul_rn(ref[2 * n + i], scale));
+                dx0 = __dmul_rn(dx0, dx0); dy0 = __dmul_rn(dy0, dy0); dz0 = __dmul_rn(dz0, dz0);
+                const double m0 = __dadd_rn(__dadd_rn(dx0, dy0), dz0);
+                sx = __dadd_rn(sx, dx0); sy = __dadd_rn(sy, dy0); sz = __dadd_rn(sz, dz0); st = __dadd_rn(st, m0);
+                if (PER_ATOM) {
+                    double *o = per_atom + (int64_t)f * 4 * n;
+                    o[i] = dx0; o[n + i] = dy0; o[2 * n + i] = dz0; o[3 * n + i] = m0;
+                }
+            }
+        }
+    }
+    sx = block_sum(sx, sm);
+    sy = block_sum(sy, sm);
+    sz = block_sum(sz, sm);
+    st = block_sum(st, sm);
+    if (threadIdx.x == 0) {
+        double *o = partial + ((int64_t)f * nchunks + blockIdx.x) * 4;
+        o[0] = sx; o[1] = sy; o[2] = sz; o[3] = st;
+    }
+}
+
+// second stage: out[f][g][c] = sum over chunks (fixed order); one warp per (f, c)
+__global__ void __launch_bounds__(128) k_partial_sum(const double *__restrict__ partial, int nchunks, int ncomp,
+                                                     double *__restrict__ out, int64_t out_stride_f)
+{
+    const int f = blockIdx.x;
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= ncomp) return;
+    double s = 0.0;
+    for (int k = lane; k < nchunks; k += 32) s = __dadd_rn(s, partial[((int64_t)f * nchunks + k) * ncomp + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (lane == 0) out[(int64_t)f * out_stride_f + c] = s;
+}
+
+// ---- msd_int (diffusion.py:225-237) ----------------------------------------------------------
+__global__ void __launch_bounds__(RB) k_msd_interval(const double *__restrict__ traj, int nframes, int64_t n, double scale,
+                                                     int stride, double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double px = __dmul_rn(traj[i], scale), py = __dmul_rn(traj[n + i], scale), pz = __dmul_rn(traj[2 * n + i], scale);
+    double sx = 0, sy = 0, sz = 0, sm = 0;
+    int nint = 1;
+    for (int f = stride; f < nframes; f += stride, ++nint) {
+        const double *t = traj + (int64_t)f * 3 * n;
+        const double x = __dmul_rn(t[i], scale), y = __dmul_rn(t[n + i], scale), z = __dmul_rn(t[2 * n + i], scale);
+        double dx = __dsub_rn(x, px), dy = __dsub_rn(y, py), dz = __dsub_rn(z, pz);
+        dx = __dmul_rn(dx, dx); dy = __dmul_rn(dy, dy); dz = __dmul_rn(dz, dz);
+        sx = __dadd_rn(sx, dx); sy = __dadd_rn(sy, dy); sz = __dadd_rn(sz, dz);
+        sm = __dadd_rn(sm, __dadd_rn(__dadd_rn(dx, dy), dz));
+        px = x; py = y; pz = z;
+    }
+    // dx2/dy2/dz2: mean over the nint-1 non-NaN rows; msd: the NaN row became 0 and counts (reference quirk)
+    const double d1 = (double)(nint - 1), d0 = (double)nint;
+    out[i] = nint > 1 ? sx / d1 : NAN;
+    out[n + i] = nint > 1 ? sy / d1 : NAN;
+    out[2 * n + i] = nint > 1 ? sz / d1 : NAN;
+    out[3 * n + i] = sm / d0;
+}
+
+// ---- MSD over all time origins (v1: one thread per (atom, lag), coalesced over atoms) ----------
+__global__ void __launch_bounds__(RB) k_msd_all_origins(const double *__restrict__ traj, int nframes, int64_t n, int64_t a0,
+                                                        int64_t a1, double scale, int max_lag, double *__restrict__ partial,
+                                                        int nchunks)
+{
+    __shared__ double sm[32];
+    const int lag = blockIdx.y;
+    const int64_t i = a0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s[3] = {0, 0, 0};
+    if (i < a1) {
+        for (int t0 = 0; t0 + lag < nframes; ++t0) {
+            const double *p0 = traj + (int64_t)t0 * 3 * n, *p1 = traj + (int64_t)(t0 + lag) * 3 * n;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double d = __dsub_rn(__dmul_rn(p1[c * n + i], scale), __dmul_rn(p0[c * n + i], scale));
+                s[c] = __dadd_rn(s[c], __dmul_rn(d, d));
+            }
+        }
+    }
+    const double rx = block_sum(s[0], sm), ry = block_sum(s[1], sm), rz = block_sum(s[2], sm);
+    if (threadIdx.x == 0) {
+        double *o = partial + ((int64_t)lag * nchunks + blockIdx.x) * 4;
+        o[0] = rx; o[1] = ry; o[2] = rz; o[3] = __dadd_rn(__dadd_rn(rx, ry), rz);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_partial_accumulate(const double *__restrict__ partial, int nchunks, int ncomp,
+                                                            double *__restrict__ out, int64_t out_stride_f)
+{
+    const int f = blockIdx.x;
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= ncomp) return;
+    double s = 0.0;
+    for (int k = lane; k < nchunks; k += 32) s = __dadd_rn(s, partial[((int64_t)f * nchunks + k) * ncomp + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (lane == 0) out[(int64_t)f * out_stride_f + c] += s;
+}
+
+// ---- per-molecule mass-weighted mean (calc_com / _define_mol_cols) ---------------------------------
+// thread per (segment, frame); sequential accumulation in atom order, one division at the end.
+__global__ void __launch_bounds__(RB) k_segment_com(const double *__restrict__ attr, int ncomp, int64_t n,
+                                                    const double *__restrict__ w, int64_t nseg,
+                                                    const int32_t *__restrict__ seg_off, double *__restrict__ out,
+                                                    double *__restrict__ wsum_out, const double *__restrict__ extra,
+                                                    double *__restrict__ extra_out)
+{
+    const int f = blockIdx.y;
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const int b = seg_off[s], e = seg_off[s + 1];
+    double ws = 0.0;
+    for (int a = b; a < e; ++a) ws = __dadd_rn(ws, w[a]);
+    for (int c = 0; c < ncomp; ++c) {
+        const double *p = attr + ((int64_t)f * ncomp + c) * n;
+        double acc = 0.0;
+        for (int a = b; a < e; ++a) acc = __dadd_rn(acc, __dmul_rn(p[a], w[a]));
+        out[((int64_t)f * ncomp + c) * nseg + s] = acc / ws;
+    }
+    if (f == 0) {
+        if (wsum_out) wsum_out[s] = ws;
+        if (extra && extra_out) {
+            double q = 0.0;
+            for (int a = b; a < e; ++a) q = __dadd_rn(q, extra[a]);
+            extra_out[s] = q;
+        }
+    }
+}
+
+// ---- charge flux (_conductivity.py:7-36) -------------------------------------------------------
+// grid (nblocks over segments [s0,s1) of one molecule type, nframes)
+__global__ void __launch_bounds__(RB) k_charge_flux(const double *__restrict__ vel, int64_t n, const double *__restrict__ mass,
+                                                    const double *__restrict__ q, const int32_t *__restrict__ seg_off,
+                                                    int64_t s0, int64_t s1, double vel_scale, double q_scale,
+                                                    double *__restrict__ partial, int nchunks)
+{
+    __shared__ double sm[32];
+    const int f = blockIdx.y;
+    const int64_t s = s0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double j[3] = {0, 0, 0};
+    if (s < s1) {
+        const int b = seg_off[s], e = seg_off[s + 1];
+        const double *v = vel + (int64_t)f * 3 * n;
+        double ws = 0.0, qs = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int a = b; a < e; ++a) {
+            const double m = mass[a];
+            ws = __dadd_rn(ws, m);
+            qs = __dadd_rn(qs, q[a]);
+            a0 = __dadd_rn(a0, __dmul_rn(ld_stream1(v + a), m));
+            a1 = __dadd_rn(a1, __dmul_rn(ld_stream1(v + n + a), m));
+            a2 = __dadd_rn(a2, __dmul_rn(ld_stream1(v + 2 * n + a), m));
+        }
+        const double qsi = __dmul_rn(qs, q_scale);
+        j[0] = __dmul_rn(__dmul_rn(a0 / ws, vel_scale), qsi);
+        j[1] = __dmul_rn(__dmul_rn(a1 / ws, vel_scale), qsi);
+        j[2] = __dmul_rn(__dmul_rn(a2 / ws, vel_scale), qsi);
+    }
+    const double r0 = block_sum(j[0], sm), r1 = block_sum(j[1], sm), r2 = block_sum(j[2], sm);
+    if (threadIdx.x == 0) {
+        double *o = partial + ((int64_t)f * nchunks + blockIdx.x) * 3;
+        o[0] = r0; o[1] = r1; o[2] = r2;
+    }
+}
+
+// out[c][g][frame0+f] = sum of chunk partials (fixed order)
+__global__ void __launch_bounds__(96) k_flux_finish(const double *__restrict__ partial, int nchunks, int g, int ngroups,
+                                                    double *__restrict__ out, int64_t out_stride, int64_t frame0)
+{
+    const int f = blockIdx.x;
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int k = lane; k < nchunks; k += 32) s = __dadd_rn(s, partial[((int64_t)f * nchunks + k) * 3 + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (lane == 0) out[((int64_t)c * ngroups + g) * out_stride + frame0 + f] = s;
+}
+
+// ---- OLS sums --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RB) k_ols_sums(const double *__restrict__ t, const double *__restrict__ y, int64_t T,
+                                                 int64_t i0, int64_t i1, double *__restrict__ out)
+{
+    __shared__ double sm[32];
+    const int c = blockIdx.x;
+    const double *yc = y + (int64_t)c * T;
+    double a = 0, b = 0, d = 0;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const double tv = t[i], yv = yc[i];
+        a = __dadd_rn(a, __dmul_rn(tv, tv));
+        b = __dadd_rn(b, __dmul_rn(tv, yv));
+        d = __dadd_rn(d, __dmul_rn(yv, yv));
+    }
+    a = block_sum(a, sm);
+    b = block_sum(b, sm);
+    d = block_sum(d, sm);
+    if (threadIdx.x == 0) {
+        out[c * 3 + 0] = a;
+        out[c * 3 + 1] = b;
+        out[c * 3 + 2] = d;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int mdp_msd_single_origin(mdp_ctx *ctx, int nframes, int64_t n, const double *traj, const double *ref, double scale,
+                          const int64_t *group_off, int ngroups, double *sums_out, double *per_atom_out, void *stream)
+{
+    MDP_REQUIRE(ctx && traj && ref && sums_out, "mdp_msd_single_origin: NULL argument");
+    MDP_REQUIRE(nframes > 0 && n > 0 && ngroups >= 1, "mdp_msd_single_origin: sizes must be positive");
+    MDP_REQUIRE(nframes <= 65535, "mdp_msd_single_origin: at most 65535 frames per call");
+    cudaStream_t st = (cudaStream_t)stream;
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    const int64_t per_chunk = RB * MSD_APT;
+    const int max_chunks = (int)ceil_div<int64_t>(n, per_chunk) + 1;
+    int rc = ctx->arena_reserve((size_t)nframes * max_chunks * 32 + 4096);
+    if (rc) return rc;
+    ctx->arena_reset();
+    double *partial = (double *)ctx->arena_take((size_t)nframes * max_chunks * 32);
+    const bool vec = (n % 2 == 0) && (((uintptr_t)traj | (uintptr_t)ref | (uintptr_t)per_atom_out) % 16 == 0);
+    for (int g = 0; g < ngroups; ++g) {
+        const int64_t a0 = group_off ? group_off[g] : 0, a1 = group_off ? group_off[g + 1] : n;
+        MDP_REQUIRE(a0 >= 0 && a1 >= a0 && a1 <= n, "mdp_msd_single_origin: bad group range");
+        if (a1 == a0) {
+            MDP_CUDA(cudaMemset2DAsync(sums_out + g * 4, (size_t)ngroups * 32, 0, 32, nframes, st));
+            continue;
+        }
+        const bool v = vec && (a0 % 2 == 0);
+        const int nchunks = (int)ceil_div<int64_t>(a1 - a0, per_chunk);
+        dim3 grid(nchunks, nframes);
+        if (v && per_atom_out)
+            k_msd_single<true, true><<<grid, RB, 0, st>>>(traj, ref, n, a0, a1, scale, partial, nchunks, per_atom_out);
+        else if (v)
+            k_msd_single<true, false><<<grid, RB, 0, st>>>(traj, ref, n, a0, a1, scale, partial, nchunks, nullptr);
+        else if (per_atom_out)
+            k_msd_single<false, true><<<grid, RB, 0, st>>>(traj, ref, n, a0, a1, scale, partial, nchunks, per_atom_out);
+        else
+            k_msd_single<false, false><<<grid, RB, 0, st>>>(traj, ref, n, a0, a1, scale, partial, nchunks, nullptr);
+        MDP_LAUNCHED(ctx);
+        k_partial_sum<<<nframes, 128, 0, st>>>(partial, nchunks, 4, sums_out + g * 4, (int64_t)ngroups * 4);
+        MDP_LAUNCHED(ctx);
+    }
+    return mdp_check_launch("k_msd_single");
+}
+
+int mdp_msd_interval(mdp_ctx *ctx, int nframes, int64_t n, const double *traj, double scale, int stride, double *out,
+                     void *stream)
+{
+    MDP_REQUIRE(ctx && traj && out, "mdp_msd_interval: NULL argument");
+    MDP_REQUIRE(nframes > 0 && n > 0 && stride > 0, "mdp_msd_interval: sizes must be positive");
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    k_msd_interval<<<(unsigned)ceil_div<int64_t>(n, RB), RB, 0, (cudaStream_t)stream>>>(traj, nframes, n, scale, stride, out);
+    MDP_LAUNCHED(ctx);
+    return mdp_check_launch("k_msd_interval");
+}
+
+int mdp_msd_all_origins(mdp_ctx *ctx, int nframes, int64_t n, const double *traj, double scale, const int64_t *group_off,
+                        int ngroups, int max_lag, double *sums_out, void *stream)
+{
+    MDP_REQUIRE(ctx && traj && sums_out, "mdp_msd_all_origins: NULL argument");
+    MDP_REQUIRE(nframes > 0 && n > 0 && ngroups >= 1 && max_lag > 0 && max_lag <= nframes && max_lag <= 65535,
+                "mdp_msd_all_origins: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    const int max_chunks = (int)ceil_div<int64_t>(n, RB) + 1;
+    int rc = ctx->arena_reserve((size_t)max_lag * max_chunks * 32 + 4096);
+    if (rc) return rc;
+    ctx->arena_reset();
+    double *partial = (double *)ctx->arena_take((size_t)max_lag * max_chunks * 32);
+    for (int g = 0; g < ngroups; ++g) {
+        const int64_t a0 = group_off ? group_off[g] : 0, a1 = group_off ? group_off[g + 1] : n;
+        MDP_REQUIRE(a0 >= 0 && a1 >= a0 && a1 <= n, "mdp_msd_all_origins: bad group range");
+        if (a1 == a0) continue;
+        const int nchunks = (int)ceil_div<int64_t>(a1 - a0, RB);
+        dim3 grid(nchunks, max_lag);
+        k_msd_all_origins<<<grid, RB, 0, st>>>(traj, nframes, n, a0, a1, scale, max_lag, partial, nchunks);
+        MDP_LAUNCHED(ctx);
+        k_partial_accumulate<<<max_lag, 128, 0, st>>>(partial, nchunks, 4, sums_out + g * 4, (int64_t)ngroups * 4);
+        MDP_LAUNCHED(ctx);
+    }
+    return mdp_check_launch("k_msd_all_origins");
+}
+
+int mdp_segment_com(mdp_ctx *ctx, int nframes, int ncomp, int64_t n, const double *attr, const double *w, int64_t nseg,
+                    const int32_t *seg_off, double *out, double *wsum_out, const double *extra, double *extra_out,
+                    void *stream)
+{
+    MDP_REQUIRE(ctx && attr && w && seg_off && out, "mdp_segment_com: NULL argument");
+    MDP_REQUIRE(nframes > 0 && nframes <= 65535 && ncomp > 0 && n > 0 && nseg > 0, "mdp_segment_com: bad sizes");
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    dim3 grid((unsigned)ceil_div<int64_t>(nseg, RB), nframes);
+    k_segment_com<<<grid, RB, 0, (cudaStream_t)stream>>>(attr, ncomp, n, w, nseg, seg_off, out, wsum_out, extra, extra_out);
+    MDP_LAUNCHED(ctx);
+    return mdp_check_launch("k_segment_com");
+}
+
+int mdp_charge_flux(mdp_ctx *ctx, int nframes, int64_t n, const double *vel, const double *mass, const double *q,
+                    int64_t nseg, const int32_t *seg_off, const int64_t *group_seg_off, int ngroups, double vel_scale,
+                    double q_scale, double *out, int64_t out_stride, int64_t frame0, void *stream)
+{
+    MDP_REQUIRE(ctx && vel && mass && q && seg_off && group_seg_off && out, "mdp_charge_flux: NULL argument");
+    MDP_REQUIRE(nframes > 0 && nframes <= 65535 && n > 0 && nseg > 0 && ngroups > 0, "mdp_charge_flux: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    const int max_chunks = (int)ceil_div<int64_t>(nseg, RB) + 1;
+    int rc = ctx->arena_reserve((size_t)nframes * max_chunks * 24 + 4096);
+    if (rc) return rc;
+    ctx->arena_reset();
+    double *partial = (double *)ctx->arena_take((size_t)nframes * max_chunks * 24);
+    for (int g = 0; g < ngroups; ++g) {
+        const int64_t s0 = group_seg_off[g], s1 = group_seg_off[g + 1];
+        MDP_REQUIRE(s0 >= 0 && s1 > s0 && s1 <= nseg, "mdp_charge_flux: bad molecule-type range");
+        const int nchunks = (int)ceil_div<int64_t>(s1 - s0, RB);
+        dim3 grid(nchunks, nframes);
+        k_charge_flux<<<grid, RB, 0, st>>>(vel, n, mass, q, seg_off, s0, s1, vel_scale, q_scale, partial, nchunks);
+        MDP_LAUNCHED(ctx);
+        k_flux_finish<<<nframes, 96, 0, st>>>(partial, nchunks, g, ngroups, out, out_stride, frame0);
+        MDP_LAUNCHED(ctx);
+    }
+    return mdp_check_launch("k_charge_flux");
+}
+
+int mdp_ols_sums(mdp_ctx *ctx, int ncol, int64_t T, const double *t, const double *y, int64_t i0, int64_t i1, double *out,
+                 void *stream)
+{
+    MDP_REQUIRE(ctx && t && y && out, "mdp_ols_sums: NULL argument");
+    MDP_REQUIRE(ncol > 0 && T > 0 && i0 >= 0 && i1 <= T && i1 > i0, "mdp_ols_sums: bad sizes");
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    k_ols_sums<<<ncol, RB, 0, (cudaStream_t)stream>>>(t, y, T, i0, i1, out);
+    MDP_LAUNCHED(ctx);
+    return mdp_check_launch("k_ols_sums");
+}
+
+} // extern "C"

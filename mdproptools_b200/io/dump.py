@@ -1,0 +1,131 @@
+"""LAMMPS dump reading through the native parser (``mdp_dump_*`` in csrc/dump_parse.cpp).
+
+Replaces ``pymatgen.io.lammps.outputs.parse_lammps_dumps`` as used by the reference (rdf_cn.py:176,
+cluster_analysis.py:100, hydration_number.py:84, diffusion.py:172, conductivity.py:87,
+residence_time.py:54): same glob ordering (files sorted by the integer that ``*`` matches), same frame
+splitting at ``ITEM: TIMESTEP``, same box handling (bounds corrected by the tilt factors; lattice lengths
+are the row norms of the cell matrix), rows delivered **already sorted by id** as SoA float64 columns in
+pinned host memory so that they can be streamed to the device with async copies.
+"""
+from __future__ import annotations
+
+import ctypes
+import glob as _glob
+import gzip
+import os
+import re
+from dataclasses import dataclass
+
+import numpy as np
+
+from .. import _lib
+
+
+@dataclass
+class Box:
+    bounds: list            # [[xlo,xhi],[ylo,yhi],[zlo,zhi]] (after pymatgen's tilt correction)
+    tilt: list | None       # [xy, xz, yz] or None
+
+    @property
+    def matrix(self) -> np.ndarray:
+        b = np.asarray(self.bounds, dtype=np.float64)
+        m = np.diag(b[:, 1] - b[:, 0])
+        if self.tilt is not None:
+            m[1, 0], m[2, 0], m[2, 1] = self.tilt
+        return m
+
+    def lattice_lengths(self):
+        """== dump.box.to_lattice().lengths (rdf_cn.py:260, residence_time.py:79)."""
+        m = self.matrix
+        return tuple(np.sqrt(np.sum(m ** 2, axis=1)).tolist())
+
+    def bound_lengths(self):
+        """== bounds[k][1]-bounds[k][0] (cluster_analysis.py:110-112, hydration_number.py:38-40, diffusion.py:75-77)."""
+        return tuple(self.bounds[k][1] - self.bounds[k][0] for k in range(3))
+
+
+@dataclass
+class DumpFrame:
+    timestep: int
+    natoms: int
+    box: Box
+    columns: list            # all column names present in the file
+    data: dict               # requested column -> float64[natoms], rows sorted by id
+
+
+def dump_files(pattern: str) -> list:
+    files = _glob.glob(pattern)
+    if len(files) > 1:
+        pat = pattern.replace("*", "([0-9]+)").replace("\\", "\\\\")
+        files = sorted(files, key=lambda f: int(re.match(pat, f).group(1)))
+    return files
+
+
+def _read_bytes(fname: str) -> bytes:
+    if fname.endswith(".gz"):
+        with gzip.open(fname, "rb") as f:
+            return f.read()
+    with open(fname, "rb") as f:
+        return f.read()
+
+
+def frame_columns(buf: bytes) -> list:
+    hdr = (ctypes.c_double * 16)()
+    cols = ctypes.create_string_buffer(4096)
+    _lib.check(_lib.lib().mdp_dump_header(buf, len(buf), hdr, cols, 4096), "mdp_dump_header")
+    return cols.value.decode().split()
+
+
+def parse_frame(buf: bytes, want, nthreads: int = 0, out: np.ndarray | None = None) -> DumpFrame:
+    """Parse one frame's text.  ``want`` = column names; result arrays are id-sorted float64."""
+    L = _lib.lib()
+    hdr = (ctypes.c_double * 16)()
+    cols = ctypes.create_string_buffer(4096)
+    _lib.check(L.mdp_dump_header(buf, len(buf), hdr, cols, 4096), "mdp_dump_header")
+    natoms = int(hdr[1])
+    columns = cols.value.decode().split()
+    want = list(want)
+    missing = [w for w in want if w not in columns]
+    if missing:
+        raise KeyError(f"column(s) {missing} not in dump file (has {columns})")
+    if out is None:
+        out = np.empty((len(want), natoms), dtype=np.float64)
+    assert out.shape[0] >= len(want) and out.shape[1] >= natoms and out.dtype == np.float64 and out.flags.c_contiguous
+    names = (ctypes.c_char_p * len(want))(*[w.encode() for w in want])
+    _lib.check(L.mdp_dump_parse(buf, len(buf), names, len(want), out.ctypes.data_as(ctypes.c_void_p), out.shape[1], hdr,
+                                int(nthreads)), "mdp_dump_parse")
+    tric = hdr[11] != 0.0
+    box = Box([[hdr[2], hdr[3]], [hdr[4], hdr[5]], [hdr[6], hdr[7]]], [hdr[8], hdr[9], hdr[10]] if tric else None)
+    return DumpFrame(int(hdr[0]), natoms, box, columns, {w: out[k, :natoms] for k, w in enumerate(want)})
+
+
+def iter_frame_buffers(pattern: str):
+    """Yield the raw text of every frame, in pymatgen's order."""
+    L = _lib.lib()
+    for fname in dump_files(pattern):
+        buf = _read_bytes(fname)
+        n = int(L.mdp_dump_scan(buf, len(buf), None, 0))
+        if n <= 1:
+            yield buf
+            continue
+        offs = (ctypes.c_int64 * n)()
+        L.mdp_dump_scan(buf, len(buf), offs, n)
+        ends = list(offs[1:]) + [len(buf)]
+        for b, e in zip(offs, ends):
+            yield buf[b:e]
+
+
+def read_dumps(pattern: str, want, nthreads: int = 0):
+    """Generator of DumpFrame (id-sorted SoA columns) over every frame matching ``pattern``."""
+    found = False
+    for buf in iter_frame_buffers(pattern):
+        found = True
+        yield parse_frame(buf, want, nthreads)
+    if not found:
+        return
+
+
+def available_columns(pattern: str) -> list:
+    for buf in iter_frame_buffers(pattern):
+        return frame_columns(buf)
+    return []

@@ -1,0 +1,122 @@
+"""Frame pipeline: dump text -> pinned SoA host buffers -> HBM on a side stream, overlapped with compute.
+
+Subsystem (a) of the north star.  A reader thread parses frames with the native parser straight into a
+ring of pinned staging tensors ``[F, C, N]`` (ctypes releases the GIL while the C++ parser runs), the copy
+to the device is issued on a dedicated copy stream and the consumer only waits on the copy's event, so
+parsing, PCIe transfer and kernels of consecutive batches overlap.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import dump as _dump
+
+
+@dataclass
+class FrameMeta:
+    index: int               # position in the trajectory (pymatgen order)
+    timestep: int
+    natoms: int
+    box: _dump.Box
+
+
+@dataclass
+class Batch:
+    metas: list              # FrameMeta per frame
+    columns: list            # column names, order of axis 1
+    host: torch.Tensor       # [F, C, N] float64 (pinned when CUDA is available)
+    dev: torch.Tensor | None # [F, C, N] on the device (None when to_device=False)
+    ready: object | None     # torch.cuda.Event recorded after the H2D copy
+
+    def wait(self):
+        if self.ready is not None:
+            torch.cuda.current_stream().wait_event(self.ready)
+        return self.dev
+
+    def col(self, name):
+        return self.columns.index(name)
+
+
+class FrameBatches:
+    """Iterate over a trajectory in batches of frames with equal atom count.
+
+    frame_slice: optional (start, stop, step) applied to the global frame index (used for frame sharding
+    across ranks and for ``get_clusters(frame=...)``); frames outside it are skipped without being parsed.
+    """
+
+    def __init__(self, pattern, columns, max_batch_bytes=192 << 20, max_batch_frames=256, to_device=True, device=None,
+                 frame_select=None, nthreads=0, prefetch=2):
+        self.pattern = pattern
+        self.columns = list(columns)
+        self.max_batch_bytes = int(max_batch_bytes)
+        self.max_batch_frames = int(max_batch_frames)
+        self.cuda = torch.cuda.is_available()
+        self.to_device = to_device and self.cuda
+        self.device = device
+        self.frame_select = frame_select
+        self.nthreads = nthreads
+        self.prefetch = prefetch
+        self.total_frames = None   # known once iteration has finished
+
+    def _produce(self, q: "queue.Queue"):
+        try:
+            copy_stream = torch.cuda.Stream(device=self.device) if self.to_device else None
+            metas, host, fill = [], None, 0
+            C = len(self.columns)
+
+            def flush():
+                nonlocal metas, host, fill
+                if not metas:
+                    return
+                h = host[:fill]
+                dev, ev = None, None
+                if self.to_device:
+                    with torch.cuda.stream(copy_stream):
+                        dev = h.to(self.device or "cuda", non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                q.put(Batch(metas, self.columns, h, dev, ev))
+                metas, host, fill = [], None, 0
+
+            idx = -1
+            for buf in _dump.iter_frame_buffers(self.pattern):
+                idx += 1
+                if self.frame_select is not None and not self.frame_select(idx):
+                    continue
+                # peek at natoms to size / reuse the staging buffer
+                import ctypes
+                from .. import _lib
+                hdr = (ctypes.c_double * 16)()
+                _lib.check(_lib.lib().mdp_dump_header(buf, len(buf), hdr, None, 0), "mdp_dump_header")
+                n = int(hdr[1])
+                if host is not None and (host.shape[2] != n or fill == host.shape[0]):
+                    flush()
+                if host is None:
+                    F = max(1, min(self.max_batch_frames, self.max_batch_bytes // max(1, C * n * 8)))
+                    host = torch.empty((F, C, n), dtype=torch.float64, pin_memory=self.cuda)
+                fr = _dump.parse_frame(buf, self.columns, self.nthreads, out=host[fill].numpy())
+                metas.append(FrameMeta(idx, fr.timestep, fr.natoms, fr.box))
+                fill += 1
+            self.total_frames = idx + 1
+            flush()
+            q.put(None)
+        except BaseException as exc:  # noqa: BLE001 - forwarded to the consumer
+            q.put(exc)
+
+    def __iter__(self):
+        q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
+        th = threading.Thread(target=self._produce, args=(q,), daemon=True)
+        th.start()
+        while True:
+            item = q.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+        th.join()

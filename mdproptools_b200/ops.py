@@ -1,0 +1,243 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/mdprop_b200.h).
+
+Inputs are CUDA torch tensors (torch is only the device-memory / stream plumbing); every function enqueues
+work on the current torch stream.  Nothing here has a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_int, c_int32, c_int64
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Context, check, lib, ptr, stream_ptr
+
+
+def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous float64 CUDA tensor")
+    return t
+
+
+def _i32(t, name: str):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous int32 CUDA tensor")
+    return t
+
+
+def _host_i64(a):
+    if a is None:
+        return None, None
+    arr = np.ascontiguousarray(a, dtype=np.int64)
+    return arr, arr.ctypes.data_as(ctypes.POINTER(c_int64))
+
+
+def sym_rows(ncls: int) -> int:
+    return ncls * (ncls + 1) // 2
+
+
+def sym_row(ci: int, cj: int, ncls: int) -> int:
+    a, b = (ci, cj) if ci <= cj else (cj, ci)
+    return a * ncls - a * (a - 1) // 2 + (b - a)
+
+
+def pair_hist(xyz_a, cls_a, ncls_a, box, rcut2, edges, uniform_ddr, xyz_b=None, cls_b=None, ncls_b=1, out=None,
+              flags=0):
+    """mdp_pair_hist.  xyz_* float64 [F,3,N]; cls_* int32 [N] or [F,N] or None; box array-like [F,3] (host).
+
+    Returns uint64 counts as an int64 tensor [F, rows, nbins] (accumulated into ``out`` when given).
+    """
+    xyz_a = _f64(xyz_a, "xyz_a")
+    F, _, na = xyz_a.shape
+    ctx = Context.get(xyz_a.device.index)
+    box = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(F, 3))
+    edges = np.ascontiguousarray(edges, dtype=np.float64)
+    nbins = edges.shape[0] - 1
+    symm = xyz_b is None
+    rows = sym_rows(ncls_a) if symm else ncls_a * ncls_b
+    if out is None:
+        out = torch.zeros((F, rows, nbins), dtype=torch.int64, device=xyz_a.device)
+    cls_a = _i32(cls_a, "cls_a")
+    sa = 0 if cls_a is None or cls_a.dim() == 1 else na
+    nb_ = 0
+    sb = 0
+    if not symm:
+        xyz_b = _f64(xyz_b, "xyz_b")
+        nb_ = xyz_b.shape[2]
+        cls_b = _i32(cls_b, "cls_b")
+        sb = 0 if cls_b is None or cls_b.dim() == 1 else nb_
+    check(lib().mdp_pair_hist(ctx.handle, F, na, ptr(xyz_a), ptr(cls_a), sa, int(ncls_a),
+                              nb_, ptr(xyz_b), ptr(cls_b), sb, int(ncls_b),
+                              _lib.dptr(box), float(rcut2), _lib.dptr(edges), int(nbins), float(uniform_ddr),
+                              ptr(out), int(flags), stream_ptr()), "mdp_pair_hist")
+    return out
+
+
+def hist_reduce(hist, weights, cumulative=False):
+    """mdp_hist_reduce: hist int64 [F, rows, nbins], weights int array [nout, rows] -> int64 [F, nout, nbins]."""
+    F, rows, nbins = hist.shape
+    w = np.ascontiguousarray(weights, dtype=np.int32).reshape(-1, rows)
+    nout = w.shape[0]
+    ctx = Context.get(hist.device.index)
+    out = torch.empty((F, nout, nbins), dtype=torch.int64, device=hist.device)
+    check(lib().mdp_hist_reduce(ctx.handle, F, rows, nbins, ptr(hist), nout, w.ctypes.data_as(ctypes.POINTER(c_int32)),
+                                1 if cumulative else 0, ptr(out), stream_ptr()), "mdp_hist_reduce")
+    return out
+
+
+def pair_list(xyz_a, xyz_b, box, r_in2, r_out2, shell_mode, exclude_same_index=False, capacity=None, want_rsq=False):
+    """mdp_pair_list -> (list int32 [M,3] = (frame, ia, ib), rsq float64 [M] or None); grows capacity as needed."""
+    xyz_a = _f64(xyz_a, "xyz_a")
+    xyz_b = _f64(xyz_b, "xyz_b")
+    F, _, na = xyz_a.shape
+    nb_ = xyz_b.shape[2]
+    ctx = Context.get(xyz_a.device.index)
+    box = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(F, 3))
+    cap = int(capacity or max(1 << 16, 64 * na * F))
+    while True:
+        lst = torch.empty((cap, 3), dtype=torch.int32, device=xyz_a.device)
+        rsq = torch.empty((cap,), dtype=torch.float64, device=xyz_a.device) if want_rsq else None
+        cnt = torch.zeros((1,), dtype=torch.int64, device=xyz_a.device)
+        check(lib().mdp_pair_list(ctx.handle, F, na, ptr(xyz_a), nb_, ptr(xyz_b), _lib.dptr(box), float(r_in2),
+                                  float(r_out2), int(shell_mode), 1 if exclude_same_index else 0, ptr(lst), ptr(rsq),
+                                  cap, ptr(cnt), stream_ptr()), "mdp_pair_list")
+        m = int(cnt.item())
+        if m <= cap:
+            return lst[:m], (rsq[:m] if want_rsq else None)
+        cap = int(m * 1.1) + 1024
+
+
+def segment_com(attr, w, seg_off, extra=None):
+    """mdp_segment_com: attr [F,C,N], w [N], seg_off int32 [S+1] -> (out [F,C,S], wsum [S], extra_sum [S] or None)."""
+    attr = _f64(attr, "attr")
+    w = _f64(w, "w")
+    seg_off = _i32(seg_off, "seg_off")
+    F, C, n = attr.shape
+    S = seg_off.shape[0] - 1
+    ctx = Context.get(attr.device.index)
+    out = torch.empty((F, C, S), dtype=torch.float64, device=attr.device)
+    wsum = torch.empty((S,), dtype=torch.float64, device=attr.device)
+    esum = torch.empty((S,), dtype=torch.float64, device=attr.device) if extra is not None else None
+    if extra is not None:
+        extra = _f64(extra, "extra")
+    check(lib().mdp_segment_com(ctx.handle, F, C, n, ptr(attr), ptr(w), S, ptr(seg_off), ptr(out), ptr(wsum), ptr(extra),
+                                ptr(esum), stream_ptr()), "mdp_segment_com")
+    return out, wsum, esum
+
+
+def msd_single_origin(traj, ref, scale=1.0, group_off=None, per_atom=False):
+    """mdp_msd_single_origin: traj [F,3,N], ref [3,N] -> (sums [F,G,4], per_atom [F,4,N] or None)."""
+    traj = _f64(traj, "traj")
+    ref = _f64(ref, "ref")
+    F, _, n = traj.shape
+    ctx = Context.get(traj.device.index)
+    garr, gptr = _host_i64(group_off)
+    G = 1 if garr is None else len(garr) - 1
+    sums = torch.empty((F, G, 4), dtype=torch.float64, device=traj.device)
+    pa = torch.empty((F, 4, n), dtype=torch.float64, device=traj.device) if per_atom else None
+    done = 0
+    while done < F:   # the ABI takes at most 65535 frames per call
+        k = min(F - done, 32768)
+        check(lib().mdp_msd_single_origin(ctx.handle, k, n, ptr(traj[done:]), ptr(ref), float(scale), gptr, G,
+                                          ptr(sums[done:]), ptr(pa[done:]) if per_atom else None, stream_ptr()),
+              "mdp_msd_single_origin")
+        done += k
+    return sums, pa
+
+
+def msd_interval(traj, scale, stride):
+    traj = _f64(traj, "traj")
+    F, _, n = traj.shape
+    ctx = Context.get(traj.device.index)
+    out = torch.empty((4, n), dtype=torch.float64, device=traj.device)
+    check(lib().mdp_msd_interval(ctx.handle, F, n, ptr(traj), float(scale), int(stride), ptr(out), stream_ptr()),
+          "mdp_msd_interval")
+    return out
+
+
+def msd_all_origins(traj, max_lag, scale=1.0, group_off=None, out=None):
+    traj = _f64(traj, "traj")
+    F, _, n = traj.shape
+    ctx = Context.get(traj.device.index)
+    garr, gptr = _host_i64(group_off)
+    G = 1 if garr is None else len(garr) - 1
+    if out is None:
+        out = torch.zeros((max_lag, G, 4), dtype=torch.float64, device=traj.device)
+    check(lib().mdp_msd_all_origins(ctx.handle, F, n, ptr(traj), float(scale), gptr, G, int(max_lag), ptr(out),
+                                    stream_ptr()), "mdp_msd_all_origins")
+    return out
+
+
+def charge_flux(vel, mass, q, seg_off, group_seg_off, vel_scale, q_scale, out=None, frame0=0):
+    """mdp_charge_flux: vel [F,3,N] -> J [3, G, F] (or written into ``out`` [3,G,Ttot] at column frame0)."""
+    vel = _f64(vel, "vel")
+    F, _, n = vel.shape
+    ctx = Context.get(vel.device.index)
+    garr, gptr = _host_i64(group_seg_off)
+    G = len(garr) - 1
+    S = seg_off.shape[0] - 1
+    if out is None:
+        out = torch.zeros((3, G, F), dtype=torch.float64, device=vel.device)
+    check(lib().mdp_charge_flux(ctx.handle, F, n, ptr(vel), ptr(_f64(mass, "mass")), ptr(_f64(q, "q")), S,
+                                ptr(_i32(seg_off, "seg_off")), gptr, G, float(vel_scale), float(q_scale), ptr(out),
+                                out.shape[2], int(frame0), stream_ptr()), "mdp_charge_flux")
+    return out
+
+
+def xcorr_unbiased(a, b, nlags=None):
+    """mdp_xcorr_unbiased: a, b [C,T] -> [C,nlags]."""
+    a = _f64(a, "a")
+    b = _f64(b, "b")
+    C, T = a.shape
+    nlags = T if nlags is None else int(nlags)
+    ctx = Context.get(a.device.index)
+    out = torch.empty((C, nlags), dtype=torch.float64, device=a.device)
+    check(lib().mdp_xcorr_unbiased(ctx.handle, C, T, ptr(a), ptr(b), nlags, ptr(out), stream_ptr()), "mdp_xcorr_unbiased")
+    return out
+
+
+def cumtrapz(y, dx, scale=1.0, leading_zero=True):
+    y = _f64(y, "y")
+    R, T = y.shape
+    ctx = Context.get(y.device.index)
+    out = torch.empty((R, T if leading_zero else T - 1), dtype=torch.float64, device=y.device)
+    check(lib().mdp_cumtrapz(ctx.handle, R, T, ptr(y), float(dx), float(scale), 1 if leading_zero else 0, ptr(out),
+                             stream_ptr()), "mdp_cumtrapz")
+    return out
+
+
+def bitmask_autocorr_from_list(lst, n_b, T):
+    """Neighbour list (frame, ia, ib) -> integer survival counts cnt[tau] (int64 [T]) and the number of ever-neighbour pairs."""
+    ctx = Context.get(lst.device.index)
+    cnt = torch.zeros((T,), dtype=torch.int64, device=lst.device)
+    if lst.shape[0] == 0:
+        return cnt, 0
+    keys = lst[:, 1].to(torch.int64) * int(n_b) + lst[:, 2].to(torch.int64)
+    ukeys = torch.unique(keys)   # sorted; plumbing only (the pair set is tiny next to the search)
+    P = int(ukeys.shape[0])
+    W = (T + 63) // 64
+    masks = torch.zeros((P, W), dtype=torch.int64, device=lst.device)
+    lst = lst.contiguous()
+    check(lib().mdp_bitmask_fill(ctx.handle, lst.shape[0], ptr(lst), int(n_b), ptr(ukeys), P, W, ptr(masks),
+                                 stream_ptr()), "mdp_bitmask_fill")
+    step = 65535 * 64
+    for p0 in range(0, P, step):
+        m = masks[p0:p0 + step]
+        check(lib().mdp_bitmask_autocorr(ctx.handle, m.shape[0], W, T, ptr(m), ptr(cnt), stream_ptr()),
+              "mdp_bitmask_autocorr")
+    return cnt, P
+
+
+def ols_sums(t, y, i0=0, i1=None):
+    t = _f64(t, "t")
+    y = _f64(y, "y")
+    C, T = y.shape
+    i1 = T if i1 is None else int(i1)
+    ctx = Context.get(t.device.index)
+    out = torch.empty((C, 3), dtype=torch.float64, device=t.device)
+    check(lib().mdp_ols_sums(ctx.handle, C, T, ptr(t), ptr(y), int(i0), i1, ptr(out), stream_ptr()), "mdp_ols_sums")
+    return out

@@ -1,0 +1,156 @@
+"""Cluster extraction around a central atom type -- drop-in for
+``mdproptools.structural.cluster_analysis.get_clusters`` (reference mdproptools/structural/cluster_analysis.py;
+citations are lines of that file).
+
+The O(n_central x N) cutoff search of every frame (:143-161, ``_calc_rsq`` + ``rsq < r_cut**2``) runs on the
+device as one rectangular neighbour-list call per batch of frames (``mdp_pair_list``, csrc/pair.cu).  What is
+left -- completing molecules, the signed force filter (:169-182), the output ordering (:185-207), the
+re-imaging relative to the central atom (:31-44) and the .xyz writer (:213-233) -- is bookkeeping on a few
+hundred atoms per cluster and is restated here on the host in numpy.
+
+Not supported (raises): element names read from an ``element`` column of the dump (pass ``elements``).
+``get_unique_configurations`` (:238-457) is out of scope of the hot path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from .. import _lib, dist, ops
+from ..io import dump as _dump
+from ..io.pipeline import FrameBatches
+from .rdf_cn import _mol_segments, calc_atom_type_ids
+
+FORCE_CONSTANT = 0.043363 / 16.0  # :28
+
+
+def _count_frames(filename: str) -> int:
+    L = _lib.lib()
+    n = 0
+    for f in _dump.dump_files(filename):
+        buf = _dump._read_bytes(f)
+        n += int(L.mdp_dump_scan(buf, len(buf), None, 0))
+    return n
+
+
+def _remove_boundary_effects(head_xyz, xyz, lx, ly, lz):
+    """_remove_boundary_effects (:31-44): shift an atom by one box length when its displacement from the
+    central atom exceeds half a box (strict compares, single shift)."""
+    out = xyz.copy()
+    d = xyz - head_xyz
+    for k, l in enumerate((lx, ly, lz)):
+        cond = (d[:, k] > l / 2) | (d[:, k] < -l / 2)
+        out[cond, k] = out[cond, k] - np.sign(d[cond, k]) * l
+    return out
+
+
+def _write_xyz(path, elements, xyz):
+    """pandas.to_csv(sep='\\t', float_format='%15.10f', header=False, index=False) of (element, x, y, z) (:229-232)."""
+    with open(path, "w") as f:
+        f.write("{}\n\n".format(len(elements)))
+        for e, (x, y, z) in zip(elements, xyz):
+            f.write("%s\t%15.10f\t%15.10f\t%15.10f\n" % (e, x, y, z))
+
+
+def get_clusters(filename, atom_type, r_cut, num_mols, num_atoms_per_mol, full_trajectory=False, frame=None, elements=None,
+                 alter_atom_types=False, max_force=0.75, working_dir=None):
+    """Extract the molecules within ``r_cut`` of every atom of ``atom_type`` and write them as
+    ``Cluster_<frame>_<k>.xyz``; returns the number of clusters written (reference docstring :60-96)."""
+    if elements:
+        elements = {i + 1: j for i, j in enumerate(elements)}
+    if not working_dir:
+        working_dir = os.getcwd()
+    cols_present = _dump.available_columns(filename)
+    if "element" not in cols_present and not elements:
+        raise ValueError("The elements of the atoms in the system should be provided if they "
+                         "are not in the dump files.")
+    if not elements:
+        raise NotImplementedError("element names from a dump column are not supported; pass `elements`")
+
+    total = _count_frames(filename)
+    if full_trajectory:
+        selected = list(range(total))
+    else:
+        selected = [range(total)[frame]]
+    n_sel = len(selected)
+    pos_of = {g: k for k, g in enumerate(selected)}
+    w, r = dist.world_size(), dist.rank()
+    mine = set(g for k, g in enumerate(selected) if k % w == r)
+
+    mol_type_m, seg_off = _mol_segments(num_mols, num_atoms_per_mol)
+    sizes = np.diff(seg_off)
+    mol_of_atom = np.repeat(np.arange(len(mol_type_m)), sizes)
+    first_col = cols_present[0]
+    want = ["id", "type", "x", "y", "z", "fx", "fy", "fz"]
+    if first_col not in want:
+        want.append(first_col)
+    rc2 = r_cut ** 2
+    cluster_count = 0
+    batches = FrameBatches(filename, want, frame_select=lambda i: i in mine)
+    for batch in batches:
+        dev = batch.wait()
+        host = batch.host.numpy()
+        F, _, n = host.shape
+        if seg_off[-1] != n:
+            raise ValueError(f"Length of values ({seg_off[-1]}) does not match length of index ({n})")
+        ci = {c: batch.col(c) for c in want}
+        # central atoms (same rows in every frame of the batch unless the type column changes)
+        per_frame = []
+        for k in range(F):
+            typ = host[k, ci["type"]]
+            if alter_atom_types:
+                # the reference feeds df.values to _calc_atom_type, i.e. the FIRST dump column (:137-139)
+                typ = calc_atom_type_ids(host[k, ci[first_col]], num_mols, num_atoms_per_mol)
+            per_frame.append(np.nonzero(typ == atom_type)[0])
+        same = all(np.array_equal(per_frame[0], p) for p in per_frame[1:])
+        xyz = dev[:, [ci["x"], ci["y"], ci["z"]], :].contiguous()
+        groups = [(0, F)] if same else [(k, k + 1) for k in range(F)]
+        hits = [[] for _ in range(F)]
+        for k0, k1 in groups:
+            cen = per_frame[k0]
+            if len(cen) == 0:
+                continue
+            idx = torch.from_numpy(cen).to(dev.device)
+            xa = xyz[k0:k1].index_select(2, idx).contiguous()
+            boxes = np.array([batch.metas[k].box.bound_lengths() for k in range(k0, k1)])
+            lst, _ = ops.pair_list(xa, xyz[k0:k1].contiguous(), boxes, 0.0, rc2, shell_mode=0)
+            lst = lst.cpu().numpy()
+            order = np.lexsort((lst[:, 2], lst[:, 1], lst[:, 0]))
+            lst = lst[order]
+            for fidx in range(k1 - k0):
+                hits[k0 + fidx] = lst[lst[:, 0] == fidx][:, 1:]
+        for k, meta in enumerate(batch.metas):
+            lx, ly, lz = meta.box.bound_lengths()
+            ids = host[k, ci["id"]]
+            x = np.stack([host[k, ci["x"]], host[k, ci["y"]], host[k, ci["z"]]], axis=1)
+            fsum = np.stack([np.add.reduceat(host[k, ci[c]], seg_off[:-1]) for c in ("fx", "fy", "fz")], axis=1)
+            min_force = fsum.min(axis=1) * FORCE_CONSTANT
+            elem = np.array([elements.get(int(t)) for t in host[k, ci["type"]]], dtype=object)
+            cen = per_frame[k]
+            index = pos_of[meta.index]
+            frame_number = "{}{}".format("0" * (len(str(n_sel)) - len(str(index))), index)
+            h = hits[k]
+            for counter, row in enumerate(cen):
+                nb_atoms = h[h[:, 0] == counter][:, 1] if len(h) else np.zeros(0, dtype=np.int64)
+                mols = np.unique(mol_of_atom[nb_atoms])                  # sorted == (mol_type, mol_id) order
+                mols = mols[min_force[mols] < max_force]                 # signed-component force filter (:169-182)
+                own = mol_of_atom[row]
+                kept_atoms = np.concatenate([np.arange(seg_off[m], seg_off[m + 1]) for m in mols]) if len(mols) else \
+                    np.zeros(0, dtype=np.int64)
+                own_rest = kept_atoms[(mol_of_atom[kept_atoms] == own) & (kept_atoms != row)]
+                others = kept_atoms[mol_of_atom[kept_atoms] != own]
+                order_rows = np.concatenate(([row], own_rest, others)).astype(np.int64)
+                # the final inner merge on id drops the central atom when its own molecule failed the filter (:213-218)
+                keep = np.isin(order_rows, kept_atoms)
+                shifted = _remove_boundary_effects(x[row], x[order_rows], lx, ly, lz)
+                fname = "Cluster_{}_{}{}.xyz".format(frame_number, "0" * (len(str(len(cen))) - len(str(counter))), counter)
+                _write_xyz(os.path.join(working_dir, fname), elem[order_rows][keep], shifted[keep])
+                cluster_count += 1
+    if w > 1:
+        t = torch.tensor([cluster_count], dtype=torch.int64, device="cuda")
+        dist.all_reduce_sum_(t)
+        cluster_count = int(t.item())
+    return cluster_count

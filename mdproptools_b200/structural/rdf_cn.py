@@ -1,0 +1,499 @@
+"""Radial distribution functions and coordination numbers from LAMMPS dump files -- drop-in for
+``mdproptools.structural.rdf_cn`` (reference file mdproptools/structural/rdf_cn.py; citations below are
+lines of that file).
+
+Public functions keep the reference's names, positional order, defaults, return types and side-effect
+files: calc_atomic_rdf (:385), calc_atomic_cn (:533), calc_molecular_rdf (:654), calc_molecular_cn (:759),
+calc_intermolecular_rdf (:857).
+
+Division of labour
+  device  all pair arithmetic (_calc_rsq/_remove_outliers/_rdf_loop/_cn_loop/_rdf_mol_loop/_cn_mol_loop,
+          :35-162) -> per-frame *integer* histograms via libmdprop_b200 (csrc/pair.cu); molecule centres of
+          mass (_define_mol_cols, :218-241) via the segmented reduction kernel;
+  host    everything that only defines how integers become the final floats (_calc_props :244-294,
+          _normalize_rdf :297-329, _normalize_cn :332-338, _save_* :341-382), restated in numpy in the
+          reference's operation order so that equal counts give bit-identical DataFrames.
+Frames are sharded round-robin over the ranks of an initialised torch.distributed group; the per-frame
+integer histograms are merged with one int64 all-reduce.
+
+Documented divergences from the reference:
+  * a bin index >= num_bins (possible when r_cut/bin_size is not an integer) is dropped instead of
+    written out of bounds (the reference corrupts memory);
+  * molecule centres of mass use sequential fp64 accumulation in atom-id order (the reference's BLAS dot
+    has a library-dependent order; differences are <= 1 ulp of the coordinate).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import dist, ops
+from .._lib import bin_edges
+from ..io.pipeline import FrameBatches
+
+CON_CONSTANT = 1.660538921  # :30
+
+VERBOSE = False   # the reference prints per-frame progress; off by default here
+
+
+def _log(*a):
+    if VERBOSE:
+        print(*a)
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side restatements
+# ------------------------------------------------------------------------------------------------
+def _num_bins(r_cut, bin_size):
+    """_initialize (:165-180)."""
+    if isinstance(r_cut, list):
+        nb = [int(i / bin_size) for i in r_cut]
+        radii = [(np.arange(i) + 0.5) * bin_size for i in nb]
+    else:
+        nb = int(r_cut / bin_size)
+        radii = (np.arange(nb) + 0.5) * bin_size
+    return nb, radii
+
+
+def _rcut_sq(r_cut) -> float:
+    """``r_cut ** 2`` as the numba kernels evaluate it (:66): exact for ints, x*x for floats."""
+    if isinstance(r_cut, (int, np.integer)):
+        return float(int(r_cut) ** 2)
+    r = float(r_cut)
+    return r * r
+
+
+def calc_atom_type_ids(ids, num_mols, num_atoms):
+    """_calc_atom_type (:197-215) vectorised: atom id -> 1-based position inside its molecule type block,
+    offset by the atoms-per-molecule of the earlier molecule types.  ids beyond the last block are left as is."""
+    ids = np.asarray(ids, dtype=np.float64)
+    cut = np.cumsum(np.multiply(num_mols, num_atoms))
+    out = ids.copy()
+    which = np.searchsorted(cut, ids, side="left")          # first block with id <= cutoff
+    for i in range(len(cut)):
+        sel = which == i
+        if not sel.any():
+            continue
+        v = np.mod(ids[sel] - cut[i], num_atoms[i])
+        v[v == 0] = num_atoms[i]
+        if i > 0:
+            v = v + np.sum(num_atoms[:i])
+        out[sel] = v
+    return out
+
+
+def _value_counts(typ):
+    u, c = np.unique(np.asarray(typ).astype(np.int64), return_counts=True)
+    return dict(zip(u.tolist(), c.tolist()))
+
+
+def _calc_props(box_lengths, n_objects, atom_types, object_types, num_types, mass, partial_relations, atom_types_col,
+                num_atoms_per_mol=None):
+    """_calc_props (:244-294): densities and the consistency checks (same exceptions)."""
+    num_relations = len(partial_relations[0])
+    volume = np.prod(box_lengths)
+    set_id = set(atom_types.keys())
+    if atom_types_col == "type":
+        if num_types != len(set_id):
+            raise ValueError(
+                f"""Consistency check failed: Number of specified
+                            atomic types is different from the calculated value
+                            specified= {num_types}, calculated= {len(set_id)}"""
+            )
+    elif atom_types_col == "id":
+        if np.sum(num_atoms_per_mol) != len(set_id):
+            raise ValueError(
+                f"""Consistency check failed: Number of specified
+                            atomic types is different from the calculated value
+                            specified= {num_atoms_per_mol},
+                            calculated= {len(set_id)}"""
+            )
+    total_mass = np.sum([float(mass[i]) * float(atom_types[i + 1]) for i in range(num_types)])
+    total_density = float((total_mass / volume) * CON_CONSTANT)
+    _log("{0:s}{1:10.8f}".format("Average density=", float(total_density)))
+    rho = n_objects / volume
+    rho_pairs = np.zeros(num_relations)
+    for index, object_type in enumerate(partial_relations[1]):
+        rho_pairs[index] = object_types[object_type] / volume
+        if rho_pairs[index] < 1.0e-22:
+            raise ValueError("Error: Density is zero for mol type: " + str(object_type))
+    return rho, rho_pairs
+
+
+def _normalize_rdf(bin_size, rho_pairs, atom_types, partial_relations, num_relations, num_bins, rdf_part, rdf_full=None,
+                   num_atoms=None, rho=None):
+    """_normalize_rdf (:297-329)."""
+    shell_volume = (
+        4 / 3 * np.pi * bin_size ** 3 * (np.arange(1, num_bins + 1) ** 3 - np.arange(num_bins) ** 3)
+    )
+    if rdf_full is not None:
+        rdf_full = rdf_full / (num_atoms * rho * shell_volume)
+    ref_atoms = np.asarray(partial_relations[0]).reshape((num_relations, 1))
+    ref_atoms_matrix = np.tile(ref_atoms, num_bins)
+    num_atoms_matrix = np.vectorize(atom_types.get)(ref_atoms_matrix)
+    rho_pairs_matrix = np.tile(rho_pairs.reshape((num_relations, 1)), num_bins)
+    shell_volume_matrix = np.tile(shell_volume, (num_relations, 1))
+    rdf_part = rdf_part / (num_atoms_matrix * rho_pairs_matrix * shell_volume_matrix)
+    return rdf_full, rdf_part
+
+
+def _normalize_cn(atom_types, partial_relations, cn):
+    """_normalize_cn (:332-338)."""
+    num_ref_atoms = [atom_types[i] for i in partial_relations[0]]
+    return cn / num_ref_atoms
+
+
+def _save_rdf(radii, relation_matrix, path_or_buf, save_mode, rdf_part_sum, rdf_full_sum=None):
+    """_save_rdf (:341-365)."""
+    if rdf_full_sum is not None:
+        result_tuple = (radii, rdf_full_sum, rdf_part_sum)
+        final_label = ["r ($\\AA$)", "g_full(r)"]
+    else:
+        result_tuple = (radii, rdf_part_sum)
+        final_label = ["r ($\\AA$)"]
+    final_array = np.vstack(result_tuple).transpose()
+    final_labels = final_label + [f"g_{str(pair[0])}-{str(pair[1])}" for pair in relation_matrix]
+    final_df = pd.DataFrame(final_array, columns=final_labels)
+    if save_mode:
+        final_df.to_csv(path_or_buf, index=False)
+        _log("Results are written to pd.DataFrame and csv file")
+    else:
+        _log(final_df)
+    return final_df
+
+
+def _save_cn(relation_matrix, path_or_buff, cn_sum, save_mode):
+    """_save_cn (:368-382)."""
+    final_array = np.vstack(cn_sum).transpose()
+    final_labels = [f"cn_{str(pair[0])}-{str(pair[1])}" for pair in relation_matrix]
+    final_df = pd.DataFrame(final_array, columns=final_labels)
+    if save_mode:
+        final_df.to_csv(path_or_buff, index=False)
+        _log("CN results are written to pd.DataFrame and csv file")
+    else:
+        _log(final_df)
+    return final_df
+
+
+# ------------------------------------------------------------------------------------------------
+# class maps: relation types -> small dense class ids for the device histogram
+# ------------------------------------------------------------------------------------------------
+class _ClassMap:
+    """Types named by the relations get their own class; everything else shares the class 'other'."""
+
+    def __init__(self, named_types):
+        self.named = sorted(set(int(t) for t in named_types))
+        self.index = {t: k for k, t in enumerate(self.named)}
+        self.ncls = len(self.named) + 1
+        self.other = self.ncls - 1
+
+    def classes_of(self, typ: np.ndarray) -> np.ndarray:
+        t = np.asarray(typ).astype(np.int64)
+        cls = np.full(t.shape, self.other, dtype=np.int32)
+        for ty, k in self.index.items():
+            cls[t == ty] = k
+        return cls
+
+    def cls(self, t):
+        return self.index.get(int(t), self.other)
+
+
+def _sym_weights(cmap: _ClassMap, relation_matrix, with_full: bool):
+    """hist_reduce weights for the symmetric kernel: g_full counts every pair twice (:85-86); relation (a,b)
+    counts a pair once per matching role order (:89-96) -> 2 on the like row, 1 on the unlike row."""
+    rows = ops.sym_rows(cmap.ncls)
+    w = []
+    if with_full:
+        w.append(np.full(rows, 2, dtype=np.int32))
+    for a, b in relation_matrix:
+        r = np.zeros(rows, dtype=np.int32)
+        r[ops.sym_row(cmap.cls(a), cmap.cls(b), cmap.ncls)] = 2 if int(a) == int(b) else 1
+        w.append(r)
+    return np.stack(w)
+
+
+def _rect_weights(cmap_a: _ClassMap, cmap_b: _ClassMap, relation_matrix):
+    rows = cmap_a.ncls * cmap_b.ncls
+    w = []
+    for a, b in relation_matrix:
+        r = np.zeros(rows, dtype=np.int32)
+        r[cmap_a.cls(a) * cmap_b.ncls + cmap_b.cls(b)] = 1
+        w.append(r)
+    return np.stack(w)
+
+
+def _cn_edges(r_cut_list):
+    """Sorted distinct squared cutoffs as a histogram edge table; bin k = #{thresholds <= rsq}."""
+    rc2 = np.array([_rcut_sq(r) for r in r_cut_list], dtype=np.float64)
+    thr = np.unique(rc2)                       # ascending
+    edges = np.concatenate(([0.0], thr))       # edges[k>=1] = thr[k-1]
+    # a pair with rsq < rc2[kl] lies in bins 0 .. (index of rc2[kl] in thr); cumulative bin index per relation
+    upto = np.searchsorted(thr, rc2)           # bins 0..upto inclusive
+    return edges, float(thr[-1]), upto
+
+
+# ------------------------------------------------------------------------------------------------
+# frame iteration shared by all entry points
+# ------------------------------------------------------------------------------------------------
+def _frame_batches(filename, columns):
+    w, r = dist.world_size(), dist.rank()
+    sel = (lambda i: i % w == r) if w > 1 else None
+    return FrameBatches(filename, columns, frame_select=sel)
+
+
+def _merge_frames(per_frame: dict, total_frames: int, shape, device):
+    """Place this rank's per-frame integer results into [T, *shape] and all-reduce (int64, exact)."""
+    out = torch.zeros((total_frames,) + tuple(shape), dtype=torch.int64, device=device)
+    for idx, t in per_frame.items():
+        out[idx] = t
+    dist.all_reduce_sum_(out)
+    return out
+
+
+def _mol_segments(num_mols, num_atoms_per_mol):
+    """Molecule membership implied by id order (:222-230): (mol_type[M], seg_off[M+1])."""
+    mt = np.repeat(np.arange(1, len(num_mols) + 1), num_mols)
+    sizes = np.repeat(np.asarray(num_atoms_per_mol), num_mols)
+    off = np.concatenate(([0], np.cumsum(sizes)))
+    return mt, off
+
+
+# ------------------------------------------------------------------------------------------------
+# public API
+# ------------------------------------------------------------------------------------------------
+def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols=None, num_atoms_per_mol=None,
+                    path_or_buff="rdf.csv", save_mode=True):
+    """Full and partial atom-atom RDF; see the reference docstring (:397-452) for the arguments."""
+    num_bins, radii = _num_bins(r_cut, bin_size)
+    num_relations = len(partial_relations[0])
+    relation_matrix = np.asarray(partial_relations).transpose()
+    altered = bool(num_mols and num_atoms_per_mol)
+    cmap = _ClassMap(list(partial_relations[0]) + list(partial_relations[1]))
+    weights = _sym_weights(cmap, relation_matrix, with_full=True)
+    edges = bin_edges(bin_size, num_bins)
+    rcut2 = _rcut_sq(r_cut)
+
+    batches = _frame_batches(filename, ["id", "type", "x", "y", "z"])
+    counts, props = {}, {}
+    device = None
+    for batch in batches:
+        dev = batch.wait()
+        device = dev.device
+        F = len(batch.metas)
+        host = batch.host.numpy()
+        cls = np.empty((F, host.shape[2]), dtype=np.int32)
+        boxes = np.empty((F, 3))
+        for k, meta in enumerate(batch.metas):
+            _log("The timestep of the current file is: " + str(meta.timestep))
+            typ = calc_atom_type_ids(host[k, 0], num_mols, num_atoms_per_mol) if altered else host[k, 1]
+            at = _value_counts(typ)
+            lengths = meta.box.lattice_lengths()
+            rho, rho_pairs = _calc_props(lengths, meta.natoms, at, at, num_types, mass, partial_relations,
+                                         "id" if altered else "type", num_atoms_per_mol)
+            props[meta.index] = (at, rho, rho_pairs, meta.natoms)
+            cls[k] = cmap.classes_of(typ)
+            boxes[k] = lengths
+        xyz = dev[:, 2:5, :].contiguous()
+        cls_d = torch.from_numpy(cls).to(device)
+        hist = ops.pair_hist(xyz, cls_d, cmap.ncls, boxes, rcut2, edges, bin_size)
+        red = ops.hist_reduce(hist, weights)                      # [F, 1+R, nb]
+        for k, meta in enumerate(batch.metas):
+            counts[meta.index] = red[k]
+    T = batches.total_frames or 0
+    if T == 0:
+        raise ValueError(f"no dump frames found for {filename!r}")
+    allc = _merge_frames(counts, T, (1 + num_relations, num_bins), device).cpu().numpy()
+    if dist.world_size() > 1:
+        props = _gather_props(props, T)
+
+    rdf_full_sum = np.zeros(num_bins)
+    rdf_part_sum = np.zeros((num_relations, num_bins))
+    for idx in range(T):
+        at, rho, rho_pairs, natoms = props[idx]
+        rdf_full = allc[idx, 0].astype(np.float64)
+        rdf_part = allc[idx, 1:].astype(np.float64)
+        rdf_full, rdf_part = _normalize_rdf(bin_size, rho_pairs, at, partial_relations, num_relations, num_bins, rdf_part,
+                                            rdf_full, natoms, rho)
+        rdf_full_sum += rdf_full
+        rdf_part_sum += rdf_part
+    rdf_full_sum = rdf_full_sum / T
+    rdf_part_sum = rdf_part_sum / T
+    return _save_rdf(radii, relation_matrix, path_or_buff, save_mode, rdf_part_sum, rdf_full_sum=rdf_full_sum)
+
+
+def _gather_props(props: dict, total_frames: int) -> dict:
+    """Every rank needs every frame's host-side normalisation inputs (tiny python objects)."""
+    import torch.distributed as d
+
+    gathered = [None] * d.get_world_size()
+    d.all_gather_object(gathered, props)
+    out = {}
+    for g in gathered:
+        out.update(g)
+    assert len(out) == total_frames
+    return out
+
+
+def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols=None, num_atoms_per_mol=None,
+                   path_or_buff="cn.csv", save_mode=True):
+    """Atom-atom coordination numbers, one cutoff per relation (:533-651)."""
+    _num_bins(r_cut, bin_size)
+    num_relations = len(partial_relations[0])
+    relation_matrix = np.asarray(partial_relations).transpose()
+    altered = bool(num_mols and num_atoms_per_mol)
+    cmap = _ClassMap(list(partial_relations[0]) + list(partial_relations[1]))
+    weights = _sym_weights(cmap, relation_matrix, with_full=False)
+    edges, rcut2_max, upto = _cn_edges(r_cut)
+    nthr = len(edges) - 1
+
+    batches = _frame_batches(filename, ["id", "type", "x", "y", "z"])
+    counts, props = {}, {}
+    device = None
+    for batch in batches:
+        dev = batch.wait()
+        device = dev.device
+        F = len(batch.metas)
+        host = batch.host.numpy()
+        cls = np.empty((F, host.shape[2]), dtype=np.int32)
+        boxes = np.empty((F, 3))
+        for k, meta in enumerate(batch.metas):
+            typ = calc_atom_type_ids(host[k, 0], num_mols, num_atoms_per_mol) if altered else host[k, 1]
+            at = _value_counts(typ)
+            lengths = meta.box.lattice_lengths()
+            _calc_props(lengths, meta.natoms, at, at, num_types, mass, partial_relations, "id" if altered else "type",
+                        num_atoms_per_mol)
+            props[meta.index] = at
+            cls[k] = cmap.classes_of(typ)
+            boxes[k] = lengths
+        xyz = dev[:, 2:5, :].contiguous()
+        hist = ops.pair_hist(xyz, torch.from_numpy(cls).to(device), cmap.ncls, boxes, rcut2_max, edges, 0.0)
+        red = ops.hist_reduce(hist, weights, cumulative=True)     # [F, R, nthr] cumulative over thresholds
+        for k, meta in enumerate(batch.metas):
+            counts[meta.index] = red[k]
+    T = batches.total_frames or 0
+    if T == 0:
+        raise ValueError(f"no dump frames found for {filename!r}")
+    allc = _merge_frames(counts, T, (num_relations, nthr), device).cpu().numpy()
+    if dist.world_size() > 1:
+        props = _gather_props(props, T)
+    cn_sum = np.zeros(num_relations)
+    for idx in range(T):
+        cn = np.array([allc[idx, kl, upto[kl]] for kl in range(num_relations)], dtype=np.float64)
+        cn_sum += _normalize_cn(props[idx], partial_relations, cn)
+    cn_sum = cn_sum / T
+    return _save_cn(relation_matrix, path_or_buff, cn_sum, save_mode)
+
+
+def _molecular_common(filename, num_types, mass, partial_relations, num_mols, num_atoms_per_mol, inter, run_pairs):
+    """Shared frame loop of the atom/molecule-COM entry points (:654-902).  ``run_pairs`` gets the device
+    tensors of one batch and returns per-frame integer results [F, R, *]."""
+    num_relations = len(partial_relations[0])
+    relation_matrix = np.asarray(partial_relations).transpose()
+    mol_type, seg_off = _mol_segments(num_mols, num_atoms_per_mol)
+    cmap_a = _ClassMap(partial_relations[0])
+    cmap_b = _ClassMap(partial_relations[1])
+    weights = _rect_weights(cmap_a, cmap_b, relation_matrix)
+    mol_types_count = _value_counts(mol_type)
+    batches = _frame_batches(filename, ["id", "type", "x", "y", "z"])
+    counts, props = {}, {}
+    device = None
+    for batch in batches:
+        dev = batch.wait()
+        device = dev.device
+        F = len(batch.metas)
+        host = batch.host.numpy()
+        n = host.shape[2]
+        if seg_off[-1] != n:
+            raise ValueError(f"Length of values ({seg_off[-1]}) does not match length of index ({n})")
+        boxes = np.empty((F, 3))
+        cls_a = np.empty((F, n), dtype=np.int32)
+        for k, meta in enumerate(batch.metas):
+            lengths = meta.box.lattice_lengths()
+            boxes[k] = lengths
+            if inter:
+                at = mol_types_count
+                n_objects = len(mol_type)
+                atc = "type"
+            else:
+                at = _value_counts(host[k, 1])
+                n_objects = len(mol_type)
+                atc = "type"
+                cls_a[k] = cmap_a.classes_of(host[k, 1])
+            rho, rho_pairs = _calc_props(lengths, n_objects, at, mol_types_count, num_types, mass, partial_relations, atc,
+                                         num_atoms_per_mol)
+            props[meta.index] = (at, rho_pairs)
+        xyz = dev[:, 2:5, :].contiguous()
+        # masses per atom from the type column of the first frame of the batch (:231); types are static per id
+        m_atom = torch.from_numpy(np.array([mass[int(t - 1)] for t in host[0, 1]], dtype=np.float64)).to(device)
+        com, _, _ = ops.segment_com(xyz, m_atom, torch.from_numpy(seg_off.astype(np.int32)).to(device))   # [F,3,M]
+        cls_m = torch.from_numpy(cmap_b.classes_of(mol_type)).to(device)
+        if inter:
+            cm_a = _ClassMap(partial_relations[0])
+            res = run_pairs(com, torch.from_numpy(cm_a.classes_of(mol_type)).to(device), cm_a.ncls, com, cls_m,
+                            cmap_b.ncls, boxes, _rect_weights(cm_a, cmap_b, relation_matrix))
+        else:
+            res = run_pairs(xyz, torch.from_numpy(cls_a).to(device), cmap_a.ncls, com, cls_m, cmap_b.ncls, boxes, weights)
+        for k, meta in enumerate(batch.metas):
+            counts[meta.index] = res[k]
+    T = batches.total_frames or 0
+    if T == 0:
+        raise ValueError(f"no dump frames found for {filename!r}")
+    return counts, props, T, device, relation_matrix, num_relations
+
+
+def calc_molecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
+                       path_or_buff="rdf_mol.csv", save_mode=True, _inter=False):
+    """Partial RDF between atoms and molecule centres of mass (:654-756)."""
+    num_bins, radii = _num_bins(r_cut, bin_size)
+    edges = bin_edges(bin_size, num_bins)
+    rcut2 = _rcut_sq(r_cut)
+
+    def run(xa, ca, na, xb, cb, nb_, boxes, w):
+        hist = ops.pair_hist(xa, ca, na, boxes, rcut2, edges, bin_size, xyz_b=xb, cls_b=cb, ncls_b=nb_)
+        return ops.hist_reduce(hist, w)
+
+    counts, props, T, device, relation_matrix, R = _molecular_common(filename, num_types, mass, partial_relations, num_mols,
+                                                                      num_atoms_per_mol, _inter, run)
+    allc = _merge_frames(counts, T, (R, num_bins), device).cpu().numpy()
+    if dist.world_size() > 1:
+        props = _gather_props(props, T)
+    rdf_part_sum = np.zeros((R, num_bins))
+    for idx in range(T):
+        at, rho_pairs = props[idx]
+        _, rdf_part = _normalize_rdf(bin_size, rho_pairs, at, partial_relations, R, num_bins, allc[idx].astype(np.float64))
+        rdf_part_sum += rdf_part
+    rdf_part_sum = rdf_part_sum / T
+    return _save_rdf(radii, relation_matrix, path_or_buff, save_mode, rdf_part_sum)
+
+
+def calc_molecular_cn(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
+                      path_or_buff="cn_mol.csv", save_mode=True):
+    """Coordination numbers between atoms and molecule centres of mass (:759-854)."""
+    _num_bins(r_cut, bin_size)
+    edges, rcut2_max, upto = _cn_edges(r_cut)
+    nthr = len(edges) - 1
+
+    def run(xa, ca, na, xb, cb, nb_, boxes, w):
+        hist = ops.pair_hist(xa, ca, na, boxes, rcut2_max, edges, 0.0, xyz_b=xb, cls_b=cb, ncls_b=nb_)
+        return ops.hist_reduce(hist, w, cumulative=True)
+
+    counts, props, T, device, relation_matrix, R = _molecular_common(filename, num_types, mass, partial_relations, num_mols,
+                                                                      num_atoms_per_mol, False, run)
+    allc = _merge_frames(counts, T, (R, nthr), device).cpu().numpy()
+    if dist.world_size() > 1:
+        props = _gather_props(props, T)
+    cn_sum = np.zeros(R)
+    for idx in range(T):
+        at, _ = props[idx]
+        cn = np.array([allc[idx, kl, upto[kl]] for kl in range(R)], dtype=np.float64)
+        cn_sum += _normalize_cn(at, partial_relations, cn)
+    cn_sum = cn_sum / T
+    return _save_cn(relation_matrix, path_or_buff, cn_sum, save_mode)
+
+
+def calc_intermolecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
+                            path_or_buff="rdf_mol.csv", save_mode=True):
+    """Molecule-COM / molecule-COM partial RDF, self pairs included as in the reference (:857-902)."""
+    return calc_molecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
+                              path_or_buff=path_or_buff, save_mode=save_mode, _inter=True)

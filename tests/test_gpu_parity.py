@@ -1,0 +1,474 @@
+"""Parity of the CUDA path (through the C ABI / the reference-facing Python API) against
+  (1) golden outputs of the unmodified reference (tests/golden/, see oracle/gen_golden.py), and
+  (2) the CPU oracle on seeded synthetic inputs (ragged sizes, several classes, triclinic-length boxes, ...).
+Integer results must be bit-exact; floating-point results carry the tolerance stated at the assert.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+from tests.conftest import ELEMENTS, GOLDEN, MASS, NUM_ATOMS, NUM_MOLS  # noqa: E402
+
+REL = [[9, 9, 9, 9], [1, 4, 6, 9]]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mdproptools_b200 import ops as _ops
+    return _ops
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def _rand_box(rng, n, L, ntypes):
+    pos = rng.uniform(0, 1, (3, n)) * np.asarray(L)[:, None]
+    typ = rng.integers(1, ntypes + 1, n).astype(np.float64)
+    return pos, typ
+
+
+# ------------------------------------------------------------------------------------------------
+# pair histogram kernel vs oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,L,rc,ddr,flags", [
+    (1000, (21.0, 22.5, 24.0), 7.0, 0.05, 0),
+    (777, (15.0, 15.0, 15.0), 7.4, 0.1, 0),          # r_cut close to L/2: general minimum-image path everywhere
+    (3000, (60.0, 40.0, 35.0), 6.0, 0.05, 0),        # culling active
+    (3000, (60.0, 40.0, 35.0), 6.0, 0.05, 1),        # MDP_PAIR_NO_CULL
+    (3000, (60.0, 40.0, 35.0), 6.0, 0.05, 3),        # no cull, no sort (brute force in caller order)
+    (257, (9.0, 9.0, 9.0), 12.0, 0.25, 0),           # r_cut > L/2 (single-shift semantics, not true MIC)
+    (31, (9.0, 9.0, 9.0), 4.0, 0.25, 0),             # less than one group
+    (1, (9.0, 9.0, 9.0), 4.0, 0.25, 0),              # a single atom: no pairs
+])
+def test_pair_hist_symmetric_vs_oracle(ops, n, L, rc, ddr, flags):
+    from mdproptools_b200._lib import bin_edges
+    rng = np.random.default_rng(n * 7 + flags)
+    pos, typ = _rand_box(rng, n, L, 3)
+    rel = np.array([[1, 1], [1, 2], [3, 2], [2, 3]])
+    nb = int(rc / ddr)
+    full, part = O.rdf_loop(typ, pos[0], pos[1], pos[2], rel, L, rc, ddr, nb, nthreads=0)
+    cls = (typ.astype(np.int64) - 1).astype(np.int32)       # 3 classes, no 'other'
+    edges = bin_edges(ddr, nb)
+    hist = ops.pair_hist(_dev(pos[None]), _dev(cls), 3, [L], O.rcut_sq(rc), edges, ddr, flags=flags)
+    w = [np.full(6, 2)]
+    for a, b in rel:
+        r = np.zeros(6, dtype=np.int64)
+        r[ops.sym_row(a - 1, b - 1, 3)] = 2 if a == b else 1
+        w.append(r)
+    red = ops.hist_reduce(hist, np.stack(w)).cpu().numpy()[0]
+    assert np.array_equal(red[0], full)
+    assert np.array_equal(red[1:], part)
+    assert int(hist.sum().item()) * 2 == int(full.sum())
+
+
+def test_pair_hist_multiframe_and_per_frame_boxes(ops):
+    from mdproptools_b200._lib import bin_edges
+    rng = np.random.default_rng(11)
+    F, n = 5, 1500
+    Ls = [(30.0 + k, 28.0, 33.0 - k) for k in range(F)]
+    pos = np.stack([rng.uniform(0, 1, (3, n)) * np.asarray(L)[:, None] for L in Ls])
+    nb, ddr, rc = 160, 0.05, 8.0
+    edges = bin_edges(ddr, nb)
+    hist = ops.pair_hist(_dev(pos), None, 1, Ls, rc * rc, edges, ddr).cpu().numpy()
+    for f in range(F):
+        full, _ = O.rdf_loop(np.ones(n), pos[f, 0], pos[f, 1], pos[f, 2], np.array([[1, 1]]), Ls[f], rc, ddr, nb, nthreads=0)
+        assert np.array_equal(hist[f, 0] * 2, full), f
+
+
+def test_pair_hist_rectangular_vs_oracle(ops):
+    from mdproptools_b200._lib import bin_edges
+    rng = np.random.default_rng(3)
+    L = (25.0, 27.0, 23.0)
+    pa, ta = _rand_box(rng, 1234, L, 3)
+    pb, tb = _rand_box(rng, 300, L, 2)
+    pb[:, :50] = pa[:, :50]                        # coincident points: rsq == 0 lands in bin 0 (no self exclusion)
+    rel = np.array([[1, 1], [2, 2], [3, 1], [1, 2]])
+    nb, ddr, rc = 100, 0.1, 10.0
+    part = O.rdf_rect(ta, pa[0], pa[1], pa[2], tb, pb[0], pb[1], pb[2], rel, L, rc, ddr, nb, nthreads=0)
+    edges = bin_edges(ddr, nb)
+    hist = ops.pair_hist(_dev(pa[None]), _dev((ta - 1).astype(np.int32)), 3, [L], rc * rc, edges, ddr,
+                         xyz_b=_dev(pb[None]), cls_b=_dev((tb - 1).astype(np.int32)), ncls_b=2)
+    w = np.zeros((len(rel), 6), dtype=np.int64)
+    for k, (a, b) in enumerate(rel):
+        w[k, (a - 1) * 2 + (b - 1)] = 1
+    red = ops.hist_reduce(hist, w).cpu().numpy()[0]
+    assert np.array_equal(red, part)
+    assert part[:, 0].sum() > 0
+
+
+def test_pair_hist_table_mode_counts(ops):
+    rng = np.random.default_rng(5)
+    L = (18.0, 18.0, 18.0)
+    pos, typ = _rand_box(rng, 2000, L, 2)
+    rel = np.array([[1, 2], [2, 2], [1, 1]])
+    rcs = [3.3, 5.125, 2.0]
+    cn = O.cn_loop(typ, pos[0], pos[1], pos[2], rel, L, rcs, nthreads=0)
+    rc2 = np.array([r * r for r in rcs])
+    thr = np.unique(rc2)
+    edges = np.concatenate(([0.0], thr))
+    hist = ops.pair_hist(_dev(pos[None]), _dev((typ - 1).astype(np.int32)), 2, [L], float(thr[-1]), edges, 0.0)
+    w = np.zeros((3, 3), dtype=np.int64)
+    for k, (a, b) in enumerate(rel):
+        w[k, ops.sym_row(a - 1, b - 1, 2)] = 2 if a == b else 1
+    red = ops.hist_reduce(hist, w, cumulative=True).cpu().numpy()[0]
+    upto = np.searchsorted(thr, rc2)
+    got = np.array([red[k, upto[k]] for k in range(3)])
+    assert np.array_equal(got, cn)
+
+
+def test_bin_edges_match_reference_formula():
+    from mdproptools_b200._lib import bin_edges
+    rng = np.random.default_rng(0)
+    for ddr, nb in [(0.05, 400), (0.07, 104), (0.1, 3), (0.013, 1000)]:
+        e = bin_edges(ddr, nb)
+        rsq = rng.uniform(0, (nb * ddr) ** 2 * 1.01, 200000)
+        rsq = np.concatenate([rsq, e[1:], np.nextafter(e[1:], 0), np.nextafter(e[1:], np.inf)])
+        ref = (np.sqrt(rsq) / ddr).astype(np.int64)
+        got = np.searchsorted(e[1:], rsq, side="right")
+        assert np.array_equal(np.minimum(ref, nb), got)
+
+
+# ------------------------------------------------------------------------------------------------
+# structural API vs golden outputs of the reference
+# ------------------------------------------------------------------------------------------------
+def test_calc_atomic_rdf_golden(sample_dir, gold_structural, tmp_path):
+    from mdproptools_b200.structural.rdf_cn import calc_atomic_rdf
+    f0 = os.path.join(sample_dir, "dump.nvt.0.dump")
+    df = calc_atomic_rdf(20, 0.05, 9, MASS, REL, f0, path_or_buff=str(tmp_path / "rdf.csv"))
+    assert list(df.columns) == list(gold_structural["atomic_rdf_columns"])
+    assert np.array_equal(df.values, gold_structural["atomic_rdf_f0"])          # bit-identical floats
+    assert os.path.exists(tmp_path / "rdf.csv")
+    df2 = calc_atomic_rdf(20, 0.05, 9, MASS, REL, os.path.join(sample_dir, "dump.nvt.*.dump"), save_mode=False)
+    assert np.array_equal(df2.values, gold_structural["atomic_rdf_2frames"])
+    df3 = calc_atomic_rdf(12, 0.05, 9, MASS, [[32, 32], [17, 32]], f0, num_mols=NUM_MOLS, num_atoms_per_mol=NUM_ATOMS,
+                          save_mode=False)
+    assert list(df3.columns) == list(gold_structural["atomic_rdf_altered_columns"])
+    assert np.array_equal(df3.values, gold_structural["atomic_rdf_altered_f0"])
+
+
+def test_calc_atomic_rdf_consistency_error(sample_dir):
+    from mdproptools_b200.structural.rdf_cn import calc_atomic_rdf
+    with pytest.raises(ValueError, match="Consistency check failed"):
+        calc_atomic_rdf(20, 0.05, 8, MASS, REL, os.path.join(sample_dir, "dump.nvt.0.dump"), save_mode=False)
+
+
+def test_calc_atomic_cn_golden(sample_dir, gold_structural):
+    from mdproptools_b200.structural.rdf_cn import calc_atomic_cn
+    f0 = os.path.join(sample_dir, "dump.nvt.0.dump")
+    df = calc_atomic_cn([2.325, 4.375, 2.375, 13.0], 0.05, 9, MASS, REL, f0, save_mode=False)
+    assert list(df.columns) == list(gold_structural["atomic_cn_columns"])
+    assert np.array_equal(df.values, gold_structural["atomic_cn_f0"])
+    df2 = calc_atomic_cn([2.325, 4.375, 2.375, 13.0], 0.05, 9, MASS, REL, os.path.join(sample_dir, "dump.nvt.*.dump"),
+                         save_mode=False)
+    assert np.array_equal(df2.values, gold_structural["atomic_cn_2frames"])
+    df3 = calc_atomic_cn([4.375, 13.0], 0.05, 9, MASS, [[32, 32], [17, 32]], f0, num_mols=NUM_MOLS,
+                         num_atoms_per_mol=NUM_ATOMS, save_mode=False)
+    assert np.array_equal(df3.values, gold_structural["atomic_cn_altered_f0"])
+
+
+def test_molecular_rdf_cn_golden(sample_dir, gold_structural):
+    from mdproptools_b200.structural.rdf_cn import calc_molecular_cn, calc_molecular_rdf
+    f0 = os.path.join(sample_dir, "dump.nvt.0.dump")
+    mrel = [[9, 9, 4], [1, 2, 3]]
+    df = calc_molecular_rdf(20, 0.05, 9, MASS, mrel, f0, NUM_MOLS, NUM_ATOMS, save_mode=False)
+    ref = gold_structural["molecular_rdf_f0"]
+    assert list(df.columns) == list(gold_structural["molecular_rdf_columns"])
+    assert np.array_equal(df.values[:, 0], ref[:, 0])
+    # molecule centres of mass: sequential fp64 here, BLAS dot in the reference -> a COM within an ulp of a bin
+    # edge may move one count (documented); everything else is bit-identical
+    assert np.count_nonzero(df.values != ref) <= 4
+    cn = calc_molecular_cn([2.325, 3.775, 4.375], 0.05, 9, MASS, mrel, f0, NUM_MOLS, NUM_ATOMS, save_mode=False)
+    assert np.allclose(cn.values, gold_structural["molecular_cn_f0"], rtol=0, atol=1e-12)
+
+
+def test_intermolecular_rdf_golden(mini_dir, gold_dynamical):
+    from mdproptools_b200.structural.rdf_cn import calc_intermolecular_rdf
+    num_mols = gold_dynamical["mini_num_mols"].tolist()
+    df = calc_intermolecular_rdf(20, 0.05, 3, MASS, [[3, 3, 2], [1, 2, 2]], os.path.join(mini_dir, "dump.mini.0.dump"),
+                                 num_mols, NUM_ATOMS, save_mode=False)
+    ref = gold_dynamical["intermolecular_rdf_mini_f0"]
+    assert np.count_nonzero(df.values != ref) <= 4
+
+
+def test_get_clusters_golden(sample_dir, tmp_path):
+    from mdproptools_b200.structural.cluster_analysis import get_clusters
+    gold = json.load(open(os.path.join(GOLDEN, "ref_clusters.json")))
+    wd = tmp_path / "c1"
+    wd.mkdir()
+    n = get_clusters(filename=os.path.join(sample_dir, "dump.nvt.*.dump"), atom_type=9, r_cut=2.3, num_mols=NUM_MOLS,
+                     num_atoms_per_mol=NUM_ATOMS, full_trajectory=False, frame=1, elements=ELEMENTS,
+                     alter_atom_types=False, max_force=0.75, working_dir=str(wd))
+    g = gold["frame1_type9"]
+    assert n == g["count"] == 33 and g["identical_to_reference_goldens"] == 33
+    for name, text in g["files"].items():
+        assert open(wd / name).read() == text, name             # byte-identical .xyz files
+    wd2 = tmp_path / "c2"
+    wd2.mkdir()
+    n2 = get_clusters(filename=os.path.join(sample_dir, "dump.nvt.*.dump"), atom_type=32, r_cut=2.3, num_mols=NUM_MOLS,
+                      num_atoms_per_mol=NUM_ATOMS, full_trajectory=True, elements=ELEMENTS, alter_atom_types=True,
+                      max_force=0.75, working_dir=str(wd2))
+    g2 = gold["full_altered32"]
+    assert n2 == g2["count"]
+    assert sorted(os.listdir(wd2)) == sorted(g2["files"])
+    for name, text in g2["files"].items():
+        assert open(wd2 / name).read() == text, name
+
+
+def test_hydration_golden(water_dir, gold_hydration, tmp_path):
+    import shutil
+    from mdproptools_b200.structural.hydration_number import get_hydration_number
+    for f in os.listdir(water_dir):
+        shutil.copy(os.path.join(water_dir, f), tmp_path)
+    df = get_hydration_number("dump.water.*.dump", cation_type=1, water_type=2, r_cut=5.0,
+                              num_mols=gold_hydration["hyd_num_mols"].tolist(),
+                              num_atoms_per_mol=gold_hydration["hyd_num_atoms"].tolist(), working_dir=str(tmp_path))
+    assert np.array_equal(df["angles_distribution"].values, gold_hydration["hyd_angles"])
+    assert df["hydration_factor"].values[0] == gold_hydration["hyd_factor"][0]
+    assert os.path.exists(tmp_path / "angles_df.csv")
+
+
+# ------------------------------------------------------------------------------------------------
+# dynamical API vs golden outputs of the reference
+# ------------------------------------------------------------------------------------------------
+def test_msd_allatom_golden(mini_dir, gold_dynamical, tmp_path):
+    from mdproptools_b200.dynamical.diffusion import Diffusion
+    d = Diffusion(timestep=1, units="real", outputs_dir=mini_dir, diff_dir=str(tmp_path))
+    msd, msd_all, msd_int = d.get_msd_from_dump("dump.mini.*.dump", msd_type="allatom", avg_interval=True, tao_coeff=4)
+    assert list(msd.columns) == list(gold_dynamical["msd_allatom_cols"])
+    assert list(msd_all.columns) == list(gold_dynamical["msd_all_allatom_cols"])
+    assert list(msd_int.columns) == list(gold_dynamical["msd_int_allatom_cols"])
+    assert np.array_equal(msd_all.values, gold_dynamical["msd_all_allatom"])       # per-atom values: bit-identical
+    assert np.allclose(msd.values, gold_dynamical["msd_allatom"], rtol=1e-12, atol=0)          # north star: <= 1e-10
+    assert np.allclose(msd_int.values, gold_dynamical["msd_int_allatom"], rtol=1e-12, atol=0)
+    diff = d.calc_diff(msd, initial_time={0: 1e-9}, final_time={0: 4e-9})
+    assert np.allclose(diff.values, gold_dynamical["diff_allatom_window"], rtol=1e-10)
+    assert os.path.exists(tmp_path / "diffusion.csv")
+
+
+def test_msd_com_golden(mini_dir, gold_dynamical, tmp_path):
+    from mdproptools_b200.dynamical.diffusion import Diffusion
+    num_mols = gold_dynamical["mini_num_mols"].tolist()
+    d = Diffusion(timestep=1, units="real", outputs_dir=mini_dir, diff_dir=str(tmp_path))
+    msd, msd_all, msd_int = d.get_msd_from_dump("dump.mini.*.dump", msd_type="com", num_mols=num_mols,
+                                                num_atoms_per_mol=NUM_ATOMS, mass=MASS, com_drift=True, avg_interval=True,
+                                                tao_coeff=4)
+    assert list(msd.columns) == list(gold_dynamical["msd_com_cols"])
+    assert list(msd_all.columns) == list(gold_dynamical["msd_all_com_cols"])
+    assert list(msd_int.columns) == list(gold_dynamical["msd_int_com_cols"])
+    # COM sums differ from the reference's BLAS / Kahan order by ~1 ulp of a 50 A coordinate (1e-26 m);
+    # squared displacements are ~1e-20 m^2, so the comparison is relative to the largest value of each column
+    for got, ref in ((msd.values, gold_dynamical["msd_com"]), (msd_all.values, gold_dynamical["msd_all_com"]),
+                     (msd_int.values, gold_dynamical["msd_int_com"])):
+        scale = np.abs(ref).max(axis=0)
+        assert np.all(np.abs(got - ref) <= 1e-10 * scale)
+    diff = d.calc_diff(msd)
+    assert np.allclose(diff.values, gold_dynamical["diff_com"], rtol=1e-9)
+    msd2, _ = d.get_msd_from_dump("dump.mini.*.dump", msd_type="com", num_mols=num_mols, num_atoms_per_mol=NUM_ATOMS,
+                                  mass=MASS, com_drift=False)
+    ref = gold_dynamical["msd_com_nodrift"]
+    assert np.all(np.abs(msd2.values - ref) <= 1e-10 * np.abs(ref).max(axis=0))
+
+
+def test_conductivity_golden(mini_dir, gold_dynamical):
+    from mdproptools_b200.dynamical.conductivity import Conductivity
+    num_mols = gold_dynamical["mini_num_mols"].tolist()
+    c = Conductivity("dump.mini.*.dump", num_mols, NUM_ATOMS, volume=49.182348836183905 ** 3, mass=MASS, temp=298.15,
+                     timestep=1, units="real", working_dir=mini_dir)
+    j = c.get_charge_flux()
+    ref = gold_dynamical["cond_flux"]
+    assert j.shape == ref.shape
+    assert np.max(np.abs(j - ref)) <= 1e-10 * np.abs(ref).max()
+    assert np.allclose(c.time, gold_dynamical["cond_time"], rtol=1e-15)
+    tot = c.correlate_charge_flux(ref)
+    rt = gold_dynamical["cond_tot_flux"]
+    assert np.max(np.abs(tot - rt)) <= 1e-10 * np.abs(rt).max()
+    integ = c.integrate_charge_flux_correlation(rt)
+    ri = gold_dynamical["cond_integral"]
+    assert np.max(np.abs(integ - ri)) <= 1e-10 * np.abs(ri).max()
+    assert np.allclose(c.green_kubo(ri[:, -1]), gold_dynamical["cond_green_kubo_of_last"], rtol=1e-14)
+    a, b = ref[0, 1], ref[1, 2]
+    assert np.max(np.abs(Conductivity.correlate(a, b) - O.correlate_fft(a, b))) <= 1e-12 * np.abs(O.correlate_fft(a, b)).max()
+
+
+def test_viscosity_golden(visc_dir, gold_dynamical):
+    import glob as _glob
+    import mdproptools_b200.dynamical.viscosity as vmod
+    from mdproptools_b200.dynamical.viscosity import Viscosity
+    v = Viscosity("log.visc_*", cutoff_time=500, volume=40.0 ** 3, temp=298.15, timestep=1, acf_method="wkt", units="real",
+                  working_dir=visc_dir)
+    real = vmod.glob.glob
+    vmod.glob.glob = lambda p: sorted(real(p))       # the fixture was generated with sorted replicate order
+    try:
+        visc_avg, visc_data, acf_data, tvec = v.calc_avg_visc(output_all_data=True)
+    finally:
+        vmod.glob.glob = real
+    ra, rv, rg = gold_dynamical["visc_acf"], gold_dynamical["visc_data"], gold_dynamical["visc_avg"]
+    assert np.max(np.abs(np.array(acf_data) - ra)) <= 1e-10 * np.abs(ra).max()
+    assert np.max(np.abs(np.array(visc_data) - rv)) <= 1e-10 * np.abs(rv).max()
+    assert np.max(np.abs(np.array(visc_avg) - rg)) <= 1e-10 * np.abs(rg).max()
+    assert np.array_equal(tvec, gold_dynamical["visc_time"])
+    s = gold_dynamical["visc_acf_bruteforce_first200_in"]
+    got = Viscosity.autocorrelate(s, "brute_force")
+    ref = gold_dynamical["visc_acf_bruteforce_first200"]
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.abs(ref).max()
+
+
+def test_residence_time_golden(mini_dir, gold_dynamical, tmp_path):
+    from mdproptools_b200.dynamical.residence_time import ResidenceTime
+    num_mols = gold_dynamical["mini_num_mols"].tolist()
+    rt = ResidenceTime([[0, 2.0], [1.9, 2.2], [0, 3.2]], [[32, 32, 1], [1, 27, 1]],
+                       os.path.join(mini_dir, "dump.mini.*.dump"), dt=1, num_mols=num_mols, num_atoms_per_mol=NUM_ATOMS,
+                       working_dir=str(tmp_path))
+    rt.calc_auto_correlation()
+    assert list(rt.corr_df.columns) == list(gold_dynamical["residence_cols"])
+    # integer counts are exact here; the reference's FFT autocovariance carries ~1e-15 round-off
+    assert np.allclose(rt.corr_df.values, gold_dynamical["residence_corr"], rtol=0, atol=1e-12)
+    assert os.path.exists(tmp_path / "auto_correlation.csv")
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels vs oracle on synthetic inputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [4096, 4097, 1, 2049])
+def test_msd_single_origin_kernel(ops, n):
+    rng = np.random.default_rng(n)
+    T = 7
+    traj = np.cumsum(rng.normal(0, 0.1, (T, 3, n)), axis=0) + rng.uniform(0, 50, (1, 3, n))
+    per_atom, mean = O.msd_single_origin(traj, 2, 1e-10)
+    t = _dev(traj)
+    sums, pa = ops.msd_single_origin(t, t[2].contiguous(), 1e-10, per_atom=True)
+    assert np.array_equal(pa.cpu().numpy(), per_atom)                           # per-atom values bit-identical
+    assert np.allclose(sums[:, 0].cpu().numpy() / n, mean, rtol=1e-13, atol=0)
+    off = np.array([0, n // 3, n // 3, n])                                        # ragged groups incl. an empty one
+    gs, _ = ops.msd_single_origin(t, t[2].contiguous(), 1e-10, group_off=off)
+    gs = gs.cpu().numpy()
+    for g in range(3):
+        ref = per_atom[:, :, off[g]:off[g + 1]].sum(axis=2)
+        assert np.allclose(gs[:, g], ref, rtol=1e-13, atol=0)
+
+
+def test_msd_interval_and_all_origins(ops):
+    rng = np.random.default_rng(8)
+    T, n = 33, 700
+    traj = np.cumsum(rng.normal(0, 0.1, (T, 3, n)), axis=0)
+    got = ops.msd_interval(_dev(traj[::4]), 1e-10, 1).cpu().numpy()
+    assert np.allclose(got, O.msd_interval(traj, 1e-10, 4), rtol=1e-13, atol=0)
+    lag = 20
+    sums = ops.msd_all_origins(_dev(traj), lag).cpu().numpy()[:, 0]
+    norm = (T - np.arange(lag))[:, None] * n
+    ref = O.msd_all_origins(traj, lag)
+    assert np.allclose(sums[1:] / norm[1:], ref[1:], rtol=1e-12, atol=0)
+    assert np.all(sums[0] == 0)
+
+
+def test_segment_com_kernel(ops):
+    rng = np.random.default_rng(2)
+    sizes = rng.integers(1, 17, 500)
+    off = np.concatenate(([0], np.cumsum(sizes)))
+    n = off[-1]
+    attr = rng.normal(0, 10, (3, 2, n))
+    w = rng.uniform(1, 30, n)
+    q = rng.normal(0, 1, n)
+    out, wsum, qsum = ops.segment_com(_dev(attr), _dev(w), _dev(off.astype(np.int32)), extra=_dev(q))
+    ref = np.empty((3, 2, 500))
+    for s in range(500):
+        ws = 0.0
+        for a in range(off[s], off[s + 1]):
+            ws += w[a]
+        for f in range(3):
+            for c in range(2):
+                acc = 0.0
+                for a in range(off[s], off[s + 1]):
+                    acc += attr[f, c, a] * w[a]
+                ref[f, c, s] = acc / ws
+    assert np.array_equal(out.cpu().numpy(), ref)          # sequential unfused fp64 in atom order: bit-identical
+    assert np.allclose(wsum.cpu().numpy(), np.add.reduceat(w, off[:-1]), rtol=1e-14)
+    assert np.allclose(qsum.cpu().numpy(), np.add.reduceat(q, off[:-1]), rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("T", [1, 2, 127, 128, 129, 2048, 5000])
+def test_xcorr_kernel_vs_long_double(ops, T):
+    rng = np.random.default_rng(T)
+    a = rng.normal(0, 1, (3, T))
+    b = rng.normal(0, 1, (3, T))
+    got = ops.xcorr_unbiased(_dev(a), _dev(b)).cpu().numpy()
+    for c in range(3):
+        ref = O.xcorr_direct(a[c], b[c])
+        assert np.max(np.abs(got[c] - ref)) <= 1e-13 * max(1.0, np.abs(ref).max()), (T, c)
+    if T > 4:
+        part = ops.xcorr_unbiased(_dev(a), _dev(b), nlags=T // 2).cpu().numpy()
+        assert np.array_equal(part, got[:, :T // 2])
+
+
+def test_cumtrapz_kernel(ops):
+    rng = np.random.default_rng(4)
+    y = rng.normal(0, 1, (3, 5001))
+    for lead in (True, False):
+        got = ops.cumtrapz(_dev(y), 0.37, 2.5, leading_zero=lead).cpu().numpy()
+        ref = np.stack([2.5 * O.cumtrapz(r, 0.37, lead) for r in y])
+        assert np.allclose(got, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+
+
+def test_pair_list_and_bitmask_autocorr(ops):
+    rng = np.random.default_rng(6)
+    T, na, nb_ = 70, 40, 300
+    L = (14.0, 15.0, 16.0)
+    base_a = rng.uniform(0, 1, (3, na)) * np.asarray(L)[:, None]
+    base_b = rng.uniform(0, 1, (3, nb_)) * np.asarray(L)[:, None]
+    xa = np.stack([base_a + rng.normal(0, 0.15, base_a.shape) for _ in range(T)])
+    xb = np.stack([base_b + rng.normal(0, 0.15, base_b.shape) for _ in range(T)])
+    r_in, r_out = 1.0, 3.0
+    lst, rsq = ops.pair_list(_dev(xa), _dev(xb), [L] * T, r_in ** 2, r_out ** 2, shell_mode=1, want_rsq=True)
+    h = np.stack([O.shell_mask(xa[t, 0], xa[t, 1], xa[t, 2], xb[t, 0], xb[t, 1], xb[t, 2], L, r_in, r_out, False)
+                  for t in range(T)])
+    got = np.zeros_like(h)
+    l = lst.cpu().numpy()
+    got[l[:, 0], l[:, 1], l[:, 2]] = 1
+    assert len(l) == h.sum() and np.array_equal(got, h)
+    # rsq values are the reference's
+    k = 0
+    ref_rsq = O.calc_rsq(xa[l[k, 0], :, l[k, 1]], xb[l[k, 0], 0], xb[l[k, 0], 1], xb[l[k, 0], 2], L)[l[k, 2]]
+    assert rsq.cpu().numpy()[k] == ref_rsq
+    cnt, npairs = ops.bitmask_autocorr_from_list(lst, nb_, T)
+    ref_cnt = O.survival_counts(h.reshape(T, -1))
+    assert np.array_equal(cnt.cpu().numpy(), ref_cnt)
+    assert npairs == int((h.sum(axis=0) > 0).sum())
+
+
+def test_ols_sums_kernel(ops):
+    rng = np.random.default_rng(9)
+    t = np.linspace(0, 5e-9, 1001)
+    y = np.stack([3e-9 * t + rng.normal(0, 1e-20, t.size), 1e-10 * t])
+    s = ops.ols_sums(_dev(t), _dev(y), 10, 900).cpu().numpy()
+    for c in range(2):
+        tt, yy = t[10:900], y[c, 10:900]
+        assert np.allclose(s[c], [np.dot(tt, tt), np.dot(tt, yy), np.dot(yy, yy)], rtol=1e-13)
+
+
+def test_large_frame_properties(ops):
+    """Full-size single frame of the headline workload (100k atoms): checks that do not need the oracle to
+    finish -- symmetry of the total count under culling on/off and a checksum against brute-force (no cull)."""
+    from mdproptools_b200._lib import bin_edges
+    rng = np.random.default_rng(20261017)
+    n, L = 100_000, (167.19, 167.19, 167.19)
+    pos = rng.uniform(0, 1, (3, n)) * np.asarray(L)[:, None]
+    edges = bin_edges(0.05, 400)
+    x = _dev(pos[None])
+    h1 = ops.pair_hist(x, None, 1, [L], 400.0, edges, 0.05)
+    h2 = ops.pair_hist(x, None, 1, [L], 400.0, edges, 0.05, flags=1)
+    assert torch.equal(h1, h2)
+    # expected number of pairs inside the cutoff for a uniform gas: N(N-1)/2 * (4/3 pi rc^3 / V)
+    expect = n * (n - 1) / 2 * (4 / 3 * np.pi * 20 ** 3) / np.prod(L)
+    assert abs(int(h1.sum().item()) - expect) < 5 * np.sqrt(expect)

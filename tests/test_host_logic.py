@@ -1,0 +1,249 @@
+"""CPU-only tests (no GPU): the C-ABI library loads and exports every declared symbol, the host-side logic
+(dump parser, bin-edge table, type remapping, class weights, normalisation, sharding) agrees with the oracle
+and with golden outputs of the reference.  No compute entry point is called."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.conftest import MASS, NUM_ATOMS, NUM_MOLS, ROOT
+
+
+def test_abi_exports_every_declared_symbol():
+    from mdproptools_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mdprop_b200.h")).read()
+    declared = set(re.findall(r"\b(mdp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mdp_version() == 100
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mdproptools_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) or "liboracle" in txt:
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_no_cuda_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mdproptools_b200._lib import Context, MdpropError
+    with pytest.raises(MdpropError, match="no CPU fallback"):
+        Context.get()
+
+
+def test_bin_edges_define_the_reference_bin_function():
+    from mdproptools_b200._lib import bin_edges
+    rng = np.random.default_rng(1)
+    for ddr, nb in [(0.05, 400), (0.07, 104), (0.1, 3), (0.05, 46), (0.3, 7)]:
+        e = bin_edges(ddr, nb)
+        assert e[0] == 0 and np.all(np.diff(e) > 0)
+        rsq = np.concatenate([rng.uniform(0, (nb * ddr) ** 2 * 1.02, 100000), e[1:], np.nextafter(e[1:], 0),
+                              np.nextafter(e[1:], np.inf)])
+        ref = np.minimum((np.sqrt(rsq) / ddr).astype(np.int64), nb)       # rdf_cn.py:68,85
+        assert np.array_equal(np.searchsorted(e[1:], rsq, side="right"), ref)
+
+
+def test_native_parser_matches_oracle_reader(sample_dir, mini_dir):
+    from mdproptools_b200.io import dump as D
+    for pat, cols in ((os.path.join(sample_dir, "dump.nvt.*.dump"), ["id", "type", "x", "y", "z", "fx", "q", "iz"]),
+                      (os.path.join(mini_dir, "dump.mini.*.dump"), ["id", "xu", "yu", "zu", "vx", "mass"])):
+        got = list(D.read_dumps(pat, cols, nthreads=3))
+        ref = list(O.read_dumps(pat))
+        assert [g.timestep for g in got] == [r.timestep for r in ref]
+        for g, r in zip(got, ref):
+            c = r.sorted_by_id()
+            assert g.natoms == r.natoms
+            assert g.box.lattice_lengths() == r.lattice_lengths and g.box.bound_lengths() == r.bound_lengths
+            for k in cols:
+                assert np.array_equal(g.data[k], c[k]), k
+
+
+def test_parser_multiframe_triclinic_and_ragged(tmp_path):
+    from mdproptools_b200.io import dump as D
+    rng = np.random.default_rng(0)
+    p = tmp_path / "traj.dump"
+    frames = []
+    with open(p, "w") as f:
+        for t, n in enumerate([5, 9, 1]):
+            ids = rng.permutation(n) + 1 + (10 if t == 1 else 0)         # frame 1: ids not contiguous from 1
+            xyz = rng.normal(0, 5, (n, 3))
+            f.write(f"ITEM: TIMESTEP\n{t * 10}\nITEM: NUMBER OF ATOMS\n{n}\n")
+            f.write("ITEM: BOX BOUNDS xy xz yz pp pp pp\n-1.0 11.5 2.0\n0.0 10.0 1.0\n0.5 9.5 -1.5\n")
+            f.write("ITEM: ATOMS id type x y z\n")
+            for i, (x, y, z) in zip(ids, xyz):
+                f.write(f"{i} {1 + i % 2} {float(x)!r} {y:.9e} {z:+.5f}\n")
+            frames.append((ids, xyz))
+    got = list(D.read_dumps(str(p), ["id", "x", "y", "z"]))
+    ref = list(O.read_dumps(str(p)))
+    assert len(got) == 3
+    for g, r, (ids, xyz) in zip(got, ref, frames):
+        c = r.sorted_by_id()
+        for k in ("id", "x", "y", "z"):
+            assert np.array_equal(g.data[k], c[k])
+        assert np.array_equal(g.data["id"], np.sort(ids))
+        assert g.box.tilt == [2.0, 1.0, -1.5]
+        # pymatgen's tilt correction of the bounds and the row norms of the cell matrix
+        assert np.allclose(np.array(g.box.bounds), r.bounds, rtol=0, atol=0)
+        assert g.box.lattice_lengths() == r.lattice_lengths
+    with pytest.raises(KeyError):
+        list(D.read_dumps(str(p), ["id", "vx"]))
+
+
+def test_parser_errors(tmp_path):
+    from mdproptools_b200 import _lib
+    from mdproptools_b200.io import dump as D
+    p = tmp_path / "bad.dump"
+    p.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n3\nITEM: BOX BOUNDS pp pp pp\n0 1\n0 1\n0 1\n"
+                 "ITEM: ATOMS id x\n1 0.5\n2 abc\n3 0.1\n")
+    with pytest.raises(_lib.MdpropError, match="cannot parse"):
+        list(D.read_dumps(str(p), ["id", "x"]))
+    q = tmp_path / "short.dump"
+    q.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n3\nITEM: BOX BOUNDS pp pp pp\n0 1\n0 1\n0 1\n"
+                 "ITEM: ATOMS id x\n1 0.5\n")
+    with pytest.raises(_lib.MdpropError, match="announces 3 atoms"):
+        list(D.read_dumps(str(q), ["id", "x"]))
+
+
+def test_frame_batches_host_only(sample_dir):
+    from mdproptools_b200.io.pipeline import FrameBatches
+    fb = FrameBatches(os.path.join(sample_dir, "dump.nvt.*.dump"), ["id", "x"], to_device=False, max_batch_frames=1)
+    batches = list(fb)
+    assert fb.total_frames == 2 and len(batches) == 2
+    assert [b.metas[0].timestep for b in batches] == [0, 2500000]
+    assert batches[0].host.shape == (1, 2, 10479)
+    only_second = list(FrameBatches(os.path.join(sample_dir, "dump.nvt.*.dump"), ["id"], to_device=False,
+                                    frame_select=lambda i: i == 1))
+    assert len(only_second) == 1 and only_second[0].metas[0].index == 1
+
+
+def test_calc_atom_type_ids_matches_oracle():
+    from mdproptools_b200.structural.rdf_cn import calc_atom_type_ids
+    n = sum(a * b for a, b in zip(NUM_MOLS, NUM_ATOMS))
+    ids = np.arange(1, n + 6, dtype=np.float64)          # a few ids beyond the last block stay untouched
+    assert np.array_equal(calc_atom_type_ids(ids, NUM_MOLS, NUM_ATOMS), O.calc_atom_type(ids, NUM_MOLS, NUM_ATOMS))
+
+
+def test_class_maps_and_weights_reproduce_reference_counting():
+    """Derive full/partial histograms from a class-pair histogram built on the CPU and compare with _rdf_loop."""
+    from mdproptools_b200 import ops
+    from mdproptools_b200.structural.rdf_cn import _ClassMap, _sym_weights
+    rng = np.random.default_rng(3)
+    n, L = 400, (12.0, 13.0, 11.0)
+    pos = rng.uniform(0, 1, (3, n)) * np.asarray(L)[:, None]
+    typ = rng.integers(1, 6, n).astype(np.float64)
+    rel = [[5, 5, 2, 1], [1, 5, 2, 3]]
+    relm = np.asarray(rel).T
+    nb, ddr, rc = 50, 0.1, 5.0
+    full, part = O.rdf_loop(typ, pos[0], pos[1], pos[2], relm, L, rc, ddr, nb)
+    cmap = _ClassMap(rel[0] + rel[1])
+    cls = cmap.classes_of(typ)
+    assert cmap.ncls == 5 and set(cls[typ == 4]) == {cmap.other}
+    rows = ops.sym_rows(cmap.ncls)
+    H = np.zeros((rows, nb), dtype=np.int64)
+    for c1 in range(cmap.ncls):
+        for c2 in range(c1, cmap.ncls):
+            a, b = cls == c1, cls == c2
+            if c1 == c2:
+                f, _ = O.rdf_loop(np.ones(a.sum()), pos[0][a], pos[1][a], pos[2][a], [[1, 1]], L, rc, ddr, nb)
+                H[ops.sym_row(c1, c2, cmap.ncls)] = f // 2
+            else:
+                p = O.rdf_rect(np.ones(a.sum()), pos[0][a], pos[1][a], pos[2][a], np.ones(b.sum()), pos[0][b], pos[1][b],
+                               pos[2][b], [[1, 1]], L, rc, ddr, nb)
+                H[ops.sym_row(c1, c2, cmap.ncls)] = p[0]
+    w = _sym_weights(cmap, relm, with_full=True)
+    red = w @ H
+    assert np.array_equal(red[0], full) and np.array_equal(red[1:], part)
+
+
+def test_host_normalisation_is_bit_identical_to_reference(sample_dir, gold_structural):
+    """Feed the reference's own raw counts through the product's host normalisation."""
+    from mdproptools_b200.io import dump as D
+    from mdproptools_b200.structural import rdf_cn as R
+    fr = next(D.read_dumps(os.path.join(sample_dir, "dump.nvt.0.dump"), ["id", "type"]))
+    rel = [[9, 9, 9, 9], [1, 4, 6, 9]]
+    at = R._value_counts(fr.data["type"])
+    L = fr.box.lattice_lengths()
+    rho, rho_pairs = R._calc_props(L, fr.natoms, at, at, 9, MASS, rel, "type")
+    full, part = R._normalize_rdf(0.05, rho_pairs, at, rel, 4, 400, gold_structural["rdf_raw_part_f0"].astype(np.float64),
+                                  gold_structural["rdf_raw_full_f0"].astype(np.float64), fr.natoms, rho)
+    df = R._save_rdf((np.arange(400) + 0.5) * 0.05, np.asarray(rel).T, None, False, part / 1, rdf_full_sum=full / 1)
+    assert list(df.columns) == list(gold_structural["atomic_rdf_columns"])
+    assert np.array_equal(df.values, gold_structural["atomic_rdf_f0"])
+    with pytest.raises(ValueError, match="Consistency check failed"):
+        R._calc_props(L, fr.natoms, at, at, 8, MASS, rel, "type")
+
+
+def test_cn_edges_table():
+    from mdproptools_b200.structural.rdf_cn import _cn_edges
+    edges, rmax, upto = _cn_edges([2.325, 4.375, 2.375, 13.0, 4.375])
+    assert rmax == 169.0 and len(edges) == 5 and edges[0] == 0
+    assert upto.tolist() == [0, 2, 1, 3, 2]
+    assert edges[1] == 2.325 * 2.325
+
+
+def test_thermo_log_parser(visc_dir):
+    from mdproptools_b200.io.log import concat_log, parse_lammps_log
+    logs = parse_lammps_log(os.path.join(visc_dir, "log.visc_1"))
+    assert len(logs) == 1 and list(logs[0].columns) == ["Step", "Temp", "Pxy", "Pxz", "Pyz"]
+    assert len(logs[0]) == 4001 and logs[0]["Step"].iloc[-1] == 20000
+    full = concat_log("log.visc_*", working_dir=visc_dir)
+    assert len(full) == 4000 + 4001
+
+
+def test_shard_ranges_cover_everything():
+    from mdproptools_b200 import dist
+    for n in (0, 1, 7, 8, 101, 1000):
+        for w in (1, 2, 3, 8):
+            r = [dist.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as d
+d.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+from mdproptools_b200 import dist
+from mdproptools_b200.structural.rdf_cn import _merge_frames, _gather_props
+r = dist.rank()
+assert dist.world_size() == 2
+# frames round-robin: rank r owns frames r, r+2, ...; integer histograms merge exactly
+T = 5
+mine = {{i: torch.full((2, 3), i + 1, dtype=torch.int64) for i in range(T) if i % 2 == r}}
+allc = _merge_frames(mine, T, (2, 3), torch.device("cpu"))
+assert allc[:, 0, 0].tolist() == [1, 2, 3, 4, 5]
+props = _gather_props({{i: ("p", i) for i in mine}}, T)
+assert sorted(props) == list(range(T))
+lo, hi = dist.shard_range(11)
+x = torch.zeros(11, dtype=torch.float64); x[lo:hi] = 1.0
+dist.all_reduce_sum_(x)
+assert x.sum().item() == 11
+d.destroy_process_group()
+print("rank", r, "ok")
+"""
+
+
+def test_two_rank_gloo_merge(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2
