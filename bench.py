@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the mdproptools hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[1], "C2"): synthetic LJ-like fluid, 100 000 atoms per frame, triclinic cell
+(lx=ly=lz=167.19 A, xy=0.2lx, xz=0.1lx, yz=-0.15ly), all-pair RDF with r_cut = 20 A, bin = 0.05 A (400 bins),
+minimum image as the reference applies it (orthogonal wrap with the lattice lengths).  One *step* is one pass of
+the RDF hot path over a batch of FRAMES_PER_STEP frames resident in HBM (154 MB of coordinates > the 126 MB L2,
+so no L2 flush is needed between steps).  The headline metric is RDF pair-evaluations per second, counted
+NOMINALLY as frames x N(N-1)/2 (what the reference's loop evaluates); the kernel actually evaluates only the
+tile/chunk pairs that survive the bounding-box test, that number is reported beside it and is what the FP64
+roofline fraction is computed from.  The same JSON line carries the second half of the BASELINE metric, MSD
+atom-frames/s (config C3 shape: 1 000 000 atoms, a resident chunk of frames), with its HBM roofline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ATOMS = 100_000
+LBOX = 167.19
+TILT = (0.20 * LBOX, 0.10 * LBOX, -0.15 * LBOX)
+R_CUT = 20
+BIN = 0.05
+NBINS = 400
+FRAMES_PER_STEP = 64
+SEED = 20261017
+FLOPS_PER_PAIR = 11            # 3 sub, 3 minimum-image add, 3 mul, 2 add, unfused
+MSD_ATOMS = 1_000_000
+MSD_FRAMES = 256               # resident chunk: 256 x 24 MB = 6.1 GB
+MSD_BYTES_PER_ATOM_FRAME = 24
+
+
+def lattice_lengths():
+    xy, xz, yz = TILT
+    return (LBOX, float(np.sqrt(xy * xy + LBOX * LBOX)), float(np.sqrt(xz * xz + yz * yz + LBOX * LBOX)))
+
+
+def make_frames(nframes, seed, xp):
+    """C2 generator: simple-cubic lattice sites (first N of 47^3) in fractional coordinates, jitter,
+    per-frame Gaussian steps of 0.05 A, wrapped into the triclinic cell.  xp = torch (device) or numpy (host)."""
+    import torch
+    g = torch.Generator(device="cuda" if xp == "cuda" else "cpu")
+    g.manual_seed(seed)
+    dev = "cuda" if xp == "cuda" else "cpu"
+    m = 47
+    idx = torch.arange(N_ATOMS, device=dev)
+    frac = torch.stack([(idx // (m * m)) % m, (idx // m) % m, idx % m]).to(torch.float64) / m
+    cell = torch.tensor([[LBOX, 0.0, 0.0], [TILT[0], LBOX, 0.0], [TILT[1], TILT[2], LBOX]], dtype=torch.float64, device=dev)
+    inv = torch.linalg.inv(cell)
+    cart = cell.T @ frac                                           # r = sx a + sy b + sz c
+    cart = cart + (torch.rand((3, N_ATOMS), generator=g, dtype=torch.float64, device=dev) - 0.5) * 2 * 0.3 * 3.405
+    out = torch.empty((nframes, 3, N_ATOMS), dtype=torch.float64, device=dev)
+    for f in range(nframes):
+        cart = cart + torch.randn((3, N_ATOMS), generator=g, dtype=torch.float64, device=dev) * 0.05
+        s = inv.T @ cart
+        s = s - torch.floor(s)
+        cart = cell.T @ s
+        out[f] = cart
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    """Driver-written MEASURED_PEAKS.json (HBM, bf16) + this repo's own FP64 micro-benchmark (tools/peaks.cu,
+    result committed as profiles/peaks_b200.json)."""
+    p = {}
+    for f in (os.path.join(ROOT, "profiles", "peaks_b200.json"), os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        if os.path.exists(f):
+            try:
+                p.update(json.load(open(f)))
+            except Exception:
+                pass
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port; the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_rdf_sample(target_seconds, host_frame=None):
+    """The reference's pair loop (oracle/oracle.c restatement of rdf_cn.py:35-97) on a bounded sample of the C2
+    workload: the first n_sub atoms of one frame against all N atoms (n_sub x N pair evaluations, same
+    arithmetic per pair), all host threads.  Returns (pair_evals_per_s, cores, description)."""
+    from oracle import oracle as O
+    if host_frame is None:
+        host_frame = make_frames(1, SEED, "cpu")[0].numpy()
+    L = lattice_lengths()
+    x, y, z = host_frame
+    ones = np.ones(N_ATOMS)
+    cores = O.max_threads()
+    rel = np.array([[1, 1]])
+
+    def run(n_sub):
+        t = time.perf_counter()
+        O.rdf_rect(ones[:n_sub], x[:n_sub], y[:n_sub], z[:n_sub], ones, x, y, z, rel, L, R_CUT, BIN, NBINS, nthreads=0)
+        return time.perf_counter() - t
+
+    run(64)                                            # warm-up (thread pool, page faults)
+    n_probe = 512
+    rate = n_probe * N_ATOMS / run(n_probe)
+    n_sub = int(min(N_ATOMS, max(n_probe, rate * target_seconds / N_ATOMS)))
+    dt = run(n_sub)
+    return n_sub * N_ATOMS / dt, cores, f"{n_sub} of {N_ATOMS} outer atoms x all atoms of one C2 frame ({dt:.1f} s)"
+
+
+def cpu_msd_sample(target_seconds):
+    from oracle import oracle as O
+    n, T = 100_000, 100                                 # BASELINE.md plan: 100k atoms x 100 frames
+    rng = np.random.default_rng(SEED + 1)
+    traj = np.cumsum(rng.normal(0, 0.1, (T, 3, n)), axis=0)
+    t = time.perf_counter()
+    reps = 0
+    while reps == 0 or (time.perf_counter() - t < target_seconds and reps < 50):
+        O.msd_single_origin(traj, 0, 1e-10)
+        reps += 1
+    dt = (time.perf_counter() - t) / reps
+    return n * T / dt, 1, f"numpy restatement of diffusion.py:207-218 on {n} atoms x {T} frames ({dt:.2f} s/pass)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # the reference arm: bounded samples of the same C2 workload on all host threads
+    host_frame = make_frames(1, SEED, "cpu")[0].numpy()
+    for _ in range(args.warmup):
+        cpu_rdf_sample(0.5, host_frame)
+    rates, descr, cores = [], "", 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, descr = cpu_rdf_sample(5.0, host_frame)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    out = {
+        "impl": "reference", "metric": "rdf_pair_evals_per_s", "value": value, "unit": "pair-evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: LJ fluid 100k atoms/frame, triclinic cell, all-pair RDF r_cut=20 bin=0.05 (400 bins)",
+                   "note": "reference algorithm (brute-force pair loop, oracle/oracle.c port of rdf_cn.py:35-97) on host cores; "
+                           "each step is a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": descr},
+        "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mdproptools_b200 import ops
+    from mdproptools_b200._lib import Context, bin_edges
+    from mdproptools_b200.dynamical.diffusion import Diffusion
+    from mdproptools_b200.structural import rdf_cn
+
+    dev = torch.device("cuda", local)
+    ctx = Context.get(local)
+    F = args.frames_per_step
+    L = lattice_lengths()
+    boxes = np.tile(np.asarray(L), (F, 1))
+    edges = bin_edges(BIN, NBINS)
+    rcut2 = float(R_CUT ** 2)
+    weights = np.array([[2], [2]], dtype=np.int32)            # g_full and the single like relation 1-1
+    frames = make_frames(F, SEED + rank, "cuda")                 # resident in HBM before the timed region
+    merged = torch.zeros((world * F, 2, NBINS), dtype=torch.int64, device=dev)
+
+    def step():
+        hist = ops.pair_hist(frames, None, 1, boxes, rcut2, edges, BIN)
+        red = ops.hist_reduce(hist, weights)
+        if world > 1:
+            merged.zero_()
+            merged[rank * F:(rank + 1) * F] = red
+            dist.all_reduce(merged)
+            return merged
+        return red
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    barrier()
+    stats = ctx.pair_stats()
+    evaluated_per_step = stats["pair_evals"]
+    nominal_per_step = F * N_ATOMS * (N_ATOMS - 1) // 2
+    # sanity: a uniform fluid has N(N-1)/2 * (4/3 pi rc^3)/V pairs inside the cutoff (V = |det cell| = L^3 here,
+    # but the reference-mode wrap uses the lattice lengths, so only the order of magnitude is checked)
+    in_cut = int(out[rank * F if world > 1 else 0, 0].sum().item()) // 2
+
+    ctx.timing(True)
+    ctx.timing_read(0), ctx.timing_read(1)
+    launches0 = ctx.launch_count()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = ctx.launch_count() - launches0
+    pair_ms, pair_n = ctx.timing_read(0)
+    prep_ms, _ = ctx.timing_read(1)
+    ctx.timing(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * nominal_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public array API: pinned host frames -> H2D -> kernels -> D2H -> normalised g(r)
+    host = torch.empty((F, 3, N_ATOMS), dtype=torch.float64, pin_memory=True)
+    host.copy_(frames)
+    rel = [[1], [1]]
+    types = np.ones(N_ATOMS)
+    for _ in range(2):
+        rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=16)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, args.steps // 2)
+    for _ in range(e2e_steps):
+        rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=16)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * nominal_per_step * e2e_steps / float(te.item())
+
+    # ---- MSD (second half of the BASELINE metric), C3 shape: 1M atoms, resident chunk of frames
+    msd = None
+    if not args.skip_msd:
+        msd = bench_msd(args, torch, dist, ops, ctx, dev, world, rank)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = measured_peaks()
+    fp64_peak = peaks.get("fp64_unfused_tflops_sustained") or peaks.get("fp64_unfused_tflops_burst")
+    peak_src = "measured (tools/peaks.cu on this pool's B200, profiles/peaks_b200.json)"
+    if not fp64_peak:
+        fp64_peak = 148 * 64 * 1.965e9 / 1e12            # nominal: 64 DP lanes/SM, unfused = 1 flop/lane/clk
+        peak_src = "nominal 148 SMs x 64 FP64 lanes x 1965 MHz, unfused (no measured FP64 peak on file yet)"
+    pair_ms_per_launch = pair_ms / max(pair_n, 1)
+    achieved = evaluated_per_step * FLOPS_PER_PAIR / (pair_ms_per_launch * 1e-3) / 1e12
+    nominal_tflops = nominal_per_step * FLOPS_PER_PAIR / (pair_ms_per_launch * 1e-3) / 1e12
+    cpu_rate, cores, sample = cpu_rdf_sample(10.0) if not args.skip_cpu else (None, None, "skipped")
+    out = {
+        "metric": "rdf_pair_evals_per_s", "value": value, "unit": "pair-evals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: LJ fluid 100k atoms/frame, triclinic cell, all-pair RDF r_cut=20 bin=0.05 (400 bins)",
+                   "frames_per_step_per_gpu": F, "mic": "reference (orthogonal wrap with lattice lengths)",
+                   "l2_policy": f"inputs larger than L2 ({F * 3 * N_ATOMS * 8 / 1e6:.0f} MB of coordinates per step)",
+                   "pair_evals": "nominal frames*N(N-1)/2; evaluated_pair_evals counts what the kernel executed after "
+                                 "bounding-box culling", "parallelism": f"frames x{world}"},
+        "evaluated_pair_evals_per_step": evaluated_per_step, "nominal_pair_evals_per_step": nominal_per_step,
+        "pairs_in_cutoff_frame0": in_cut,
+        "gpu_launches": launches,
+        "kernel_share": {"pair_kernel_ms_per_step": pair_ms / args.steps, "prep_ms_per_step": prep_ms / args.steps,
+                         "step_ms": ms / args.steps},
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "note": f"pair kernel only; achieved = evaluated pair-evals x {FLOPS_PER_PAIR} unfused fp64 flops / "
+                             f"CUDA-event kernel time; nominal-pair equivalent = {nominal_tflops:.1f} TFLOP/s "
+                             f"({nominal_tflops / fp64_peak:.2f} of peak) because culling skips work the reference does"},
+        "e2e": {"value": e2e_value, "unit": "pair-evals/s", "h2d_bytes_per_step": F * 3 * N_ATOMS * 8,
+                "d2h_bytes_per_step": F * 2 * NBINS * 8, "api": "rdf_cn.calc_atomic_rdf_from_arrays (pinned host frames)"},
+        "clocks": clk,
+        "cpu_baseline": {"value": cpu_rate, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample},
+    }
+    if msd:
+        out["msd"] = msd
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_msd(args, torch, dist, ops, ctx, dev, world, rank):
+    n, T = args.msd_atoms, args.msd_frames
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED + 100 + rank)
+    traj = torch.empty((T, 3, n), dtype=torch.float64, device=dev)
+    cur = torch.rand((3, n), generator=g, dtype=torch.float64, device=dev) * 215.0
+    for f in range(T):
+        cur = cur + torch.randn((3, n), generator=g, dtype=torch.float64, device=dev) * 0.1
+        traj[f] = cur
+    ref = traj[0].contiguous()
+
+    def step():
+        sums, _ = ops.msd_single_origin(traj, ref, 1e-10)
+        if world > 1:
+            dist.all_reduce(sums)                       # atoms are split over ranks: fp64 all-reduce of [T,1,4]
+        return sums
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ctx.timing(True)
+    ctx.timing_read(2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(args.steps, 10)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    kms, kn = ctx.timing_read(2)
+    ctx.timing(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n * T * steps / (ms * 1e-3)
+    # end to end: pinned host frames through Diffusion.get_msd_from_arrays
+    from mdproptools_b200.dynamical.diffusion import Diffusion
+    Te = min(T, 64)
+    host = torch.empty((Te, 3, n), dtype=torch.float64, pin_memory=True)
+    host.copy_(traj[:Te])
+    d = Diffusion(timestep=1, units="real")
+    steps_e = np.arange(Te) * 1000
+    d.get_msd_from_arrays(host, steps_e, batch_frames=16)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d.get_msd_from_arrays(host, steps_e, batch_frames=16)
+    torch.cuda.synchronize()
+    e2e = world * n * Te / (time.perf_counter() - t0)
+    peaks = measured_peaks()
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    achieved = n * T * MSD_BYTES_PER_ATOM_FRAME / (kms / max(kn, 1) * 1e-3) / 1e9
+    cpu = cpu_msd_sample(5.0) if (rank == 0 and not args.skip_cpu) else (None, None, "skipped")
+    return {
+        "metric": "msd_atom_frames_per_s", "value": value, "unit": "atom-frames/s",
+        "config": {"workload": f"C3 shape: {n} atoms, resident chunk of {T} frames ({n * T * 24 / 1e9:.1f} GB, larger than L2), "
+                               "single-origin MSD (diffusion.py:207-218)", "parallelism": f"atoms x{world}"},
+        "ms_per_step": ms / steps, "steps": steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                     "peak_source": src, "note": "k_msd_single only; 24 algorithmic bytes per atom-frame"},
+        "e2e": {"value": e2e, "unit": "atom-frames/s", "h2d_bytes_per_step": Te * 3 * n * 8, "d2h_bytes_per_step": Te * 32,
+                "api": "Diffusion.get_msd_from_arrays (pinned host frames)"},
+        "cpu_baseline": {"value": cpu[0], "unit": "atom-frames/s", "cores": cpu[1], "kind": "port", "sample": cpu[2]},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
+    ap.add_argument("--msd-atoms", type=int, default=MSD_ATOMS)
+    ap.add_argument("--msd-frames", type=int, default=MSD_FRAMES)
+    ap.add_argument("--skip-msd", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -42,6 +42,12 @@ int64_t mdp_ctx_scratch_bytes(mdp_ctx *ctx);
 int mdp_ctx_set_scratch_limit(mdp_ctx *ctx, int64_t bytes);
 /* counters: number of kernels this library launched since creation (bench.py's gpu_launches) */
 int64_t mdp_ctx_launch_count(mdp_ctx *ctx);
+/* optional kernel timing for benchmarks: when enabled, the library brackets its main kernels with CUDA events
+ * on the launching stream.  tag 0 = pair kernel (k_pair), 1 = pair preparation (sort, boxes, work list),
+ * 2 = streaming MSD kernel, 3 = correlation kernel, 4 = charge-flux kernel.  mdp_ctx_timing_read synchronises
+ * on the recorded events, returns the summed milliseconds and the number of launches, and clears them. */
+int mdp_ctx_timing(mdp_ctx *ctx, int enable);
+int mdp_ctx_timing_read(mdp_ctx *ctx, int tag, double *ms_total, int64_t *count);
 /* statistics of the last pair call: [0]=tile-pair items evaluated, [1]=nominal tile pairs,
  * [2]=pair distance evaluations actually executed (32 x chunk steps), device->host sync. */
 int mdp_ctx_pair_stats(mdp_ctx *ctx, int64_t out[4]);

@@ -36,6 +36,8 @@ _PROTOS = {
     "mdp_ctx_set_scratch_limit": (c_int, [c_void_p, c_int64]),
     "mdp_ctx_launch_count": (c_int64, [c_void_p]),
     "mdp_ctx_pair_stats": (c_int, [c_void_p, POINTER(c_int64)]),
+    "mdp_ctx_timing": (c_int, [c_void_p, c_int]),
+    "mdp_ctx_timing_read": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),
     "mdp_bin_edges": (c_int, [c_double, c_int, POINTER(c_double)]),
     "mdp_pair_hist": (c_int, [c_void_p, c_int,
                               c_int64, c_void_p, c_void_p, c_int64, c_int,
@@ -133,6 +135,15 @@ class Context:
 
     def scratch_bytes(self) -> int:
         return int(lib().mdp_ctx_scratch_bytes(self.handle))
+
+    def timing(self, enable: bool) -> None:
+        check(lib().mdp_ctx_timing(self.handle, 1 if enable else 0), "mdp_ctx_timing")
+
+    def timing_read(self, tag: int):
+        """(total milliseconds, launches) of the kernels recorded under ``tag`` since the last read."""
+        ms, n = c_double(), c_int64()
+        check(lib().mdp_ctx_timing_read(self.handle, int(tag), ctypes.byref(ms), ctypes.byref(n)), "mdp_ctx_timing_read")
+        return float(ms.value), int(n.value)
 
     def pair_stats(self) -> dict:
         out = (c_int64 * 4)()

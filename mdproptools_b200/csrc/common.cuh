@@ -49,6 +49,29 @@ struct mdp_ctx {
     // last pair call statistics (device side, 4 x int64) and pinned host mirror
     unsigned long long *d_stats = nullptr;
 
+    // optional per-kernel timing (bench.py): CUDA event pairs recorded on the launching stream
+    struct Timed {
+        int tag;
+        cudaEvent_t e0, e1;
+    };
+    bool timing = false;
+    std::vector<Timed> timed;
+    cudaEvent_t timer_begin(int tag, cudaStream_t st)
+    {
+        if (!timing) return nullptr;
+        Timed t;
+        t.tag = tag;
+        cudaEventCreate(&t.e0);
+        cudaEventCreate(&t.e1);
+        cudaEventRecord(t.e0, st);
+        timed.push_back(t);
+        return t.e1;
+    }
+    void timer_end(cudaEvent_t e1, cudaStream_t st)
+    {
+        if (e1) cudaEventRecord(e1, st);
+    }
+
     void arena_reset() { slab_used = 0; }
     int arena_reserve(size_t bytes);              // make sure the slab holds at least `bytes`
     void *arena_take(size_t bytes)

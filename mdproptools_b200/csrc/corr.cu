@@ -189,7 +189,9 @@ int mdp_xcorr_unbiased(mdp_ctx *ctx, int nchan, int64_t T, const double *a, cons
     MDP_REQUIRE(nchan > 0 && nchan <= 65535 && T > 0 && nlags > 0 && nlags <= T, "mdp_xcorr_unbiased: bad sizes");
     MDP_CUDA(cudaSetDevice(ctx->device));
     dim3 grid((unsigned)ceil_div<int64_t>(nlags, XC_LAGS), nchan);
+    cudaEvent_t tk = ctx->timer_begin(3, (cudaStream_t)stream);
     k_xcorr<<<grid, XC_THREADS, 0, (cudaStream_t)stream>>>(a, b, T, nlags, out);
+    ctx->timer_end(tk, (cudaStream_t)stream);
     MDP_LAUNCHED(ctx);
     return mdp_check_launch("k_xcorr");
 }

@@ -96,6 +96,38 @@ int mdp_ctx_set_scratch_limit(mdp_ctx *ctx, int64_t bytes)
 
 int64_t mdp_ctx_launch_count(mdp_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int mdp_ctx_timing(mdp_ctx *ctx, int enable)
+{
+    MDP_REQUIRE(ctx, "mdp_ctx_timing: NULL context");
+    ctx->timing = enable != 0;
+    return 0;
+}
+
+int mdp_ctx_timing_read(mdp_ctx *ctx, int tag, double *ms_total, int64_t *count)
+{
+    MDP_REQUIRE(ctx && ms_total && count, "mdp_ctx_timing_read: NULL argument");
+    double total = 0.0;
+    int64_t n = 0;
+    std::vector<mdp_ctx::Timed> keep;
+    for (auto &t : ctx->timed) {
+        if (t.tag != tag) {
+            keep.push_back(t);
+            continue;
+        }
+        MDP_CUDA(cudaEventSynchronize(t.e1));
+        float ms = 0.f;
+        MDP_CUDA(cudaEventElapsedTime(&ms, t.e0, t.e1));
+        total += ms;
+        ++n;
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    ctx->timed.swap(keep);
+    *ms_total = total;
+    *count = n;
+    return 0;
+}
+
 int mdp_ctx_pair_stats(mdp_ctx *ctx, int64_t out[4])
 {
     MDP_REQUIRE(ctx && out, "mdp_ctx_pair_stats: bad argument");

@@ -943,6 +943,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         }
         MDP_CUDA(cudaMemcpyAsync(d_box, c.box + (size_t)f0 * 3, (size_t)F * 24, cudaMemcpyHostToDevice, st));
 
+        cudaEvent_t tp = ctx->timer_begin(1, st);
         rc = sort_set(ctx, A, F, c.xyz_a + (size_t)f0 * 3 * c.n_a, c.cls_a ? c.cls_a + (size_t)f0 * c.cls_stride_a : nullptr,
                       c.cls_stride_a, +1.0, st);
         if (rc) return rc;
@@ -963,6 +964,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         k_items<true><<<gi, 256, 0, st>>>(A.taabb, Bs.taabb, A.ntiles, Bs.ntiles, symm, nocull, d_box, c.rcut2, F, rowcnt,
                                           rowoff, items);
         MDP_LAUNCHED(ctx);
+        ctx->timer_end(tp, st);
 
         PairParams p;
         memset(&p, 0, sizeof(p));
@@ -998,7 +1000,9 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         p.list_count = (unsigned long long *)c.list_count;
         p.frame0 = f0;
         p.nocull = nocull ? 1 : 0;
+        cudaEvent_t tk = ctx->timer_begin(0, st);
         kern<<<ctx->sm_count * 3, NWARP * 32, smem, st>>>(p);
+        ctx->timer_end(tk, st);
         MDP_LAUNCHED(ctx);
         rc = mdp_check_launch("k_pair");
         if (rc) return rc;

@@ -338,6 +338,7 @@ int mdp_msd_single_origin(mdp_ctx *ctx, int nframes, int64_t n, const double *tr
         const bool v = vec && (a0 % 2 == 0);
         const int nchunks = (int)ceil_div<int64_t>(a1 - a0, per_chunk);
         dim3 grid(nchunks, nframes);
+        cudaEvent_t tk = ctx->timer_begin(2, st);
         if (v && per_atom_out)
             k_msd_single<true, true><<<grid, RB, 0, st>>>(traj, ref, n, a0, a1, scale, partial, nchunks, per_atom_out);
         else if (v)
@@ -346,6 +347,7 @@ int mdp_msd_single_origin(mdp_ctx *ctx, int nframes, int64_t n, const double *tr
             k_msd_single<false, true><<<grid, RB, 0, st>>>(traj, ref, n, a0, a1, scale, partial, nchunks, per_atom_out);
         else
             k_msd_single<false, false><<<grid, RB, 0, st>>>(traj, ref, n, a0, a1, scale, partial, nchunks, nullptr);
+        ctx->timer_end(tk, st);
         MDP_LAUNCHED(ctx);
         k_partial_sum<<<nframes, 128, 0, st>>>(partial, nchunks, 4, sums_out + g * 4, (int64_t)ngroups * 4);
         MDP_LAUNCHED(ctx);
@@ -422,7 +424,9 @@ int mdp_charge_flux(mdp_ctx *ctx, int nframes, int64_t n, const double *vel, con
         MDP_REQUIRE(s0 >= 0 && s1 > s0 && s1 <= nseg, "mdp_charge_flux: bad molecule-type range");
         const int nchunks = (int)ceil_div<int64_t>(s1 - s0, RB);
         dim3 grid(nchunks, nframes);
+        cudaEvent_t tk = ctx->timer_begin(4, st);
         k_charge_flux<<<grid, RB, 0, st>>>(vel, n, mass, q, seg_off, s0, s1, vel_scale, q_scale, partial, nchunks);
+        ctx->timer_end(tk, st);
         MDP_LAUNCHED(ctx);
         k_flux_finish<<<nframes, 96, 0, st>>>(partial, nchunks, g, ngroups, out, out_stride, frame0);
         MDP_LAUNCHED(ctx);

@@ -176,6 +176,46 @@ class Diffusion:
         return msd, msd_all
 
     # ------------------------------------------------------------------------------------------
+    def get_msd_from_arrays(self, positions, timesteps, batch_frames=64):
+        """Array front end of the all-atom MSD for trajectories already in memory (the single-origin arithmetic
+        of :207-218 without building the T*N-row ``msd_all`` frame, which cannot exist at 10^10 atom-frames).
+
+        positions float64 [T, 3, N] host array (numpy or pinned torch tensor) of UNWRAPPED coordinates in id order,
+        timesteps [T] LAMMPS step numbers (the frame with step 0 is the origin, :213).  Frames stream through the
+        device in batches (copy of batch k+1 overlaps the reduction of batch k).  Returns the ``msd`` DataFrame.
+        """
+        pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(positions, dtype=np.float64))
+        T, _, N = pos.shape
+        conv = constants.DISTANCE_CONVERSION[self.units]
+        times = np.asarray(timesteps) * self.timestep * constants.TIME_CONVERSION[self.units]
+        t0 = self._time_zero_index(times)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ref = pos[t0].to(dev)
+        copy_stream = torch.cuda.Stream()
+        sums = torch.empty((T, 1, 4), dtype=torch.float64, device=dev)
+
+        def stage(f0):
+            f1 = min(T, f0 + batch_frames)
+            with torch.cuda.stream(copy_stream):
+                x = pos[f0:f1].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return f0, f1, x, ev
+
+        nxt = stage(0)
+        while nxt is not None:
+            f0, f1, x, ev = nxt
+            nxt = stage(f1) if f1 < T else None
+            torch.cuda.current_stream().wait_event(ev)
+            s, _ = ops.msd_single_origin(x, ref, conv)
+            sums[f0:f1] = s
+            x.record_stream(torch.cuda.current_stream())
+        mean = (sums[:, 0, :] / N).cpu().numpy()
+        msd = pd.DataFrame(mean, columns=["dx2", "dy2", "dz2", "msd"])
+        msd.insert(0, "Time (s)", times)
+        return msd
+
     def get_msd_all_origins(self, filename, max_lag=None, msd_type="allatom", num_mols=None, num_atoms_per_mol=None,
                             mass=None):
         """North-star extension (no reference counterpart): MSD averaged over ALL time origins,

@@ -182,17 +182,22 @@ def _save_cn(relation_matrix, path_or_buff, cn_sum, save_mode):
 class _ClassMap:
     """Types named by the relations get their own class; everything else shares the class 'other'."""
 
-    def __init__(self, named_types):
+    def __init__(self, named_types, present_types=None):
         self.named = sorted(set(int(t) for t in named_types))
         self.index = {t: k for k, t in enumerate(self.named)}
-        self.ncls = len(self.named) + 1
-        self.other = self.ncls - 1
+        # the class 'other' is only materialised when some point actually has an unnamed type (one class fewer
+        # keeps single-species runs on the kernel variant without per-pair class bookkeeping)
+        self.has_other = present_types is None or bool(set(int(t) for t in present_types) - set(self.named))
+        self.ncls = len(self.named) + (1 if self.has_other else 0)
+        self.other = self.ncls - 1 if self.has_other else -1
 
     def classes_of(self, typ: np.ndarray) -> np.ndarray:
         t = np.asarray(typ).astype(np.int64)
         cls = np.full(t.shape, self.other, dtype=np.int32)
         for ty, k in self.index.items():
             cls[t == ty] = k
+        if not self.has_other and (cls < 0).any():
+            raise ValueError("a frame contains atom types that were absent from the first frame")
         return cls
 
     def cls(self, t):
@@ -269,8 +274,8 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
     num_relations = len(partial_relations[0])
     relation_matrix = np.asarray(partial_relations).transpose()
     altered = bool(num_mols and num_atoms_per_mol)
-    cmap = _ClassMap(list(partial_relations[0]) + list(partial_relations[1]))
-    weights = _sym_weights(cmap, relation_matrix, with_full=True)
+    named = list(partial_relations[0]) + list(partial_relations[1])
+    cmap = weights = None          # fixed by the types present in this rank's first frame
     edges = bin_edges(bin_size, num_bins)
     rcut2 = _rcut_sq(r_cut)
 
@@ -292,6 +297,9 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
             rho, rho_pairs = _calc_props(lengths, meta.natoms, at, at, num_types, mass, partial_relations,
                                          "id" if altered else "type", num_atoms_per_mol)
             props[meta.index] = (at, rho, rho_pairs, meta.natoms)
+            if cmap is None:
+                cmap = _ClassMap(named, present_types=at.keys())
+                weights = _sym_weights(cmap, relation_matrix, with_full=True)
             cls[k] = cmap.classes_of(typ)
             boxes[k] = lengths
         xyz = dev[:, 2:5, :].contiguous()
@@ -342,8 +350,8 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
     num_relations = len(partial_relations[0])
     relation_matrix = np.asarray(partial_relations).transpose()
     altered = bool(num_mols and num_atoms_per_mol)
-    cmap = _ClassMap(list(partial_relations[0]) + list(partial_relations[1]))
-    weights = _sym_weights(cmap, relation_matrix, with_full=False)
+    named = list(partial_relations[0]) + list(partial_relations[1])
+    cmap = weights = None
     edges, rcut2_max, upto = _cn_edges(r_cut)
     nthr = len(edges) - 1
 
@@ -364,6 +372,9 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
             _calc_props(lengths, meta.natoms, at, at, num_types, mass, partial_relations, "id" if altered else "type",
                         num_atoms_per_mol)
             props[meta.index] = at
+            if cmap is None:
+                cmap = _ClassMap(named, present_types=at.keys())
+                weights = _sym_weights(cmap, relation_matrix, with_full=False)
             cls[k] = cmap.classes_of(typ)
             boxes[k] = lengths
         xyz = dev[:, 2:5, :].contiguous()
@@ -490,6 +501,69 @@ def calc_molecular_cn(r_cut, bin_size, num_types, mass, partial_relations, filen
         cn_sum += _normalize_cn(at, partial_relations, cn)
     cn_sum = cn_sum / T
     return _save_cn(relation_matrix, path_or_buff, cn_sum, save_mode)
+
+
+def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, partial_relations, batch_frames=64,
+                                return_counts=False):
+    """Array front end of :func:`calc_atomic_rdf` for trajectories that are already in memory.
+
+    positions   float64 [T, 3, N] host array (numpy, or a pinned torch tensor for async copies), rows in id order
+    types       [N] or [T, N] atom types (ints or floats, as the dump's ``type`` column)
+    box_lengths [3] or [T, 3] box lengths as ``dump.box.to_lattice().lengths`` gives them
+    Everything else as in calc_atomic_rdf; same per-frame normalisation (rdf_cn.py:297-329, 502-521), same DataFrame.
+    Frames stream through pinned staging buffers: the copy of batch k+1 overlaps the kernels of batch k.
+    With ``return_counts`` the raw integer histograms [T, 1+R, nbins] (g_full row first) are returned as well.
+    """
+    pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, dtype=np.float64))
+    T, _, N = pos.shape
+    num_bins, radii = _num_bins(r_cut, bin_size)
+    num_relations = len(partial_relations[0])
+    relation_matrix = np.asarray(partial_relations).transpose()
+    types = np.asarray(types)
+    cmap = _ClassMap(list(partial_relations[0]) + list(partial_relations[1]), present_types=np.unique(types.astype(np.int64)))
+    weights = _sym_weights(cmap, relation_matrix, with_full=True)
+    edges = bin_edges(bin_size, num_bins)
+    rcut2 = _rcut_sq(r_cut)
+    boxes = np.broadcast_to(np.asarray(box_lengths, dtype=np.float64), (T, 3))
+    static_types = types.ndim == 1
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if static_types:
+        cls_static = torch.from_numpy(cmap.classes_of(types)).to(dev)
+        at_static = _value_counts(types)
+    copy_stream = torch.cuda.Stream()
+    out = torch.empty((T, 1 + num_relations, num_bins), dtype=torch.int64, device=dev)
+
+    def stage(f0):
+        f1 = min(T, f0 + batch_frames)
+        with torch.cuda.stream(copy_stream):
+            x = pos[f0:f1].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return f0, f1, x, ev
+
+    nxt = stage(0)
+    while nxt is not None:
+        f0, f1, x, ev = nxt
+        nxt = stage(f1) if f1 < T else None
+        torch.cuda.current_stream().wait_event(ev)
+        cls = cls_static if static_types else torch.from_numpy(np.stack([cmap.classes_of(t) for t in types[f0:f1]])).to(dev)
+        hist = ops.pair_hist(x, cls, cmap.ncls, boxes[f0:f1], rcut2, edges, bin_size)
+        out[f0:f1] = ops.hist_reduce(hist, weights)
+        x.record_stream(torch.cuda.current_stream())
+    counts = out.cpu().numpy()
+    rdf_full_sum = np.zeros(num_bins)
+    rdf_part_sum = np.zeros((num_relations, num_bins))
+    for t in range(T):
+        at = at_static if static_types else _value_counts(types[t])
+        volume = np.prod(boxes[t])
+        rho = N / volume
+        rho_pairs = np.array([at[b] / volume for b in partial_relations[1]])
+        full, part = _normalize_rdf(bin_size, rho_pairs, at, partial_relations, num_relations, num_bins,
+                                    counts[t, 1:].astype(np.float64), counts[t, 0].astype(np.float64), N, rho)
+        rdf_full_sum += full
+        rdf_part_sum += part
+    df = _save_rdf(radii, relation_matrix, None, False, rdf_part_sum / T, rdf_full_sum=rdf_full_sum / T)
+    return (df, counts) if return_counts else df
 
 
 def calc_intermolecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
