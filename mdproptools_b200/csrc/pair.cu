@@ -13,14 +13,19 @@
 //      operation order) are dropped when the work list is built; inside a tile pair every warp
 //      repeats the test per 32-point chunk.  The set of pairs with rsq < rcut2 is unchanged, each
 //      surviving pair's rsq is computed in the reference's unfused fp64 order, so counts are bit-exact;
-//   3. persistent CTAs (2 per SM) pull tile pairs from a global counter; the j tile is staged in
-//      shared memory, each lane keeps one i point in registers; chunk pairs whose displacement
-//      interval lies inside [-l/2, l/2] on all axes take a path with no minimum-image work at all
-//      (8 fp64 ops / pair), the others the general path (11 fp64 ops + integer compares);
+//   3. persistent CTAs (3 per SM) walk the frames of the batch (each CTA starts at a different frame);
+//      inside a frame every WARP pulls its own work items -- (32 i points, one 256-point j tile) -- from
+//      the frame's global counter, so there is no CTA barrier on the pair path (a barrier-per-tile
+//      version lost 45 % of its issue slots waiting, profiles/r01a_k_pair.txt).  Each lane keeps one i
+//      point in registers; the needed 32-point j chunks are streamed into a warp-private, double
+//      buffered shared-memory stage with cp.async (1 KB contiguous per chunk: records are stored
+//      group-blocked, [32 x (x,y)][32 x (z,meta)]).  Chunk pairs whose displacement interval lies inside
+//      [-l/2, l/2] on all axes take a path with no minimum-image work at all (8 fp64 ops / pair), the
+//      others the general path (11 fp64 ops + integer compares);
 //   4. in-cutoff pairs are compacted into a per-warp shared-memory queue (ballot + popc) and binned
 //      32 at a time at full lane utilisation: bin index from an fp32 sqrt estimate corrected against
-//      the exact fp64 edge table, then a shared-memory histogram atomic; per-CTA histograms are
-//      flushed to the per-frame uint64 global histogram when the frame changes.
+//      the exact fp64 edge table, then a shared-memory histogram atomic; the per-CTA histogram is
+//      flushed to the per-frame uint64 global histogram when the CTA leaves a frame (the only barrier).
 #include <float.h>
 #include <math.h>
 
@@ -38,12 +43,14 @@ constexpr int NWARP = 8;       // warps per CTA of the pair kernel
 constexpr int QCAP = 160;      // queue entries per warp (32 carried + 4 steps x 32)
 constexpr int MAX_CLS = 64;
 
-struct __align__(16) AtomRec {
-    double x, y, z;
-    int32_t cls;
-    int32_t idx;   // row in the caller's order, -1 for padding
-};
-static_assert(sizeof(AtomRec) == 32, "AtomRec must be 32 bytes");
+// Sorted points are stored group-blocked: group g (32 points) occupies 64 consecutive double2,
+//   [g*64 + l]      = (x, y)  of point l
+//   [g*64 + 32 + l] = (z, meta), meta = the bit pattern {lo: class, hi: row in the caller's order or -1 for padding}
+// so that one 32-point chunk is a single contiguous 1 KB block and both halves are bank-conflict free.
+constexpr int GREC = 64;       // double2 per group
+__host__ __device__ __forceinline__ int64_t rec_xy(int64_t pos) { return (pos >> 5) * GREC + (pos & 31); }
+__host__ __device__ __forceinline__ int64_t rec_zw(int64_t pos) { return (pos >> 5) * GREC + 32 + (pos & 31); }
+constexpr size_t REC_BYTES = 32;   // bytes per point
 
 enum { MODE_HIST_UNIFORM = 0, MODE_HIST_TABLE = 1, MODE_LIST = 2 };
 
@@ -112,6 +119,75 @@ __device__ __forceinline__ bool boxes_may_interact(const double *a, const double
     const double bz = axis_lower_bound(a[2], a[5], b[2], b[5], lz, lz * 0.5, general);
     const double lb = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
     return lb < rcut2;
+}
+
+// ---- chunk-level test in fp32 with directed rounding ------------------------------------------------
+// Group boxes are also kept as floats rounded OUTWARD (lo down, hi up), box lengths as (down, up) pairs.
+// Every bound below is rounded towards "keep the pair", so the test can only err on the side of evaluating
+// a chunk pair that has no hit; the per-axis classification is exact in the same sense:
+//   AX_NONE   every pair of the two boxes has |d| <= l/2           -> no minimum-image work
+//   AX_SHIFT  every pair has |d| > l/2                              -> d' = |d| - l for all of them
+//   AX_MIXED  undecided                                            -> d' = min(|d|, ||d| - l|), which has the
+//             same magnitude as the reference's strict single shift (rdf_cn.py:50-55) for every d
+enum { AX_NONE = 0, AX_SHIFT = 1, AX_MIXED = 2 };
+
+struct AxisF {
+    float l_dn, l_up, h_dn, h_up;
+};
+
+__device__ __forceinline__ AxisF make_axis(double l)
+{
+    AxisF a;
+    a.l_dn = __double2float_rd(l);
+    a.l_up = __double2float_ru(l);
+    const double h = l * 0.5;
+    a.h_dn = __double2float_rd(h);
+    a.h_up = __double2float_ru(h);
+    return a;
+}
+
+__device__ __forceinline__ float interval_min_abs(float lo, float hi)
+{
+    return (lo <= 0.f && hi >= 0.f) ? 0.f : fminf(fabsf(lo), fabsf(hi));
+}
+
+// lower bound of the wrapped |d| over the two intervals + the class of the axis
+__device__ __forceinline__ float axis_test_f32(float alo, float ahi, float blo, float bhi, const AxisF &ax, int &cls)
+{
+    const float dlo = __fsub_rd(alo, bhi), dhi = __fsub_ru(ahi, blo);
+    const bool may_plus = dhi > ax.h_dn, may_minus = dlo < -ax.h_dn;
+    float best = 3.0e38f;
+    if (dlo > ax.h_up) {
+        cls = AX_SHIFT;
+        best = interval_min_abs(__fsub_rd(dlo, ax.l_up), __fsub_ru(dhi, ax.l_dn));
+    } else if (dhi < -ax.h_up) {
+        cls = AX_SHIFT;
+        best = interval_min_abs(__fadd_rd(dlo, ax.l_dn), __fadd_ru(dhi, ax.l_up));
+    } else {
+        cls = (may_plus || may_minus) ? AX_MIXED : AX_NONE;
+        {
+            const float lo = fmaxf(dlo, -ax.h_up), hi = fminf(dhi, ax.h_up);
+            if (lo <= hi) best = interval_min_abs(lo, hi);
+        }
+        if (may_plus) best = fminf(best, interval_min_abs(__fsub_rd(fmaxf(dlo, ax.h_dn), ax.l_up), __fsub_ru(dhi, ax.l_dn)));
+        if (may_minus) best = fminf(best, interval_min_abs(__fadd_rd(dlo, ax.l_dn), __fadd_ru(fminf(dhi, -ax.h_dn), ax.l_up)));
+    }
+    return best;
+}
+
+// a, b: float[6] outward-rounded boxes.  Returns need; code = cls_x | cls_y << 2 | cls_z << 4
+__device__ __forceinline__ bool chunk_test_f32(const float *a, const float *b, const AxisF &X, const AxisF &Y, const AxisF &Z,
+                                               float rcut2_up, int &code)
+{
+    code = 0;
+    if (a[0] > a[3] || b[0] > b[3]) return false;   // empty box (padding only)
+    int cx, cy, cz;
+    const float bx = axis_test_f32(a[0], a[3], b[0], b[3], X, cx);
+    const float by = axis_test_f32(a[1], a[4], b[1], b[4], Y, cy);
+    const float bz = axis_test_f32(a[2], a[5], b[2], b[5], Z, cz);
+    code = cx | (cy << 2) | (cz << 4);
+    const float lb = __fadd_rd(__fadd_rd(__fmul_rd(bx, bx), __fmul_rd(by, by)), __fmul_rd(bz, bz));
+    return lb < rcut2_up;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -231,45 +307,50 @@ __global__ void __launch_bounds__(1024) k_cell_scan(uint32_t *__restrict__ cnt, 
 __global__ void __launch_bounds__(256) k_scatter(const double *__restrict__ xyz, const int32_t *__restrict__ cls,
                                                  int64_t cls_stride, int64_t n, int64_t npad, int bits,
                                                  const uint32_t *__restrict__ code, const uint32_t *__restrict__ rank,
-                                                 const uint32_t *__restrict__ cnt, double pad_sign, AtomRec *__restrict__ rec)
+                                                 const uint32_t *__restrict__ cnt, double pad_sign, double2 *__restrict__ rec)
 {
     const int f = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npad) return;
-    AtomRec r;
+    double x, y, z;
+    int32_t c, idx;
     int64_t pos;
     if (i < n) {
         const double *p = xyz + (int64_t)f * 3 * n;
         const int64_t ncode = (int64_t)1 << (3 * bits);
         pos = (int64_t)cnt[(int64_t)f * ncode + code[(int64_t)f * n + i]] + rank[(int64_t)f * n + i];
-        r.x = p[i];
-        r.y = p[n + i];
-        r.z = p[2 * n + i];
-        r.cls = cls ? cls[(int64_t)f * cls_stride + i] : 0;
-        r.idx = (int32_t)i;
+        x = p[i];
+        y = p[n + i];
+        z = p[2 * n + i];
+        c = cls ? cls[(int64_t)f * cls_stride + i] : 0;
+        idx = (int32_t)i;
     } else {
         // padding: far away, pairwise distinct, opposite sign for the two sets so that no pad-pad
         // pair of a rectangular call can coincide
         pos = i;
-        r.x = pad_sign * (1.0e30 + (double)(i - n) * 1.0e25);
-        r.y = 0.0;
-        r.z = 0.0;
-        r.cls = 0;
-        r.idx = -1;
+        x = pad_sign * (1.0e30 + (double)(i - n) * 1.0e25);
+        y = 0.0;
+        z = 0.0;
+        c = 0;
+        idx = -1;
     }
-    rec[(int64_t)f * npad + pos] = r;
+    double2 *r = rec + (int64_t)f * npad * 2;
+    r[rec_xy(pos)] = make_double2(x, y);
+    r[rec_zw(pos)] = make_double2(z, __hiloint2double(idx, c));
 }
 
 // group (32 points) and tile (256 points) bounding boxes over the valid points; one CTA per tile
-__global__ void __launch_bounds__(TS) k_aabb(const AtomRec *__restrict__ rec, int64_t npad, int ngroups, int ntiles,
-                                             double *__restrict__ gaabb, double *__restrict__ taabb)
+__global__ void __launch_bounds__(TS) k_aabb(const double2 *__restrict__ rec, int64_t npad, int ngroups, int ntiles,
+                                             double *__restrict__ taabb, float4 *__restrict__ gbox32)
 {
     const int f = blockIdx.y, t = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const AtomRec r = rec[(int64_t)f * npad + (int64_t)t * TS + threadIdx.x];
-    const bool valid = r.idx >= 0;
-    double lo[3] = {valid ? r.x : DBL_MAX, valid ? r.y : DBL_MAX, valid ? r.z : DBL_MAX};
-    double hi[3] = {valid ? r.x : -DBL_MAX, valid ? r.y : -DBL_MAX, valid ? r.z : -DBL_MAX};
+    const double2 *r = rec + (int64_t)f * npad * 2;
+    const int64_t pos = (int64_t)t * TS + threadIdx.x;
+    const double2 xy = r[rec_xy(pos)], zw = r[rec_zw(pos)];
+    const bool valid = __double2hiint(zw.y) >= 0;
+    double lo[3] = {valid ? xy.x : DBL_MAX, valid ? xy.y : DBL_MAX, valid ? zw.x : DBL_MAX};
+    double hi[3] = {valid ? xy.x : -DBL_MAX, valid ? xy.y : -DBL_MAX, valid ? zw.x : -DBL_MAX};
     __shared__ double s[GPT][6];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -277,13 +358,14 @@ __global__ void __launch_bounds__(TS) k_aabb(const AtomRec *__restrict__ rec, in
         hi[c] = warp_max(hi[c]);
     }
     if (lane == 0) {
-        double *g = gaabb + ((int64_t)f * ngroups + (int64_t)t * GPT + w) * 6;
         for (int c = 0; c < 3; ++c) {
-            g[c] = lo[c];
-            g[3 + c] = hi[c];
             s[w][c] = lo[c];
             s[w][3 + c] = hi[c];
         }
+        // outward-rounded float copy for the chunk-level test of the pair kernel (empty group: lo > hi survives)
+        float4 *g32 = gbox32 + ((int64_t)f * ngroups + (int64_t)t * GPT + w) * 2;
+        g32[0] = make_float4(__double2float_rd(lo[0]), __double2float_rd(lo[1]), __double2float_rd(lo[2]), 0.f);
+        g32[1] = make_float4(__double2float_ru(hi[0]), __double2float_ru(hi[1]), __double2float_ru(hi[2]), 0.f);
     }
     __syncthreads();
     if (threadIdx.x < 6) {
@@ -382,18 +464,21 @@ __global__ void __launch_bounds__(1024) k_row_scan(const uint32_t *__restrict__ 
 // the pair kernel
 // ---------------------------------------------------------------------------------------------
 struct PairParams {
-    const AtomRec *recA, *recB;
-    const double *gaabbA, *gaabbB;
+    const double2 *recA, *recB;      // group-blocked records, [F][npad*2] double2
+    const float4 *gboxA, *gboxB;     // outward-rounded float boxes of the 32-point groups, 2 x float4 each
     int64_t npadA, npadB;
     int ngA, ngB;
+    int ntA;                         // tiles of set A per frame (rows of the work list per frame)
+    int nframes;
     const double *box;               // device [F][3]
-    const uint64_t *items;
-    const unsigned long long *total;
-    unsigned int *counter;
+    const uint64_t *items;           // tile pairs, grouped by frame
+    const uint32_t *rowoff;          // [F*ntA] exclusive offsets into items
+    const unsigned long long *total; // number of items
+    unsigned int *counters;          // [F] per-frame warp-item counters (zeroed before launch)
     unsigned long long *stats;
     double rcut2;                    // pre-filter cutoff (max of all cutoffs)
     // histogram modes
-    int nbins, nrows, nclsB;
+    int nbins, nrows, nclsB, ncp;
     const double2 *edges2;           // device [nbins+1]: {e[k], e[k+1]}, e[nbins+1] = +inf
     const int *cptab;                // device [nclsA*nclsB] -> histogram row
     float inv_ddr;
@@ -411,14 +496,28 @@ struct PairParams {
 };
 
 struct Shared {
-    AtomRec *tileB;
-    double *baabb;
-    double *qr;
-    uint2 *qm;
     const double2 *edges2;
     const int *cptab;
     unsigned int *hist;
 };
+
+// bytes of the warp-private region: two chunk stages + the hit queue (+ its metadata)
+__host__ __device__ constexpr size_t warp_region_bytes(bool meta)
+{
+    return 2 * GREC * sizeof(double2) + QCAP * sizeof(double) + (meta ? QCAP * sizeof(uint2) : 0);
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 template <int MODE, bool MULTICLS>
 __device__ __forceinline__ void drain(const PairParams &p, const Shared &sh, int lane, int m, const double *qr,
@@ -480,53 +579,68 @@ __device__ __forceinline__ void drain(const PairParams &p, const Shared &sh, int
     __syncwarp();
 }
 
-template <int MODE, bool MULTICLS, bool GENERAL, bool TRI>
-__device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh, const AtomRec *__restrict__ cb,
-                                           double xi, double yi, double zi, uint32_t mi, double lx, double ly, double lz,
-                                           long long hxb, long long hyb, long long hzb, int rc_hi, int lane, int &qn,
-                                           double *qr, uint2 *qm, int frame)
+// one 32 x 32 chunk pair: lane = i point, loop over the 32 j points of the staged chunk, four at a time so that
+// four independent fp64 chains are in flight; the hits of the four steps are compacted with one branch.
+//   VAR_FAST   no axis needs the minimum image           8 fp64 ops / pair
+//   VAR_SHIFT  per axis d' = |d| - s, s = 0 or l          11 fp64 ops / pair (|d| - 0 is exact)
+//   VAR_MIXED  per axis d' = min(|d|, ||d| - l|)          14 fp64 ops / pair (see AX_MIXED)
+// In every variant only the square of d' is used and it equals the reference's (rdf_cn.py:50-56) bit for bit.
+enum { VAR_FAST = 0, VAR_SHIFT = 1, VAR_MIXED = 2 };
+
+template <int MODE, bool MULTICLS, int VAR, bool TRI>
+__device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh, const double2 *__restrict__ jb, double xi,
+                                           double yi, double zi, uint32_t mi, double sx, double sy, double sz, int rc_hi,
+                                           int lane, int &qn, double *qr, uint2 *qm, int frame)
 {
     constexpr bool META = MULTICLS || MODE == MODE_LIST;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
     for (int j0 = 0; j0 < GS; j0 += 4) {
+        double r2[4];
+        double meta[4];
+        bool hit[4];
+        unsigned m[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int jj = j0 + u;
-            const double2 xy = *reinterpret_cast<const double2 *>(&cb[jj]);
-            const double2 zw = *(reinterpret_cast<const double2 *>(&cb[jj]) + 1);
+            const double2 xy = jb[jj];
+            const double2 zw = jb[32 + jj];
             double ax = __dsub_rn(xi, xy.x), ay = __dsub_rn(yi, xy.y), az = __dsub_rn(zi, zw.x);
-            if (GENERAL) {
-                // single-shift minimum image (rdf_cn.py:50-55); only the square is used, so
-                // (d - sign(d) l)^2 == (|d| - l)^2 bit for bit
-                ax = fabs(ax);
-                ay = fabs(ay);
-                az = fabs(az);
-                if (__double_as_longlong(ax) > hxb) ax = __dsub_rn(ax, lx);
-                if (__double_as_longlong(ay) > hyb) ay = __dsub_rn(ay, ly);
-                if (__double_as_longlong(az) > hzb) az = __dsub_rn(az, lz);
+            if (VAR == VAR_SHIFT) {
+                ax = __dsub_rn(fabs(ax), sx);
+                ay = __dsub_rn(fabs(ay), sy);
+                az = __dsub_rn(fabs(az), sz);
+            } else if (VAR == VAR_MIXED) {
+                ax = fmin(fabs(ax), fabs(__dsub_rn(fabs(ax), sx)));
+                ay = fmin(fabs(ay), fabs(__dsub_rn(fabs(ay), sy)));
+                az = fmin(fabs(az), fabs(__dsub_rn(fabs(az), sz)));
             }
-            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-            bool hit = __double2hiint(r2) <= rc_hi;   // superset of rsq < rcut2; settled exactly in drain()
-            if (TRI) hit = hit && (jj > lane);
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-                if (hit) {
-                    const int pos = qn + __popc(m & lt);
-                    qr[pos] = r2;
+            r2[u] = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+            hit[u] = __double2hiint(r2[u]) <= rc_hi;   // superset of rsq < rcut2; settled exactly in drain()
+            if (TRI) hit[u] = hit[u] && (jj > lane);
+            if (META) meta[u] = zw.y;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(0xffffffffu, hit[u]);
+        if (m[0] | m[1] | m[2] | m[3]) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (hit[u]) {
+                    const int pos = qn + __popc(m[u] & lt);
+                    qr[pos] = r2[u];
                     if (META) {
                         if (MODE == MODE_LIST)
-                            qm[pos] = make_uint2(mi, (uint32_t)__double2hiint(zw.y));
+                            qm[pos] = make_uint2(mi, (uint32_t)__double2hiint(meta[u]));
                         else
-                            qm[pos] = make_uint2(mi + (uint32_t)__double2loint(zw.y), 0u);
+                            qm[pos] = make_uint2(mi + (uint32_t)__double2loint(meta[u]), 0u);
                     }
                 }
-                qn += __popc(m);
+                qn += __popc(m[u]);
             }
-        }
-        while (qn >= 32) {
-            qn -= 32;
-            drain<MODE, MULTICLS>(p, sh, lane, 32, qr, qm, qn, frame);
+            while (qn >= 32) {
+                qn -= 32;
+                drain<MODE, MULTICLS>(p, sh, lane, 32, qr, qm, qn, frame);
+            }
         }
     }
 }
@@ -536,165 +650,169 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool META = MULTICLS || MODE == MODE_LIST;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    // warp-private region
+    unsigned char *wp = smem_raw + (size_t)w * warp_region_bytes(META);
+    double2 *jbuf = reinterpret_cast<double2 *>(wp);                       // [2][GREC]
+    double *qr = reinterpret_cast<double *>(wp + 2 * GREC * sizeof(double2));
+    uint2 *qm = reinterpret_cast<uint2 *>(wp + 2 * GREC * sizeof(double2) + QCAP * sizeof(double));
+    // CTA-shared region
+    unsigned char *sp = smem_raw + (size_t)NWARP * warp_region_bytes(META);
     Shared sh;
-    unsigned char *sp = smem_raw;
-    sh.tileB = reinterpret_cast<AtomRec *>(sp);
-    sp += TS * sizeof(AtomRec);
-    sh.baabb = reinterpret_cast<double *>(sp);
-    sp += GPT * 6 * sizeof(double);
-    sh.qr = reinterpret_cast<double *>(sp);
-    sp += NWARP * QCAP * sizeof(double);
-    sh.qm = reinterpret_cast<uint2 *>(sp);
-    if (META) sp += NWARP * QCAP * sizeof(uint2);
     double2 *edges_s = reinterpret_cast<double2 *>(sp);
     if (MODE != MODE_LIST && p.edges_in_smem) sp += (size_t)(p.nbins + 1) * sizeof(double2);
     int *cptab_s = reinterpret_cast<int *>(sp);
-    if (MULTICLS) sp += (size_t)((MAX_CLS * MAX_CLS * 4 + 15) & ~15);
+    if (MULTICLS) sp += (size_t)((p.ncp * 4 + 15) & ~15);
     sh.hist = reinterpret_cast<unsigned int *>(sp);
-    __shared__ unsigned int s_item;
+    sh.edges2 = p.edges2;
+    sh.cptab = p.cptab;
 
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nhist = MODE == MODE_LIST ? 0 : p.nrows * p.nbins;
-
     if (MODE != MODE_LIST) {
         if (p.edges_in_smem) {
             for (int k = tid; k <= p.nbins; k += blockDim.x) edges_s[k] = p.edges2[k];
             sh.edges2 = edges_s;
-        } else {
-            sh.edges2 = p.edges2;
         }
         for (int k = tid; k < nhist; k += blockDim.x) sh.hist[k] = 0u;
     }
     if (MULTICLS) {
-        for (int k = tid; k < MAX_CLS * MAX_CLS; k += blockDim.x) cptab_s[k] = p.cptab[k];
+        for (int k = tid; k < p.ncp; k += blockDim.x) cptab_s[k] = p.cptab[k];
         sh.cptab = cptab_s;
     }
-    double *qr = sh.qr + w * QCAP;
-    uint2 *qm = sh.qm + w * QCAP;
+    __syncthreads();
+
     int qn = 0;
     const int rc_hi = __double2hiint(p.rcut2);
+    const float rcut2_up = __double2float_ru(p.rcut2);
     const unsigned long long total = *p.total;
-
-    int cur_frame = -1;
-    double lx = 0, ly = 0, lz = 0;
-    long long hxb = 0, hyb = 0, hzb = 0;
     unsigned long long my_chunks = 0;
+    const int F = p.nframes;
+    // every CTA starts at a different frame and walks all of them, so the frames' tails do not line up
+    const int fstart = (int)(((long long)blockIdx.x * F) / gridDim.x);
 
-    unsigned int nxt = 0;
-    if (tid == 0) nxt = atomicAdd(p.counter, 1u);
-    for (;;) {
-        __syncthreads();   // every warp is done with tileB / s_item of the previous item
-        if (tid == 0) s_item = nxt;
-        __syncthreads();
-        const unsigned int it = s_item;
-        if ((unsigned long long)it >= total) break;
-        if (tid == 0) nxt = atomicAdd(p.counter, 1u);   // prefetch the next work index
-        const uint64_t item = p.items[it];
-        const int f = (int)(item >> 44), ta = (int)((item >> 22) & 0x3fffffu), tb = (int)(item & 0x3fffffu);
+#pragma unroll 1
+    for (int fk = 0; fk < F; ++fk) {
+        int f = fstart + fk;
+        if (f >= F) f -= F;
+        const unsigned int ibeg = p.rowoff[(int64_t)f * p.ntA];
+        const unsigned int iend = f + 1 < F ? p.rowoff[(int64_t)(f + 1) * p.ntA] : (unsigned int)total;
+        const unsigned int nwi = (iend - ibeg) * GPT;   // warp items of this frame
+        const double lx = p.box[f * 3 + 0], ly = p.box[f * 3 + 1], lz = p.box[f * 3 + 2];
+        const AxisF AX = make_axis(lx), AY = make_axis(ly), AZ = make_axis(lz);
+        const int frame = p.frame0 + f;
+        const double2 *rA = p.recA + (int64_t)f * p.npadA * 2;
+        const double2 *rB = p.recB + (int64_t)f * p.npadB * 2;
+        bool did = false;
 
-        if (f != cur_frame) {
-            if (cur_frame >= 0) {
-                // finish the previous frame: drain the queues, flush the CTA histogram
-                if (qn > 0) {
-                    drain<MODE, MULTICLS>(p, sh, lane, qn, qr, qm, 0, p.frame0 + cur_frame);
-                    qn = 0;
-                }
-                if (MODE != MODE_LIST) {
-                    __syncthreads();
-                    unsigned long long *hg = p.hist + (int64_t)(p.frame0 + cur_frame) * nhist;
-                    for (int k = tid; k < nhist; k += blockDim.x) {
-                        const unsigned int v = sh.hist[k];
-                        if (v) {
-                            atomicAdd(&hg[k], (unsigned long long)v);
-                            sh.hist[k] = 0u;
-                        }
+        unsigned int q = 0;
+        if (lane == 0) q = atomicAdd(&p.counters[f], 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+#pragma unroll 1
+        while (q < nwi) {
+            unsigned int qnext = 0;
+            if (lane == 0) qnext = atomicAdd(&p.counters[f], 1u);   // prefetch the next work index
+            did = true;
+            const uint64_t item = p.items[ibeg + (q >> 3)];
+            const int wi = (int)(q & 7u);
+            const int ta = (int)((item >> 22) & 0x3fffffu), tb = (int)(item & 0x3fffffu);
+            const int64_t gi = (int64_t)ta * GPT + wi;
+            // my i point; lanes 0..7 test my group's box against the 8 chunk boxes of the j tile
+            const double2 ixy = rA[gi * GREC + lane], izw = rA[gi * GREC + 32 + lane];
+            const bool diag = SYMM && ta == tb;
+            bool need = false;
+            int code = 0;
+            {
+                const float4 *ga4 = p.gboxA + ((int64_t)f * p.ngA + gi) * 2;
+                const float4 alo = ga4[0], ahi = ga4[1];
+                const float ga[6] = {alo.x, alo.y, alo.z, ahi.x, ahi.y, ahi.z};
+                if (lane < GPT && !(diag && lane < wi)) {
+                    const float4 *gb4 = p.gboxB + ((int64_t)f * p.ngB + (int64_t)tb * GPT + lane) * 2;
+                    const float4 blo = gb4[0], bhi = gb4[1];
+                    const float gb[6] = {blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z};
+                    need = chunk_test_f32(ga, gb, AX, AY, AZ, rcut2_up, code);
+                    if (p.nocull) {
+                        need = !(ga[0] > ga[3] || gb[0] > gb[3]);
+                        code = AX_MIXED | (AX_MIXED << 2) | (AX_MIXED << 4);
                     }
                 }
             }
-            cur_frame = f;
-            lx = p.box[f * 3 + 0];
-            ly = p.box[f * 3 + 1];
-            lz = p.box[f * 3 + 2];
-            hxb = __double_as_longlong(lx * 0.5);
-            hyb = __double_as_longlong(ly * 0.5);
-            hzb = __double_as_longlong(lz * 0.5);
-        }
-
-        // stage the j tile and its chunk boxes
-        {
-            const AtomRec *src = p.recB + (int64_t)f * p.npadB + (int64_t)tb * TS;
-            const double2 *s2 = reinterpret_cast<const double2 *>(src);
-            double2 *d2 = reinterpret_cast<double2 *>(sh.tileB);
-            d2[2 * tid] = s2[2 * tid];
-            d2[2 * tid + 1] = s2[2 * tid + 1];
-            if (tid < GPT * 6) sh.baabb[tid] = p.gaabbB[((int64_t)f * p.ngB + (int64_t)tb * GPT) * 6 + tid];
-        }
-        // my i point and my group's box
-        const AtomRec me = p.recA[(int64_t)f * p.npadA + (int64_t)ta * TS + tid];
-        double ga[6];
-        {
-            const double *g = p.gaabbA + ((int64_t)f * p.ngA + (int64_t)ta * GPT + w) * 6;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) ga[c] = g[c];
-        }
-        __syncthreads();
-
-        const bool diag = SYMM && ta == tb;
-        bool need = false, gen = false;
-        if (lane < GPT) {
-            const int c = lane;
-            if (!(diag && c < w)) {
-                double bb[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) bb[k] = sh.baabb[c * 6 + k];
-                need = boxes_may_interact(ga, bb, lx, ly, lz, p.rcut2, gen);
-                if (p.nocull) {
-                    need = !(ga[0] > ga[3] || bb[0] > bb[3]);
-                    gen = true;
+            unsigned needmask = __ballot_sync(0xffffffffu, need);
+            const uint32_t mi = MODE == MODE_LIST ? (uint32_t)__double2hiint(izw.y)
+                                                  : (uint32_t)(__double2loint(izw.y) * p.nclsB);
+            const double2 *jsrc = rB + (int64_t)tb * GPT * GREC;
+            int buf = 0;
+            int c = -1;
+            if (needmask) {
+                c = __ffs(needmask) - 1;
+                needmask &= needmask - 1;
+                cp_async16(&jbuf[lane], &jsrc[c * GREC + lane]);
+                cp_async16(&jbuf[32 + lane], &jsrc[c * GREC + 32 + lane]);
+                cp_async_commit();
+            }
+#pragma unroll 1
+            while (c >= 0) {
+                int cn = -1;
+                if (needmask) {
+                    cn = __ffs(needmask) - 1;
+                    needmask &= needmask - 1;
+                    double2 *nb = jbuf + (buf ^ 1) * GREC;
+                    cp_async16(&nb[lane], &jsrc[cn * GREC + lane]);
+                    cp_async16(&nb[32 + lane], &jsrc[cn * GREC + 32 + lane]);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
                 }
+                __syncwarp();
+                const double2 *jb = jbuf + buf * GREC;
+                const int cc = __shfl_sync(0xffffffffu, code, c);
+                const bool tri = diag && c == wi;
+                ++my_chunks;
+                const bool mixed = ((cc | (cc >> 2) | (cc >> 4)) & AX_MIXED) != 0;
+                if (cc == 0) {
+                    if (tri)
+                        chunk_loop<MODE, MULTICLS, VAR_FAST, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, 0.0, 0.0, 0.0, rc_hi, lane,
+                                                                   qn, qr, qm, frame);
+                    else
+                        chunk_loop<MODE, MULTICLS, VAR_FAST, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, 0.0, 0.0, 0.0, rc_hi, lane,
+                                                                    qn, qr, qm, frame);
+                } else if (!mixed && !tri) {
+                    chunk_loop<MODE, MULTICLS, VAR_SHIFT, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, (cc & 1) ? lx : 0.0,
+                                                                 (cc & 4) ? ly : 0.0, (cc & 16) ? lz : 0.0, rc_hi, lane, qn, qr,
+                                                                 qm, frame);
+                } else {
+                    // undecided axes (small boxes, huge groups) and the rare wrapped diagonal chunk: exact for every d
+                    if (tri)
+                        chunk_loop<MODE, MULTICLS, VAR_MIXED, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, lx, ly, lz, rc_hi, lane, qn,
+                                                                    qr, qm, frame);
+                    else
+                        chunk_loop<MODE, MULTICLS, VAR_MIXED, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, lx, ly, lz, rc_hi, lane,
+                                                                     qn, qr, qm, frame);
+                }
+                __syncwarp();   // everyone is done with this stage before it is refilled
+                buf ^= 1;
+                c = cn;
             }
+            q = __shfl_sync(0xffffffffu, qnext, 0);
         }
-        unsigned needmask = __ballot_sync(0xffffffffu, need);
-        const unsigned genmask = __ballot_sync(0xffffffffu, gen);
-        const uint32_t mi = MODE == MODE_LIST ? (uint32_t)me.idx : (uint32_t)(me.cls * p.nclsB);
-        const int frame = p.frame0 + f;
-        while (needmask) {
-            const int c = __ffs(needmask) - 1;
-            needmask &= needmask - 1;
-            const AtomRec *cb = sh.tileB + c * GS;
-            const bool g = (genmask >> c) & 1u;
-            const bool tri = diag && c == w;
-            ++my_chunks;
-            if (g) {
-                if (tri)
-                    chunk_loop<MODE, MULTICLS, true, true>(p, sh, cb, me.x, me.y, me.z, mi, lx, ly, lz, hxb, hyb, hzb, rc_hi,
-                                                           lane, qn, qr, qm, frame);
-                else
-                    chunk_loop<MODE, MULTICLS, true, false>(p, sh, cb, me.x, me.y, me.z, mi, lx, ly, lz, hxb, hyb, hzb,
-                                                            rc_hi, lane, qn, qr, qm, frame);
-            } else {
-                if (tri)
-                    chunk_loop<MODE, MULTICLS, false, true>(p, sh, cb, me.x, me.y, me.z, mi, lx, ly, lz, hxb, hyb, hzb,
-                                                            rc_hi, lane, qn, qr, qm, frame);
-                else
-                    chunk_loop<MODE, MULTICLS, false, false>(p, sh, cb, me.x, me.y, me.z, mi, lx, ly, lz, hxb, hyb, hzb,
-                                                             rc_hi, lane, qn, qr, qm, frame);
-            }
-        }
-    }
 
-    // tail: last frame of this CTA
-    if (cur_frame >= 0) {
+        // this warp is done with frame f: empty its queue, then the CTA flushes its histogram
         if (qn > 0) {
-            drain<MODE, MULTICLS>(p, sh, lane, qn, qr, qm, 0, p.frame0 + cur_frame);
+            drain<MODE, MULTICLS>(p, sh, lane, qn, qr, qm, 0, frame);
             qn = 0;
         }
         if (MODE != MODE_LIST) {
-            __syncthreads();
-            unsigned long long *hg = p.hist + (int64_t)(p.frame0 + cur_frame) * nhist;
-            for (int k = tid; k < nhist; k += blockDim.x) {
-                const unsigned int v = sh.hist[k];
-                if (v) atomicAdd(&hg[k], (unsigned long long)v);
+            if (__syncthreads_or(did ? 1 : 0)) {
+                unsigned long long *hg = p.hist + (int64_t)frame * nhist;
+                for (int k = tid; k < nhist; k += blockDim.x) {
+                    const unsigned int v = sh.hist[k];
+                    if (v) {
+                        atomicAdd(&hg[k], (unsigned long long)v);
+                        sh.hist[k] = 0u;
+                    }
+                }
+                __syncthreads();
             }
         }
     }
@@ -739,8 +857,9 @@ struct SetPlan {
     int ntiles = 0, ngroups = 0, bits = 0;
     int64_t ncode = 1;
     // device scratch (per sub-batch)
-    AtomRec *rec = nullptr;
-    double *gaabb = nullptr, *taabb = nullptr, *mm = nullptr;
+    double2 *rec = nullptr;
+    float4 *gbox32 = nullptr;
+    double *taabb = nullptr, *mm = nullptr;
     uint32_t *code = nullptr, *rank = nullptr, *cnt = nullptr;
 };
 
@@ -761,20 +880,20 @@ static void plan_set(SetPlan &s, int64_t n, bool nosort)
 
 static size_t set_bytes_per_frame(const SetPlan &s)
 {
-    return align256(s.npad * sizeof(AtomRec)) + align256(s.ngroups * 48) + align256(s.ntiles * 48) + align256(48) +
+    return align256(s.npad * REC_BYTES) + align256(s.ngroups * 32) + align256(s.ntiles * 48) + align256(48) +
            2 * align256(s.n * 4) + align256(s.ncode * 4) + 4096;
 }
 
 static int carve_set(mdp_ctx *ctx, SetPlan &s, int F)
 {
-    s.rec = (AtomRec *)ctx->arena_take((size_t)F * s.npad * sizeof(AtomRec));
-    s.gaabb = (double *)ctx->arena_take((size_t)F * s.ngroups * 48);
+    s.rec = (double2 *)ctx->arena_take((size_t)F * s.npad * REC_BYTES);
+    s.gbox32 = (float4 *)ctx->arena_take((size_t)F * s.ngroups * 32);
     s.taabb = (double *)ctx->arena_take((size_t)F * s.ntiles * 48);
     s.mm = (double *)ctx->arena_take((size_t)F * 48);
     s.code = (uint32_t *)ctx->arena_take((size_t)F * s.n * 4);
     s.rank = (uint32_t *)ctx->arena_take((size_t)F * s.n * 4);
     s.cnt = (uint32_t *)ctx->arena_take((size_t)F * s.ncode * 4);
-    if (!s.rec || !s.gaabb || !s.taabb || !s.mm || !s.code || !s.rank || !s.cnt) {
+    if (!s.rec || !s.gbox32 || !s.taabb || !s.mm || !s.code || !s.rank || !s.cnt) {
         mdp_set_error("internal: scratch arena exhausted while carving a point set");
         return MDP_ERR_OOM;
     }
@@ -798,7 +917,7 @@ static int sort_set(mdp_ctx *ctx, SetPlan &s, int F, const double *xyz, const in
     k_scatter<<<g2, 256, 0, st>>>(xyz, cls, cls_stride, s.n, s.npad, s.bits, s.code, s.rank, s.cnt, pad_sign, s.rec);
     MDP_LAUNCHED(ctx);
     dim3 g3(s.ntiles, F);
-    k_aabb<<<g3, TS, 0, st>>>(s.rec, s.npad, s.ngroups, s.ntiles, s.gaabb, s.taabb);
+    k_aabb<<<g3, TS, 0, st>>>(s.rec, s.npad, s.ngroups, s.ntiles, s.taabb, s.gbox32);
     MDP_LAUNCHED(ctx);
     return mdp_check_launch("pair prep");
 }
@@ -854,14 +973,14 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
     MDP_REQUIRE(A.ntiles < (1 << 22) && Bp.ntiles < (1 << 22), "pair: too many tiles");
 
     // shared memory budget of the pair kernel
-    size_t smem = TS * sizeof(AtomRec) + GPT * 6 * sizeof(double) + NWARP * QCAP * sizeof(double);
     const bool meta = multicls || !hist_mode;
-    if (meta) smem += NWARP * QCAP * sizeof(uint2);
+    size_t smem = NWARP * warp_region_bytes(meta);
+    const int ncp = c.ncls_a * nclsB;
     int edges_in_smem = 0;
     if (hist_mode) {
         const size_t hist_bytes = (size_t)nrows * c.nbins * 4;
         const size_t edge_bytes = (size_t)(c.nbins + 1) * sizeof(double2);
-        if (multicls) smem += (MAX_CLS * MAX_CLS * 4 + 15) & ~15;
+        if (multicls) smem += (size_t)((ncp * 4 + 15) & ~15);
         const size_t cap = std::min<size_t>(ctx->smem_optin, 72 * 1024);   // keep 3 CTAs per SM
         MDP_REQUIRE(smem + hist_bytes <= ctx->smem_optin,
                     "pair: histogram of %d rows x %d bins does not fit in shared memory (%zu B needed); "
@@ -877,7 +996,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
     // sub-batching over frames so that scratch stays bounded
     const size_t items_worst = symm ? (size_t)A.ntiles * (A.ntiles + 1) / 2 : (size_t)A.ntiles * Bp.ntiles;
     const size_t per_frame = set_bytes_per_frame(A) + (symm ? 0 : set_bytes_per_frame(B)) + align256(items_worst * 8) +
-                             2 * align256((size_t)A.ntiles * 4) + 64;
+                             2 * align256((size_t)A.ntiles * 4) + 64 + 4;
     const size_t fixed = align256((size_t)(c.nbins + 2) * sizeof(double2)) + align256(MAX_CLS * MAX_CLS * 4) + 8192;
     const size_t target = std::min<size_t>(ctx->slab_limit, (size_t)3 << 29);   // 1.5 GiB working set
     int Fsub = (int)std::max<size_t>(1, std::min<size_t>((size_t)c.nframes, (target - std::min(target, fixed)) / per_frame));
@@ -924,6 +1043,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         double *d_box = (double *)ctx->arena_take((size_t)F * 24);
         unsigned long long *d_total = (unsigned long long *)ctx->arena_take(16);
         unsigned int *d_counter = (unsigned int *)(d_total + 1);
+        unsigned int *d_fcount = (unsigned int *)ctx->arena_take((size_t)F * 4);
         rc = carve_set(ctx, A, F);
         if (rc) return rc;
         if (!symm) {
@@ -933,7 +1053,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         uint32_t *rowcnt = (uint32_t *)ctx->arena_take((size_t)F * A.ntiles * 4);
         uint32_t *rowoff = (uint32_t *)ctx->arena_take((size_t)F * A.ntiles * 4);
         uint64_t *items = (uint64_t *)ctx->arena_take((size_t)F * items_worst * 8);
-        if (!d_e2 || !d_cpt || !d_box || !d_total || !rowcnt || !rowoff || !items) {
+        if (!d_e2 || !d_cpt || !d_box || !d_total || !d_fcount || !rowcnt || !rowoff || !items) {
             mdp_set_error("internal: scratch arena exhausted");
             return MDP_ERR_OOM;
         }
@@ -970,16 +1090,20 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         memset(&p, 0, sizeof(p));
         p.recA = A.rec;
         p.recB = Bs.rec;
-        p.gaabbA = A.gaabb;
-        p.gaabbB = Bs.gaabb;
+        p.gboxA = A.gbox32;
+        p.gboxB = Bs.gbox32;
         p.npadA = A.npad;
         p.npadB = Bs.npad;
         p.ngA = A.ngroups;
         p.ngB = Bs.ngroups;
+        p.ntA = A.ntiles;
+        p.nframes = F;
         p.box = d_box;
         p.items = items;
+        p.rowoff = rowoff;
         p.total = d_total;
-        p.counter = d_counter;
+        p.counters = d_fcount;
+        p.ncp = ncp;
         p.stats = ctx->d_stats;
         p.rcut2 = c.rcut2;
         p.nbins = c.nbins;
@@ -1000,6 +1124,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         p.list_count = (unsigned long long *)c.list_count;
         p.frame0 = f0;
         p.nocull = nocull ? 1 : 0;
+        MDP_CUDA(cudaMemsetAsync(d_fcount, 0, (size_t)F * 4, st));
         cudaEvent_t tk = ctx->timer_begin(0, st);
         kern<<<ctx->sm_count * 3, NWARP * 32, smem, st>>>(p);
         ctx->timer_end(tk, st);
