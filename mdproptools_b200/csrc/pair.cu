@@ -5,7 +5,7 @@
 // (cluster_analysis.py:150-161, hydration_number.py:16-19, residence_time.py:100-104).
 //
 // Design (B200-first, not a translation of the row-by-row reference loop):
-//   1. per frame the point set is binned on a Morton grid by a counting sort and written out as
+//   1. per frame the point set is binned on a grid of cells ordered along a Hilbert curve by a counting sort and written out as
 //      32-byte AoS records (x, y, z, class|index), padded to 256-point tiles; every 32-point group and
 //      every tile gets an axis-aligned bounding box;
 //   2. tile pairs whose boxes cannot contain a pair inside the cutoff (under the REFERENCE's
@@ -259,7 +259,34 @@ __global__ void __launch_bounds__(256) k_cell_count(const double *__restrict__ x
             v = v < 0 ? 0 : (v >= nc ? nc - 1 : v);
             q[a] = (uint32_t)v;
         }
-        c = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+        // Hilbert index of the cell (Skilling's transpose algorithm): consecutive indices are face-adjacent
+        // cells, so 32 consecutive points form a compact blob; a Morton order jumps across the box at every
+        // octant boundary, which gave 6 % of the groups boxes that interact with everything.
+        {
+            const uint32_t M = 1u << (bits - 1);
+            for (uint32_t Q = M; Q > 1u; Q >>= 1) {
+                const uint32_t P = Q - 1u;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    if (q[a] & Q) {
+                        q[0] ^= P;
+                    } else {
+                        const uint32_t t = (q[0] ^ q[a]) & P;
+                        q[0] ^= t;
+                        q[a] ^= t;
+                    }
+                }
+            }
+            q[1] ^= q[0];
+            q[2] ^= q[1];
+            uint32_t t = 0;
+            for (uint32_t Q = M; Q > 1u; Q >>= 1)
+                if (q[2] & Q) t ^= Q - 1u;
+            q[0] ^= t;
+            q[1] ^= t;
+            q[2] ^= t;
+        }
+        c = (spread3(q[0]) << 2) | (spread3(q[1]) << 1) | spread3(q[2]);
     }
     const int64_t ncode = (int64_t)1 << (3 * bits);
     code[(int64_t)f * n + i] = c;
@@ -496,7 +523,7 @@ struct PairParams {
 };
 
 struct Shared {
-    const double2 *edges2;
+    const double2 *edges_s;          // shared-memory copy of the edge table (valid when edges_in_smem)
     const int *cptab;
     unsigned int *hist;
 };
@@ -562,12 +589,12 @@ __device__ __forceinline__ void drain(const PairParams &p, const Shared &sh, int
                     s *= p.inv_ddr;
                     k = (int)s;
                     k = k < 0 ? 0 : (k > p.nbins ? p.nbins : k);
-                    const double2 e = sh.edges2[k];
+                    const double2 e = p.edges_in_smem ? sh.edges_s[k] : p.edges2[k];
                     k += (r2 >= e.y) ? 1 : 0;
                     k -= (r2 < e.x) ? 1 : 0;
                 } else {
                     k = 0;
-                    for (int j = 1; j <= p.nbins; ++j) k += (sh.edges2[j].x <= r2) ? 1 : 0;
+                    for (int j = 1; j <= p.nbins; ++j) k += ((p.edges_in_smem ? sh.edges_s[j].x : p.edges2[j].x) <= r2) ? 1 : 0;
                 }
                 if (k >= 0 && k < p.nbins) {
                     const int row = MULTICLS ? sh.cptab[qm[base + lane].x] : 0;
@@ -665,14 +692,13 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
     int *cptab_s = reinterpret_cast<int *>(sp);
     if (MULTICLS) sp += (size_t)((p.ncp * 4 + 15) & ~15);
     sh.hist = reinterpret_cast<unsigned int *>(sp);
-    sh.edges2 = p.edges2;
+    sh.edges_s = edges_s;
     sh.cptab = p.cptab;
 
     const int nhist = MODE == MODE_LIST ? 0 : p.nrows * p.nbins;
     if (MODE != MODE_LIST) {
         if (p.edges_in_smem) {
             for (int k = tid; k <= p.nbins; k += blockDim.x) edges_s[k] = p.edges2[k];
-            sh.edges2 = edges_s;
         }
         for (int k = tid; k < nhist; k += blockDim.x) sh.hist[k] = 0u;
     }
@@ -869,7 +895,7 @@ static void plan_set(SetPlan &s, int64_t n, bool nosort)
     s.ntiles = (int)ceil_div<int64_t>(n, TS);
     s.npad = (int64_t)s.ntiles * TS;
     s.ngroups = s.ntiles * GPT;
-    // ~4 points per Morton cell
+    // ~4 points per cell
     int bits = 0;
     if (!nosort) {
         while (bits < 7 && ((int64_t)1 << (3 * (bits + 1))) * 4 <= n * 2) ++bits;
