@@ -285,6 +285,44 @@ def run_gpu(args):
     ms = float(t.item())
     value = world * nominal_per_step * args.steps / (ms * 1e-3)
 
+    # ---- the same workload with the general triclinic image (mic="triclinic": true nearest image in the tilted cell;
+    # an extension, the reference wraps tilted cells as if they were orthogonal)
+    tric = None
+    if not args.skip_triclinic:
+        from mdproptools_b200._lib import PAIR_TRICLINIC
+        cells = np.tile(np.asarray((LBOX, LBOX, LBOX) + TILT), (F, 1))
+
+        def step_tri():
+            hist = ops.pair_hist(frames, None, 1, cells, rcut2, edges, BIN, flags=PAIR_TRICLINIC)
+            return ops.hist_reduce(hist, weights)
+
+        for _ in range(3):
+            out_t = step_tri()
+        barrier()
+        ev_t = ctx.pair_stats()["pair_evals"]
+        in_cut_t = int(out_t[0, 0].sum().item()) // 2
+        ctx.timing(True)
+        ctx.timing_read(0), ctx.timing_read(1)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(args.steps):
+            step_tri()
+        t1e.record()
+        barrier()
+        ms_t = t0e.elapsed_time(t1e)
+        pair_ms_t, pair_n_t = ctx.timing_read(0)
+        ctx.timing_read(1)
+        ctx.timing(False)
+        tt = torch.tensor([ms_t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_t = float(tt.item())
+        tric = {"value": world * nominal_per_step * args.steps / (ms_t * 1e-3), "unit": "pair-evals/s",
+                "ms_per_step": ms_t / args.steps, "pair_kernel_ms_per_step": pair_ms_t / args.steps,
+                "evaluated_pair_evals_per_step": ev_t, "pairs_in_cutoff_frame0": in_cut_t,
+                "achieved_tflops_11_per_pair": ev_t * FLOPS_PER_PAIR / (pair_ms_t / max(pair_n_t, 1) * 1e-3) / 1e12,
+                "mic": "triclinic (sequential z,y,x single shift of the restricted triclinic cell; oracle-defined extension)"}
+
     # ---- end to end through the public array API: pinned host frames -> H2D -> kernels -> D2H -> normalised g(r)
     host = torch.empty((F, 3, N_ATOMS), dtype=torch.float64, pin_memory=True)
     host.copy_(frames)
@@ -348,6 +386,9 @@ def run_gpu(args):
         "clocks": clk,
         "cpu_baseline": {"value": cpu_rate, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample},
     }
+    if tric:
+        tric["roofline_frac"] = tric["achieved_tflops_11_per_pair"] / fp64_peak
+        out["rdf_triclinic"] = tric
     if msd:
         out["msd"] = msd
     print(json.dumps(out))
@@ -395,6 +436,41 @@ def bench_msd(args, torch, dist, ops, ctx, dev, world, rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * n * T * steps / (ms * 1e-3)
+    # ---- windowed MSD over all time origins (north-star extension): FP64-pipe bound, 2 pipe slots (DADD + DFMA) per
+    # (atom, axis, origin, lag); same C3-shaped random walk re-cut as n/4 atoms x 4T frames so that a long window fits
+    allo = None
+    if not args.skip_msd_window:
+        nw, Tw = n // 4, T * 4
+        W = min(args.msd_window, Tw)
+        trajw = traj.view(-1)[: Tw * 3 * nw].view(Tw, 3, nw)      # any fp64 data serves the throughput measurement
+        outw = torch.zeros((W, 1, 4), dtype=torch.float64, device=dev)
+        for _ in range(2):
+            ops.msd_all_origins(trajw, W, 1e-10, out=outw)
+        torch.cuda.synchronize()
+        ctx.timing(True)
+        ctx.timing_read(5)
+        reps = 3
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(reps):
+            ops.msd_all_origins(trajw, W, 1e-10, out=outw)
+        w1.record()
+        torch.cuda.synchronize()
+        msw = w0.elapsed_time(w1) / reps
+        kmsw, knw = ctx.timing_read(5)
+        ctx.timing(False)
+        triples = nw * (W * Tw - W * (W - 1) // 2)                # (atom, origin, lag) with origin + lag < T
+        slots = triples * 3 * 2
+        peaks_ = measured_peaks()
+        pk = peaks_.get("fp64_unfused_tflops_sustained") or 148 * 64 * 1.965e9 / 1e12
+        ach = slots / (kmsw / reps * 1e-3) / 1e12
+        allo = {"metric": "msd_all_origins_lag_pairs_per_s", "value": world * triples / (msw * 1e-3), "unit": "(atom,origin,lag)/s",
+                "config": {"workload": f"{nw} atoms x {Tw} frames resident ({nw * Tw * 24 / 1e9:.1f} GB), window {W} lags"},
+                "ms_per_step": msw, "launches_per_step": knw // reps,
+                "roofline": {"bound": "fp64", "achieved": ach, "peak": pk, "unit": "T fp64-instr/s", "frac": ach / pk,
+                             "traffic": None,
+                             "note": "k_msd_window only; 6 FP64 pipe slots (3 DADD + 3 DFMA) per (atom, origin, lag); peak = measured "
+                                     "DADD/DMUL issue rate (tools/peaks.cu), which is also the DFMA issue rate"}}
     # end to end: pinned host frames through Diffusion.get_msd_from_arrays
     from mdproptools_b200.dynamical.diffusion import Diffusion
     Te = min(T, 64)
@@ -423,6 +499,7 @@ def bench_msd(args, torch, dist, ops, ctx, dev, world, rank):
         "e2e": {"value": e2e, "unit": "atom-frames/s", "h2d_bytes_per_step": Te * 3 * n * 8, "d2h_bytes_per_step": Te * 32,
                 "api": "Diffusion.get_msd_from_arrays (pinned host frames)"},
         "cpu_baseline": {"value": cpu[0], "unit": "atom-frames/s", "cores": cpu[1], "kind": "port", "sample": cpu[2]},
+        "all_origins": allo,
     }
 
 
@@ -437,6 +514,9 @@ def main():
     ap.add_argument("--msd-frames", type=int, default=MSD_FRAMES)
     ap.add_argument("--skip-msd", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-triclinic", action="store_true")
+    ap.add_argument("--skip-msd-window", action="store_true")
+    ap.add_argument("--msd-window", type=int, default=512)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -44,7 +44,8 @@ int mdp_ctx_set_scratch_limit(mdp_ctx *ctx, int64_t bytes);
 int64_t mdp_ctx_launch_count(mdp_ctx *ctx);
 /* optional kernel timing for benchmarks: when enabled, the library brackets its main kernels with CUDA events
  * on the launching stream.  tag 0 = pair kernel (k_pair), 1 = pair preparation (sort, boxes, work list),
- * 2 = streaming MSD kernel, 3 = correlation kernel, 4 = charge-flux kernel.  mdp_ctx_timing_read synchronises
+ * 2 = streaming MSD kernel, 3 = correlation kernel, 4 = charge-flux kernel, 5 = windowed (all-origins) MSD kernel,
+ * 6 = bitmask autocorrelation kernel.  mdp_ctx_timing_read synchronises
  * on the recorded events, returns the summed milliseconds and the number of launches, and clears them. */
 int mdp_ctx_timing(mdp_ctx *ctx, int enable);
 int mdp_ctx_timing_read(mdp_ctx *ctx, int tag, double *ms_total, int64_t *count);
@@ -96,6 +97,14 @@ int mdp_pair_hist(mdp_ctx *ctx, int nframes,
                   uint64_t *hist_out, int flags, void *stream);
 #define MDP_PAIR_NO_CULL 1     /* evaluate every tile pair (brute force, for A/B measurements) */
 #define MDP_PAIR_NO_SORT 2     /* keep caller order inside tiles (no spatial sort; implies little culling) */
+/* General triclinic minimum image (north-star extension: the reference has none and wraps tilted cells as if
+ * they were orthogonal).  box = HOST [nframes][6] = {lx, ly, lz, xy, xz, yz} of the restricted
+ * triclinic cell a=(lx,0,0), b=(xy,ly,0), c=(xz,yz,lz); the image is the sequential single shift z, y, x
+ * (if |dz| > lz/2: dz -= s*lz, dy -= s*yz, dx -= s*xz; then y with xy; then x), each step an unfused fp64
+ * subtraction in that order, everything else as above.  Nearest image whenever the cutoff is at most half
+ * the smallest cell width and |xy|,|xz| <= lx/2, |yz| <= ly/2.  Definition and checker: oracle/oracle.c
+ * pair_rsq_tri (parity unpinned by the reference). */
+#define MDP_PAIR_TRICLINIC 4
 
 /*
  * out[f][r][b] = sum_rows weights[r][row] * hist[f][row][b]     (all integer)
@@ -116,11 +125,12 @@ int mdp_hist_reduce(mdp_ctx *ctx, int nframes, int rows, int nbins, const uint64
  * caller's row order, unordered within the list; list_out = DEVICE int32 [capacity][3];
  * rsq_out = DEVICE double[capacity] or NULL; count_out = DEVICE int64 (total found; if it exceeds
  * capacity only `capacity` entries were written -- call again with a bigger list).
+ * flags: 0 or MDP_PAIR_TRICLINIC (box = [nframes][6]) / MDP_PAIR_NO_CULL / MDP_PAIR_NO_SORT.
  */
 int mdp_pair_list(mdp_ctx *ctx, int nframes,
                   int64_t n_a, const double *xyz_a, int64_t n_b, const double *xyz_b,
                   const double *box, double rin2, double rout2, int shell_mode, int exclude_same_index,
-                  int32_t *list_out, double *rsq_out, int64_t capacity, int64_t *count_out, void *stream);
+                  int32_t *list_out, double *rsq_out, int64_t capacity, int64_t *count_out, int flags, void *stream);
 
 /* ---- segmented (per-molecule) reductions ------------------------------------------------------
  * calc_com (com_mols.py:5-62) / _define_mol_cols (rdf_cn.py:218-241): for each segment s (molecule;
@@ -151,9 +161,11 @@ int mdp_msd_single_origin(mdp_ctx *ctx, int nframes, int64_t n, const double *tr
  * out = DEVICE [4][n]. */
 int mdp_msd_interval(mdp_ctx *ctx, int nframes, int64_t n, const double *traj, double scale, int stride,
                      double *out, void *stream);
-/* Windowed MSD over all time origins (north-star extension, no reference implementation):
- * sums_out = DEVICE [max_lag][ngroups][4] accumulate: sum over atoms of the group and over all origins
- * t0 with t0+lag < nframes of the squared displacement; divide by count*(nframes-lag). */
+/* Windowed MSD over all time origins (north-star extension, no reference implementation; defined by
+ * oracle/oracle.c orc_msd_all_origins, 1e-10 relative):
+ * sums_out = DEVICE [max_lag][ngroups][4] accumulate: scale^2 * sum over atoms of the group and over all
+ * origins t0 with t0+lag < nframes of the squared displacement per axis, [3] = (x+y)+z; the caller divides
+ * by count*(nframes-lag).  fp64 with FMA, fixed summation order (run-to-run deterministic). */
 int mdp_msd_all_origins(mdp_ctx *ctx, int nframes, int64_t n, const double *traj, double scale,
                         const int64_t *group_off, int ngroups, int max_lag, double *sums_out, void *stream);
 

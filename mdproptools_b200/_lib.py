@@ -47,7 +47,7 @@ _PROTOS = {
     "mdp_hist_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p,
                                 c_void_p]),
     "mdp_pair_list": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, POINTER(c_double), c_double,
-                              c_double, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+                              c_double, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "mdp_segment_com": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "mdp_msd_single_origin": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_double, POINTER(c_int64), c_int,
@@ -69,6 +69,8 @@ _PROTOS = {
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+PAIR_NO_CULL, PAIR_NO_SORT, PAIR_TRICLINIC = 1, 2, 4   # flags of mdp_pair_hist / mdp_pair_list
 
 
 def lib() -> ctypes.CDLL:

@@ -231,8 +231,10 @@ int mdp_bitmask_autocorr(mdp_ctx *ctx, int64_t npairs, int nwords, int64_t T, co
     MDP_CUDA(cudaFuncSetAttribute((const void *)k_bitmask_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div<int64_t>(T, 256), (unsigned)ceil_div<int64_t>(npairs, BM_PAIRS));
     MDP_REQUIRE(grid.y <= 65535, "mdp_bitmask_autocorr: too many pairs per call (%lld); split the call", (long long)npairs);
+    cudaEvent_t tk = ctx->timer_begin(6, (cudaStream_t)stream);
     k_bitmask_autocorr<<<grid, 256, smem, (cudaStream_t)stream>>>((const unsigned long long *)masks, npairs, nwords, T,
                                                                   (unsigned long long *)cnt_out);
+    ctx->timer_end(tk, (cudaStream_t)stream);
     MDP_LAUNCHED(ctx);
     return mdp_check_launch("k_bitmask_autocorr");
 }

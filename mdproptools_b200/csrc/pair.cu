@@ -190,6 +190,150 @@ __device__ __forceinline__ bool chunk_test_f32(const float *a, const float *b, c
     return lb < rcut2_up;
 }
 
+// ---- general triclinic cells (MDP_PAIR_TRICLINIC) -----------------------------------------------------
+// Image convention (an extension -- the reference has no triclinic image; defined by oracle/oracle.c
+// pair_rsq_tri): sequential single shifts in the order z, y, x for the restricted triclinic cell a=(lx,0,0),
+// b=(xy,ly,0), c=(xz,yz,lz):  kz from dz; dy -= kz*yz, dx -= kz*xz;  ky from dy; dx -= ky*xy;  kx from dx.
+// The box tests enumerate the image vectors (kz, ky, kx) that some pair of the two boxes can take, with
+// every operation rounded outward, so (i) the lower bound on rsq can only be too small and (ii) a box pair
+// is called uniform only when a single image vector is possible for every pair in it.
+struct DirF64 {
+    typedef double T;
+    static __device__ __forceinline__ T sub_dn(T a, T b) { return __dsub_rd(a, b); }
+    static __device__ __forceinline__ T sub_up(T a, T b) { return __dsub_ru(a, b); }
+    static __device__ __forceinline__ T add_dn(T a, T b) { return __dadd_rd(a, b); }
+    static __device__ __forceinline__ T add_up(T a, T b) { return __dadd_ru(a, b); }
+    static __device__ __forceinline__ T mul_dn(T a, T b) { return __dmul_rd(a, b); }
+    static __device__ __forceinline__ T dn(double v) { return v; }
+    static __device__ __forceinline__ T up(double v) { return v; }
+    static __device__ __forceinline__ T big() { return DBL_MAX; }
+};
+struct DirF32 {
+    typedef float T;
+    static __device__ __forceinline__ T sub_dn(T a, T b) { return __fsub_rd(a, b); }
+    static __device__ __forceinline__ T sub_up(T a, T b) { return __fsub_ru(a, b); }
+    static __device__ __forceinline__ T add_dn(T a, T b) { return __fadd_rd(a, b); }
+    static __device__ __forceinline__ T add_up(T a, T b) { return __fadd_ru(a, b); }
+    static __device__ __forceinline__ T mul_dn(T a, T b) { return __fmul_rd(a, b); }
+    static __device__ __forceinline__ T dn(double v) { return __double2float_rd(v); }
+    static __device__ __forceinline__ T up(double v) { return __double2float_ru(v); }
+    static __device__ __forceinline__ T big() { return 3.0e38f; }
+};
+
+template <class D>
+struct TriConst {
+    typename D::T l_dn[3], l_up[3], h_dn[3], h_up[3];   // x, y, z lengths and half lengths
+    typename D::T c_dn[3], c_up[3];                     // xy, xz, yz
+    __device__ __forceinline__ void set(const double *cell)
+    {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            l_dn[a] = D::dn(cell[a]);
+            l_up[a] = D::up(cell[a]);
+            h_dn[a] = D::dn(cell[a] * 0.5);
+            h_up[a] = D::up(cell[a] * 0.5);
+            c_dn[a] = D::dn(cell[3 + a]);
+            c_up[a] = D::up(cell[3 + a]);
+        }
+    }
+};
+
+template <class T>
+__device__ __forceinline__ T iv_min_abs(T lo, T hi)
+{
+    return (lo <= (T)0 && hi >= (T)0) ? (T)0 : (fabs(lo) < fabs(hi) ? fabs(lo) : fabs(hi));
+}
+
+// part of [lo, hi] whose image index is k, after the shift by k*l: [ol, oh]; false when no d of the interval has index k
+template <class D>
+__device__ __forceinline__ bool tri_region(typename D::T lo, typename D::T hi, int k, typename D::T l_dn, typename D::T l_up,
+                                           typename D::T h_dn, typename D::T h_up, typename D::T &ol, typename D::T &oh)
+{
+    typedef typename D::T T;
+    if (k == 0) {
+        if (lo > h_up || hi < -h_up) return false;
+        ol = lo > -h_up ? lo : -h_up;
+        oh = hi < h_up ? hi : h_up;
+        return true;
+    }
+    if (k > 0) {
+        if (!(hi > h_dn)) return false;
+        const T c = lo > h_dn ? lo : h_dn;
+        ol = D::sub_dn(c, l_up);
+        oh = D::sub_up(hi, l_dn);
+        return true;
+    }
+    if (!(lo < -h_dn)) return false;
+    const T c = hi < -h_dn ? hi : -h_dn;
+    ol = D::add_dn(lo, l_dn);
+    oh = D::add_up(c, l_up);
+    return true;
+}
+
+// [lo, hi] -= k * c, c in [c_dn, c_up]
+template <class D>
+__device__ __forceinline__ void tri_shift(typename D::T &lo, typename D::T &hi, int k, typename D::T c_dn, typename D::T c_up)
+{
+    if (k > 0) {
+        lo = D::sub_dn(lo, c_up);
+        hi = D::sub_up(hi, c_dn);
+    } else if (k < 0) {
+        lo = D::add_dn(lo, c_dn);
+        hi = D::add_up(hi, c_up);
+    }
+}
+
+constexpr int TRI_MIXED = 0x3f;
+__device__ __forceinline__ int tri_enc(int k) { return k == 0 ? 0 : (k > 0 ? 1 : 2); }
+__device__ __forceinline__ double tri_dec(int c2, double v) { return c2 == 0 ? 0.0 : (c2 == 1 ? v : -v); }
+
+// a, b: boxes {lo[3], hi[3]} (supersets of the points).  Returns true when some pair may have rsq < rcut2_up;
+// code = enc(kx) | enc(ky) << 2 | enc(kz) << 4 when one image vector serves every pair, TRI_MIXED otherwise.
+template <class D>
+__device__ __forceinline__ bool tri_box_test(const typename D::T *a, const typename D::T *b, const TriConst<D> &C,
+                                             typename D::T rcut2_up, int &code)
+{
+    typedef typename D::T T;
+    code = 0;
+    if (a[0] > a[3] || b[0] > b[3]) return false;   // empty box (padding only)
+    const T x0lo = D::sub_dn(a[0], b[3]), x0hi = D::sub_up(a[3], b[0]);
+    const T y0lo = D::sub_dn(a[1], b[4]), y0hi = D::sub_up(a[4], b[1]);
+    const T z0lo = D::sub_dn(a[2], b[5]), z0hi = D::sub_up(a[5], b[2]);
+    T best = D::big();
+    int nfeas = 0;
+#pragma unroll 1
+    for (int kz = 1; kz >= -1; --kz) {
+        T zl, zh;
+        if (!tri_region<D>(z0lo, z0hi, kz, C.l_dn[2], C.l_up[2], C.h_dn[2], C.h_up[2], zl, zh)) continue;
+        const T bz = iv_min_abs(zl, zh);
+        const T bz2 = D::mul_dn(bz, bz);
+        T y1lo = y0lo, y1hi = y0hi, x1lo = x0lo, x1hi = x0hi;
+        tri_shift<D>(y1lo, y1hi, kz, C.c_dn[2], C.c_up[2]);   // yz
+        tri_shift<D>(x1lo, x1hi, kz, C.c_dn[1], C.c_up[1]);   // xz
+#pragma unroll 1
+        for (int ky = 1; ky >= -1; --ky) {
+            T yl, yh;
+            if (!tri_region<D>(y1lo, y1hi, ky, C.l_dn[1], C.l_up[1], C.h_dn[1], C.h_up[1], yl, yh)) continue;
+            const T by = iv_min_abs(yl, yh);
+            const T byz2 = D::add_dn(D::mul_dn(by, by), bz2);
+            T x2lo = x1lo, x2hi = x1hi;
+            tri_shift<D>(x2lo, x2hi, ky, C.c_dn[0], C.c_up[0]);   // xy
+#pragma unroll 1
+            for (int kx = 1; kx >= -1; --kx) {
+                T xl, xh;
+                if (!tri_region<D>(x2lo, x2hi, kx, C.l_dn[0], C.l_up[0], C.h_dn[0], C.h_up[0], xl, xh)) continue;
+                const T bx = iv_min_abs(xl, xh);
+                const T lb = D::add_dn(D::mul_dn(bx, bx), byz2);
+                best = lb < best ? lb : best;
+                ++nfeas;
+                code = tri_enc(kx) | (tri_enc(ky) << 2) | (tri_enc(kz) << 4);
+            }
+        }
+    }
+    if (nfeas != 1) code = TRI_MIXED;
+    return best < rcut2_up;
+}
+
 // ---------------------------------------------------------------------------------------------
 // preparation kernels
 // ---------------------------------------------------------------------------------------------
@@ -406,7 +550,7 @@ __global__ void __launch_bounds__(TS) k_aabb(const double2 *__restrict__ rec, in
 // one warp per (frame, ta) row: count (FILL=false) or emit (FILL=true) the tile pairs that may interact
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_items(const double *__restrict__ taabbA, const double *__restrict__ taabbB, int ntA,
-                                               int ntB, bool symm, bool nocull, const double *__restrict__ box,
+                                               int ntB, bool symm, bool nocull, bool tric, const double *__restrict__ box,
                                                double rcut2, int nframes, uint32_t *__restrict__ rowcnt,
                                                const uint32_t *__restrict__ rowoff, uint64_t *__restrict__ items)
 {
@@ -414,7 +558,9 @@ __global__ void __launch_bounds__(256) k_items(const double *__restrict__ taabbA
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= (int64_t)nframes * ntA) return;
     const int f = (int)(row / ntA), ta = (int)(row % ntA);
-    const double lx = box[f * 3 + 0], ly = box[f * 3 + 1], lz = box[f * 3 + 2];
+    const double lx = box[f * 6 + 0], ly = box[f * 6 + 1], lz = box[f * 6 + 2];
+    TriConst<DirF64> TC;
+    if (tric) TC.set(box + f * 6);
     double a[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) a[c] = taabbA[((int64_t)f * ntA + ta) * 6 + c];
@@ -428,7 +574,12 @@ __global__ void __launch_bounds__(256) k_items(const double *__restrict__ taabbA
 #pragma unroll
             for (int c = 0; c < 6; ++c) b[c] = taabbB[((int64_t)f * ntB + tb) * 6 + c];
             bool general;
-            ok = boxes_may_interact(a, b, lx, ly, lz, rcut2, general);
+            if (tric) {
+                int code;
+                ok = tri_box_test<DirF64>(a, b, TC, rcut2, code);
+            } else {
+                ok = boxes_may_interact(a, b, lx, ly, lz, rcut2, general);
+            }
             if (nocull) ok = !(a[0] > a[3] || b[0] > b[3]);
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -612,13 +763,23 @@ __device__ __forceinline__ void drain(const PairParams &p, const Shared &sh, int
 //   VAR_SHIFT  per axis d' = |d| - s, s = 0 or l          11 fp64 ops / pair (|d| - 0 is exact)
 //   VAR_MIXED  per axis d' = min(|d|, ||d| - l|)          14 fp64 ops / pair (see AX_MIXED)
 // In every variant only the square of d' is used and it equals the reference's (rdf_cn.py:50-56) bit for bit.
-enum { VAR_FAST = 0, VAR_SHIFT = 1, VAR_MIXED = 2 };
+//   VAR_TSHIFT triclinic, one image vector for the chunk    14 fp64 ops / pair (sequential shifts, oracle order)
+//   VAR_TMIXED triclinic, image vector decided per pair      14 fp64 ops + selects
+enum { VAR_FAST = 0, VAR_SHIFT = 1, VAR_MIXED = 2, VAR_TSHIFT = 3, VAR_TMIXED = 4 };
+
+// shifts of one chunk pair.  Orthogonal variants use x, y, z only (0 or l).  VAR_TSHIFT: x = kx*lx, y = ky*ly,
+// z = kz*lz, xy = ky*xy, xz = kz*xz, yz = kz*yz.  VAR_TMIXED: the cell itself (lx, ly, lz, xy, xz, yz).
+struct Shift {
+    double x, y, z, xy, xz, yz;
+};
 
 template <int MODE, bool MULTICLS, int VAR, bool TRI>
 __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh, const double2 *__restrict__ jb, double xi,
-                                           double yi, double zi, uint32_t mi, double sx, double sy, double sz, int rc_hi,
+                                           double yi, double zi, uint32_t mi, const Shift S, int rc_hi,
                                            int lane, int &qn, double *qr, uint2 *qm, int frame)
 {
+    const double sx = S.x, sy = S.y, sz = S.z;
+    const double hx = S.x * 0.5, hy = S.y * 0.5, hz = S.z * 0.5;   // VAR_TMIXED only
     constexpr bool META = MULTICLS || MODE == MODE_LIST;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
@@ -641,6 +802,20 @@ __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh
                 ax = fmin(fabs(ax), fabs(__dsub_rn(fabs(ax), sx)));
                 ay = fmin(fabs(ay), fabs(__dsub_rn(fabs(ay), sy)));
                 az = fmin(fabs(az), fabs(__dsub_rn(fabs(az), sz)));
+            } else if (VAR == VAR_TSHIFT) {
+                az = __dsub_rn(az, sz);
+                ay = __dsub_rn(__dsub_rn(ay, S.yz), sy);
+                ax = __dsub_rn(__dsub_rn(__dsub_rn(ax, S.xz), S.xy), sx);
+            } else if (VAR == VAR_TMIXED) {
+                const bool pz = az > hz, nz = az < -hz;
+                az = __dsub_rn(az, pz ? sz : (nz ? -sz : 0.0));
+                ay = __dsub_rn(ay, pz ? S.yz : (nz ? -S.yz : 0.0));
+                ax = __dsub_rn(ax, pz ? S.xz : (nz ? -S.xz : 0.0));
+                const bool py = ay > hy, ny = ay < -hy;
+                ay = __dsub_rn(ay, py ? sy : (ny ? -sy : 0.0));
+                ax = __dsub_rn(ax, py ? S.xy : (ny ? -S.xy : 0.0));
+                const bool px = ax > hx, nx = ax < -hx;
+                ax = __dsub_rn(ax, px ? sx : (nx ? -sx : 0.0));
             }
             r2[u] = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
             hit[u] = __double2hiint(r2[u]) <= rc_hi;   // superset of rsq < rcut2; settled exactly in drain()
@@ -672,7 +847,7 @@ __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh
     }
 }
 
-template <int MODE, bool MULTICLS, bool SYMM>
+template <int MODE, bool MULTICLS, bool SYMM, bool TRICL>
 __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -724,7 +899,7 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
         const unsigned int ibeg = p.rowoff[(int64_t)f * p.ntA];
         const unsigned int iend = f + 1 < F ? p.rowoff[(int64_t)(f + 1) * p.ntA] : (unsigned int)total;
         const unsigned int nwi = (iend - ibeg) * GPT;   // warp items of this frame
-        const double lx = p.box[f * 3 + 0], ly = p.box[f * 3 + 1], lz = p.box[f * 3 + 2];
+        const double lx = p.box[f * 6 + 0], ly = p.box[f * 6 + 1], lz = p.box[f * 6 + 2];
         const AxisF AX = make_axis(lx), AY = make_axis(ly), AZ = make_axis(lz);
         const int frame = p.frame0 + f;
         const double2 *rA = p.recA + (int64_t)f * p.npadA * 2;
@@ -756,10 +931,16 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
                     const float4 *gb4 = p.gboxB + ((int64_t)f * p.ngB + (int64_t)tb * GPT + lane) * 2;
                     const float4 blo = gb4[0], bhi = gb4[1];
                     const float gb[6] = {blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z};
-                    need = chunk_test_f32(ga, gb, AX, AY, AZ, rcut2_up, code);
+                    if (TRICL) {
+                        TriConst<DirF32> TC;
+                        TC.set(p.box + f * 6);
+                        need = tri_box_test<DirF32>(ga, gb, TC, rcut2_up, code);
+                    } else {
+                        need = chunk_test_f32(ga, gb, AX, AY, AZ, rcut2_up, code);
+                    }
                     if (p.nocull) {
                         need = !(ga[0] > ga[3] || gb[0] > gb[3]);
-                        code = AX_MIXED | (AX_MIXED << 2) | (AX_MIXED << 4);
+                        code = TRICL ? TRI_MIXED : (AX_MIXED | (AX_MIXED << 2) | (AX_MIXED << 4));
                     }
                 }
             }
@@ -795,26 +976,56 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
                 const int cc = __shfl_sync(0xffffffffu, code, c);
                 const bool tri = diag && c == wi;
                 ++my_chunks;
-                const bool mixed = ((cc | (cc >> 2) | (cc >> 4)) & AX_MIXED) != 0;
-                if (cc == 0) {
-                    if (tri)
-                        chunk_loop<MODE, MULTICLS, VAR_FAST, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, 0.0, 0.0, 0.0, rc_hi, lane,
-                                                                   qn, qr, qm, frame);
-                    else
-                        chunk_loop<MODE, MULTICLS, VAR_FAST, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, 0.0, 0.0, 0.0, rc_hi, lane,
-                                                                    qn, qr, qm, frame);
-                } else if (!mixed && !tri) {
-                    chunk_loop<MODE, MULTICLS, VAR_SHIFT, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, (cc & 1) ? lx : 0.0,
-                                                                 (cc & 4) ? ly : 0.0, (cc & 16) ? lz : 0.0, rc_hi, lane, qn, qr,
-                                                                 qm, frame);
+                if (TRICL) {
+                    const Shift Z0 = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                    if (cc == 0) {
+                        if (tri)
+                            chunk_loop<MODE, MULTICLS, VAR_FAST, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, Z0, rc_hi, lane, qn, qr, qm,
+                                                                       frame);
+                        else
+                            chunk_loop<MODE, MULTICLS, VAR_FAST, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, Z0, rc_hi, lane, qn, qr,
+                                                                        qm, frame);
+                    } else if (cc != TRI_MIXED && !tri) {
+                        const double *cell = p.box + f * 6;
+                        const int kx = cc & 3, ky = (cc >> 2) & 3, kz = (cc >> 4) & 3;
+                        const Shift S = {tri_dec(kx, lx), tri_dec(ky, ly), tri_dec(kz, lz), tri_dec(ky, cell[3]),
+                                         tri_dec(kz, cell[4]), tri_dec(kz, cell[5])};
+                        chunk_loop<MODE, MULTICLS, VAR_TSHIFT, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr, qm,
+                                                                      frame);
+                    } else {
+                        const double *cell = p.box + f * 6;
+                        const Shift S = {lx, ly, lz, cell[3], cell[4], cell[5]};
+                        if (tri)
+                            chunk_loop<MODE, MULTICLS, VAR_TMIXED, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr,
+                                                                         qm, frame);
+                        else
+                            chunk_loop<MODE, MULTICLS, VAR_TMIXED, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr,
+                                                                          qm, frame);
+                    }
                 } else {
-                    // undecided axes (small boxes, huge groups) and the rare wrapped diagonal chunk: exact for every d
-                    if (tri)
-                        chunk_loop<MODE, MULTICLS, VAR_MIXED, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, lx, ly, lz, rc_hi, lane, qn,
-                                                                    qr, qm, frame);
-                    else
-                        chunk_loop<MODE, MULTICLS, VAR_MIXED, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, lx, ly, lz, rc_hi, lane,
-                                                                     qn, qr, qm, frame);
+                    const bool mixed = ((cc | (cc >> 2) | (cc >> 4)) & AX_MIXED) != 0;
+                    const Shift Z0 = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                    if (cc == 0) {
+                        if (tri)
+                            chunk_loop<MODE, MULTICLS, VAR_FAST, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, Z0, rc_hi, lane, qn, qr, qm,
+                                                                       frame);
+                        else
+                            chunk_loop<MODE, MULTICLS, VAR_FAST, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, Z0, rc_hi, lane, qn, qr,
+                                                                        qm, frame);
+                    } else if (!mixed && !tri) {
+                        const Shift S = {(cc & 1) ? lx : 0.0, (cc & 4) ? ly : 0.0, (cc & 16) ? lz : 0.0, 0.0, 0.0, 0.0};
+                        chunk_loop<MODE, MULTICLS, VAR_SHIFT, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr, qm,
+                                                                     frame);
+                    } else {
+                        // undecided axes (small boxes, huge groups) and the rare wrapped diagonal chunk: exact for every d
+                        const Shift S = {lx, ly, lz, 0.0, 0.0, 0.0};
+                        if (tri)
+                            chunk_loop<MODE, MULTICLS, VAR_MIXED, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr, qm,
+                                                                        frame);
+                        else
+                            chunk_loop<MODE, MULTICLS, VAR_MIXED, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr,
+                                                                         qm, frame);
+                    }
                 }
                 __syncwarp();   // everyone is done with this stage before it is refilled
                 buf ^= 1;
@@ -950,11 +1161,16 @@ static int sort_set(mdp_ctx *ctx, SetPlan &s, int F, const double *xyz, const in
 
 typedef void (*pair_kernel_t)(const PairParams);
 
-template <int MODE>
-static pair_kernel_t pick_kernel(bool multicls, bool symm)
+template <int MODE, bool TRICL>
+static pair_kernel_t pick_kernel2(bool multicls, bool symm)
 {
-    if (multicls) return symm ? k_pair<MODE, true, true> : k_pair<MODE, true, false>;
-    return symm ? k_pair<MODE, false, true> : k_pair<MODE, false, false>;
+    if (multicls) return symm ? k_pair<MODE, true, true, TRICL> : k_pair<MODE, true, false, TRICL>;
+    return symm ? k_pair<MODE, false, true, TRICL> : k_pair<MODE, false, false, TRICL>;
+}
+template <int MODE>
+static pair_kernel_t pick_kernel(bool multicls, bool symm, bool tric)
+{
+    return tric ? pick_kernel2<MODE, true>(multicls, symm) : pick_kernel2<MODE, false>(multicls, symm);
 }
 
 struct PairCall {
@@ -987,6 +1203,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
     const bool symm = c.xyz_b == nullptr;
     const bool nosort = (c.flags & MDP_PAIR_NO_SORT) != 0;
     const bool nocull = (c.flags & MDP_PAIR_NO_CULL) != 0;
+    const bool tric = (c.flags & MDP_PAIR_TRICLINIC) != 0;
     const bool hist_mode = c.mode != MODE_LIST;
     const int nclsB = symm ? c.ncls_a : c.ncls_b;
     const int nrows = symm ? c.ncls_a * (c.ncls_a + 1) / 2 : c.ncls_a * c.ncls_b;
@@ -1028,7 +1245,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
     int Fsub = (int)std::max<size_t>(1, std::min<size_t>((size_t)c.nframes, (target - std::min(target, fixed)) / per_frame));
     Fsub = std::min(Fsub, 1 << 19);
     MDP_REQUIRE((size_t)Fsub * items_worst < ((size_t)1 << 32), "pair: work list too long");
-    int rc = ctx->arena_reserve(fixed + (size_t)Fsub * per_frame + (size_t)Fsub * 24 + 65536);
+    int rc = ctx->arena_reserve(fixed + (size_t)Fsub * per_frame + (size_t)Fsub * 48 + 65536);
     if (rc) return rc;
 
     // edge pairs / class-pair table (host side staging)
@@ -1054,9 +1271,9 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         }
     }
 
-    pair_kernel_t kern = c.mode == MODE_HIST_UNIFORM ? pick_kernel<MODE_HIST_UNIFORM>(multicls, symm)
-                         : c.mode == MODE_HIST_TABLE ? pick_kernel<MODE_HIST_TABLE>(multicls, symm)
-                                                     : pick_kernel<MODE_LIST>(false, symm);
+    pair_kernel_t kern = c.mode == MODE_HIST_UNIFORM ? pick_kernel<MODE_HIST_UNIFORM>(multicls, symm, tric)
+                         : c.mode == MODE_HIST_TABLE ? pick_kernel<MODE_HIST_TABLE>(multicls, symm, tric)
+                                                     : pick_kernel<MODE_LIST>(false, symm, tric);
     MDP_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     MDP_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), st));
@@ -1066,7 +1283,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         ctx->arena_reset();
         double2 *d_e2 = (double2 *)ctx->arena_take((size_t)(c.nbins + 2) * sizeof(double2));
         int *d_cpt = (int *)ctx->arena_take(MAX_CLS * MAX_CLS * 4);
-        double *d_box = (double *)ctx->arena_take((size_t)F * 24);
+        double *d_box = (double *)ctx->arena_take((size_t)F * 48);
         unsigned long long *d_total = (unsigned long long *)ctx->arena_take(16);
         unsigned int *d_counter = (unsigned int *)(d_total + 1);
         unsigned int *d_fcount = (unsigned int *)ctx->arena_take((size_t)F * 4);
@@ -1087,7 +1304,14 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
             MDP_CUDA(cudaMemcpyAsync(d_e2, e2.data(), e2.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
             MDP_CUDA(cudaMemcpyAsync(d_cpt, cpt.data(), cpt.size() * 4, cudaMemcpyHostToDevice, st));
         }
-        MDP_CUDA(cudaMemcpyAsync(d_box, c.box + (size_t)f0 * 3, (size_t)F * 24, cudaMemcpyHostToDevice, st));
+        // device cell rows are always {lx, ly, lz, xy, xz, yz} (pageable source: the copy is staged before it returns)
+        {
+            const int bs = tric ? 6 : 3;
+            std::vector<double> hb((size_t)F * 6, 0.0);
+            for (int f = 0; f < F; ++f)
+                for (int k = 0; k < bs; ++k) hb[(size_t)f * 6 + k] = c.box[(size_t)(f0 + f) * bs + k];
+            MDP_CUDA(cudaMemcpyAsync(d_box, hb.data(), (size_t)F * 48, cudaMemcpyHostToDevice, st));
+        }
 
         cudaEvent_t tp = ctx->timer_begin(1, st);
         rc = sort_set(ctx, A, F, c.xyz_a + (size_t)f0 * 3 * c.n_a, c.cls_a ? c.cls_a + (size_t)f0 * c.cls_stride_a : nullptr,
@@ -1101,13 +1325,13 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         const SetPlan &Bs = symm ? A : B;
         const int64_t nrows_items = (int64_t)F * A.ntiles;
         const unsigned gi = (unsigned)ceil_div<int64_t>(nrows_items * 32, 256);
-        k_items<false><<<gi, 256, 0, st>>>(A.taabb, Bs.taabb, A.ntiles, Bs.ntiles, symm, nocull, d_box, c.rcut2, F, rowcnt,
+        k_items<false><<<gi, 256, 0, st>>>(A.taabb, Bs.taabb, A.ntiles, Bs.ntiles, symm, nocull, tric, d_box, c.rcut2, F, rowcnt,
                                            rowoff, items);
         MDP_LAUNCHED(ctx);
         k_row_scan<<<1, 1024, 0, st>>>(rowcnt, rowoff, nrows_items, d_total, d_counter, ctx->d_stats,
                                        (unsigned long long)F * (unsigned long long)items_worst);
         MDP_LAUNCHED(ctx);
-        k_items<true><<<gi, 256, 0, st>>>(A.taabb, Bs.taabb, A.ntiles, Bs.ntiles, symm, nocull, d_box, c.rcut2, F, rowcnt,
+        k_items<true><<<gi, 256, 0, st>>>(A.taabb, Bs.taabb, A.ntiles, Bs.ntiles, symm, nocull, tric, d_box, c.rcut2, F, rowcnt,
                                           rowoff, items);
         MDP_LAUNCHED(ctx);
         ctx->timer_end(tp, st);
@@ -1235,7 +1459,7 @@ int mdp_pair_hist(mdp_ctx *ctx, int nframes, int64_t n_a, const double *xyz_a, c
 
 int mdp_pair_list(mdp_ctx *ctx, int nframes, int64_t n_a, const double *xyz_a, int64_t n_b, const double *xyz_b,
                   const double *box, double rin2, double rout2, int shell_mode, int exclude_same_index, int32_t *list_out,
-                  double *rsq_out, int64_t capacity, int64_t *count_out, void *stream)
+                  double *rsq_out, int64_t capacity, int64_t *count_out, int flags, void *stream)
 {
     MDP_REQUIRE(ctx && xyz_a && xyz_b && box && list_out && count_out, "mdp_pair_list: NULL argument");
     MDP_REQUIRE(nframes > 0 && n_a > 0 && n_b > 0 && capacity > 0, "mdp_pair_list: sizes must be positive");
@@ -1259,6 +1483,7 @@ int mdp_pair_list(mdp_ctx *ctx, int nframes, int64_t n_a, const double *xyz_a, i
     c.list_rsq = rsq_out;
     c.capacity = capacity;
     c.list_count = count_out;
+    c.flags = flags;
     return run_pair_call(ctx, c, (cudaStream_t)stream);
 }
 

@@ -7,6 +7,8 @@
 // fixed order (two-stage, no floating-point atomics) so results are run-to-run deterministic.
 #include <float.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -168,43 +170,150 @@ __global__ void __launch_bounds__(RB) k_msd_interval(const double *__restrict__ 
     out[3 * n + i] = sm / d0;
 }
 
-// ---- MSD over all time origins (v1: one thread per (atom, lag), coalesced over atoms) ----------
-__global__ void __launch_bounds__(RB) k_msd_all_origins(const double *__restrict__ traj, int nframes, int64_t n, int64_t a0,
-                                                        int64_t a1, double scale, int max_lag, double *__restrict__ partial,
-                                                        int nchunks)
+// ---- MSD over all time origins (windowed) ---------------------------------------------------------
+// out[lag] = sum_atoms sum_{t0, t0+lag < T} (x(t0+lag) - x(t0))^2 per axis.  FP64-pipe bound for any window longer
+// than ~12 lags (2 pipe slots -- DADD + DFMA -- per (atom, axis, origin, lag) against 24 B per atom-frame).
+// Tiling: lane = atom (32 consecutive atoms, rows of 256 B are read coalesced), warp = 16 consecutive lags held
+// as 16 register accumulators + a 16-deep register window that slides along t0, so one step costs 2 shared-memory
+// loads for 32 FP64 instructions.  A CTA (8 warps = 128 lags per pass) stages MW_TT origins and the MW_TT+128 rows
+// they pair with in shared memory with cp.async (zero fill beyond the trajectory / the atom range), walks the lag
+// blocks of the launch for every time tile (the rows come from L2 after the first touch, HBM is streamed once),
+// and keeps the per-lag sums of its atoms in shared memory; CTAs are persistent over (atom block, time chunk)
+// items in a fixed order and write one partial row each, which a second kernel adds up in a fixed order
+// (deterministic, no floating-point atomics).
+constexpr int MW_LB = 16;                    // lags per thread
+constexpr int MW_WARPS = 8;
+constexpr int MW_LBW = MW_LB * MW_WARPS;     // 128 lags per pass
+constexpr int MW_TT = 96;                    // origins per time tile (multiple of MW_LB)
+constexpr int MW_BROWS = MW_TT + MW_LBW;     // rows of the partner tile
+constexpr int MW_WCAP = 1024;                // lags per launch (per-CTA accumulator 3 x 1024 doubles)
+
+__device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gmem_src, bool valid)
 {
-    __shared__ double sm[32];
-    const int lag = blockIdx.y;
-    const int64_t i = a0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double s[3] = {0, 0, 0};
-    if (i < a1) {
-        for (int t0 = 0; t0 + lag < nframes; ++t0) {
-            const double *p0 = traj + (int64_t)t0 * 3 * n, *p1 = traj + (int64_t)(t0 + lag) * 3 * n;
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void mw_tile(const double *__restrict__ A, const double *__restrict__ B, int lane, int l0, int steps,
+                                        int64_t npair0, double (&acc)[MW_LB])
+{
+    // B row r holds x(ta + lagbase + r); the pair (origin s, lag l0+k) reads B[s + l0 + k].
+    // EDGE: origin s is valid for s < steps, partner valid while s + l0 + k < npair0 (= T - ta - lagbase).
+    double win[MW_LB];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const double d = __dsub_rn(__dmul_rn(p1[c * n + i], scale), __dmul_rn(p0[c * n + i], scale));
-                s[c] = __dadd_rn(s[c], __dmul_rn(d, d));
+    for (int k = 0; k < MW_LB - 1; ++k) win[k] = B[(l0 + k) * 32 + lane];
+#pragma unroll 1
+    for (int s = 0; s < MW_TT; s += MW_LB) {
+        if (EDGE && s >= steps) break;
+#pragma unroll
+        for (int u = 0; u < MW_LB; ++u) {
+            win[(u + MW_LB - 1) % MW_LB] = B[(s + u + l0 + MW_LB - 1) * 32 + lane];
+            const double a = A[(s + u) * 32 + lane];
+            if (EDGE) {
+                const int64_t kmax = (s + u < steps) ? npair0 - (s + u) - l0 : 0;
+#pragma unroll
+                for (int k = 0; k < MW_LB; ++k) {
+                    const double d = win[(u + k) % MW_LB] - a;
+                    if (k < kmax) acc[k] = fma(d, d, acc[k]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < MW_LB; ++k) {
+                    const double d = win[(u + k) % MW_LB] - a;
+                    acc[k] = fma(d, d, acc[k]);
+                }
             }
         }
     }
-    const double rx = block_sum(s[0], sm), ry = block_sum(s[1], sm), rz = block_sum(s[2], sm);
-    if (threadIdx.x == 0) {
-        double *o = partial + ((int64_t)lag * nchunks + blockIdx.x) * 4;
-        o[0] = rx; o[1] = ry; o[2] = rz; o[3] = __dadd_rn(__dadd_rn(rx, ry), rz);
+}
+
+// grid = persistent CTAs; items = nblk atom blocks x ntc time chunks
+__global__ void __launch_bounds__(MW_WARPS * 32, 2) k_msd_window(const double *__restrict__ traj, int T, int64_t n, int64_t a0,
+                                                                 int64_t a1, int lag0, int nl, int nblk, int ntc, int tc_len,
+                                                                 double *__restrict__ partial)
+{
+    extern __shared__ __align__(16) double mw_smem[];
+    double *A = mw_smem;                          // [MW_TT][32]
+    double *B = A + MW_TT * 32;                   // [MW_BROWS][32]
+    double *accs = B + MW_BROWS * 32;             // [3][nlp]
+    const int nlp = (nl + MW_LBW - 1) / MW_LBW * MW_LBW;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int l0 = w * MW_LB;
+    for (int k = tid; k < 3 * nlp; k += blockDim.x) accs[k] = 0.0;
+
+    const int nitems = nblk * ntc;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int blk = item / ntc, tc = item % ntc;
+        const int64_t atom0 = a0 + (int64_t)blk * 32;
+        const int tbeg = tc * tc_len;
+        const int tend = tbeg + tc_len < T ? tbeg + tc_len : T;
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+            const double *xc = traj + (int64_t)c * n + atom0;     // row t of this axis: xc + t*3n
+#pragma unroll 1
+            for (int lb0 = 0; lb0 < nlp; lb0 += MW_LBW) {
+                const int lagbase = lag0 + lb0;
+                double acc[MW_LB];
+#pragma unroll
+                for (int k = 0; k < MW_LB; ++k) acc[k] = 0.0;
+#pragma unroll 1
+                for (int ta = tbeg; ta < tend; ta += MW_TT) {
+                    if (ta + lagbase >= T) break;                 // no partner inside the trajectory
+                    __syncthreads();                              // previous tile fully consumed
+                    for (int i = tid; i < (MW_TT + MW_BROWS) * 32; i += blockDim.x) {
+                        const int r = i >> 5, l = i & 31;
+                        const int t = r < MW_TT ? ta + r : ta + lagbase + (r - MW_TT);
+                        const bool ok = t < T && atom0 + l < a1;
+                        cp_async8_zfill(&A[i], xc + (int64_t)(ok ? t : 0) * 3 * n + (ok ? l : 0), ok);
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncthreads();
+                    const int steps = tend - ta < MW_TT ? tend - ta : MW_TT;
+                    const int64_t npair0 = (int64_t)T - ta - lagbase;     // partner row r is inside the trajectory iff r < npair0
+                    const bool edge = steps < MW_TT || npair0 < MW_TT + MW_LBW - 1;
+                    if (edge)
+                        mw_tile<true>(A, B, lane, l0, steps, npair0, acc);
+                    else
+                        mw_tile<false>(A, B, lane, l0, steps, npair0, acc);
+                }
+                // sum over the 32 atoms of the block (fixed shuffle tree), then into this CTA's per-lag sums
+#pragma unroll
+                for (int k = 0; k < MW_LB; ++k) {
+                    double v = acc[k];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == k) accs[c * nlp + lb0 + l0 + k] += v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < 3 * nl; k += blockDim.x) {
+        const int c = k / nl, l = k % nl;
+        partial[((int64_t)blockIdx.x * 3 + c) * nl + l] = accs[c * nlp + l];
     }
 }
 
-__global__ void __launch_bounds__(128) k_partial_accumulate(const double *__restrict__ partial, int nchunks, int ncomp,
-                                                            double *__restrict__ out, int64_t out_stride_f)
+// out[lag0 + l][g][0..3] += scale^2 * sum over CTAs (fixed order); one thread per lag
+__global__ void __launch_bounds__(128) k_msd_window_finish(const double *__restrict__ partial, int nctas, int nl, int lag0,
+                                                           double scale2, double *__restrict__ out, int64_t out_stride)
 {
-    const int f = blockIdx.x;
-    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (c >= ncomp) return;
-    double s = 0.0;
-    for (int k = lane; k < nchunks; k += 32) s = __dadd_rn(s, partial[((int64_t)f * nchunks + k) * ncomp + c]);
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nl) return;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int b = 0; b < nctas; ++b)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
-    if (lane == 0) out[(int64_t)f * out_stride_f + c] += s;
+        for (int c = 0; c < 3; ++c) s[c] += partial[((int64_t)b * 3 + c) * nl + l];
+    double *o = out + (int64_t)(lag0 + l) * out_stride;
+    const double x = s[0] * scale2, y = s[1] * scale2, z = s[2] * scale2;
+    o[0] += x;
+    o[1] += y;
+    o[2] += z;
+    o[3] += (x + y) + z;
 }
 
 // ---- per-molecule mass-weighted mean (calc_com / _define_mol_cols) ---------------------------------
@@ -370,27 +479,45 @@ int mdp_msd_all_origins(mdp_ctx *ctx, int nframes, int64_t n, const double *traj
                         int ngroups, int max_lag, double *sums_out, void *stream)
 {
     MDP_REQUIRE(ctx && traj && sums_out, "mdp_msd_all_origins: NULL argument");
-    MDP_REQUIRE(nframes > 0 && n > 0 && ngroups >= 1 && max_lag > 0 && max_lag <= nframes && max_lag <= 65535,
+    MDP_REQUIRE(nframes > 0 && n > 0 && ngroups >= 1 && max_lag > 0 && max_lag <= nframes,
                 "mdp_msd_all_origins: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     MDP_CUDA(cudaSetDevice(ctx->device));
-    const int max_chunks = (int)ceil_div<int64_t>(n, RB) + 1;
-    int rc = ctx->arena_reserve((size_t)max_lag * max_chunks * 32 + 4096);
+    const int nctas_max = ctx->sm_count * 2;
+    int rc = ctx->arena_reserve((size_t)nctas_max * 3 * MW_WCAP * 8 + 4096);
     if (rc) return rc;
     ctx->arena_reset();
-    double *partial = (double *)ctx->arena_take((size_t)max_lag * max_chunks * 32);
+    double *partial = (double *)ctx->arena_take((size_t)nctas_max * 3 * MW_WCAP * 8);
+    MDP_REQUIRE(partial != nullptr, "mdp_msd_all_origins: scratch arena exhausted");
+    const size_t smem = (size_t)(MW_TT + MW_BROWS) * 32 * 8 + (size_t)3 * MW_WCAP * 8;
+    MDP_CUDA(cudaFuncSetAttribute((const void *)k_msd_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int g = 0; g < ngroups; ++g) {
         const int64_t a0 = group_off ? group_off[g] : 0, a1 = group_off ? group_off[g + 1] : n;
         MDP_REQUIRE(a0 >= 0 && a1 >= a0 && a1 <= n, "mdp_msd_all_origins: bad group range");
         if (a1 == a0) continue;
-        const int nchunks = (int)ceil_div<int64_t>(a1 - a0, RB);
-        dim3 grid(nchunks, max_lag);
-        k_msd_all_origins<<<grid, RB, 0, st>>>(traj, nframes, n, a0, a1, scale, max_lag, partial, nchunks);
-        MDP_LAUNCHED(ctx);
-        k_partial_accumulate<<<max_lag, 128, 0, st>>>(partial, nchunks, 4, sums_out + g * 4, (int64_t)ngroups * 4);
-        MDP_LAUNCHED(ctx);
+        const int64_t nblk64 = ceil_div<int64_t>(a1 - a0, 32);
+        MDP_REQUIRE(nblk64 < (1 << 26), "mdp_msd_all_origins: too many atoms in one group");
+        const int nblk = (int)nblk64;
+        // few atom blocks (molecule centres of mass): split the origins into chunks so that every SM has work
+        int ntc = 1;
+        const int tiles = (int)ceil_div<int64_t>(nframes, MW_TT);
+        while ((int64_t)nblk * ntc < 4LL * nctas_max && ntc < tiles) ntc *= 2;
+        if (ntc > tiles) ntc = tiles;
+        const int tc_len = (int)ceil_div<int64_t>(tiles, ntc) * MW_TT;
+        ntc = (int)ceil_div<int64_t>(nframes, tc_len);
+        const int nctas = (int)std::min<int64_t>(nctas_max, (int64_t)nblk * ntc);
+        for (int lag0 = 0; lag0 < max_lag; lag0 += MW_WCAP) {
+            const int nl = std::min(MW_WCAP, max_lag - lag0);
+            cudaEvent_t tk = ctx->timer_begin(5, st);
+            k_msd_window<<<nctas, MW_WARPS * 32, smem, st>>>(traj, nframes, n, a0, a1, lag0, nl, nblk, ntc, tc_len, partial);
+            ctx->timer_end(tk, st);
+            MDP_LAUNCHED(ctx);
+            k_msd_window_finish<<<(unsigned)ceil_div<int>(nl, 128), 128, 0, st>>>(partial, nctas, nl, lag0, scale * scale,
+                                                                                sums_out + g * 4, (int64_t)ngroups * 4);
+            MDP_LAUNCHED(ctx);
+        }
     }
-    return mdp_check_launch("k_msd_all_origins");
+    return mdp_check_launch("k_msd_window");
 }
 
 int mdp_segment_com(mdp_ctx *ctx, int nframes, int ncomp, int64_t n, const double *attr, const double *w, int64_t nseg,

@@ -45,16 +45,26 @@ def sym_row(ci: int, cj: int, ncls: int) -> int:
     return a * ncls - a * (a - 1) // 2 + (b - a)
 
 
+def _host_box(box, F, flags):
+    """[F,3] box lengths, or [F,6] = (lx, ly, lz, xy, xz, yz) when the triclinic image is requested."""
+    box = np.asarray(box, dtype=np.float64)
+    w = 6 if flags & _lib.PAIR_TRICLINIC else 3
+    if box.size != F * w:
+        raise ValueError(f"box must hold {w} values per frame ({F} frames), got shape {box.shape}")
+    return np.ascontiguousarray(box.reshape(F, w))
+
+
 def pair_hist(xyz_a, cls_a, ncls_a, box, rcut2, edges, uniform_ddr, xyz_b=None, cls_b=None, ncls_b=1, out=None,
               flags=0):
-    """mdp_pair_hist.  xyz_* float64 [F,3,N]; cls_* int32 [N] or [F,N] or None; box array-like [F,3] (host).
+    """mdp_pair_hist.  xyz_* float64 [F,3,N]; cls_* int32 [N] or [F,N] or None; box array-like [F,3] (host), or
+    [F,6] = (lx, ly, lz, xy, xz, yz) with ``flags & PAIR_TRICLINIC``.
 
     Returns uint64 counts as an int64 tensor [F, rows, nbins] (accumulated into ``out`` when given).
     """
     xyz_a = _f64(xyz_a, "xyz_a")
     F, _, na = xyz_a.shape
     ctx = Context.get(xyz_a.device.index)
-    box = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(F, 3))
+    box = _host_box(box, F, flags)
     edges = np.ascontiguousarray(edges, dtype=np.float64)
     nbins = edges.shape[0] - 1
     symm = xyz_b is None
@@ -89,14 +99,15 @@ def hist_reduce(hist, weights, cumulative=False):
     return out
 
 
-def pair_list(xyz_a, xyz_b, box, r_in2, r_out2, shell_mode, exclude_same_index=False, capacity=None, want_rsq=False):
+def pair_list(xyz_a, xyz_b, box, r_in2, r_out2, shell_mode, exclude_same_index=False, capacity=None, want_rsq=False,
+              flags=0):
     """mdp_pair_list -> (list int32 [M,3] = (frame, ia, ib), rsq float64 [M] or None); grows capacity as needed."""
     xyz_a = _f64(xyz_a, "xyz_a")
     xyz_b = _f64(xyz_b, "xyz_b")
     F, _, na = xyz_a.shape
     nb_ = xyz_b.shape[2]
     ctx = Context.get(xyz_a.device.index)
-    box = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(F, 3))
+    box = _host_box(box, F, flags)
     cap = int(capacity or max(1 << 16, 64 * na * F))
     while True:
         lst = torch.empty((cap, 3), dtype=torch.int32, device=xyz_a.device)
@@ -104,7 +115,7 @@ def pair_list(xyz_a, xyz_b, box, r_in2, r_out2, shell_mode, exclude_same_index=F
         cnt = torch.zeros((1,), dtype=torch.int64, device=xyz_a.device)
         check(lib().mdp_pair_list(ctx.handle, F, na, ptr(xyz_a), nb_, ptr(xyz_b), _lib.dptr(box), float(r_in2),
                                   float(r_out2), int(shell_mode), 1 if exclude_same_index else 0, ptr(lst), ptr(rsq),
-                                  cap, ptr(cnt), stream_ptr()), "mdp_pair_list")
+                                  cap, ptr(cnt), int(flags), stream_ptr()), "mdp_pair_list")
         m = int(cnt.item())
         if m <= cap:
             return lst[:m], (rsq[:m] if want_rsq else None)

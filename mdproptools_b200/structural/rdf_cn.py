@@ -16,6 +16,12 @@ Division of labour
 Frames are sharded round-robin over the ranks of an initialised torch.distributed group; the per-frame
 integer histograms are merged with one int64 all-reduce.
 
+Extension (keyword ``mic``, default "reference"): the reference has no triclinic minimum image -- it wraps tilted
+cells as if they were orthogonal with the lattice-vector lengths and takes volume = prod(lengths) (:260-261).
+``mic="reference"`` reproduces exactly that; ``mic="triclinic"`` uses the general triclinic image of
+MDP_PAIR_TRICLINIC (include/mdprop_b200.h) with the cell (lx, ly, lz, xy, xz, yz) from the dump header and the true
+cell volume lx*ly*lz.  For orthogonal boxes the two are identical bit for bit.
+
 Documented divergences from the reference:
   * a bin index >= num_bins (possible when r_cut/bin_size is not an integer) is dropped instead of
     written out of bounds (the reference corrupts memory, SURVEY 5);
@@ -29,7 +35,7 @@ import pandas as pd
 import torch
 
 from .. import dist, ops
-from .._lib import bin_edges
+from .._lib import PAIR_TRICLINIC, bin_edges
 from ..io.pipeline import FrameBatches
 
 CON_CONSTANT = 1.660538921  # :30
@@ -239,6 +245,27 @@ def _cn_edges(r_cut_list):
 
 
 # ------------------------------------------------------------------------------------------------
+# minimum-image convention
+# ------------------------------------------------------------------------------------------------
+def _mic_flags(mic) -> int:
+    if mic == "reference":
+        return 0
+    if mic == "triclinic":
+        return PAIR_TRICLINIC
+    raise ValueError(f"mic must be 'reference' or 'triclinic', got {mic!r}")
+
+
+def _frame_box(box, flags):
+    """(lengths whose product is the normalisation volume, the row handed to the pair kernel)."""
+    if flags & PAIR_TRICLINIC:
+        lengths = box.bound_lengths()
+        tilt = box.tilt if box.tilt is not None else (0.0, 0.0, 0.0)
+        return lengths, tuple(lengths) + tuple(tilt)
+    lengths = box.lattice_lengths()          # :260
+    return lengths, lengths
+
+
+# ------------------------------------------------------------------------------------------------
 # frame iteration shared by all entry points
 # ------------------------------------------------------------------------------------------------
 def _frame_batches(filename, columns):
@@ -268,8 +295,9 @@ def _mol_segments(num_mols, num_atoms_per_mol):
 # public API
 # ------------------------------------------------------------------------------------------------
 def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols=None, num_atoms_per_mol=None,
-                    path_or_buff="rdf.csv", save_mode=True):
+                    path_or_buff="rdf.csv", save_mode=True, mic="reference"):
     """Full and partial atom-atom RDF; see the reference docstring (:397-452) for the arguments."""
+    flags = _mic_flags(mic)
     num_bins, radii = _num_bins(r_cut, bin_size)
     num_relations = len(partial_relations[0])
     relation_matrix = np.asarray(partial_relations).transpose()
@@ -288,12 +316,12 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
         F = len(batch.metas)
         host = batch.host.numpy()
         cls = np.empty((F, host.shape[2]), dtype=np.int32)
-        boxes = np.empty((F, 3))
+        boxes = np.empty((F, 6 if flags else 3))
         for k, meta in enumerate(batch.metas):
             _log("The timestep of the current file is: " + str(meta.timestep))
             typ = calc_atom_type_ids(host[k, 0], num_mols, num_atoms_per_mol) if altered else host[k, 1]
             at = _value_counts(typ)
-            lengths = meta.box.lattice_lengths()
+            lengths, boxrow = _frame_box(meta.box, flags)
             rho, rho_pairs = _calc_props(lengths, meta.natoms, at, at, num_types, mass, partial_relations,
                                          "id" if altered else "type", num_atoms_per_mol)
             props[meta.index] = (at, rho, rho_pairs, meta.natoms)
@@ -301,10 +329,10 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
                 cmap = _ClassMap(named, present_types=at.keys())
                 weights = _sym_weights(cmap, relation_matrix, with_full=True)
             cls[k] = cmap.classes_of(typ)
-            boxes[k] = lengths
+            boxes[k] = boxrow
         xyz = dev[:, 2:5, :].contiguous()
         cls_d = torch.from_numpy(cls).to(device)
-        hist = ops.pair_hist(xyz, cls_d, cmap.ncls, boxes, rcut2, edges, bin_size)
+        hist = ops.pair_hist(xyz, cls_d, cmap.ncls, boxes, rcut2, edges, bin_size, flags=flags)
         red = ops.hist_reduce(hist, weights)                      # [F, 1+R, nb]
         for k, meta in enumerate(batch.metas):
             counts[meta.index] = red[k]
@@ -344,8 +372,9 @@ def _gather_props(props: dict, total_frames: int) -> dict:
 
 
 def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols=None, num_atoms_per_mol=None,
-                   path_or_buff="cn.csv", save_mode=True):
+                   path_or_buff="cn.csv", save_mode=True, mic="reference"):
     """Atom-atom coordination numbers, one cutoff per relation (:533-651)."""
+    flags = _mic_flags(mic)
     _num_bins(r_cut, bin_size)
     num_relations = len(partial_relations[0])
     relation_matrix = np.asarray(partial_relations).transpose()
@@ -364,11 +393,11 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
         F = len(batch.metas)
         host = batch.host.numpy()
         cls = np.empty((F, host.shape[2]), dtype=np.int32)
-        boxes = np.empty((F, 3))
+        boxes = np.empty((F, 6 if flags else 3))
         for k, meta in enumerate(batch.metas):
             typ = calc_atom_type_ids(host[k, 0], num_mols, num_atoms_per_mol) if altered else host[k, 1]
             at = _value_counts(typ)
-            lengths = meta.box.lattice_lengths()
+            lengths, boxrow = _frame_box(meta.box, flags)
             _calc_props(lengths, meta.natoms, at, at, num_types, mass, partial_relations, "id" if altered else "type",
                         num_atoms_per_mol)
             props[meta.index] = at
@@ -376,9 +405,9 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
                 cmap = _ClassMap(named, present_types=at.keys())
                 weights = _sym_weights(cmap, relation_matrix, with_full=False)
             cls[k] = cmap.classes_of(typ)
-            boxes[k] = lengths
+            boxes[k] = boxrow
         xyz = dev[:, 2:5, :].contiguous()
-        hist = ops.pair_hist(xyz, torch.from_numpy(cls).to(device), cmap.ncls, boxes, rcut2_max, edges, 0.0)
+        hist = ops.pair_hist(xyz, torch.from_numpy(cls).to(device), cmap.ncls, boxes, rcut2_max, edges, 0.0, flags=flags)
         red = ops.hist_reduce(hist, weights, cumulative=True)     # [F, R, nthr] cumulative over thresholds
         for k, meta in enumerate(batch.metas):
             counts[meta.index] = red[k]
@@ -396,7 +425,7 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
     return _save_cn(relation_matrix, path_or_buff, cn_sum, save_mode)
 
 
-def _molecular_common(filename, num_types, mass, partial_relations, num_mols, num_atoms_per_mol, inter, run_pairs):
+def _molecular_common(filename, num_types, mass, partial_relations, num_mols, num_atoms_per_mol, inter, run_pairs, flags=0):
     """Shared frame loop of the atom/molecule-COM entry points (:654-902).  ``run_pairs`` gets the device
     tensors of one batch and returns per-frame integer results [F, R, *]."""
     num_relations = len(partial_relations[0])
@@ -417,11 +446,10 @@ def _molecular_common(filename, num_types, mass, partial_relations, num_mols, nu
         n = host.shape[2]
         if seg_off[-1] != n:
             raise ValueError(f"Length of values ({seg_off[-1]}) does not match length of index ({n})")
-        boxes = np.empty((F, 3))
+        boxes = np.empty((F, 6 if flags else 3))
         cls_a = np.empty((F, n), dtype=np.int32)
         for k, meta in enumerate(batch.metas):
-            lengths = meta.box.lattice_lengths()
-            boxes[k] = lengths
+            lengths, boxes[k] = _frame_box(meta.box, flags)
             if inter:
                 at = mol_types_count
                 n_objects = len(mol_type)
@@ -454,18 +482,19 @@ def _molecular_common(filename, num_types, mass, partial_relations, num_mols, nu
 
 
 def calc_molecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
-                       path_or_buff="rdf_mol.csv", save_mode=True, _inter=False):
+                       path_or_buff="rdf_mol.csv", save_mode=True, _inter=False, mic="reference"):
     """Partial RDF between atoms and molecule centres of mass (:654-756)."""
+    flags = _mic_flags(mic)
     num_bins, radii = _num_bins(r_cut, bin_size)
     edges = bin_edges(bin_size, num_bins)
     rcut2 = _rcut_sq(r_cut)
 
     def run(xa, ca, na, xb, cb, nb_, boxes, w):
-        hist = ops.pair_hist(xa, ca, na, boxes, rcut2, edges, bin_size, xyz_b=xb, cls_b=cb, ncls_b=nb_)
+        hist = ops.pair_hist(xa, ca, na, boxes, rcut2, edges, bin_size, xyz_b=xb, cls_b=cb, ncls_b=nb_, flags=flags)
         return ops.hist_reduce(hist, w)
 
     counts, props, T, device, relation_matrix, R = _molecular_common(filename, num_types, mass, partial_relations, num_mols,
-                                                                      num_atoms_per_mol, _inter, run)
+                                                                      num_atoms_per_mol, _inter, run, flags)
     allc = _merge_frames(counts, T, (R, num_bins), device).cpu().numpy()
     if dist.world_size() > 1:
         props = _gather_props(props, T)
@@ -479,18 +508,19 @@ def calc_molecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, file
 
 
 def calc_molecular_cn(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
-                      path_or_buff="cn_mol.csv", save_mode=True):
+                      path_or_buff="cn_mol.csv", save_mode=True, mic="reference"):
     """Coordination numbers between atoms and molecule centres of mass (:759-854)."""
+    flags = _mic_flags(mic)
     _num_bins(r_cut, bin_size)
     edges, rcut2_max, upto = _cn_edges(r_cut)
     nthr = len(edges) - 1
 
     def run(xa, ca, na, xb, cb, nb_, boxes, w):
-        hist = ops.pair_hist(xa, ca, na, boxes, rcut2_max, edges, 0.0, xyz_b=xb, cls_b=cb, ncls_b=nb_)
+        hist = ops.pair_hist(xa, ca, na, boxes, rcut2_max, edges, 0.0, xyz_b=xb, cls_b=cb, ncls_b=nb_, flags=flags)
         return ops.hist_reduce(hist, w, cumulative=True)
 
     counts, props, T, device, relation_matrix, R = _molecular_common(filename, num_types, mass, partial_relations, num_mols,
-                                                                      num_atoms_per_mol, False, run)
+                                                                      num_atoms_per_mol, False, run, flags)
     allc = _merge_frames(counts, T, (R, nthr), device).cpu().numpy()
     if dist.world_size() > 1:
         props = _gather_props(props, T)
@@ -504,12 +534,13 @@ def calc_molecular_cn(r_cut, bin_size, num_types, mass, partial_relations, filen
 
 
 def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, partial_relations, batch_frames=64,
-                                return_counts=False):
+                                return_counts=False, mic="reference"):
     """Array front end of :func:`calc_atomic_rdf` for trajectories that are already in memory.
 
     positions   float64 [T, 3, N] host array (numpy, or a pinned torch tensor for async copies), rows in id order
     types       [N] or [T, N] atom types (ints or floats, as the dump's ``type`` column)
-    box_lengths [3] or [T, 3] box lengths as ``dump.box.to_lattice().lengths`` gives them
+    box_lengths [3] or [T, 3] box lengths as ``dump.box.to_lattice().lengths`` gives them; with ``mic="triclinic"``
+                [6] or [T, 6] = (lx, ly, lz, xy, xz, yz) and the normalisation volume is lx*ly*lz
     Everything else as in calc_atomic_rdf; same per-frame normalisation (rdf_cn.py:297-329, 502-521), same DataFrame.
     Frames stream through pinned staging buffers: the copy of batch k+1 overlaps the kernels of batch k.
     With ``return_counts`` the raw integer histograms [T, 1+R, nbins] (g_full row first) are returned as well.
@@ -524,7 +555,8 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
     weights = _sym_weights(cmap, relation_matrix, with_full=True)
     edges = bin_edges(bin_size, num_bins)
     rcut2 = _rcut_sq(r_cut)
-    boxes = np.broadcast_to(np.asarray(box_lengths, dtype=np.float64), (T, 3))
+    flags = _mic_flags(mic)
+    boxes = np.broadcast_to(np.asarray(box_lengths, dtype=np.float64), (T, 6 if flags else 3))
     static_types = types.ndim == 1
     dev = torch.device("cuda", torch.cuda.current_device())
     if static_types:
@@ -547,7 +579,7 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
         nxt = stage(f1) if f1 < T else None
         torch.cuda.current_stream().wait_event(ev)
         cls = cls_static if static_types else torch.from_numpy(np.stack([cmap.classes_of(t) for t in types[f0:f1]])).to(dev)
-        hist = ops.pair_hist(x, cls, cmap.ncls, boxes[f0:f1], rcut2, edges, bin_size)
+        hist = ops.pair_hist(x, cls, cmap.ncls, boxes[f0:f1], rcut2, edges, bin_size, flags=flags)
         out[f0:f1] = ops.hist_reduce(hist, weights)
         x.record_stream(torch.cuda.current_stream())
     counts = out.cpu().numpy()
@@ -555,7 +587,7 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
     rdf_part_sum = np.zeros((num_relations, num_bins))
     for t in range(T):
         at = at_static if static_types else _value_counts(types[t])
-        volume = np.prod(boxes[t])
+        volume = np.prod(boxes[t, :3])
         rho = N / volume
         rho_pairs = np.array([at[b] / volume for b in partial_relations[1]])
         full, part = _normalize_rdf(bin_size, rho_pairs, at, partial_relations, num_relations, num_bins,
@@ -567,7 +599,7 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
 
 
 def calc_intermolecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
-                            path_or_buff="rdf_mol.csv", save_mode=True):
+                            path_or_buff="rdf_mol.csv", save_mode=True, mic="reference"):
     """Molecule-COM / molecule-COM partial RDF, self pairs included as in the reference (:857-902)."""
     return calc_molecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
-                              path_or_buff=path_or_buff, save_mode=save_mode, _inter=True)
+                              path_or_buff=path_or_buff, save_mode=save_mode, _inter=True, mic=mic)

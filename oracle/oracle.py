@@ -146,6 +146,72 @@ def shell_mask(xa, ya, za, xb, yb, zb, lengths, r_in, r_out, same_set):
     return out
 
 
+# ---- general triclinic minimum image (extension, parity unpinned by the reference; see oracle.c) ----
+def _cell(cell):
+    """cell = (lx, ly, lz, xy, xz, yz)"""
+    c = np.ascontiguousarray(cell, dtype=np.float64).reshape(6)
+    return c, c.ctypes.data_as(c_dp)
+
+
+def calc_rsq_tri(head, x, y, z, cell):
+    head, hp = _d(head); x, xp = _d(x); y, yp = _d(y); z, zp = _d(z)
+    cell, cp = _cell(cell)
+    out = np.empty(len(x))
+    lib().orc_calc_rsq_tri(hp, xp, yp, zp, ctypes.c_int64(len(x)), cp, out.ctypes.data_as(c_dp))
+    return out
+
+
+def rdf_loop_tri(typ, x, y, z, rel, cell, r_cut, ddr, nb, nthreads=1):
+    """_rdf_loop counting rules with the LAMMPS-style triclinic image -> (full int64[nb], part int64[R, nb])."""
+    typ, tp = _d(typ); x, xp = _d(x); y, yp = _d(y); z, zp = _d(z)
+    rel, rp = _i(np.asarray(rel).reshape(-1, 2))
+    cell, cp = _cell(cell)
+    R = rel.shape[0]
+    full = np.zeros(nb); part = np.zeros((R, nb))
+    lib().orc_rdf_loop_tri(tp, xp, yp, zp, ctypes.c_int64(len(x)), rp, ctypes.c_int64(R), cp,
+                           ctypes.c_double(rcut_sq(r_cut)), ctypes.c_double(ddr), ctypes.c_int64(nb),
+                           full.ctypes.data_as(c_dp), part.ctypes.data_as(c_dp), ctypes.c_int(nthreads))
+    return full.astype(np.int64), part.astype(np.int64)
+
+
+def rdf_rect_tri(ta, xa, ya, za, tb, xb, yb, zb, rel, cell, r_cut, ddr, nb, nthreads=1):
+    ta, tap = _d(ta); xa, xap = _d(xa); ya, yap = _d(ya); za, zap = _d(za)
+    tb, tbp = _d(tb); xb, xbp = _d(xb); yb, ybp = _d(yb); zb, zbp = _d(zb)
+    rel, rp = _i(np.asarray(rel).reshape(-1, 2))
+    cell, cp = _cell(cell)
+    R = rel.shape[0]
+    part = np.zeros((R, nb))
+    lib().orc_rdf_rect_tri(tap, xap, yap, zap, ctypes.c_int64(len(xa)), tbp, xbp, ybp, zbp, ctypes.c_int64(len(xb)),
+                           rp, ctypes.c_int64(R), cp, ctypes.c_double(rcut_sq(r_cut)), ctypes.c_double(ddr),
+                           ctypes.c_int64(nb), part.ctypes.data_as(c_dp), ctypes.c_int(nthreads))
+    return part.astype(np.int64)
+
+
+def shell_mask_tri(xa, ya, za, xb, yb, zb, cell, r_in, r_out, same_set):
+    xa, xap = _d(xa); ya, yap = _d(ya); za, zap = _d(za)
+    xb, xbp = _d(xb); yb, ybp = _d(yb); zb, zbp = _d(zb)
+    cell, cp = _cell(cell)
+    out = np.zeros((len(xa), len(xb)), dtype=np.uint8)
+    lib().orc_shell_mask_tri(xap, yap, zap, ctypes.c_int64(len(xa)), xbp, ybp, zbp, ctypes.c_int64(len(xb)), cp,
+                             ctypes.c_double(rcut_sq(r_in)), ctypes.c_double(rcut_sq(r_out)),
+                             ctypes.c_int(1 if same_set else 0), out.ctypes.data_as(c_bp))
+    return out
+
+
+def nearest_image_rsq_bruteforce(head, x, y, z, cell):
+    """min over the 27 neighbouring images of |head - other - (i a + j b + k c)|^2 (numpy; definition check only)."""
+    lx, ly, lz, xy, xz, yz = [float(v) for v in cell]
+    a = np.array([lx, 0.0, 0.0]); b = np.array([xy, ly, 0.0]); c = np.array([xz, yz, lz])
+    d = np.stack([head[0] - np.asarray(x), head[1] - np.asarray(y), head[2] - np.asarray(z)], axis=1)
+    best = np.full(len(d), np.inf)
+    for i in (-1, 0, 1):
+        for j in (-1, 0, 1):
+            for k in (-1, 0, 1):
+                v = d - (i * a + j * b + k * c)
+                best = np.minimum(best, np.sum(v * v, axis=1))
+    return best
+
+
 def survival_counts(h):
     """cnt[tau] = sum_pairs sum_t h(t) h(t+tau) for h uint8[T, npairs] (residence_time.py:112-143)."""
     h = np.ascontiguousarray(h, dtype=np.uint8)
@@ -325,7 +391,7 @@ def normalize_rdf(bin_size, rho_pairs, atom_types, partial_relations, num_bins, 
 
 
 def atomic_rdf(frames, r_cut, bin_size, partial_relations, num_mols=None, num_atoms_per_mol=None, nthreads=0,
-               return_counts=False):
+               return_counts=False, mic="reference"):
     """calc_atomic_rdf (rdf_cn.py:385-530) on a list of Frames -> float64[nb, 2+R] like df.values."""
     nb = int(r_cut / bin_size)
     radii = (np.arange(nb) + 0.5) * bin_size
@@ -338,13 +404,21 @@ def atomic_rdf(frames, r_cut, bin_size, partial_relations, num_mols=None, num_at
         typ = c["type"]
         if num_mols and num_atoms_per_mol:
             typ = calc_atom_type(c["id"], num_mols, num_atoms_per_mol)
-        lengths = fr.lattice_lengths
+        if mic == "triclinic":      # extension (no reference implementation): true cell volume, general triclinic image
+            lengths = fr.bound_lengths
+            tilt = fr.tilt if fr.tilt is not None else (0.0, 0.0, 0.0)
+        else:
+            lengths = fr.lattice_lengths
         volume = np.prod(lengths)
         at = type_counts(typ)
         n = len(typ)
         rho = n / volume
         rho_pairs = np.array([at[b] / volume for b in partial_relations[1]])
-        full, part = rdf_loop(typ, c["x"], c["y"], c["z"], rel, lengths, r_cut, bin_size, nb, nthreads)
+        if mic == "triclinic":
+            full, part = rdf_loop_tri(typ, c["x"], c["y"], c["z"], rel, tuple(lengths) + tuple(tilt), r_cut, bin_size, nb,
+                                      nthreads)
+        else:
+            full, part = rdf_loop(typ, c["x"], c["y"], c["z"], rel, lengths, r_cut, bin_size, nb, nthreads)
         counts.append((full, part))
         f, p = normalize_rdf(bin_size, rho_pairs, at, partial_relations, nb, part.astype(np.float64),
                              full.astype(np.float64), n, rho)

@@ -108,6 +108,88 @@ def test_pair_hist_rectangular_vs_oracle(ops):
     assert part[:, 0].sum() > 0
 
 
+def _tri_points(rng, n, cell, wrapped=True):
+    """n points inside the triclinic cell (lx, ly, lz, xy, xz, yz) -- or, unwrapped, spilling one cell beyond it"""
+    lx, ly, lz, xy, xz, yz = cell
+    s = rng.uniform(0, 1, (n, 3)) if wrapped else rng.uniform(-0.4, 1.4, (n, 3))
+    pos = s[:, 0:1] * np.array([lx, 0, 0]) + s[:, 1:2] * np.array([xy, ly, 0]) + s[:, 2:3] * np.array([xz, yz, lz])
+    return np.ascontiguousarray(pos.T)
+
+
+@pytest.mark.parametrize("n,cell,rc,ddr,flags,wrapped", [
+    (1000, (21.0, 22.5, 24.0, 4.2, 2.1, -3.3), 7.0, 0.05, 4, True),
+    (3000, (60.0, 40.0, 35.0, 12.0, 6.0, -6.0), 6.0, 0.05, 4, True),       # culling active, uniform image vectors
+    (3000, (60.0, 40.0, 35.0, 12.0, 6.0, -6.0), 6.0, 0.05, 4 | 1, True),   # + MDP_PAIR_NO_CULL (per-pair image path)
+    (3000, (60.0, 40.0, 35.0, 12.0, 6.0, -6.0), 6.0, 0.05, 4 | 3, True),   # brute force in caller order
+    (777, (15.0, 15.0, 15.0, 7.5, -7.5, 7.5), 7.4, 0.1, 4, True),          # extreme tilt, r_cut close to L/2
+    (1500, (30.0, 28.0, 26.0, 6.0, 3.0, -4.2), 9.0, 0.05, 4, False),       # unwrapped points: sequential shift semantics
+    (257, (9.0, 9.0, 9.0, 1.0, 2.0, 3.0), 12.0, 0.25, 4, True),            # r_cut > L/2
+    (31, (9.0, 9.0, 9.0, 1.0, 2.0, 3.0), 4.0, 0.25, 4, True),
+    (2000, (30.0, 28.0, 26.0, 0.0, 0.0, 0.0), 9.0, 0.05, 4, True),         # zero tilt: must equal the orthogonal path
+])
+def test_pair_hist_triclinic_vs_oracle(ops, n, cell, rc, ddr, flags, wrapped):
+    """MDP_PAIR_TRICLINIC (extension, defined by oracle.c pair_rsq_tri): bit-exact counts against the CPU restatement."""
+    from mdproptools_b200._lib import bin_edges
+    rng = np.random.default_rng(n * 13 + flags)
+    pos = _tri_points(rng, n, cell, wrapped)
+    typ = rng.integers(1, 4, n).astype(np.float64)
+    rel = np.array([[1, 1], [1, 2], [3, 2]])
+    nb = int(rc / ddr)
+    full, part = O.rdf_loop_tri(typ, pos[0], pos[1], pos[2], rel, cell, rc, ddr, nb, nthreads=0)
+    cls = (typ.astype(np.int64) - 1).astype(np.int32)
+    hist = ops.pair_hist(_dev(pos[None]), _dev(cls), 3, [cell], O.rcut_sq(rc), bin_edges(ddr, nb), ddr, flags=flags)
+    w = [np.full(6, 2)]
+    for a, b in rel:
+        r = np.zeros(6, dtype=np.int64)
+        r[ops.sym_row(a - 1, b - 1, 3)] = 2 if a == b else 1
+        w.append(r)
+    red = ops.hist_reduce(hist, np.stack(w)).cpu().numpy()[0]
+    assert np.array_equal(red[0], full)
+    assert np.array_equal(red[1:], part)
+    if cell[3] == cell[4] == cell[5] == 0.0:
+        full_o, _ = O.rdf_loop(typ, pos[0], pos[1], pos[2], rel, cell[:3], rc, ddr, nb, nthreads=0)
+        assert np.array_equal(red[0], full_o)
+
+
+def test_pair_hist_triclinic_rect_and_multiframe(ops):
+    from mdproptools_b200._lib import bin_edges
+    rng = np.random.default_rng(21)
+    F = 3
+    cells = [(25.0 + k, 27.0, 23.0 - k, 5.0, -2.0 + k, 4.0) for k in range(F)]
+    na, nbp = 1234, 300
+    pa = np.stack([_tri_points(rng, na, c) for c in cells])
+    pb = np.stack([_tri_points(rng, nbp, c) for c in cells])
+    ta = rng.integers(1, 4, na).astype(np.float64)
+    tb = rng.integers(1, 3, nbp).astype(np.float64)
+    rel = np.array([[1, 1], [2, 2], [3, 1], [1, 2]])
+    nb, ddr, rc = 100, 0.1, 10.0
+    hist = ops.pair_hist(_dev(pa), _dev((ta - 1).astype(np.int32)), 3, cells, rc * rc, bin_edges(ddr, nb), ddr,
+                         xyz_b=_dev(pb), cls_b=_dev((tb - 1).astype(np.int32)), ncls_b=2, flags=4)
+    w = np.zeros((len(rel), 6), dtype=np.int64)
+    for k, (a, b) in enumerate(rel):
+        w[k, (a - 1) * 2 + (b - 1)] = 1
+    red = ops.hist_reduce(hist, w).cpu().numpy()
+    for f in range(F):
+        part = O.rdf_rect_tri(ta, pa[f, 0], pa[f, 1], pa[f, 2], tb, pb[f, 0], pb[f, 1], pb[f, 2], rel, cells[f], rc, ddr, nb,
+                              nthreads=0)
+        assert np.array_equal(red[f], part), f
+
+
+def test_pair_list_triclinic_shell(ops):
+    rng = np.random.default_rng(22)
+    cell = (22.0, 20.0, 19.0, 4.0, -3.0, 2.5)
+    pa = _tri_points(rng, 150, cell)
+    pb = _tri_points(rng, 900, cell)
+    r_in, r_out = 2.0, 6.5
+    h = O.shell_mask_tri(pa[0], pa[1], pa[2], pb[0], pb[1], pb[2], cell, r_in, r_out, False)
+    lst, _ = ops.pair_list(_dev(pa[None]), _dev(pb[None]), [cell], r_in * r_in, r_out * r_out, 1, flags=4)
+    got = np.zeros_like(h)
+    l = lst.cpu().numpy()
+    got[l[:, 1], l[:, 2]] = 1
+    assert len(l) == int(h.sum())
+    assert np.array_equal(got, h)
+
+
 def test_pair_hist_table_mode_counts(ops):
     rng = np.random.default_rng(5)
     L = (18.0, 18.0, 18.0)
@@ -373,6 +455,34 @@ def test_msd_interval_and_all_origins(ops):
     assert np.all(sums[0] == 0)
 
 
+@pytest.mark.parametrize("T,n,lag,groups", [
+    (33, 700, 20, None),                       # one time tile, edge path only
+    (300, 70, 300, None),                      # full window: several time tiles and lag blocks, 3 atom blocks (ragged)
+    (517, 33, 130, [0, 1, 20, 33]),            # groups with ragged atom blocks (1 atom, 19 atoms, 13 atoms)
+    (1300, 40, 1100, None),                    # more lags than one launch holds (MW_WCAP = 1024)
+    (97, 1, 97, None),                         # a single atom
+])
+def test_msd_all_origins_windowed(ops, T, n, lag, groups):
+    """Extension (no reference implementation; oracle.c orc_msd_all_origins is the definition): 1e-10 relative."""
+    rng = np.random.default_rng(T + n)
+    traj = 50.0 + np.cumsum(rng.normal(0, 0.1, (T, 3, n)), axis=0)
+    scale = 1e-10
+    sums = ops.msd_all_origins(_dev(traj), lag, scale, group_off=groups).cpu().numpy()     # [lag, G, 4]
+    offs = groups if groups is not None else [0, n]
+    assert sums.shape == (lag, len(offs) - 1, 4)
+    for g in range(len(offs) - 1):
+        a0, a1 = offs[g], offs[g + 1]
+        ref = O.msd_all_origins(np.ascontiguousarray(traj[:, :, a0:a1]), lag) * scale * scale
+        norm = (T - np.arange(lag))[:, None] * (a1 - a0)
+        got = sums[:, g] / norm
+        assert np.all(sums[0, g] == 0)
+        assert np.allclose(got[1:], ref[1:], rtol=1e-10, atol=0), (g, np.abs(got[1:] / ref[1:] - 1).max())
+    # accumulate semantics: a second call adds
+    out = ops.msd_all_origins(_dev(traj), lag, scale, group_off=groups)
+    ops.msd_all_origins(_dev(traj), lag, scale, group_off=groups, out=out)
+    assert np.allclose(out.cpu().numpy(), 2 * sums, rtol=1e-14, atol=0)
+
+
 def test_segment_com_kernel(ops):
     rng = np.random.default_rng(2)
     sizes = rng.integers(1, 17, 500)
@@ -472,3 +582,48 @@ def test_large_frame_properties(ops):
     # expected number of pairs inside the cutoff for a uniform gas: N(N-1)/2 * (4/3 pi rc^3 / V)
     expect = n * (n - 1) / 2 * (4 / 3 * np.pi * 20 ** 3) / np.prod(L)
     assert abs(int(h1.sum().item()) - expect) < 5 * np.sqrt(expect)
+
+
+# ------------------------------------------------------------------------------------------------
+# mic="triclinic" through the public API (extension; oracle-defined)
+# ------------------------------------------------------------------------------------------------
+def _write_triclinic_dump(path, rng, nframes, n, cell):
+    lx, ly, lz, xy, xz, yz = cell
+    xlo, ylo, zlo = -1.0, 0.5, 2.0
+    # LAMMPS writes the bounding box of the tilted cell (pymatgen undoes it, oracle.read_dumps restates that)
+    xs = (0.0, xy, xz, xy + xz)
+    with open(path, "w") as f:
+        for t in range(nframes):
+            pos = _tri_points(rng, n, cell) + np.array([[xlo], [ylo], [zlo]])
+            ids = rng.permutation(n) + 1
+            f.write(f"ITEM: TIMESTEP\n{t * 100}\nITEM: NUMBER OF ATOMS\n{n}\n")
+            f.write("ITEM: BOX BOUNDS xy xz yz pp pp pp\n")
+            f.write(f"{xlo + min(xs)!r} {xlo + lx + max(xs)!r} {xy!r}\n")
+            f.write(f"{ylo + min(0.0, yz)!r} {ylo + ly + max(0.0, yz)!r} {xz!r}\n")
+            f.write(f"{zlo!r} {zlo + lz!r} {yz!r}\n")
+            f.write("ITEM: ATOMS id type x y z\n")
+            for k, i in enumerate(ids):
+                f.write(f"{i} {1 + (i % 3)} {float(pos[0, k])!r} {float(pos[1, k])!r} {float(pos[2, k])!r}\n")
+
+
+def test_calc_atomic_rdf_triclinic_api(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mdproptools_b200.structural import rdf_cn
+    rng = np.random.default_rng(31)
+    cell = (24.0, 22.0, 20.0, 4.8, 2.4, -3.3)
+    p = str(tmp_path / "tri.dump")
+    _write_triclinic_dump(p, rng, 3, 1500, cell)
+    rel = [[1, 2, 3], [1, 3, 3]]
+    frames = list(O.read_dumps(p))
+    for mic in ("triclinic", "reference"):
+        want = O.atomic_rdf(frames, 8.0, 0.05, rel, mic=mic)
+        df = rdf_cn.calc_atomic_rdf(8.0, 0.05, 3, [1.0, 2.0, 3.0], rel, p, save_mode=False, mic=mic)
+        assert np.array_equal(df.values, want), mic          # equal integer counts -> bit-identical floats
+    a = rdf_cn.calc_atomic_rdf(8.0, 0.05, 3, [1.0, 2.0, 3.0], rel, p, save_mode=False, mic="triclinic").values
+    b = rdf_cn.calc_atomic_rdf(8.0, 0.05, 3, [1.0, 2.0, 3.0], rel, p, save_mode=False).values
+    assert not np.array_equal(a, b)                           # the tilted cell is where the two conventions differ
+    # a uniform fluid must give g(r) ~ 1 with the true image and the true volume
+    assert abs(a[40:, 1].mean() - 1.0) < 0.02
+    with pytest.raises(ValueError):
+        rdf_cn.calc_atomic_rdf(8.0, 0.05, 3, [1.0, 2.0, 3.0], rel, p, save_mode=False, mic="nearest")

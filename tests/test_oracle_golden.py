@@ -219,3 +219,31 @@ def test_msd_all_origins_oracle_consistency():
     d = traj[lag:] - traj[:-lag]
     assert np.allclose(out[lag, :3], (d ** 2).mean(axis=(0, 2)), rtol=1e-13)
     assert np.allclose(out[lag, 3], (d ** 2).sum(axis=1).mean(), rtol=1e-13)
+
+
+def test_triclinic_image_is_the_nearest_image_within_half_the_cell_width():
+    """mic="triclinic" is an extension with no reference implementation: the oracle's sequential z,y,x shift
+    (oracle.c pair_rsq_tri) is checked against a 27-image brute force wherever the nearest-image distance is
+    below half the smallest cell width, for wrapped points and LAMMPS-legal tilts."""
+    rng = np.random.default_rng(5)
+    for cell in [(30.0, 28.0, 26.0, 6.0, 3.0, -4.2), (20.0, 20.0, 20.0, 10.0, -10.0, 10.0), (167.19, 167.19, 167.19, 33.438, 16.719, -25.0785)]:
+        lx, ly, lz, xy, xz, yz = cell
+        n = 3000
+        s = rng.uniform(0, 1, (n, 3))
+        pos = s[:, 0:1] * np.array([lx, 0, 0]) + s[:, 1:2] * np.array([xy, ly, 0]) + s[:, 2:3] * np.array([xz, yz, lz])
+        x, y, z = np.ascontiguousarray(pos.T)
+        a, b, c = np.array([lx, 0, 0]), np.array([xy, ly, 0]), np.array([xz, yz, lz])
+        vol = lx * ly * lz
+        widths = [vol / np.linalg.norm(np.cross(b, c)), vol / np.linalg.norm(np.cross(c, a)), vol / np.linalg.norm(np.cross(a, b))]
+        rmax2 = (0.5 * min(widths)) ** 2
+        for h in range(0, n, 250):
+            got = O.calc_rsq_tri(pos[h], x, y, z, cell)
+            ref = O.nearest_image_rsq_bruteforce(pos[h], x, y, z, cell)
+            m = ref < rmax2
+            assert m.sum() > 10
+            assert np.allclose(got[m], ref[m], rtol=1e-12, atol=1e-12)
+            assert (got >= ref - 1e-9).all()      # never closer than the true nearest image
+    # zero tilt: identical bits to the reference's orthogonal single shift
+    x, y, z = rng.uniform(0, 25, (3, 2000))
+    assert np.array_equal(O.calc_rsq_tri((3.0, 4.0, 5.0), x, y, z, (25.0, 25.0, 25.0, 0, 0, 0)),
+                          O.calc_rsq((3.0, 4.0, 5.0), x, y, z, (25.0, 25.0, 25.0)))
