@@ -105,6 +105,9 @@ int mdp_pair_hist(mdp_ctx *ctx, int nframes,
  * the smallest cell width and |xy|,|xz| <= lx/2, |yz| <= ly/2.  Definition and checker: oracle/oracle.c
  * pair_rsq_tri (parity unpinned by the reference). */
 #define MDP_PAIR_TRICLINIC 4
+/* Uniform-bin histograms: compact the hits into the per-warp queue before binning (the pre-direct-binning path;
+ * kept for A/B measurements and as the fallback when the edge table does not fit in shared memory). */
+#define MDP_PAIR_QUEUE_BINNING 8
 
 /*
  * out[f][r][b] = sum_rows weights[r][row] * hist[f][row][b]     (all integer)

@@ -70,7 +70,7 @@ _PROTOS = {
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 
-PAIR_NO_CULL, PAIR_NO_SORT, PAIR_TRICLINIC = 1, 2, 4   # flags of mdp_pair_hist / mdp_pair_list
+PAIR_NO_CULL, PAIR_NO_SORT, PAIR_TRICLINIC, PAIR_QUEUE_BINNING = 1, 2, 4, 8   # flags of mdp_pair_hist / mdp_pair_list
 
 
 def lib() -> ctypes.CDLL:

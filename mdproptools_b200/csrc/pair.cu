@@ -42,17 +42,21 @@ constexpr int GPT = TS / GS;   // groups per tile
 constexpr int NWARP = 8;       // warps per CTA of the pair kernel
 constexpr int QCAP = 160;      // queue entries per warp (32 carried + 4 steps x 32)
 constexpr int MAX_CLS = 64;
+constexpr int CTAS_PER_SM = 2;   // resident CTAs of the pair kernel per SM (register budget 65536 / (CTAS_PER_SM * 256))
 
 // Sorted points are stored group-blocked: group g (32 points) occupies 64 consecutive double2,
 //   [g*64 + l]      = (x, y)  of point l
 //   [g*64 + 32 + l] = (z, meta), meta = the bit pattern {lo: class, hi: row in the caller's order or -1 for padding}
 // so that one 32-point chunk is a single contiguous 1 KB block and both halves are bank-conflict free.
 constexpr int GREC = 64;       // double2 per group
+constexpr int RING = 64;       // candidate ring of the pair kernel: entries per warp
 __host__ __device__ __forceinline__ int64_t rec_xy(int64_t pos) { return (pos >> 5) * GREC + (pos & 31); }
 __host__ __device__ __forceinline__ int64_t rec_zw(int64_t pos) { return (pos >> 5) * GREC + 32 + (pos & 31); }
 constexpr size_t REC_BYTES = 32;   // bytes per point
 
-enum { MODE_HIST_UNIFORM = 0, MODE_HIST_TABLE = 1, MODE_LIST = 2 };
+// MODE_HIST_DIRECT = uniform bins with the edge table in shared memory: every lane bins its own hits inside the pair loop
+// (no compaction queue); the other modes compact the hits into a per-warp queue first.
+enum { MODE_HIST_UNIFORM = 0, MODE_HIST_TABLE = 1, MODE_LIST = 2, MODE_HIST_DIRECT = 3 };
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers
@@ -332,6 +336,58 @@ __device__ __forceinline__ bool tri_box_test(const typename D::T *a, const typen
     }
     if (nfeas != 1) code = TRI_MIXED;
     return best < rcut2_up;
+}
+
+// ---- point-level test ----------------------------------------------------------------------------------
+// One j point against the box of an i group, for a chunk pair whose image class (code) is already known from
+// the box-box test.  Same rounding discipline as chunk_test_f32: every bound errs towards "keep".
+// code == 0 (no axis needs the minimum image for any pair of the two boxes) is the common, cheap case.
+__device__ __forceinline__ bool point_test_f32(const float *a, double x, double y, double z, const AxisF &X, const AxisF &Y,
+                                               const AxisF &Z, float rcut2_up, int code)
+{
+    const float xd = __double2float_rd(x), xu = __double2float_ru(x);
+    const float yd = __double2float_rd(y), yu = __double2float_ru(y);
+    const float zd = __double2float_rd(z), zu = __double2float_ru(z);
+    float bx, by, bz;
+    if (code == 0) {
+        bx = fmaxf(fmaxf(__fsub_rd(a[0], xu), __fsub_rd(xd, a[3])), 0.f);
+        by = fmaxf(fmaxf(__fsub_rd(a[1], yu), __fsub_rd(yd, a[4])), 0.f);
+        bz = fmaxf(fmaxf(__fsub_rd(a[2], zu), __fsub_rd(zd, a[5])), 0.f);
+    } else {
+        int cls;
+        bx = axis_test_f32(a[0], a[3], xd, xu, X, cls);
+        by = axis_test_f32(a[1], a[4], yd, yu, Y, cls);
+        bz = axis_test_f32(a[2], a[5], zd, zu, Z, cls);
+    }
+    const float lb = __fadd_rd(__fadd_rd(__fmul_rd(bx, bx), __fmul_rd(by, by)), __fmul_rd(bz, bz));
+    return lb < rcut2_up;
+}
+
+// triclinic, single image vector (kx, ky, kz) for every pair of the chunk pair (code != TRI_MIXED)
+__device__ __forceinline__ bool tri_point_test_f32(const float *a, double x, double y, double z, const double *cell,
+                                                   float rcut2_up, int code)
+{
+    typedef DirF32 D;
+    float xl = __fsub_rd(a[0], __double2float_ru(x)), xh = __fsub_ru(a[3], __double2float_rd(x));
+    float yl = __fsub_rd(a[1], __double2float_ru(y)), yh = __fsub_ru(a[4], __double2float_rd(y));
+    float zl = __fsub_rd(a[2], __double2float_ru(z)), zh = __fsub_ru(a[5], __double2float_rd(z));
+    if (code != 0) {
+        const int ex = code & 3, ey = (code >> 2) & 3, ez = (code >> 4) & 3;
+        const int kx = ex == 0 ? 0 : (ex == 1 ? 1 : -1), ky = ey == 0 ? 0 : (ey == 1 ? 1 : -1), kz = ez == 0 ? 0 : (ez == 1 ? 1 : -1);
+        if (kz) {
+            tri_shift<D>(zl, zh, kz, D::dn(cell[2]), D::up(cell[2]));
+            tri_shift<D>(yl, yh, kz, D::dn(cell[5]), D::up(cell[5]));   // yz
+            tri_shift<D>(xl, xh, kz, D::dn(cell[4]), D::up(cell[4]));   // xz
+        }
+        if (ky) {
+            tri_shift<D>(yl, yh, ky, D::dn(cell[1]), D::up(cell[1]));
+            tri_shift<D>(xl, xh, ky, D::dn(cell[3]), D::up(cell[3]));   // xy
+        }
+        if (kx) tri_shift<D>(xl, xh, kx, D::dn(cell[0]), D::up(cell[0]));
+    }
+    const float bx = iv_min_abs(xl, xh), by = iv_min_abs(yl, yh), bz = iv_min_abs(zl, zh);
+    const float lb = __fadd_rd(__fadd_rd(__fmul_rd(bx, bx), __fmul_rd(by, by)), __fmul_rd(bz, bz));
+    return lb < rcut2_up;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -662,6 +718,7 @@ struct PairParams {
     float inv_ddr;
     unsigned long long *hist;        // device [F][nrows][nbins]
     int edges_in_smem;
+    float inv_ddr_biased;            // MODE_HIST_DIRECT: inv_ddr * (1 - 2^-18)
     // list mode
     double rin2, rout2;
     int shell_mode, exclude_same;
@@ -677,24 +734,13 @@ struct Shared {
     const double2 *edges_s;          // shared-memory copy of the edge table (valid when edges_in_smem)
     const int *cptab;
     unsigned int *hist;
+    unsigned edges_a, cptab_a, hist_a;   // the same three as 32-bit shared-window addresses (MODE_HIST_DIRECT)
 };
 
 // bytes of the warp-private region: two chunk stages + the hit queue (+ its metadata)
 __host__ __device__ constexpr size_t warp_region_bytes(bool meta)
 {
-    return 2 * GREC * sizeof(double2) + QCAP * sizeof(double) + (meta ? QCAP * sizeof(uint2) : 0);
-}
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+    return 2 * RING * sizeof(double2) + QCAP * sizeof(double) + (meta ? QCAP * sizeof(uint2) : 0);
 }
 
 template <int MODE, bool MULTICLS>
@@ -732,7 +778,7 @@ __device__ __forceinline__ void drain(const PairParams &p, const Shared &sh, int
             const double r2 = qr[base + lane];
             if (r2 < p.rcut2) {
                 int k;
-                if (MODE == MODE_HIST_UNIFORM) {
+                if (MODE == MODE_HIST_UNIFORM || MODE == MODE_HIST_DIRECT) {
                     // fp32 estimate of sqrt(rsq)/ddr is within +-1 of the reference bin; the exact fp64
                     // edge pair {e[k], e[k+1]} settles it (see mdp_bin_edges)
                     float s;
@@ -773,17 +819,116 @@ struct Shift {
     double x, y, z, xy, xz, yz;
 };
 
+// explicit shared-window accesses (32-bit addresses: no generic-to-shared conversion inside the pair loop)
+__device__ __forceinline__ void lds_f64x2(double &a, double &b, unsigned addr)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void lds_f64(double &a, unsigned addr) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr)); }
+
+// squared minimum-image distance of one pair from the raw differences (ax, ay, az) = (xi - xj, ...), in the operation
+// order of the reference (rdf_cn.py:50-56) / of oracle.c pair_rsq_tri for the triclinic variants
+template <int VAR>
+__device__ __forceinline__ double image_r2(double ax, double ay, double az, const Shift &S, double hx, double hy, double hz)
+{
+    const double sx = S.x, sy = S.y, sz = S.z;
+    if (VAR == VAR_SHIFT) {
+        ax = __dsub_rn(fabs(ax), sx);
+        ay = __dsub_rn(fabs(ay), sy);
+        az = __dsub_rn(fabs(az), sz);
+    } else if (VAR == VAR_MIXED) {
+        ax = fmin(fabs(ax), fabs(__dsub_rn(fabs(ax), sx)));
+        ay = fmin(fabs(ay), fabs(__dsub_rn(fabs(ay), sy)));
+        az = fmin(fabs(az), fabs(__dsub_rn(fabs(az), sz)));
+    } else if (VAR == VAR_TSHIFT) {
+        az = __dsub_rn(az, sz);
+        ay = __dsub_rn(__dsub_rn(ay, S.yz), sy);
+        ax = __dsub_rn(__dsub_rn(__dsub_rn(ax, S.xz), S.xy), sx);
+    } else if (VAR == VAR_TMIXED) {
+        const bool pz = az > hz, nz = az < -hz;
+        az = __dsub_rn(az, pz ? sz : (nz ? -sz : 0.0));
+        ay = __dsub_rn(ay, pz ? S.yz : (nz ? -S.yz : 0.0));
+        ax = __dsub_rn(ax, pz ? S.xz : (nz ? -S.xz : 0.0));
+        const bool py = ay > hy, ny = ay < -hy;
+        ay = __dsub_rn(ay, py ? sy : (ny ? -sy : 0.0));
+        ax = __dsub_rn(ax, py ? S.xy : (ny ? -S.xy : 0.0));
+        const bool px = ax > hx, nx = ax < -hx;
+        ax = __dsub_rn(ax, px ? sx : (nx ? -sx : 0.0));
+    }
+    return __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+}
+
 template <int MODE, bool MULTICLS, int VAR, bool TRI>
-__device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh, const double2 *__restrict__ jb, double xi,
+__device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh, const double2 *__restrict__ jb, int nj, double xi,
                                            double yi, double zi, uint32_t mi, const Shift S, int rc_hi,
                                            int lane, int &qn, double *qr, uint2 *qm, int frame)
 {
-    const double sx = S.x, sy = S.y, sz = S.z;
     const double hx = S.x * 0.5, hy = S.y * 0.5, hz = S.z * 0.5;   // VAR_TMIXED only
     constexpr bool META = MULTICLS || MODE == MODE_LIST;
+    if (MODE == MODE_HIST_DIRECT) {
+        // Direct binning: with point-level culling ~40 % of the evaluated pairs are hits, so compacting them first no
+        // longer pays.  Branch-free per pair: float(rsq) from the bit pattern, MUFU.SQRT, one FFMA whose multiplier is
+        // biased DOWN by 2^-18 (more than the fp32 error of the estimate, less than 0.02 bin for nbins <= 4096), so that
+        // k_est = floor(x') is the reference bin or the one below it; ONE exact fp64 compare against edge[k_est + 1]
+        // settles it (mdp_bin_edges: bin(rsq) >= k  <=>  rsq >= edge[k]); misses go to the invalid bin nbins.
+        const unsigned ja = (unsigned)__cvta_generic_to_shared(jb);
+        const unsigned nb = (unsigned)p.nbins;
+        const float inv = p.inv_ddr_biased;
+#pragma unroll 1
+        for (int j0 = 0; j0 < nj; j0 += 4) {
+            const unsigned a0 = ja + (unsigned)j0 * 16u;
+            double r2[4];
+            int cj[4];
+            bool hit[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                double jx, jy, jz, jm = 0.0;
+                lds_f64x2(jx, jy, a0 + u * 16);   // constant offsets after unrolling: folded into the LDS immediates
+                if (MULTICLS)
+                    lds_f64x2(jz, jm, a0 + RING * 16 + u * 16);
+                else
+                    lds_f64(jz, a0 + RING * 16 + u * 16);
+                r2[u] = image_r2<VAR>(__dsub_rn(xi, jx), __dsub_rn(yi, jy), __dsub_rn(zi, jz), S, hx, hy, hz);
+                hit[u] = __double2hiint(r2[u]) <= rc_hi;   // superset of rsq < rcut2; edge[nbins] <= rcut2 settles it
+                if (TRI) hit[u] = hit[u] && (j0 + u > lane);
+                cj[u] = MULTICLS ? __double2loint(jm) : 0;
+            }
+            if (!__any_sync(0xffffffffu, hit[0] | hit[1] | hit[2] | hit[3])) continue;
+            unsigned kb[4], ha[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // rsq beyond the cutoff (and the +inf padding) needs no test of its own: its estimate is >= nbins, the
+                // clamp sends it to the invalid bin (the float conversion saturates, sqrt/FFMA keep +inf)
+                const float f = __double2float_rz(r2[u]);
+                float sq;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(f));
+                unsigned k = __float_as_uint(__fmaf_rd(sq, inv, 12582912.0f)) - 0x4b400000u;   // floor(sq*inv), 2^23 trick
+                if (TRI) k = hit[u] ? k : nb;
+                k = k < nb ? k : nb;
+                double e1;
+                lds_f64(e1, sh.edges_a + k * 8u + 8u);
+                k += (r2[u] >= e1) ? 1u : 0u;
+                kb[u] = k;
+                ha[u] = sh.hist_a + k * 4u;
+                if (MULTICLS) {
+                    unsigned row;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(sh.cptab_a + (mi + (uint32_t)cj[u]) * 4u));
+                    ha[u] += row * nb * 4u;
+                }
+            }
+            // the four increments last: ptxas wraps every predicated shared atomic in its own branch region, and
+            // keeping those out of the arithmetic above leaves it one straight block to schedule
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                asm volatile("{\n .reg .pred p;\n setp.lt.u32 p, %1, %2;\n @p red.shared.add.u32 [%0], 1;\n}" ::"r"(ha[u]), "r"(kb[u]),
+                             "r"(nb)
+                             : "memory");
+        }
+        return;
+    }
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
-    for (int j0 = 0; j0 < GS; j0 += 4) {
+    for (int j0 = 0; j0 < nj; j0 += 4) {   // nj is a multiple of 4 (candidate batches are padded with +inf points)
         double r2[4];
         double meta[4];
         bool hit[4];
@@ -792,32 +937,8 @@ __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh
         for (int u = 0; u < 4; ++u) {
             const int jj = j0 + u;
             const double2 xy = jb[jj];
-            const double2 zw = jb[32 + jj];
-            double ax = __dsub_rn(xi, xy.x), ay = __dsub_rn(yi, xy.y), az = __dsub_rn(zi, zw.x);
-            if (VAR == VAR_SHIFT) {
-                ax = __dsub_rn(fabs(ax), sx);
-                ay = __dsub_rn(fabs(ay), sy);
-                az = __dsub_rn(fabs(az), sz);
-            } else if (VAR == VAR_MIXED) {
-                ax = fmin(fabs(ax), fabs(__dsub_rn(fabs(ax), sx)));
-                ay = fmin(fabs(ay), fabs(__dsub_rn(fabs(ay), sy)));
-                az = fmin(fabs(az), fabs(__dsub_rn(fabs(az), sz)));
-            } else if (VAR == VAR_TSHIFT) {
-                az = __dsub_rn(az, sz);
-                ay = __dsub_rn(__dsub_rn(ay, S.yz), sy);
-                ax = __dsub_rn(__dsub_rn(__dsub_rn(ax, S.xz), S.xy), sx);
-            } else if (VAR == VAR_TMIXED) {
-                const bool pz = az > hz, nz = az < -hz;
-                az = __dsub_rn(az, pz ? sz : (nz ? -sz : 0.0));
-                ay = __dsub_rn(ay, pz ? S.yz : (nz ? -S.yz : 0.0));
-                ax = __dsub_rn(ax, pz ? S.xz : (nz ? -S.xz : 0.0));
-                const bool py = ay > hy, ny = ay < -hy;
-                ay = __dsub_rn(ay, py ? sy : (ny ? -sy : 0.0));
-                ax = __dsub_rn(ax, py ? S.xy : (ny ? -S.xy : 0.0));
-                const bool px = ax > hx, nx = ax < -hx;
-                ax = __dsub_rn(ax, px ? sx : (nx ? -sx : 0.0));
-            }
-            r2[u] = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+            const double2 zw = jb[RING + jj];
+            r2[u] = image_r2<VAR>(__dsub_rn(xi, xy.x), __dsub_rn(yi, xy.y), __dsub_rn(zi, zw.x), S, hx, hy, hz);
             hit[u] = __double2hiint(r2[u]) <= rc_hi;   // superset of rsq < rcut2; settled exactly in drain()
             if (TRI) hit[u] = hit[u] && (jj > lane);
             if (META) meta[u] = zw.y;
@@ -847,8 +968,50 @@ __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh
     }
 }
 
+// evaluate the nj queued j points at jb (a multiple of 4; (x,y) at jb[k], (z,meta) at jb[RING + k]) against the 32 i points
+// of the warp, under the image class `cc` of the chunk pair they came from
+template <int MODE, bool MULTICLS, bool TRICL>
+__device__ __forceinline__ void run_batch(const PairParams &p, const Shared &sh, const double2 *jb, int nj, int cc, bool tri,
+                                          double xi, double yi, double zi, uint32_t mi, double lx, double ly, double lz,
+                                          const double *cell, int rc_hi, int lane, int &qn, double *qr, uint2 *qm, int frame)
+{
+    const Shift Z0 = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (cc == 0) {
+        if (tri)
+            chunk_loop<MODE, MULTICLS, VAR_FAST, true>(p, sh, jb, nj, xi, yi, zi, mi, Z0, rc_hi, lane, qn, qr, qm, frame);
+        else
+            chunk_loop<MODE, MULTICLS, VAR_FAST, false>(p, sh, jb, nj, xi, yi, zi, mi, Z0, rc_hi, lane, qn, qr, qm, frame);
+    } else if (TRICL) {
+        if (cc != TRI_MIXED && !tri) {
+            const int kx = cc & 3, ky = (cc >> 2) & 3, kz = (cc >> 4) & 3;
+            const Shift S = {tri_dec(kx, lx), tri_dec(ky, ly), tri_dec(kz, lz), tri_dec(ky, cell[3]), tri_dec(kz, cell[4]),
+                             tri_dec(kz, cell[5])};
+            chunk_loop<MODE, MULTICLS, VAR_TSHIFT, false>(p, sh, jb, nj, xi, yi, zi, mi, S, rc_hi, lane, qn, qr, qm, frame);
+        } else {
+            const Shift S = {lx, ly, lz, cell[3], cell[4], cell[5]};
+            if (tri)
+                chunk_loop<MODE, MULTICLS, VAR_TMIXED, true>(p, sh, jb, nj, xi, yi, zi, mi, S, rc_hi, lane, qn, qr, qm, frame);
+            else
+                chunk_loop<MODE, MULTICLS, VAR_TMIXED, false>(p, sh, jb, nj, xi, yi, zi, mi, S, rc_hi, lane, qn, qr, qm, frame);
+        }
+    } else {
+        const bool mixed = ((cc | (cc >> 2) | (cc >> 4)) & AX_MIXED) != 0;
+        if (!mixed && !tri) {
+            const Shift S = {(cc & 1) ? lx : 0.0, (cc & 4) ? ly : 0.0, (cc & 16) ? lz : 0.0, 0.0, 0.0, 0.0};
+            chunk_loop<MODE, MULTICLS, VAR_SHIFT, false>(p, sh, jb, nj, xi, yi, zi, mi, S, rc_hi, lane, qn, qr, qm, frame);
+        } else {
+            // undecided axes (small boxes, huge groups) and the rare wrapped diagonal chunk: exact for every d
+            const Shift S = {lx, ly, lz, 0.0, 0.0, 0.0};
+            if (tri)
+                chunk_loop<MODE, MULTICLS, VAR_MIXED, true>(p, sh, jb, nj, xi, yi, zi, mi, S, rc_hi, lane, qn, qr, qm, frame);
+            else
+                chunk_loop<MODE, MULTICLS, VAR_MIXED, false>(p, sh, jb, nj, xi, yi, zi, mi, S, rc_hi, lane, qn, qr, qm, frame);
+        }
+    }
+}
+
 template <int MODE, bool MULTICLS, bool SYMM, bool TRICL>
-__global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
+__global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool META = MULTICLS || MODE == MODE_LIST;
@@ -856,9 +1019,9 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
 
     // warp-private region
     unsigned char *wp = smem_raw + (size_t)w * warp_region_bytes(META);
-    double2 *jbuf = reinterpret_cast<double2 *>(wp);                       // [2][GREC]
-    double *qr = reinterpret_cast<double *>(wp + 2 * GREC * sizeof(double2));
-    uint2 *qm = reinterpret_cast<uint2 *>(wp + 2 * GREC * sizeof(double2) + QCAP * sizeof(double));
+    double2 *ring = reinterpret_cast<double2 *>(wp);                       // [RING] (x,y) then [RING] (z,meta)
+    double *qr = reinterpret_cast<double *>(wp + 2 * RING * sizeof(double2));
+    uint2 *qm = reinterpret_cast<uint2 *>(wp + 2 * RING * sizeof(double2) + QCAP * sizeof(double));
     // CTA-shared region
     unsigned char *sp = smem_raw + (size_t)NWARP * warp_region_bytes(META);
     Shared sh;
@@ -869,10 +1032,17 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
     sh.hist = reinterpret_cast<unsigned int *>(sp);
     sh.edges_s = edges_s;
     sh.cptab = p.cptab;
+    sh.edges_a = (unsigned)__cvta_generic_to_shared(edges_s);
+    sh.cptab_a = (unsigned)__cvta_generic_to_shared(cptab_s);
+    sh.hist_a = (unsigned)__cvta_generic_to_shared(sh.hist);
 
     const int nhist = MODE == MODE_LIST ? 0 : p.nrows * p.nbins;
     if (MODE != MODE_LIST) {
-        if (p.edges_in_smem) {
+        if (MODE == MODE_HIST_DIRECT) {
+            // plain edge table e[0..nbins+1] (e[nbins+1] = +inf) in the space the edge pairs would take
+            double *e1 = reinterpret_cast<double *>(edges_s);
+            for (int k = tid; k <= p.nbins + 1; k += blockDim.x) e1[k] = p.edges2[k].x;
+        } else if (p.edges_in_smem) {
             for (int k = tid; k <= p.nbins; k += blockDim.x) edges_s[k] = p.edges2[k];
         }
         for (int k = tid; k < nhist; k += blockDim.x) sh.hist[k] = 0u;
@@ -887,7 +1057,7 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
     const int rc_hi = __double2hiint(p.rcut2);
     const float rcut2_up = __double2float_ru(p.rcut2);
     const unsigned long long total = *p.total;
-    unsigned long long my_chunks = 0;
+    unsigned long long my_evals = 0;   // 32-pair evaluation steps executed by this warp
     const int F = p.nframes;
     // every CTA starts at a different frame and walks all of them, so the frames' tails do not line up
     const int fstart = (int)(((long long)blockIdx.x * F) / gridDim.x);
@@ -896,140 +1066,159 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
     for (int fk = 0; fk < F; ++fk) {
         int f = fstart + fk;
         if (f >= F) f -= F;
-        const unsigned int ibeg = p.rowoff[(int64_t)f * p.ntA];
-        const unsigned int iend = f + 1 < F ? p.rowoff[(int64_t)(f + 1) * p.ntA] : (unsigned int)total;
-        const unsigned int nwi = (iend - ibeg) * GPT;   // warp items of this frame
+        const unsigned int nunits = (unsigned int)p.ntA * GPT;   // work units of this frame: one per 32-point i group
         const double lx = p.box[f * 6 + 0], ly = p.box[f * 6 + 1], lz = p.box[f * 6 + 2];
         const AxisF AX = make_axis(lx), AY = make_axis(ly), AZ = make_axis(lz);
         const int frame = p.frame0 + f;
         const double2 *rA = p.recA + (int64_t)f * p.npadA * 2;
         const double2 *rB = p.recB + (int64_t)f * p.npadB * 2;
+        const float4 *gbB = p.gboxB + (int64_t)f * p.ngB * 2;
         bool did = false;
 
         unsigned int q = 0;
         if (lane == 0) q = atomicAdd(&p.counters[f], 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
 #pragma unroll 1
-        while (q < nwi) {
+        while (q < nunits) {
             unsigned int qnext = 0;
             if (lane == 0) qnext = atomicAdd(&p.counters[f], 1u);   // prefetch the next work index
             did = true;
-            const uint64_t item = p.items[ibeg + (q >> 3)];
-            const int wi = (int)(q & 7u);
-            const int ta = (int)((item >> 22) & 0x3fffffu), tb = (int)(item & 0x3fffffu);
+            // One unit = one i group (32 points, one per lane) against every j tile of its tile row of the work list.
+            const int ta = (int)(q >> 3), wi = (int)(q & 7u);
+            const int64_t row = (int64_t)f * p.ntA + ta;
+            unsigned int t0 = p.rowoff[row];
+            const unsigned int tend = row + 1 < (int64_t)F * p.ntA ? p.rowoff[row + 1] : (unsigned int)total;
             const int64_t gi = (int64_t)ta * GPT + wi;
-            // my i point; lanes 0..7 test my group's box against the 8 chunk boxes of the j tile
             const double2 ixy = rA[gi * GREC + lane], izw = rA[gi * GREC + 32 + lane];
-            const bool diag = SYMM && ta == tb;
-            bool need = false;
-            int code = 0;
-            {
-                const float4 *ga4 = p.gboxA + ((int64_t)f * p.ngA + gi) * 2;
-                const float4 alo = ga4[0], ahi = ga4[1];
-                const float ga[6] = {alo.x, alo.y, alo.z, ahi.x, ahi.y, ahi.z};
-                if (lane < GPT && !(diag && lane < wi)) {
-                    const float4 *gb4 = p.gboxB + ((int64_t)f * p.ngB + (int64_t)tb * GPT + lane) * 2;
-                    const float4 blo = gb4[0], bhi = gb4[1];
-                    const float gb[6] = {blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z};
-                    if (TRICL) {
-                        TriConst<DirF32> TC;
-                        TC.set(p.box + f * 6);
-                        need = tri_box_test<DirF32>(ga, gb, TC, rcut2_up, code);
-                    } else {
-                        need = chunk_test_f32(ga, gb, AX, AY, AZ, rcut2_up, code);
-                    }
-                    if (p.nocull) {
-                        need = !(ga[0] > ga[3] || gb[0] > gb[3]);
-                        code = TRICL ? TRI_MIXED : (AX_MIXED | (AX_MIXED << 2) | (AX_MIXED << 4));
-                    }
-                }
-            }
-            unsigned needmask = __ballot_sync(0xffffffffu, need);
+            const float4 *ga4 = p.gboxA + ((int64_t)f * p.ngA + gi) * 2;
+            const float4 alo = ga4[0], ahi = ga4[1];
+            const float ga[6] = {alo.x, alo.y, alo.z, ahi.x, ahi.y, ahi.z};
             const uint32_t mi = MODE == MODE_LIST ? (uint32_t)__double2hiint(izw.y)
                                                   : (uint32_t)(__double2loint(izw.y) * p.nclsB);
-            const double2 *jsrc = rB + (int64_t)tb * GPT * GREC;
-            int buf = 0;
-            int c = -1;
-            if (needmask) {
-                c = __ffs(needmask) - 1;
-                needmask &= needmask - 1;
-                cp_async16(&jbuf[lane], &jsrc[c * GREC + lane]);
-                cp_async16(&jbuf[32 + lane], &jsrc[c * GREC + 32 + lane]);
-                cp_async_commit();
-            }
+
+            // Chunk level: 32 lanes test the boxes of 32 j chunks (4 tiles x 8 chunks) against my group's box at a time.
+            // Point level: the needed chunks are filtered point by point -- lane l keeps j point l of the chunk only if
+            // it can be inside the cutoff of SOME point of my group's box (fp32, rounded outward, under the chunk pair's
+            // image class).  The survivors are appended to a 64-entry ring; whenever 32 are queued they are evaluated
+            // against the 32 i points with the 4-way unrolled loop.  A change of image class, the triangular self chunk
+            // and the end of the unit flush the ring (padded to a multiple of 4 with +inf points, which can never be
+            // inside the cutoff).  One chunk is always in flight (registers) while the previous one is processed.
+            unsigned needmask = 0;
+            int tbl = -1, code = 0;                       // per lane: tile and image class of "my" chunk of the current 32
+            int head = 0, tail = 0, cur = 0;              // ring state; cur = image class of the queued candidates
+            bool cvalid = false, nvalid = false, cself = false, nself = false;
+            int ccode = 0, ncode = 0;
+            double2 jxy = make_double2(0.0, 0.0), jzw = jxy, nxy = jxy, nzw = jxy;
 #pragma unroll 1
-            while (c >= 0) {
-                int cn = -1;
-                if (needmask) {
-                    cn = __ffs(needmask) - 1;
-                    needmask &= needmask - 1;
-                    double2 *nb = jbuf + (buf ^ 1) * GREC;
-                    cp_async16(&nb[lane], &jsrc[cn * GREC + lane]);
-                    cp_async16(&nb[32 + lane], &jsrc[cn * GREC + 32 + lane]);
-                    cp_async_commit();
-                    cp_async_wait<1>();
+            while (true) {
+                if (!nvalid) {
+                    // fetch: next needed chunk of the row into the "next" registers
+#pragma unroll 1
+                    while (needmask == 0u && t0 < tend) {
+                        const unsigned int it = t0 + (unsigned)(lane >> 3);
+                        const int cj = lane & 7;
+                        tbl = it < tend ? (int)(p.items[it] & 0x3fffffu) : -1;
+                        bool need = false;
+                        code = 0;
+                        if (tbl >= 0 && !(SYMM && tbl == ta && cj < wi)) {
+                            const float4 *gb4 = gbB + ((int64_t)tbl * GPT + cj) * 2;
+                            const float4 blo = gb4[0], bhi = gb4[1];
+                            const float gb[6] = {blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z};
+                            if (TRICL) {
+                                TriConst<DirF32> TC;
+                                TC.set(p.box + f * 6);
+                                need = tri_box_test<DirF32>(ga, gb, TC, rcut2_up, code);
+                            } else {
+                                need = chunk_test_f32(ga, gb, AX, AY, AZ, rcut2_up, code);
+                            }
+                            if (p.nocull) {
+                                need = !(ga[0] > ga[3] || gb[0] > gb[3]);
+                                code = TRICL ? TRI_MIXED : (AX_MIXED | (AX_MIXED << 2) | (AX_MIXED << 4));
+                            }
+                        }
+                        needmask = __ballot_sync(0xffffffffu, need);
+                        t0 += 4;
+                    }
+                    if (needmask) {
+                        const int l = __ffs(needmask) - 1;
+                        needmask &= needmask - 1;
+                        const int tb = __shfl_sync(0xffffffffu, tbl, l);
+                        ncode = __shfl_sync(0xffffffffu, code, l);
+                        nself = SYMM && tb == ta && (l & 7) == wi;
+                        const double2 *jsrc = rB + ((int64_t)tb * GPT + (l & 7)) * GREC;
+                        nxy = __ldg(&jsrc[lane]);
+                        nzw = __ldg(&jsrc[32 + lane]);
+                        nvalid = true;
+                    }
+                }
+                int run_n = 0, run_base = 0, run_code = cur;
+                bool run_tri = false;
+                if (!cvalid) {
+                    if (nvalid) {
+                        cvalid = true;
+                        nvalid = false;
+                        ccode = ncode;
+                        cself = nself;
+                        jxy = nxy;
+                        jzw = nzw;
+                        continue;
+                    }
+                    if (tail == head) break;
+                    run_n = -1;   // end of the unit: flush
+                } else if ((cself || ccode != cur) && tail != head) {
+                    run_n = -1;   // flush first; the chunk is looked at again in the next round
+                } else if (cself) {
+                    ring[lane] = jxy;
+                    ring[RING + lane] = jzw;
+                    run_n = 32;
+                    run_code = ccode;
+                    run_tri = true;
+                    cvalid = false;
                 } else {
-                    cp_async_wait<0>();
+                    cur = ccode;
+                    run_code = ccode;
+                    bool ok;
+                    if (TRICL)
+                        ok = (ccode == TRI_MIXED) || tri_point_test_f32(ga, jxy.x, jxy.y, jzw.x, p.box + f * 6, rcut2_up, ccode);
+                    else
+                        ok = point_test_f32(ga, jxy.x, jxy.y, jzw.x, AX, AY, AZ, rcut2_up, ccode);
+                    if (p.nocull) ok = true;
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (ok) {
+                        const int pos = (tail + __popc(m & ((1u << lane) - 1u))) & (RING - 1);
+                        ring[pos] = jxy;
+                        ring[RING + pos] = jzw;
+                    }
+                    tail += __popc(m);
+                    cvalid = false;
+                    if (tail - head >= 32) {
+                        run_n = 32;
+                        run_base = head & 32;
+                    }
+                }
+                if (run_n == 0) continue;
+                const bool flush = run_n < 0;
+                if (flush) {
+                    const int n = tail - head;
+                    run_n = (n + 3) & ~3;
+                    run_base = head & 32;
+                    if (lane < run_n - n) {
+                        const int pos = (tail + lane) & (RING - 1);
+                        ring[pos] = make_double2(INFINITY, 0.0);
+                        ring[RING + pos] = make_double2(0.0, 0.0);
+                    }
                 }
                 __syncwarp();
-                const double2 *jb = jbuf + buf * GREC;
-                const int cc = __shfl_sync(0xffffffffu, code, c);
-                const bool tri = diag && c == wi;
-                ++my_chunks;
-                if (TRICL) {
-                    const Shift Z0 = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                    if (cc == 0) {
-                        if (tri)
-                            chunk_loop<MODE, MULTICLS, VAR_FAST, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, Z0, rc_hi, lane, qn, qr, qm,
-                                                                       frame);
-                        else
-                            chunk_loop<MODE, MULTICLS, VAR_FAST, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, Z0, rc_hi, lane, qn, qr,
-                                                                        qm, frame);
-                    } else if (cc != TRI_MIXED && !tri) {
-                        const double *cell = p.box + f * 6;
-                        const int kx = cc & 3, ky = (cc >> 2) & 3, kz = (cc >> 4) & 3;
-                        const Shift S = {tri_dec(kx, lx), tri_dec(ky, ly), tri_dec(kz, lz), tri_dec(ky, cell[3]),
-                                         tri_dec(kz, cell[4]), tri_dec(kz, cell[5])};
-                        chunk_loop<MODE, MULTICLS, VAR_TSHIFT, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr, qm,
-                                                                      frame);
-                    } else {
-                        const double *cell = p.box + f * 6;
-                        const Shift S = {lx, ly, lz, cell[3], cell[4], cell[5]};
-                        if (tri)
-                            chunk_loop<MODE, MULTICLS, VAR_TMIXED, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr,
-                                                                         qm, frame);
-                        else
-                            chunk_loop<MODE, MULTICLS, VAR_TMIXED, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr,
-                                                                          qm, frame);
-                    }
+                my_evals += (unsigned long long)run_n;
+                run_batch<MODE, MULTICLS, TRICL>(p, sh, ring + run_base, run_n, run_code, run_tri, ixy.x, ixy.y, izw.x, mi, lx, ly, lz,
+                                                 p.box + f * 6, rc_hi, lane, qn, qr, qm, frame);
+                __syncwarp();   // everyone is done with the batch before the ring is written again
+                if (flush || run_tri) {
+                    head = 0;
+                    tail = 0;
                 } else {
-                    const bool mixed = ((cc | (cc >> 2) | (cc >> 4)) & AX_MIXED) != 0;
-                    const Shift Z0 = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                    if (cc == 0) {
-                        if (tri)
-                            chunk_loop<MODE, MULTICLS, VAR_FAST, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, Z0, rc_hi, lane, qn, qr, qm,
-                                                                       frame);
-                        else
-                            chunk_loop<MODE, MULTICLS, VAR_FAST, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, Z0, rc_hi, lane, qn, qr,
-                                                                        qm, frame);
-                    } else if (!mixed && !tri) {
-                        const Shift S = {(cc & 1) ? lx : 0.0, (cc & 4) ? ly : 0.0, (cc & 16) ? lz : 0.0, 0.0, 0.0, 0.0};
-                        chunk_loop<MODE, MULTICLS, VAR_SHIFT, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr, qm,
-                                                                     frame);
-                    } else {
-                        // undecided axes (small boxes, huge groups) and the rare wrapped diagonal chunk: exact for every d
-                        const Shift S = {lx, ly, lz, 0.0, 0.0, 0.0};
-                        if (tri)
-                            chunk_loop<MODE, MULTICLS, VAR_MIXED, true>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr, qm,
-                                                                        frame);
-                        else
-                            chunk_loop<MODE, MULTICLS, VAR_MIXED, false>(p, sh, jb, ixy.x, ixy.y, izw.x, mi, S, rc_hi, lane, qn, qr,
-                                                                         qm, frame);
-                    }
+                    head += 32;
                 }
-                __syncwarp();   // everyone is done with this stage before it is refilled
-                buf ^= 1;
-                c = cn;
             }
             q = __shfl_sync(0xffffffffu, qnext, 0);
         }
@@ -1053,7 +1242,7 @@ __global__ void __launch_bounds__(NWARP * 32, 3) k_pair(const PairParams p)
             }
         }
     }
-    if (lane == 0 && my_chunks) atomicAdd(&p.stats[2], my_chunks * (unsigned long long)(GS * GS));
+    if (lane == 0 && my_evals) atomicAdd(&p.stats[2], my_evals * (unsigned long long)GS);
 }
 
 // out[f][r][b] = sum_rows w[r][row] * (cumulative ? prefix : value) hist[f][row][b]
@@ -1224,7 +1413,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         const size_t hist_bytes = (size_t)nrows * c.nbins * 4;
         const size_t edge_bytes = (size_t)(c.nbins + 1) * sizeof(double2);
         if (multicls) smem += (size_t)((ncp * 4 + 15) & ~15);
-        const size_t cap = std::min<size_t>(ctx->smem_optin, 72 * 1024);   // keep 3 CTAs per SM
+        const size_t cap = std::min<size_t>(ctx->smem_optin, (216 / CTAS_PER_SM) * 1024);   // keep CTAS_PER_SM CTAs per SM
         MDP_REQUIRE(smem + hist_bytes <= ctx->smem_optin,
                     "pair: histogram of %d rows x %d bins does not fit in shared memory (%zu B needed); "
                     "reduce the number of distinct classes or bins per call",
@@ -1271,7 +1460,12 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         }
     }
 
-    pair_kernel_t kern = c.mode == MODE_HIST_UNIFORM ? pick_kernel<MODE_HIST_UNIFORM>(multicls, symm, tric)
+    // direct binning needs the edge pairs in shared memory (entries 0..nbins are read)
+    // and rsq >= rcut2 must imply bin >= nbins (edge[nbins] <= rcut2), which holds whenever nbins = int(r_cut/bin_size)
+    const bool direct = c.mode == MODE_HIST_UNIFORM && edges_in_smem && c.nbins <= 4096 && c.edges[c.nbins] <= c.rcut2 &&
+                        !(c.flags & MDP_PAIR_QUEUE_BINNING);
+    pair_kernel_t kern = direct                        ? pick_kernel<MODE_HIST_DIRECT>(multicls, symm, tric)
+                         : c.mode == MODE_HIST_UNIFORM ? pick_kernel<MODE_HIST_UNIFORM>(multicls, symm, tric)
                          : c.mode == MODE_HIST_TABLE ? pick_kernel<MODE_HIST_TABLE>(multicls, symm, tric)
                                                      : pick_kernel<MODE_LIST>(false, symm, tric);
     MDP_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1364,6 +1558,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         p.inv_ddr = c.uniform_ddr > 0 ? (float)(1.0 / c.uniform_ddr) : 0.f;
         p.hist = (unsigned long long *)c.hist_out;
         p.edges_in_smem = edges_in_smem;
+        p.inv_ddr_biased = p.inv_ddr * (1.0f - 1.0f / 262144.0f);
         p.rin2 = c.rin2;
         p.rout2 = c.rout2;
         p.shell_mode = c.shell_mode;
@@ -1376,7 +1571,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         p.nocull = nocull ? 1 : 0;
         MDP_CUDA(cudaMemsetAsync(d_fcount, 0, (size_t)F * 4, st));
         cudaEvent_t tk = ctx->timer_begin(0, st);
-        kern<<<ctx->sm_count * 3, NWARP * 32, smem, st>>>(p);
+        kern<<<ctx->sm_count * CTAS_PER_SM, NWARP * 32, smem, st>>>(p);
         ctx->timer_end(tk, st);
         MDP_LAUNCHED(ctx);
         rc = mdp_check_launch("k_pair");
