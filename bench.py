@@ -347,6 +347,9 @@ def run_gpu(args):
     if not args.skip_msd:
         msd = bench_msd(args, torch, dist, ops, ctx, dev, world, rank)
 
+    gk = None if args.skip_gk else bench_green_kubo(args, torch, dist, ops, ctx, dev, world, rank)
+    res = None if args.skip_residence else bench_residence(args, torch, dist, ops, ctx, dev, world, rank)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -391,6 +394,10 @@ def run_gpu(args):
         out["rdf_triclinic"] = tric
     if msd:
         out["msd"] = msd
+    if gk:
+        out["green_kubo"] = gk
+    if res:
+        out["residence"] = res
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -503,6 +510,148 @@ def bench_msd(args, torch, dist, ops, ctx, dev, world, rank):
     }
 
 
+def _timed(ctx, torch, tag, fn, reps):
+    """Run fn reps times; return (ms per rep by CUDA events on the current stream, kernel ms per rep from the library's own
+    event pairs around kernel `tag`, launches of that kernel per rep)."""
+    fn()
+    torch.cuda.synchronize()
+    ctx.timing(True)
+    ctx.timing_read(tag)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    kms, kn = ctx.timing_read(tag)
+    ctx.timing(False)
+    return e0.elapsed_time(e1) / reps, kms / reps, kn // reps
+
+
+def bench_green_kubo(args, torch, dist, ops, ctx, dev, world, rank):
+    """C4 shape: ionic liquid, 50 000 atoms = 2 500 cations + 2 500 anions of 10 atoms.  (i) charge-flux
+    reduction over a resident chunk of velocity frames (HBM-bound, 24 B per atom-frame); (ii) the unbiased time
+    correlations of a 100 000-step series: 27 conductivity channels (3 axes x 9 ordered type pairs incl. totals) + 3
+    pressure-tensor channels = 30 channels, direct sum in fp64 FMA (FP64-pipe bound: T(T+1)/2 FMAs per channel).
+    Channels are split over the ranks."""
+    n, nmol, per = 50_000, 5_000, 10
+    Tf = args.gk_flux_frames
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED + 200 + rank)
+    vel = torch.randn((Tf, 3, n), generator=g, dtype=torch.float64, device=dev) * 1e-3
+    masses = torch.tensor([12.01, 1.008, 14.01, 16.0, 19.0, 32.06, 12.01, 1.008, 16.0, 19.0], dtype=torch.float64, device=dev).repeat(nmol)
+    q = torch.cat([torch.full((n // 2,), 0.1, dtype=torch.float64, device=dev), torch.full((n // 2,), -0.1, dtype=torch.float64, device=dev)])
+    seg_off = torch.arange(0, n + 1, per, dtype=torch.int32, device=dev)
+    type_off = np.array([0, nmol // 2, nmol], dtype=np.int64)
+    out = torch.zeros((3, 2, Tf), dtype=torch.float64, device=dev)
+    # the ABI takes <= 65535 frames per call
+    ms_f, kms_f, kn_f = _timed(ctx, torch, 4, lambda: ops.charge_flux(vel, masses, q, seg_off, type_off, 1e5, 1.602e-19, out=out), 5)
+    peaks = measured_peaks()
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    flux_gbs = n * Tf * 24 / (kms_f * 1e-3) / 1e9
+    del vel
+    T = args.gk_steps
+    C_all = 30
+    c0, c1 = (rank * C_all) // world, ((rank + 1) * C_all) // world
+    C = max(1, c1 - c0)
+    a = torch.randn((C, T), generator=g, dtype=torch.float64, device=dev)
+    b = torch.randn((C, T), generator=g, dtype=torch.float64, device=dev)
+    ms_x, kms_x, kn_x = _timed(ctx, torch, 3, lambda: ops.xcorr_unbiased(a, b), 3)
+    t = torch.tensor([ms_x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_x_max = float(t.item())
+    fma = C * T * (T + 1) // 2
+    fma_peak = peaks.get("fp64_fma_tflops_burst", 2 * 148 * 64 * 1.965e9 / 1e12)
+    ach = 2 * fma / (kms_x * 1e-3) / 1e12
+    # the integral on device as well (conductivity.py:231)
+    corr = ops.xcorr_unbiased(a, b)
+    ms_c, _, _ = _timed(ctx, torch, 7, lambda: ops.cumtrapz(corr, 1.0, 1.0, True), 3)
+    return {
+        "metric": "acf_lag_products_per_s", "value": C_all * T * (T + 1) // 2 / (ms_x_max * 1e-3), "unit": "fp64 FMA/s",
+        "config": {"workload": f"C4 shape: {C_all} channels x {T} steps, unbiased correlation at every lag (direct sum), "
+                               f"channels x{world}; charge flux on {n} atoms x {Tf} resident frames ({n * Tf * 24 / 1e9:.1f} GB)"},
+        "ms_per_step": ms_x_max, "cumtrapz_ms": ms_c,
+        "roofline": {"bound": "fp64", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s", "frac": ach / fma_peak, "traffic": None,
+                     "note": "k_xcorr only; 2 flops per fp64 FMA, T(T+1)/2 FMAs per channel; peak = measured DFMA rate "
+                             "(tools/peaks.cu); inputs are a few MB, HBM bandwidth is not a meaningful bound here"},
+        "charge_flux": {"value": world * n * Tf / (ms_f * 1e-3), "unit": "atom-frames/s", "ms_per_step": ms_f,
+                        "roofline": {"bound": "hbm", "achieved": flux_gbs, "peak": hbm, "unit": "GB/s", "frac": flux_gbs / hbm,
+                                     "traffic": None, "note": "k_charge_flux only (two molecule types = two launches, each reads "
+                                                              "its own molecules); 24 B per atom-frame in total"}},
+    }
+
+
+def bench_residence(args, torch, dist, ops, ctx, dev, world, rank):
+    """C5 shape (SURVEY 8d): 2 000 cations and 62 666 water oxygens in a 126 A cubic box, T frames of a random walk;
+    residence shell r <= 3.0 A.  (i) neighbour search mdp_pair_list (cations x oxygens per frame, the pair engine in list
+    mode), (ii) time bitmasks of the ever-neighbour pairs, (iii) survival counts cnt[tau] = sum_p popc(m_p & m_p >> tau).
+    Central atoms are split over the ranks."""
+    ncat_all, nox, L = 2_000, 62_666, 126.0
+    T = args.res_frames
+    c0, c1 = (rank * ncat_all) // world, ((rank + 1) * ncat_all) // world
+    ncat = c1 - c0
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED + 300)
+    cat = torch.empty((T, 3, ncat), dtype=torch.float64, device=dev)
+    ox = torch.empty((T, 3, nox), dtype=torch.float64, device=dev)
+    pc = torch.rand((3, ncat_all), generator=g, dtype=torch.float64, device=dev)[:, c0:c1] * L
+    po = torch.rand((3, nox), generator=g, dtype=torch.float64, device=dev) * L
+    CH = 250
+    for f0 in range(0, T, CH):          # random walk, sigma = 0.15 A per frame, wrapped
+        k = min(CH, T - f0)
+        sc = torch.randn((k, 3, ncat), generator=g, dtype=torch.float64, device=dev).mul_(0.15).cumsum_(0)
+        so = torch.randn((k, 3, nox), generator=g, dtype=torch.float64, device=dev).mul_(0.15).cumsum_(0)
+        cat[f0:f0 + k] = torch.remainder(pc + sc, L)
+        ox[f0:f0 + k] = torch.remainder(po + so, L)
+        pc, po = pc + sc[-1], po + so[-1]
+        del sc, so
+    boxes = np.tile(np.array([L, L, L]), (T, 1))
+    FB = 500                              # frames per search call
+
+    def search():
+        parts = []
+        for f0 in range(0, T, FB):
+            lst, _ = ops.pair_list(cat[f0:f0 + FB], ox[f0:f0 + FB], boxes[f0:f0 + FB], 0.0, 9.0, 1, capacity=16 * ncat * FB)
+            lst[:, 0] += f0
+            parts.append(lst)
+        return torch.cat(parts)
+
+    lst = search()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lst = search()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_search = e0.elapsed_time(e1)
+    holder = {}
+
+    def corr():
+        holder["cnt"], holder["P"] = ops.bitmask_autocorr_from_list(lst, nox, T)
+
+    ms_c, kms_c, kn_c = _timed(ctx, torch, 6, corr, 3)
+    P, cnt = holder["P"], holder["cnt"]
+    W = (T + 63) // 64
+    words = P * sum(W - (tau >> 6) for tau in range(T))            # 64-bit AND+POPC per (pair, lag, word)
+    gpop = words / (kms_c * 1e-3) / 1e9
+    peak = 148 * 16 * 1.965 / 2                                     # POPC runs at 16 lanes/clk/SM; popcll = 2 POPC
+    t = torch.tensor([ms_search + ms_c], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    return {
+        "metric": "residence_pair_evals_per_s", "value": ncat_all * nox * T / (total_ms * 1e-3), "unit": "pair-evals/s",
+        "config": {"workload": f"C5 shape: {ncat_all} cations x {nox} water O x {T} frames, shell r <= 3.0 A, search + bitmask "
+                               f"survival correlation at all {T} lags; central atoms x{world}"},
+        "ms_per_step": total_ms, "search_ms": ms_search, "correlation_ms": ms_c, "neighbour_entries": int(lst.shape[0]),
+        "ever_neighbour_pairs": P, "cnt0": int(cnt[0].item()),
+        "roofline": {"bound": "int", "achieved": gpop, "peak": peak, "unit": "G popc64/s", "frac": gpop / peak, "traffic": None,
+                     "note": "k_bitmask_autocorr only; one 64-bit AND + POPC per (pair, lag, word); peak = nominal XU rate "
+                             "16 POPC/clk/SM x 148 SMs x 1965 MHz / 2 (popcll = 2 POPC)"},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -517,6 +666,11 @@ def main():
     ap.add_argument("--skip-triclinic", action="store_true")
     ap.add_argument("--skip-msd-window", action="store_true")
     ap.add_argument("--msd-window", type=int, default=512)
+    ap.add_argument("--skip-gk", action="store_true")
+    ap.add_argument("--skip-residence", action="store_true")
+    ap.add_argument("--gk-steps", type=int, default=100_000)
+    ap.add_argument("--gk-flux-frames", type=int, default=4096)
+    ap.add_argument("--res-frames", type=int, default=5000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

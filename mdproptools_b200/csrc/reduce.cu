@@ -263,11 +263,28 @@ __global__ void __launch_bounds__(MW_WARPS * 32, 2) k_msd_window(const double *_
                 for (int ta = tbeg; ta < tend; ta += MW_TT) {
                     if (ta + lagbase >= T) break;                 // no partner inside the trajectory
                     __syncthreads();                              // previous tile fully consumed
-                    for (int i = tid; i < (MW_TT + MW_BROWS) * 32; i += blockDim.x) {
-                        const int r = i >> 5, l = i & 31;
-                        const int t = r < MW_TT ? ta + r : ta + lagbase + (r - MW_TT);
-                        const bool ok = t < T && atom0 + l < a1;
-                        cp_async8_zfill(&A[i], xc + (int64_t)(ok ? t : 0) * 3 * n + (ok ? l : 0), ok);
+                    {
+                        // warp w copies rows w, w+8, ... (lane = atom): one pointer bump per copy, no index arithmetic
+                        const int64_t rs = (int64_t)3 * n;
+                        const bool lane_ok = atom0 + lane < a1;
+                        const double *src = xc + (int64_t)(ta + w) * rs + lane;
+                        double *dst = A + w * 32 + lane;
+#pragma unroll 4
+                        for (int r = w; r < MW_TT; r += MW_WARPS) {
+                            const bool ok = lane_ok && ta + r < T;
+                            cp_async8_zfill(dst, ok ? src : xc, ok);
+                            src += MW_WARPS * rs;
+                            dst += MW_WARPS * 32;
+                        }
+                        src = xc + (int64_t)(ta + lagbase + w) * rs + lane;
+                        dst = B + w * 32 + lane;
+#pragma unroll 4
+                        for (int r = w; r < MW_BROWS; r += MW_WARPS) {
+                            const bool ok = lane_ok && ta + lagbase + r < T;
+                            cp_async8_zfill(dst, ok ? src : xc, ok);
+                            src += MW_WARPS * rs;
+                            dst += MW_WARPS * 32;
+                        }
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -347,29 +364,82 @@ __global__ void __launch_bounds__(RB) k_segment_com(const double *__restrict__ a
 }
 
 // ---- charge flux (_conductivity.py:7-36) -------------------------------------------------------
-// grid (nblocks over segments [s0,s1) of one molecule type, nframes)
+// per-molecule mass and charge (sequential sums in atom order); static over the frames of a call
+__global__ void __launch_bounds__(RB) k_seg_static(const double *__restrict__ mass, const double *__restrict__ q,
+                                                   const int32_t *__restrict__ seg_off, int64_t nseg, double *__restrict__ wsum,
+                                                   double *__restrict__ qsum)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    double ws = 0.0, qs = 0.0;
+    for (int a = seg_off[s]; a < seg_off[s + 1]; ++a) {
+        ws = __dadd_rn(ws, mass[a]);
+        qs = __dadd_rn(qs, q[a]);
+    }
+    wsum[s] = ws;
+    qsum[s] = qs;
+}
+
+// grid (nblocks over segments [s0,s1) of one molecule type, nframes).  A CTA owns RB consecutive molecules, i.e. one
+// contiguous atom range (molecule membership is positional).  Thread-per-atom, coalesced: the three
+// velocity components (streamed once from HBM) times the atom's mass (L2-resident) go to shared memory in tiles of
+// FLUX_TILE atoms; thread-per-molecule then adds its own atoms from shared memory in atom order, as the reference
+// does.  (A thread-per-molecule gather straight from global touches 32 sectors per warp load and is L1-throughput
+// bound at half the HBM rate.)
+constexpr int FLUX_TILE = 1536;
 __global__ void __launch_bounds__(RB) k_charge_flux(const double *__restrict__ vel, int64_t n, const double *__restrict__ mass,
-                                                    const double *__restrict__ q, const int32_t *__restrict__ seg_off,
-                                                    int64_t s0, int64_t s1, double vel_scale, double q_scale,
-                                                    double *__restrict__ partial, int nchunks)
+                                                    const double *__restrict__ wsum, const double *__restrict__ qsum,
+                                                    const int32_t *__restrict__ seg_off, int64_t s0, int64_t s1,
+                                                    double vel_scale, double q_scale, double *__restrict__ partial, int nchunks)
 {
     __shared__ double sm[32];
+    __shared__ double sv[3][FLUX_TILE];
     const int f = blockIdx.y;
-    const int64_t s = s0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double j[3] = {0, 0, 0};
-    if (s < s1) {
-        const int b = seg_off[s], e = seg_off[s + 1];
-        const double *v = vel + (int64_t)f * 3 * n;
-        double ws = 0.0, qs = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int a = b; a < e; ++a) {
-            const double m = mass[a];
-            ws = __dadd_rn(ws, m);
-            qs = __dadd_rn(qs, q[a]);
-            a0 = __dadd_rn(a0, __dmul_rn(ld_stream1(v + a), m));
-            a1 = __dadd_rn(a1, __dmul_rn(ld_stream1(v + n + a), m));
-            a2 = __dadd_rn(a2, __dmul_rn(ld_stream1(v + 2 * n + a), m));
+    const int64_t sfirst = s0 + (int64_t)blockIdx.x * blockDim.x;
+    const int64_t slast = sfirst + blockDim.x < s1 ? sfirst + blockDim.x : s1;   // one past my CTA's last molecule
+    const int64_t s = sfirst + threadIdx.x;
+    const int A0 = seg_off[sfirst], A1 = seg_off[slast];
+    const bool mine = s < s1;
+    const int b = mine ? seg_off[s] : A1, e = mine ? seg_off[s + 1] : A1;
+    const double *v = vel + (int64_t)f * 3 * n;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int t0 = A0; t0 < A1; t0 += FLUX_TILE) {
+        const int cnt = A1 - t0 < FLUX_TILE ? A1 - t0 : FLUX_TILE;
+        // all 18 loads of a thread are issued before anything depends on them (memory-level parallelism: the tile is
+        // only 36 KB, the CTA has nothing else in flight)
+        double r[3][FLUX_TILE / RB], mm[FLUX_TILE / RB];
+#pragma unroll
+        for (int k = 0; k < FLUX_TILE / RB; ++k) {
+            const int i = threadIdx.x + k * RB;
+            const bool ok = i < cnt;
+            const double *pv = v + t0 + (ok ? i : 0);
+            r[0][k] = ld_stream1(pv);
+            r[1][k] = ld_stream1(pv + n);
+            r[2][k] = ld_stream1(pv + 2 * n);
+            mm[k] = mass[t0 + (ok ? i : 0)];
         }
-        const double qsi = __dmul_rn(qs, q_scale);
+        __syncthreads();   // previous tile fully consumed
+#pragma unroll
+        for (int k = 0; k < FLUX_TILE / RB; ++k) {
+            const int i = threadIdx.x + k * RB;
+            if (i < cnt) {
+                sv[0][i] = __dmul_rn(r[0][k], mm[k]);
+                sv[1][i] = __dmul_rn(r[1][k], mm[k]);
+                sv[2][i] = __dmul_rn(r[2][k], mm[k]);
+            }
+        }
+        __syncthreads();
+        const int lo = b > t0 ? b : t0, hi = e < t0 + cnt ? e : t0 + cnt;
+        for (int a = lo; a < hi; ++a) {
+            a0 = __dadd_rn(a0, sv[0][a - t0]);
+            a1 = __dadd_rn(a1, sv[1][a - t0]);
+            a2 = __dadd_rn(a2, sv[2][a - t0]);
+        }
+    }
+    double j[3] = {0, 0, 0};
+    if (mine) {
+        const double ws = wsum[s];
+        const double qsi = __dmul_rn(qsum[s], q_scale);
         j[0] = __dmul_rn(__dmul_rn(a0 / ws, vel_scale), qsi);
         j[1] = __dmul_rn(__dmul_rn(a1 / ws, vel_scale), qsi);
         j[2] = __dmul_rn(__dmul_rn(a2 / ws, vel_scale), qsi);
@@ -542,17 +612,25 @@ int mdp_charge_flux(mdp_ctx *ctx, int nframes, int64_t n, const double *vel, con
     cudaStream_t st = (cudaStream_t)stream;
     MDP_CUDA(cudaSetDevice(ctx->device));
     const int max_chunks = (int)ceil_div<int64_t>(nseg, RB) + 1;
-    int rc = ctx->arena_reserve((size_t)nframes * max_chunks * 24 + 4096);
+    int rc = ctx->arena_reserve((size_t)nframes * max_chunks * 24 + (size_t)nseg * 16 + 8192);
     if (rc) return rc;
     ctx->arena_reset();
     double *partial = (double *)ctx->arena_take((size_t)nframes * max_chunks * 24);
+    double *wsum = (double *)ctx->arena_take((size_t)nseg * 8);
+    double *qsum = (double *)ctx->arena_take((size_t)nseg * 8);
+    if (!partial || !wsum || !qsum) {
+        mdp_set_error("internal: scratch arena exhausted (charge flux)");
+        return MDP_ERR_OOM;
+    }
+    k_seg_static<<<(unsigned)ceil_div<int64_t>(nseg, RB), RB, 0, st>>>(mass, q, seg_off, nseg, wsum, qsum);
+    MDP_LAUNCHED(ctx);
     for (int g = 0; g < ngroups; ++g) {
         const int64_t s0 = group_seg_off[g], s1 = group_seg_off[g + 1];
         MDP_REQUIRE(s0 >= 0 && s1 > s0 && s1 <= nseg, "mdp_charge_flux: bad molecule-type range");
         const int nchunks = (int)ceil_div<int64_t>(s1 - s0, RB);
         dim3 grid(nchunks, nframes);
         cudaEvent_t tk = ctx->timer_begin(4, st);
-        k_charge_flux<<<grid, RB, 0, st>>>(vel, n, mass, q, seg_off, s0, s1, vel_scale, q_scale, partial, nchunks);
+        k_charge_flux<<<grid, RB, 0, st>>>(vel, n, mass, wsum, qsum, seg_off, s0, s1, vel_scale, q_scale, partial, nchunks);
         ctx->timer_end(tk, st);
         MDP_LAUNCHED(ctx);
         k_flux_finish<<<nframes, 96, 0, st>>>(partial, nchunks, g, ngroups, out, out_stride, frame0);

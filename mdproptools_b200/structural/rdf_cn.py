@@ -127,20 +127,29 @@ def _calc_props(box_lengths, n_objects, atom_types, object_types, num_types, mas
     return rho, rho_pairs
 
 
-def _normalize_rdf(bin_size, rho_pairs, atom_types, partial_relations, num_relations, num_bins, rdf_part, rdf_full=None,
-                   num_atoms=None, rho=None):
-    """_normalize_rdf (:297-329)."""
+def _rdf_denominators(bin_size, rho_pairs, atom_types, partial_relations, num_relations, num_bins, num_atoms=None, rho=None):
+    """The divisors of _normalize_rdf (:297-329), built with the reference's expressions in the reference's order, so that
+    ``counts / divisor`` is bit-identical to the reference whether it is evaluated per frame or for a batch of frames."""
     shell_volume = (
         4 / 3 * np.pi * bin_size ** 3 * (np.arange(1, num_bins + 1) ** 3 - np.arange(num_bins) ** 3)
     )
-    if rdf_full is not None:
-        rdf_full = rdf_full / (num_atoms * rho * shell_volume)
+    den_full = None if num_atoms is None else num_atoms * rho * shell_volume
     ref_atoms = np.asarray(partial_relations[0]).reshape((num_relations, 1))
     ref_atoms_matrix = np.tile(ref_atoms, num_bins)
     num_atoms_matrix = np.vectorize(atom_types.get)(ref_atoms_matrix)
     rho_pairs_matrix = np.tile(rho_pairs.reshape((num_relations, 1)), num_bins)
     shell_volume_matrix = np.tile(shell_volume, (num_relations, 1))
-    rdf_part = rdf_part / (num_atoms_matrix * rho_pairs_matrix * shell_volume_matrix)
+    return den_full, num_atoms_matrix * rho_pairs_matrix * shell_volume_matrix
+
+
+def _normalize_rdf(bin_size, rho_pairs, atom_types, partial_relations, num_relations, num_bins, rdf_part, rdf_full=None,
+                   num_atoms=None, rho=None):
+    """_normalize_rdf (:297-329)."""
+    den_full, den_part = _rdf_denominators(bin_size, rho_pairs, atom_types, partial_relations, num_relations, num_bins,
+                                           num_atoms if rdf_full is not None else None, rho)
+    if rdf_full is not None:
+        rdf_full = rdf_full / den_full
+    rdf_part = rdf_part / den_part
     return rdf_full, rdf_part
 
 
@@ -585,15 +594,18 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
     counts = out.cpu().numpy()
     rdf_full_sum = np.zeros(num_bins)
     rdf_part_sum = np.zeros((num_relations, num_bins))
+    den_cache = {}   # frames with the same composition and volume share their divisors (the usual NVT case: one entry)
     for t in range(T):
         at = at_static if static_types else _value_counts(types[t])
         volume = np.prod(boxes[t, :3])
-        rho = N / volume
-        rho_pairs = np.array([at[b] / volume for b in partial_relations[1]])
-        full, part = _normalize_rdf(bin_size, rho_pairs, at, partial_relations, num_relations, num_bins,
-                                    counts[t, 1:].astype(np.float64), counts[t, 0].astype(np.float64), N, rho)
-        rdf_full_sum += full
-        rdf_part_sum += part
+        key = (volume,) if static_types else (volume, tuple(sorted(at.items())))
+        den = den_cache.get(key)
+        if den is None:
+            rho = N / volume
+            rho_pairs = np.array([at[b] / volume for b in partial_relations[1]])
+            den = den_cache[key] = _rdf_denominators(bin_size, rho_pairs, at, partial_relations, num_relations, num_bins, N, rho)
+        rdf_full_sum += counts[t, 0].astype(np.float64) / den[0]
+        rdf_part_sum += counts[t, 1:].astype(np.float64) / den[1]
     df = _save_rdf(radii, relation_matrix, None, False, rdf_part_sum / T, rdf_full_sum=rdf_full_sum / T)
     return (df, counts) if return_counts else df
 
