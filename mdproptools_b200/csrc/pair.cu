@@ -874,6 +874,8 @@ __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh
         const unsigned ja = (unsigned)__cvta_generic_to_shared(jb);
         const unsigned nb = (unsigned)p.nbins;
         const float inv = p.inv_ddr_biased;
+        const unsigned dummy_a = sh.hist_a + (unsigned)(p.nrows * p.nbins + lane) * 4u;
+        const unsigned hist_end = sh.hist_a + nb * 4u;   // single-row histogram (!MULTICLS)
 #pragma unroll 1
         for (int j0 = 0; j0 < nj; j0 += 4) {
             const unsigned a0 = ja + (unsigned)j0 * 16u;
@@ -894,7 +896,7 @@ __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh
                 cj[u] = MULTICLS ? __double2loint(jm) : 0;
             }
             if (!__any_sync(0xffffffffu, hit[0] | hit[1] | hit[2] | hit[3])) continue;
-            unsigned kb[4], ha[4];
+            unsigned ha[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 // rsq beyond the cutoff (and the +inf padding) needs no test of its own: its estimate is >= nbins, the
@@ -907,22 +909,22 @@ __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh
                 k = k < nb ? k : nb;
                 double e1;
                 lds_f64(e1, sh.edges_a + k * 8u + 8u);
-                k += (r2[u] >= e1) ? 1u : 0u;
-                kb[u] = k;
-                ha[u] = sh.hist_a + k * 4u;
+                // misses (final bin == nbins) increment a per-lane dummy word behind the histogram instead of being
+                // predicated off: ptxas wraps every predicated shared atomic in its own branch region (4 extra instructions
+                // and a reconvergence point per pair); the dummy words sit in 32 different banks
                 if (MULTICLS) {
+                    k += (r2[u] >= e1) ? 1u : 0u;
                     unsigned row;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(sh.cptab_a + (mi + (uint32_t)cj[u]) * 4u));
-                    ha[u] += row * nb * 4u;
+                    ha[u] = k < nb ? sh.hist_a + (row * nb + k) * 4u : dummy_a;
+                } else {
+                    unsigned a = sh.hist_a + k * 4u;
+                    a += (r2[u] >= e1) ? 4u : 0u;
+                    ha[u] = a < hist_end ? a : dummy_a;
                 }
             }
-            // the four increments last: ptxas wraps every predicated shared atomic in its own branch region, and
-            // keeping those out of the arithmetic above leaves it one straight block to schedule
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                asm volatile("{\n .reg .pred p;\n setp.lt.u32 p, %1, %2;\n @p red.shared.add.u32 [%0], 1;\n}" ::"r"(ha[u]), "r"(kb[u]),
-                             "r"(nb)
-                             : "memory");
+            for (int u = 0; u < 4; ++u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(ha[u]) : "memory");
         }
         return;
     }
@@ -1414,15 +1416,15 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         const size_t edge_bytes = (size_t)(c.nbins + 1) * sizeof(double2);
         if (multicls) smem += (size_t)((ncp * 4 + 15) & ~15);
         const size_t cap = std::min<size_t>(ctx->smem_optin, (216 / CTAS_PER_SM) * 1024);   // keep CTAS_PER_SM CTAs per SM
-        MDP_REQUIRE(smem + hist_bytes <= ctx->smem_optin,
+        MDP_REQUIRE(smem + hist_bytes + 128 <= ctx->smem_optin,
                     "pair: histogram of %d rows x %d bins does not fit in shared memory (%zu B needed); "
                     "reduce the number of distinct classes or bins per call",
                     nrows, c.nbins, smem + hist_bytes);
-        if (smem + hist_bytes + edge_bytes <= cap) {
+        if (smem + hist_bytes + 128 + edge_bytes <= cap) {
             edges_in_smem = 1;
             smem += edge_bytes;
         }
-        smem += hist_bytes;
+        smem += hist_bytes + 128;   // + one dummy word per lane (direct binning sends misses there)
     }
 
     // sub-batching over frames so that scratch stays bounded
