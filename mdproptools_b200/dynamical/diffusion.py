@@ -23,7 +23,7 @@ from .. import dist, ops
 from ..common import constants
 from ..common.com_mols import atom_masses, mol_membership
 from ..io import dump as _dump
-from ..io.pipeline import FrameBatches
+from ..io.pipeline import ArrayBatches, FrameBatches
 
 
 class Diffusion:
@@ -192,25 +192,10 @@ class Diffusion:
         t0 = self._time_zero_index(times)
         dev = torch.device("cuda", torch.cuda.current_device())
         ref = pos[t0].to(dev)
-        copy_stream = torch.cuda.Stream()
         sums = torch.empty((T, 1, 4), dtype=torch.float64, device=dev)
-
-        def stage(f0):
-            f1 = min(T, f0 + batch_frames)
-            with torch.cuda.stream(copy_stream):
-                x = pos[f0:f1].to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return f0, f1, x, ev
-
-        nxt = stage(0)
-        while nxt is not None:
-            f0, f1, x, ev = nxt
-            nxt = stage(f1) if f1 < T else None
-            torch.cuda.current_stream().wait_event(ev)
+        for f0, f1, x in ArrayBatches(pos, batch_frames, dev):   # copy of batch k+1 overlaps the reduction of batch k
             s, _ = ops.msd_single_origin(x, ref, conv)
             sums[f0:f1] = s
-            x.record_stream(torch.cuda.current_stream())
         mean = (sums[:, 0, :] / N).cpu().numpy()
         msd = pd.DataFrame(mean, columns=["dx2", "dy2", "dz2", "msd"])
         msd.insert(0, "Time (s)", times)

@@ -120,3 +120,60 @@ class FrameBatches:
                 raise item
             yield item
         th.join()
+
+
+class ArrayBatches:
+    """Stream an in-memory host trajectory ``pos`` [T, C, N] (pinned torch tensor for truly asynchronous copies) to the
+    device in batches of frames through TWO persistent device buffers: the copy of batch k+1 runs on a dedicated copy
+    stream while the kernels of batch k run on the current stream, and a buffer is refilled only after the kernels that
+    read it have finished (event recorded by ``done``).  No allocation happens inside the loop.
+
+        for f0, f1, x in (ab := ArrayBatches(pos, batch_frames)):
+            ... launch kernels reading x on the current stream ...
+            ab.done()
+    """
+
+    def __init__(self, pos: torch.Tensor, batch_frames: int, device=None):
+        self.pos = pos
+        self.T = pos.shape[0]
+        self.nb = max(1, min(int(batch_frames), self.T))
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        shape = (self.nb,) + tuple(pos.shape[1:])
+        self.bufs = [torch.empty(shape, dtype=pos.dtype, device=self.device) for _ in range(2 if self.T > self.nb else 1)]
+        self.consumed = [None] * len(self.bufs)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.main = torch.cuda.current_stream(self.device)
+        self._k = None
+
+    def _stage(self, f0, k):
+        f1 = min(self.T, f0 + self.nb)
+        k %= len(self.bufs)
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[k] is not None:
+                self.copy_stream.wait_event(self.consumed[k])
+            else:
+                self.copy_stream.wait_stream(self.main)      # the buffers were allocated on the current stream
+            x = self.bufs[k][: f1 - f0]
+            x.copy_(self.pos[f0:f1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return f0, f1, x, ev, k
+
+    def __iter__(self):
+        nxt = self._stage(0, 0)
+        while nxt is not None:
+            f0, f1, x, ev, k = nxt
+            nxt = self._stage(f1, k + 1) if f1 < self.T else None
+            self.main.wait_event(ev)
+            self._k = k
+            yield f0, f1, x
+            if self._k is not None:
+                self.done()
+        self.main.wait_stream(self.copy_stream)
+
+    def done(self):
+        """Call after the last kernel reading the current batch has been launched."""
+        if self._k is not None:
+            self.consumed[self._k] = torch.cuda.Event()
+            self.consumed[self._k].record(self.main)
+            self._k = None

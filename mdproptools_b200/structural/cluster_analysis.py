@@ -9,14 +9,22 @@ re-imaging relative to the central atom (:31-44) and the .xyz writer (:213-233) 
 hundred atoms per cluster and is restated here on the host in numpy.
 
 Not supported (raises): element names read from an ``element`` column of the dump (pass ``elements``).
-``get_unique_configurations`` (:238-457) is out of scope of the hot path.
+
+``get_unique_configurations`` (:238-457) is host-side bookkeeping on the few-hundred-atom cluster
+files; it is restated here without pymatgen (``molecules`` may be pymatgen Molecules, anything with ``.species``, plain
+lists of element symbols, or paths of .pdb/.xyz files).
 """
 from __future__ import annotations
 
 import ctypes
+import glob
 import os
+import shutil
+import warnings
+from collections import Counter
 
 import numpy as np
+import pandas as pd
 import torch
 
 from .. import _lib, dist, ops
@@ -154,3 +162,116 @@ def get_clusters(filename, atom_type, r_cut, num_mols, num_atoms_per_mol, full_t
         dist.all_reduce_sum_(t)
         cluster_count = int(t.item())
     return cluster_count
+
+
+# ------------------------------------------------------------------------------------------------
+# unique configurations (:238-457)
+# ------------------------------------------------------------------------------------------------
+def _read_xyz(path):
+    """(symbols, coords) of an .xyz file: atom count, comment line, then ``sym x y z`` rows."""
+    with open(path) as f:
+        lines = f.read().splitlines()
+    n = int(lines[0].split()[0])
+    sym, xyz = [], np.empty((n, 3))
+    for k, ln in enumerate(lines[2:2 + n]):
+        p = ln.split()
+        sym.append(p[0])
+        xyz[k] = (float(p[1]), float(p[2]), float(p[3]))
+    return sym, xyz
+
+
+def _species_of(mol):
+    """Element symbols of one entry of ``molecules``: pymatgen Molecule (``.species``), list of symbols, or a file."""
+    if isinstance(mol, (str, os.PathLike)):
+        path = str(mol)
+        if path.lower().endswith(".pdb"):
+            with open(path) as f:
+                return [ln[76:78].strip().capitalize() for ln in f if ln.startswith(("HETATM", "ATOM"))]
+        return _read_xyz(path)[0]
+    if hasattr(mol, "species"):
+        return [str(x) for x in mol.species]
+    return [str(x) for x in mol]
+
+
+def get_unique_configurations(cluster_pattern, r_cut, molecules, mol_num, type_coord_atoms=None, working_dir=None,
+                              find_top=True, perc=None, cum_perc=90, mol_names=None, zip=True):
+    """Group the ``Cluster_*.xyz`` files written by :func:`get_clusters` into configurations -- same arguments, result
+    DataFrames, csv files (clusters.csv, configurations.csv, top_conf.csv), ``conf_N.xyz`` copies and optional
+    ``Clusters.zip`` as the reference (:238-457).
+
+    Per cluster file: the atoms within ``r_cut`` of the first atom (the atom of interest; ``<=``, Molecule.get_neighbors
+    :346), optionally restricted to ``type_coord_atoms`` (:349-352); the atoms after the central molecule are cut into
+    molecules by matching the element sequences of ``molecules`` in order (:360-373); for every molecule type the number
+    of molecules and, per molecule, the coordinating atoms written as ``<count><first letter of the element>`` sorted by
+    letter, the per-molecule strings sorted and joined by ``:`` (:387-397).  Configurations = distinct rows of
+    (numbers, strings), counted and ranked (:420-428); the top ones by cumulative share ``cum_perc`` (or share >=
+    ``perc``) get the first cluster file (by name) showing them copied to ``conf_<rank>.xyz`` (:429-447).
+    """
+    working_dir = working_dir or os.getcwd()
+    cluster_files = glob.glob(f"{working_dir}/{cluster_pattern}")
+    main_atoms = [_species_of(m) for m in molecules]
+    n_types = len(main_atoms)
+    n_central = len(main_atoms[mol_num])
+    rows = {"cluster": [], "num_mols": [], "coordinating_atoms": []}
+    for path in cluster_files:
+        sym, xyz = _read_xyz(path)
+        rows["cluster"].append(os.path.basename(path))
+        d0 = np.sqrt(np.sum((xyz - xyz[0]) ** 2, axis=1))
+        near = [j for j in range(1, len(sym)) if d0[j] <= r_cut]
+        if near and type_coord_atoms:
+            near = [j for j in near if sym[j] in type_coord_atoms]
+        rest = sym[n_central:]
+        sites = [[] for _ in range(n_types)]        # per molecule type: one list of coordinating symbols per molecule
+        idx = 0
+        while idx < len(rest):
+            for t, atoms in enumerate(main_atoms):
+                if rest[idx: idx + len(atoms)] == atoms:
+                    lo = idx + n_central
+                    sites[t].append([sym[j] for j in near if lo <= j < lo + len(atoms)])
+                    idx += len(atoms)
+                    break
+            # (like the reference, a tail that matches no molecule would loop forever; get_clusters never writes one)
+        rows["num_mols"].append([len(s) for s in sites])
+        labels = []
+        for t in range(n_types):
+            per_mol = []
+            for coord in sites[t]:
+                c = Counter(x[0] for x in coord if x)
+                per_mol.append("".join(f"{c[k]}{k}" for k in sorted(c)))
+            labels.append(":".join(sorted(per_mol)))
+        rows["coordinating_atoms"].append(labels)
+    if mol_names:
+        num_cols = [f"num_{i}" for i in mol_names]
+        atom_cols = [f"atoms_{i}" for i in mol_names]
+    else:
+        num_cols = [f"num_{i + 1}" for i in range(n_types)]
+        atom_cols = [f"atoms_{i + 1}" for i in range(n_types)]
+    df = pd.concat([pd.DataFrame({"cluster": rows["cluster"]}), pd.DataFrame(rows["num_mols"], columns=num_cols),
+                    pd.DataFrame(rows["coordinating_atoms"], columns=atom_cols)], axis=1)
+    df1 = df.groupby([c for c in df.columns if c != "cluster"]).size().rename("count").reset_index()
+    df1.sort_values("count", ascending=False, inplace=True)
+    df1["%"] = df1["count"] * 100 / sum(df1["count"])
+    if find_top:
+        if cum_perc and perc:
+            warnings.warn("Two percentage types are provided for determining the top configurations; using cum_perc")
+        if cum_perc:
+            top = df1[df1["%"].cumsum() <= cum_perc]
+        elif perc:
+            top = df1[df1["%"] >= perc]
+        else:
+            raise ValueError("No percentage type is provided for determining the top configurations")
+        df = df.sort_values("cluster").reset_index(drop=True)
+        top = top.merge(df[["cluster"] + atom_cols], on=atom_cols).drop_duplicates(atom_cols)
+        for rank, cluster in enumerate(top["cluster"]):
+            shutil.copy(f"{working_dir}/{cluster}", f"{working_dir}/conf_{rank + 1}.xyz")
+        top.to_csv(f"{working_dir}/top_conf.csv", index=False)
+    df.to_csv(f"{working_dir}/clusters.csv", index=False)
+    df1.to_csv(f"{working_dir}/configurations.csv", index=False)
+    if zip:
+        clusters_dir = f"{working_dir}/Clusters"
+        os.mkdir(clusters_dir)
+        for path in cluster_files:
+            shutil.move(path, f"{clusters_dir}/{os.path.basename(path)}")
+        shutil.make_archive(f"{working_dir}/Clusters", "zip", clusters_dir)
+        shutil.rmtree(clusters_dir)
+    return df, df1

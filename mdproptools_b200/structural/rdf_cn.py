@@ -36,7 +36,7 @@ import torch
 
 from .. import dist, ops
 from .._lib import PAIR_TRICLINIC, bin_edges
-from ..io.pipeline import FrameBatches
+from ..io.pipeline import ArrayBatches, FrameBatches
 
 CON_CONSTANT = 1.660538921  # :30
 
@@ -571,40 +571,11 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
     if static_types:
         cls_static = torch.from_numpy(cmap.classes_of(types)).to(dev)
         at_static = _value_counts(types)
-    copy_stream = torch.cuda.Stream()
     out = torch.empty((T, 1 + num_relations, num_bins), dtype=torch.int64, device=dev)
-    # two persistent device staging buffers, used alternately: the copy of batch k+1 (copy stream) overlaps the kernels
-    # of batch k (current stream); a buffer is refilled only after the kernels that read it have finished
-    nb_ = min(batch_frames, T)
-    stage_buf = [torch.empty((nb_, 3, N), dtype=torch.float64, device=dev) for _ in range(2 if T > nb_ else 1)]
-    consumed = [None, None]
-    main = torch.cuda.current_stream()
-
-    def stage(f0, k):
-        f1 = min(T, f0 + nb_)
-        k %= len(stage_buf)
-        with torch.cuda.stream(copy_stream):
-            if consumed[k] is not None:
-                copy_stream.wait_event(consumed[k])
-            else:
-                copy_stream.wait_stream(main)        # the buffers were allocated on the current stream
-            x = stage_buf[k][: f1 - f0]
-            x.copy_(pos[f0:f1], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return f0, f1, x, ev, k
-
-    nxt = stage(0, 0)
-    while nxt is not None:
-        f0, f1, x, ev, k = nxt
-        nxt = stage(f1, k + 1) if f1 < T else None
-        main.wait_event(ev)
+    for f0, f1, x in ArrayBatches(pos, batch_frames, dev):       # copy of batch k+1 overlaps the kernels of batch k
         cls = cls_static if static_types else torch.from_numpy(np.stack([cmap.classes_of(t) for t in types[f0:f1]])).to(dev)
         hist = ops.pair_hist(x, cls, cmap.ncls, boxes[f0:f1], rcut2, edges, bin_size, flags=flags)
         out[f0:f1] = ops.hist_reduce(hist, weights)
-        consumed[k] = torch.cuda.Event()
-        consumed[k].record(main)
-    main.wait_stream(copy_stream)
     counts = out.cpu().numpy()
     rdf_full_sum = np.zeros(num_bins)
     rdf_part_sum = np.zeros((num_relations, num_bins))

@@ -8,7 +8,7 @@ Inputs that travel with the repo (so the GPU box, which has no /root/reference, 
   tests/golden/visc_log.tar.gz       two synthetic LAMMPS thermo logs (Step Pxy Pxz Pyz), seeded
   tests/golden/water_box.tar.gz      synthetic cation + 3-site water box (3 frames), seeded
 Outputs of the reference on those inputs:
-  tests/golden/ref_structural.npz, ref_clusters.json, ref_dynamical.npz, ref_hydration.npz
+  tests/golden/ref_structural.npz, ref_clusters.json, ref_unique_conf.json, ref_dynamical.npz, ref_hydration.npz
 """
 from __future__ import annotations
 
@@ -330,6 +330,38 @@ def run_hydration(water_dir, num_mols, num_atoms, out):
     out["hyd_num_mols"] = np.array(num_mols); out["hyd_num_atoms"] = np.array(num_atoms)
 
 
+def run_unique_configurations(work):
+    """get_unique_configurations (cluster_analysis.py:238-457) exactly as the reference's own test drives it
+    (tests/structural/test_cluster_analysis.py:62-100): clusters of frame 50 around the altered atom type 32, then the
+    configuration table.  The reference's five conf_*.xyz goldens are checked here; its csv goldens are git-lfs stubs,
+    so the DataFrames of this run are what gets stored (together with the cluster files that are the function's input)."""
+    import pandas as pd
+    from mdproptools.structural.cluster_analysis import get_clusters, get_unique_configurations
+    data_dir = os.path.join(H.REFERENCE_ROOT, "data", "mg_tfsi_dme")
+    wd = os.path.join(work, "uniq")
+    os.makedirs(wd)
+    get_clusters(filename=os.path.join(data_dir, "dump.nvt.*.dump"), atom_type=32, r_cut=2.3, num_mols=NUM_MOLS,
+                 num_atoms_per_mol=NUM_ATOMS, full_trajectory=False, frame=50, elements=ELEMENTS, alter_atom_types=True,
+                 max_force=0.75, working_dir=wd)
+    inputs = {os.path.basename(p): open(p).read() for p in sorted(glob.glob(os.path.join(wd, "Cluster_*.xyz")))}
+    mols = [H.ShimMolecule.from_file(os.path.join(data_dir, f)) for f in ("dme.pdb", "tfsi.pdb", "mg.pdb")]
+    species = [[str(x) for x in m.species] for m in mols]
+    df, df1 = get_unique_configurations(cluster_pattern="Cluster_*.xyz", r_cut=2.3, molecules=mols, mol_num=2,
+                                        type_coord_atoms=["O", "N", "Mg"], working_dir=wd, find_top=True, perc=None,
+                                        cum_perc=100, mol_names=["dme", "tfsi", "mg"], zip=False)
+    ref_dir = os.path.join(H.REFERENCE_ROOT, "tests", "structural", "test_files")
+    conf = {os.path.basename(p): open(p).read() for p in sorted(glob.glob(os.path.join(wd, "conf_*.xyz")))}
+    same = sum(open(os.path.join(ref_dir, k)).read() == v for k, v in conf.items())
+    print(f"  get_unique_configurations: {len(inputs)} clusters, {len(conf)} conf files, {same} byte-identical to the "
+          f"reference's own goldens; counts {df1['count'].tolist()}")
+    with open(os.path.join(GOLD, "ref_unique_conf.json"), "w") as f:
+        json.dump({"cluster_files": inputs, "species": species, "conf_files": conf, "conf_identical_to_reference_goldens": same,
+                   "clusters_csv": open(os.path.join(wd, "clusters.csv")).read(),
+                   "configurations_csv": open(os.path.join(wd, "configurations.csv")).read(),
+                   "top_conf_csv": open(os.path.join(wd, "top_conf.csv")).read(),
+                   "counts": df1["count"].tolist(), "percent": df1["%"].tolist()}, f)
+
+
 def main():
     H.install()
     os.makedirs(GOLD, exist_ok=True)
@@ -339,13 +371,15 @@ def main():
     mini_dir, mini_num_mols = make_mini_traj(work)
     visc_dir = make_visc_logs(work)
     water_dir, w_mols, w_atoms = make_water_box(work)
-    which = sys.argv[1:] or ["structural", "clusters", "dynamical", "hydration"]
+    which = sys.argv[1:] or ["structural", "clusters", "unique", "dynamical", "hydration"]
     if "structural" in which:
         out = {}
         run_structural(sample_dir, out)
         np.savez_compressed(os.path.join(GOLD, "ref_structural.npz"), **out)
     if "clusters" in which:
         run_clusters(sample_dir, work)
+    if "unique" in which:
+        run_unique_configurations(work)
     if "dynamical" in which:
         out = {}
         run_dynamical(mini_dir, mini_num_mols, visc_dir, out)

@@ -13,7 +13,7 @@ What it does (all of it is glue written for this repo; no reference source is co
 * provides a stand-in for the un-vendored third-party dependency **pymatgen**
   (``requirements.txt:1`` -> fork ``molmd/pymatgen@molmd_fix_3-9``, branch-pinned, not in
   ``/root/reference``): ``pymatgen.io.lammps.outputs.{parse_lammps_dumps, parse_lammps_log,
-  LammpsDump, LammpsBox}`` and ``pymatgen.core.structure.Molecule`` (placeholder), restating the
+  LammpsDump, LammpsBox}`` and ``pymatgen.core.structure.Molecule`` (the few methods get_unique_configurations calls), restating the
   published upstream behaviour (glob + integer sort of ``*``, frame split at ``ITEM: TIMESTEP``,
   box bounds/tilt handling, ``pandas.read_csv`` of the atom block, thermo-block log parsing);
 * mocks matplotlib / seaborn / statsmodels (plotting only) and supplies the two numerical
@@ -48,6 +48,79 @@ def available() -> bool:
 # ----------------------------------------------------------------------------------------------
 # pymatgen stand-in
 # ----------------------------------------------------------------------------------------------
+
+class _Site:
+    """pymatgen.core.sites.Site as far as get_unique_configurations (cluster_analysis.py:337-372) uses it: species_string,
+    coords, equality = same species and coordinates within Site.position_atol (1e-5)."""
+
+    def __init__(self, sym, xyz):
+        self.species_string = sym
+        self.coords = np.asarray(xyz, dtype=np.float64)
+
+    def __eq__(self, other):
+        return (isinstance(other, _Site) and self.species_string == other.species_string
+                and bool(np.allclose(self.coords, other.coords, atol=1e-5)))
+
+    def __hash__(self):
+        return hash(self.species_string)
+
+    def __str__(self):
+        return self.species_string
+
+
+class _Species(str):
+    """str(mol.species[i]) is the element symbol"""
+
+
+class ShimMolecule:
+    """Stand-in for pymatgen.core.structure.Molecule restricted to what the reference calls:
+    ``Molecule.from_file`` (.xyz: count line, comment line, ``sym x y z`` rows; .pdb: HETATM/ATOM records, element in
+    columns 77-78), ``.species``, ``mol[i]`` / ``mol[a:b]`` (site / list of sites), ``site in mol``, and
+    ``get_neighbors(site, r)`` = the sites within r of site.coords (``<= r``), the site itself excluded, in site order
+    (published upstream behaviour: IMolecule.get_sites_in_sphere / get_neighbors)."""
+
+    def __init__(self, sites):
+        self.sites = list(sites)
+
+    @classmethod
+    def from_file(cls, filename):
+        filename = str(filename)
+        sites = []
+        with open(filename) as f:
+            lines = f.read().splitlines()
+        if filename.lower().endswith(".pdb"):
+            for ln in lines:
+                if ln.startswith(("HETATM", "ATOM")):
+                    sym = ln[76:78].strip().capitalize()
+                    sites.append(_Site(sym, [float(ln[30:38]), float(ln[38:46]), float(ln[46:54])]))
+        else:
+            n = int(lines[0].split()[0])
+            for ln in lines[2:2 + n]:
+                p = ln.split()
+                sites.append(_Site(p[0], [float(p[1]), float(p[2]), float(p[3])]))
+        return cls(sites)
+
+    @property
+    def species(self):
+        return [_Species(s.species_string) for s in self.sites]
+
+    def __len__(self):
+        return len(self.sites)
+
+    def __iter__(self):
+        return iter(self.sites)
+
+    def __getitem__(self, i):
+        return self.sites[i]
+
+    def get_neighbors(self, site, r):
+        out = []
+        for s in self.sites:
+            d = float(np.linalg.norm(s.coords - site.coords))
+            if d <= r and not (s is site or s == site):
+                out.append(s)
+        return out
+
 class _Lattice:
     def __init__(self, matrix):
         self._matrix = np.array(matrix, dtype=np.float64).reshape((3, 3))
@@ -276,7 +349,7 @@ def install():
         setattr(outputs, sym, getattr(this, sym))
     sys.modules["pymatgen.io.lammps.outputs"] = outputs
     structure = types.ModuleType("pymatgen.core.structure")
-    structure.Molecule = mock.MagicMock(name="Molecule")
+    structure.Molecule = ShimMolecule
     sys.modules["pymatgen.core.structure"] = structure
 
     # plotting mocks

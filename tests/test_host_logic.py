@@ -204,6 +204,39 @@ def test_thermo_log_parser(visc_dir):
     assert len(full) == 4000 + 4001
 
 
+def test_unique_configurations_reproduce_reference(tmp_path):
+    """get_unique_configurations (cluster_analysis.py:238-457) on the 33 frame-50 clusters the reference's own test uses
+    (tests/structural/test_cluster_analysis.py:62-100).  Golden = the unmodified reference run by oracle/gen_golden.py,
+    whose five conf_*.xyz files were byte-identical to the reference's committed goldens and whose counts are the
+    notebook's 20/8/3/1/1 (60.6/24.2/9.1/3.0/3.0 %)."""
+    import io
+    import json
+    import pandas as pd
+    from mdproptools_b200.structural.cluster_analysis import get_unique_configurations
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_unique_conf.json")))
+    assert g["conf_identical_to_reference_goldens"] == 5 and g["counts"] == [20, 8, 3, 1, 1]
+    for name, text in g["cluster_files"].items():
+        (tmp_path / name).write_text(text)
+    df, df1 = get_unique_configurations(cluster_pattern="Cluster_*.xyz", r_cut=2.3, molecules=g["species"], mol_num=2,
+                                        type_coord_atoms=["O", "N", "Mg"], working_dir=str(tmp_path), find_top=True,
+                                        perc=None, cum_perc=100, mol_names=["dme", "tfsi", "mg"], zip=False)
+    assert df1["count"].tolist() == g["counts"]
+    assert np.allclose(df1["%"].values, g["percent"], rtol=0, atol=0)
+    for name, text in g["conf_files"].items():
+        assert (tmp_path / name).read_text() == text, name
+    for key, fname in (("clusters_csv", "clusters.csv"), ("configurations_csv", "configurations.csv"), ("top_conf_csv", "top_conf.csv")):
+        ours = pd.read_csv(tmp_path / fname).fillna("")
+        ref = pd.read_csv(io.StringIO(g[key])).fillna("")
+        pd.testing.assert_frame_equal(ours, ref, check_dtype=False)
+    ref_clusters = pd.read_csv(io.StringIO(g["clusters_csv"])).fillna("")
+    pd.testing.assert_frame_equal(df.fillna(""), ref_clusters, check_dtype=False)
+    # zip=True moves the cluster files into Clusters.zip
+    for name in g["conf_files"]:
+        os.remove(tmp_path / name)
+    get_unique_configurations("Cluster_*.xyz", 2.3, g["species"], 2, ["O", "N", "Mg"], str(tmp_path), find_top=False, zip=True)
+    assert (tmp_path / "Clusters.zip").exists() and not list(tmp_path.glob("Cluster_*.xyz"))
+
+
 def test_shard_ranges_cover_everything():
     from mdproptools_b200 import dist
     for n in (0, 1, 7, 8, 101, 1000):
