@@ -73,6 +73,45 @@ def test_pair_hist_symmetric_vs_oracle(ops, n, L, rc, ddr, flags):
     assert int(hist.sum().item()) * 2 == int(full.sum())
 
 
+@pytest.mark.parametrize("n,L,rc,ddr,nb,why", [
+    (2500, (40.0, 38.0, 36.0), 7.3, 0.05, None, "direct binning, r_cut/ddr = 146 exactly representable or not"),
+    (2500, (40.0, 38.0, 36.0), 5.03, 0.1, None, "direct: r_cut/ddr not an integer, edge[nbins] < rcut2 (index nbins dropped)"),
+    (2500, (40.0, 38.0, 36.0), 4.99, 0.1, 50, "edge[nbins] > rcut2: the explicit rsq < rcut2 test is needed -> queue path"),
+    (1500, (30.0, 30.0, 30.0), 6.0, 0.001, None, "6000 bins: edge table too large for direct binning -> queue path"),
+    (1500, (30.0, 30.0, 30.0), 6.0, 6.0, None, "a single bin"),
+])
+def test_pair_hist_binning_paths_agree_with_oracle(ops, n, L, rc, ddr, nb, why):
+    """The uniform-bin histogram has two device paths (per-lane direct binning / compacted queue, MDP_PAIR_QUEUE_BINNING);
+    both must give the reference's bin(rsq) = int64(sqrt(rsq)/ddr) (rdf_cn.py:68,85) for every pair, including the
+    cases where the library has to fall back to the queue path by itself."""
+    from mdproptools_b200._lib import PAIR_QUEUE_BINNING, bin_edges
+    rng = np.random.default_rng(int(rc * 1000) + n)
+    pos, typ = _rand_box(rng, n, L, 2)
+    # plant pairs exactly ON bin edges and on the cutoff: x-separated partners at k*ddr and at r_cut
+    for k in range(1, 40):
+        pos[:, 2 * k] = pos[:, 2 * k + 1]
+        pos[0, 2 * k] = pos[0, 2 * k + 1] + (k * ddr if k < 38 else rc)
+    nb = int(rc / ddr) if nb is None else nb
+    rel = np.array([[1, 1], [1, 2], [2, 2]])
+    full, part = O.rdf_loop(typ, pos[0], pos[1], pos[2], rel, L, rc, ddr, nb, nthreads=0)
+    cls = (typ.astype(np.int64) - 1).astype(np.int32)
+    edges = bin_edges(ddr, nb)
+    w = [np.full(3, 2)]
+    for a, b in rel:
+        r = np.zeros(3, dtype=np.int64)
+        r[ops.sym_row(a - 1, b - 1, 2)] = 2 if a == b else 1
+        w.append(r)
+    for flags in (0, PAIR_QUEUE_BINNING):
+        for c, ncls in ((cls, 2), (None, 1)):                 # multi-class and single-class kernels
+            hist = ops.pair_hist(_dev(pos[None]), None if c is None else _dev(c), ncls, [L], O.rcut_sq(rc), edges, ddr, flags=flags)
+            if c is None:
+                assert np.array_equal(hist.cpu().numpy()[0, 0] * 2, full), (why, flags)
+            else:
+                red = ops.hist_reduce(hist, np.stack(w)).cpu().numpy()[0]
+                assert np.array_equal(red[0], full), (why, flags)
+                assert np.array_equal(red[1:], part), (why, flags)
+
+
 def test_pair_hist_multiframe_and_per_frame_boxes(ops):
     from mdproptools_b200._lib import bin_edges
     rng = np.random.default_rng(11)
