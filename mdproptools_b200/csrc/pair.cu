@@ -722,6 +722,7 @@ struct PairParams {
     // list mode
     double rin2, rout2;
     int shell_mode, exclude_same;
+    int swap_out;                    // list mode: sets A and B were exchanged by the host, write (frame, j, i)
     int32_t *list;
     double *list_rsq;
     long long capacity;
@@ -767,8 +768,8 @@ __device__ __forceinline__ void drain(const PairParams &p, const Shared &sh, int
                 const long long pos = (long long)b0 + __popc(mask & ((1u << lane) - 1u));
                 if (pos < p.capacity) {
                     p.list[pos * 3 + 0] = frame;
-                    p.list[pos * 3 + 1] = (int32_t)me.x;
-                    p.list[pos * 3 + 2] = (int32_t)me.y;
+                    p.list[pos * 3 + 1] = (int32_t)(p.swap_out ? me.y : me.x);
+                    p.list[pos * 3 + 2] = (int32_t)(p.swap_out ? me.x : me.y);
                     if (p.list_rsq) p.list_rsq[pos] = r2;
                 }
             }
@@ -1064,11 +1065,28 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
     // every CTA starts at a different frame and walks all of them, so the frames' tails do not line up
     const int fstart = (int)(((long long)blockIdx.x * F) / gridDim.x);
 
+    // Histogram modes: a CTA works on one frame at a time (its shared-memory histogram belongs to that frame) and its
+    // warps pull units from the frame's counter.  List mode has no per-frame state, so every warp pulls from ONE counter
+    // over all (frame, unit) pairs -- with thousands of small frames (residence-time searches) walking every frame
+    // from every CTA would cost more than the search itself.
+    const unsigned int nunits = (unsigned int)p.ntA * GPT;   // work units per frame: one per 32-point i group
+    const unsigned int all_units = MODE == MODE_LIST ? nunits * (unsigned int)F : 0u;
+    unsigned int gq = 0;
+    if (MODE == MODE_LIST) {
+        if (lane == 0) gq = atomicAdd(&p.counters[0], 1u);
+        gq = __shfl_sync(0xffffffffu, gq, 0);
+    }
 #pragma unroll 1
-    for (int fk = 0; fk < F; ++fk) {
-        int f = fstart + fk;
-        if (f >= F) f -= F;
-        const unsigned int nunits = (unsigned int)p.ntA * GPT;   // work units of this frame: one per 32-point i group
+    for (int fk = 0;; ++fk) {
+        int f;
+        if (MODE == MODE_LIST) {
+            if (gq >= all_units) break;
+            f = (int)(gq / nunits);
+        } else {
+            if (fk >= F) break;
+            f = fstart + fk;
+            if (f >= F) f -= F;
+        }
         const double lx = p.box[f * 6 + 0], ly = p.box[f * 6 + 1], lz = p.box[f * 6 + 2];
         const AxisF AX = make_axis(lx), AY = make_axis(ly), AZ = make_axis(lz);
         const int frame = p.frame0 + f;
@@ -1078,12 +1096,16 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
         bool did = false;
 
         unsigned int q = 0;
-        if (lane == 0) q = atomicAdd(&p.counters[f], 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
+        if (MODE == MODE_LIST) {
+            q = gq - (unsigned int)f * nunits;
+        } else {
+            if (lane == 0) q = atomicAdd(&p.counters[f], 1u);
+            q = __shfl_sync(0xffffffffu, q, 0);
+        }
 #pragma unroll 1
         while (q < nunits) {
             unsigned int qnext = 0;
-            if (lane == 0) qnext = atomicAdd(&p.counters[f], 1u);   // prefetch the next work index
+            if (lane == 0) qnext = atomicAdd(&p.counters[MODE == MODE_LIST ? 0 : f], 1u);   // prefetch the next work index
             did = true;
             // One unit = one i group (32 points, one per lane) against every j tile of its tile row of the work list.
             const int ta = (int)(q >> 3), wi = (int)(q & 7u);
@@ -1223,6 +1245,10 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
                 }
             }
             q = __shfl_sync(0xffffffffu, qnext, 0);
+            if (MODE == MODE_LIST) {
+                gq = q;                                   // global index; beyond this frame it ends the unit loop
+                q -= (unsigned int)f * nunits;
+            }
         }
 
         // this warp is done with frame f: empty its queue, then the CTA flushes its histogram
@@ -1381,7 +1407,7 @@ struct PairCall {
     int flags = 0;
     // list
     double rin2 = 0, rout2 = 0;
-    int shell_mode = 0, exclude_same = 0;
+    int shell_mode = 0, exclude_same = 0, swap_out = 0;
     int32_t *list = nullptr;
     double *list_rsq = nullptr;
     int64_t capacity = 0;
@@ -1565,6 +1591,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         p.rout2 = c.rout2;
         p.shell_mode = c.shell_mode;
         p.exclude_same = c.exclude_same;
+        p.swap_out = c.swap_out;
         p.list = c.list;
         p.list_rsq = c.list_rsq;
         p.capacity = c.capacity;
@@ -1665,10 +1692,15 @@ int mdp_pair_list(mdp_ctx *ctx, int nframes, int64_t n_a, const double *xyz_a, i
     PairCall c;
     c.mode = MODE_LIST;
     c.nframes = nframes;
-    c.n_a = n_a;
-    c.xyz_a = xyz_a;
-    c.n_b = n_b;
-    c.xyz_b = xyz_b;
+    // The lanes of a warp hold 32 points of set A and stream candidates of set B past them; culling works on the box of
+    // those 32 points, so the denser (larger) set belongs on the lanes: 2 000 ions spread over the cell make 30 A boxes
+    // that touch everything, 60 000 solvent atoms make 10 A boxes.  Swapping the roles only swaps the output columns.
+    const bool swap = n_a < n_b;
+    c.swap_out = swap ? 1 : 0;
+    c.n_a = swap ? n_b : n_a;
+    c.xyz_a = swap ? xyz_b : xyz_a;
+    c.n_b = swap ? n_a : n_b;
+    c.xyz_b = swap ? xyz_a : xyz_b;
     c.box = box;
     // pre-filter must pass rsq <= rout2 too: use the next double above rout2 as the strict cutoff
     c.rcut2 = nextafter(rout2, INFINITY);
