@@ -136,6 +136,22 @@ def measured_peaks():
     return p
 
 
+def ncu_traffic(name, scale=1.0):
+    """DRAM bytes (read + write) of one launch of kernel `name` from the committed ncu --set full summary
+    (profiles/r01e_k_<name>.txt, written by tools/ncu_summary.py), times `scale` when the bench launch is that much larger
+    than the captured one (traffic is linear in the number of frames for every kernel here).  None when absent."""
+    path = os.path.join(ROOT, "profiles", f"r01e_k_{name}.txt")
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for ln in open(path):
+        p = ln.split()
+        if len(p) >= 3 and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(p[1]) * unit.get(p[2], 1.0)
+    return total * scale if total else None
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU legs (oracle port; the only place bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------
@@ -381,7 +397,9 @@ def run_gpu(args):
         "kernel_share": {"pair_kernel_ms_per_step": pair_ms / args.steps, "prep_ms_per_step": prep_ms / args.steps,
                          "step_ms": ms / args.steps},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": ncu_traffic("pair", F / 16.0), "peak_source": peak_src,
+                     "traffic_note": "dram bytes of the 16-frame launch captured in profiles/r01e_k_pair.txt (55 MB = the sorted "
+                                     "records read once), scaled to this launch's frames; irrelevant to an FP64/issue-bound kernel",
                      "note": f"pair kernel only; achieved = evaluated pair-evals x {FLOPS_PER_PAIR} unfused fp64 flops / "
                              f"CUDA-event kernel time; nominal-pair equivalent = {nominal_tflops:.1f} TFLOP/s "
                              f"({nominal_tflops / fp64_peak:.2f} of peak) because culling skips work the reference does"},
@@ -506,8 +524,11 @@ def bench_msd(args, torch, dist, ops, ctx, dev, world, rank):
         "config": {"workload": f"C3 shape: {n} atoms, resident chunk of {T} frames ({n * T * 24 / 1e9:.1f} GB, larger than L2), "
                                "single-origin MSD (diffusion.py:207-218)", "parallelism": f"atoms x{world}"},
         "ms_per_step": ms / steps, "steps": steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                     "peak_source": src, "note": "k_msd_single only; 24 algorithmic bytes per atom-frame"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": ncu_traffic("msd_single", n * T / (1_000_000 * 64.0)),
+                     "peak_source": src, "note": "k_msd_single only; 24 algorithmic bytes per atom-frame; traffic = dram bytes of "
+                                                 "the 64-frame launch in profiles/r01e_k_msd_single.txt (1.545 GB for 1.536 GB "
+                                                 "algorithmic) scaled to this launch"},
         "e2e": {"value": e2e, "unit": "atom-frames/s", "h2d_bytes_per_step": Te * 3 * n * 8, "d2h_bytes_per_step": Te * 32,
                 "api": "Diffusion.get_msd_from_arrays (pinned host frames)"},
         "cpu_baseline": {"value": cpu[0], "unit": "atom-frames/s", "cores": cpu[1], "kind": "port", "sample": cpu[2]},

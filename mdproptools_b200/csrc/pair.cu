@@ -28,6 +28,7 @@
 //      flushed to the per-frame uint64 global histogram when the CTA leaves a frame (the only barrier).
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -719,6 +720,7 @@ struct PairParams {
     unsigned long long *hist;        // device [F][nrows][nbins]
     int edges_in_smem;
     float inv_ddr_biased;            // MODE_HIST_DIRECT: inv_ddr * (1 - 2^-18)
+    int pipeline;                    // MODE_HIST_DIRECT: dense hits expected, use the software-pipelined pair loop
     // list mode
     double rin2, rout2;
     int shell_mode, exclude_same;
@@ -859,6 +861,67 @@ __device__ __forceinline__ double image_r2(double ax, double ay, double az, cons
     return __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
 }
 
+// ---- direct binning (MODE_HIST_DIRECT) ---------------------------------------------------------------------
+struct DirectBin {
+    unsigned nb, edges_a, hist_a, cptab_a, dummy_a, hist_end;
+    uint32_t mi;
+    float inv;
+};
+
+// rsq of my i point against the 4 queued j points at shared address a0 ((x,y) at a0 + 16u, (z,meta) RING entries later)
+template <bool MULTICLS, int VAR>
+__device__ __forceinline__ void direct_eval4(unsigned a0, double xi, double yi, double zi, const Shift &S, double hx, double hy,
+                                             double hz, double (&r2)[4], int (&cj)[4])
+{
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        double jx, jy, jz, jm = 0.0;
+        lds_f64x2(jx, jy, a0 + u * 16);   // constant offsets after unrolling: folded into the LDS immediates
+        if (MULTICLS)
+            lds_f64x2(jz, jm, a0 + RING * 16 + u * 16);
+        else
+            lds_f64(jz, a0 + RING * 16 + u * 16);
+        r2[u] = image_r2<VAR>(__dsub_rn(xi, jx), __dsub_rn(yi, jy), __dsub_rn(zi, jz), S, hx, hy, hz);
+        cj[u] = MULTICLS ? __double2loint(jm) : 0;
+    }
+}
+
+// Branch-free binning of 4 pairs per lane: float(rsq) (F2F, toward zero; saturates, so rsq beyond the cutoff and the
+// +inf padding need no test of their own: their estimate is >= nbins and the clamp sends them to the invalid bin) ->
+// MUFU.SQRT -> one FFMA.RM whose multiplier is biased DOWN by 2^-18 (more than the fp32 error of the estimate, less
+// than 0.02 bin for nbins <= 4096) with the 2^23 trick, so that k_est = floor(x') is the reference bin or the one
+// below it -> ONE exact fp64 compare against edge[k_est + 1] (mdp_bin_edges: bin(rsq) >= k <=> rsq >= edge[k]) ->
+// unpredicated shared-memory increment.  Misses (final bin == nbins) increment a per-lane dummy word behind the
+// histogram: ptxas wraps every predicated shared atomic in its own branch region (4 extra instructions and a
+// reconvergence point per pair); the dummy words sit in 32 different banks.
+template <bool MULTICLS>
+__device__ __forceinline__ void direct_bin4(const DirectBin &db, const double (&r2)[4], const int (&cj)[4])
+{
+    unsigned ha[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float f = __double2float_rz(r2[u]);
+        float sq;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(f));
+        unsigned k = __float_as_uint(__fmaf_rd(sq, db.inv, 12582912.0f)) - 0x4b400000u;   // floor(sq*inv), 2^23 trick
+        k = k < db.nb ? k : db.nb;
+        double e1;
+        lds_f64(e1, db.edges_a + k * 8u + 8u);
+        if (MULTICLS) {
+            k += (r2[u] >= e1) ? 1u : 0u;
+            unsigned row;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(db.cptab_a + (db.mi + (uint32_t)cj[u]) * 4u));
+            ha[u] = k < db.nb ? db.hist_a + (row * db.nb + k) * 4u : db.dummy_a;
+        } else {
+            unsigned a = db.hist_a + k * 4u;
+            a += (r2[u] >= e1) ? 4u : 0u;
+            ha[u] = a < db.hist_end ? a : db.dummy_a;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(ha[u]) : "memory");
+}
+
 template <int MODE, bool MULTICLS, int VAR, bool TRI>
 __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh, const double2 *__restrict__ jb, int nj, double xi,
                                            double yi, double zi, uint32_t mi, const Shift S, int rc_hi,
@@ -867,65 +930,57 @@ __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh
     const double hx = S.x * 0.5, hy = S.y * 0.5, hz = S.z * 0.5;   // VAR_TMIXED only
     constexpr bool META = MULTICLS || MODE == MODE_LIST;
     if (MODE == MODE_HIST_DIRECT) {
-        // Direct binning: with point-level culling ~40 % of the evaluated pairs are hits, so compacting them first no
-        // longer pays.  Branch-free per pair: float(rsq) from the bit pattern, MUFU.SQRT, one FFMA whose multiplier is
-        // biased DOWN by 2^-18 (more than the fp32 error of the estimate, less than 0.02 bin for nbins <= 4096), so that
-        // k_est = floor(x') is the reference bin or the one below it; ONE exact fp64 compare against edge[k_est + 1]
-        // settles it (mdp_bin_edges: bin(rsq) >= k  <=>  rsq >= edge[k]); misses go to the invalid bin nbins.
+        // Direct binning: with point-level culling ~30 % of the evaluated pairs are hits, so compacting them first no
+        // longer pays (direct_bin4).  Two loop shapes: the plain one skips the binning of a 4-step round without any hit
+        // (sparse hits: small cutoffs); the pipelined one (p.pipeline, chosen by the host for dense hits) evaluates the
+        // distances of round n+1 in the same basic block as the binning of round n, so that the FP64 chains and the
+        // ALU/MUFU/LSU chains of the binning fill each other's latency slots.
         const unsigned ja = (unsigned)__cvta_generic_to_shared(jb);
-        const unsigned nb = (unsigned)p.nbins;
-        const float inv = p.inv_ddr_biased;
-        const unsigned dummy_a = sh.hist_a + (unsigned)(p.nrows * p.nbins + lane) * 4u;
-        const unsigned hist_end = sh.hist_a + nb * 4u;   // single-row histogram (!MULTICLS)
+        DirectBin db;
+        db.nb = (unsigned)p.nbins;
+        db.inv = p.inv_ddr_biased;
+        db.edges_a = sh.edges_a;
+        db.hist_a = sh.hist_a;
+        db.cptab_a = sh.cptab_a;
+        db.dummy_a = sh.hist_a + (unsigned)(p.nrows * p.nbins + lane) * 4u;
+        db.hist_end = sh.hist_a + db.nb * 4u;
+        db.mi = mi;
+        if (!TRI && p.pipeline) {
+            double r2c[4];
+            int cjc[4];
+            direct_eval4<MULTICLS, VAR>(ja, xi, yi, zi, S, hx, hy, hz, r2c, cjc);
 #pragma unroll 1
-        for (int j0 = 0; j0 < nj; j0 += 4) {
-            const unsigned a0 = ja + (unsigned)j0 * 16u;
-            double r2[4];
-            int cj[4];
-            bool hit[4];
+            for (int j0 = 0; j0 < nj; j0 += 4) {
+                const int jn = j0 + 4 < nj ? j0 + 4 : j0;   // the last round re-evaluates itself (unused)
+                double r2n[4];
+                int cjn[4];
+                direct_eval4<MULTICLS, VAR>(ja + (unsigned)jn * 16u, xi, yi, zi, S, hx, hy, hz, r2n, cjn);
+                direct_bin4<MULTICLS>(db, r2c, cjc);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                double jx, jy, jz, jm = 0.0;
-                lds_f64x2(jx, jy, a0 + u * 16);   // constant offsets after unrolling: folded into the LDS immediates
-                if (MULTICLS)
-                    lds_f64x2(jz, jm, a0 + RING * 16 + u * 16);
-                else
-                    lds_f64(jz, a0 + RING * 16 + u * 16);
-                r2[u] = image_r2<VAR>(__dsub_rn(xi, jx), __dsub_rn(yi, jy), __dsub_rn(zi, jz), S, hx, hy, hz);
-                hit[u] = __double2hiint(r2[u]) <= rc_hi;   // superset of rsq < rcut2; edge[nbins] <= rcut2 settles it
-                if (TRI) hit[u] = hit[u] && (j0 + u > lane);
-                cj[u] = MULTICLS ? __double2loint(jm) : 0;
-            }
-            if (!__any_sync(0xffffffffu, hit[0] | hit[1] | hit[2] | hit[3])) continue;
-            unsigned ha[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                // rsq beyond the cutoff (and the +inf padding) needs no test of its own: its estimate is >= nbins, the
-                // clamp sends it to the invalid bin (the float conversion saturates, sqrt/FFMA keep +inf)
-                const float f = __double2float_rz(r2[u]);
-                float sq;
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(f));
-                unsigned k = __float_as_uint(__fmaf_rd(sq, inv, 12582912.0f)) - 0x4b400000u;   // floor(sq*inv), 2^23 trick
-                if (TRI) k = hit[u] ? k : nb;
-                k = k < nb ? k : nb;
-                double e1;
-                lds_f64(e1, sh.edges_a + k * 8u + 8u);
-                // misses (final bin == nbins) increment a per-lane dummy word behind the histogram instead of being
-                // predicated off: ptxas wraps every predicated shared atomic in its own branch region (4 extra instructions
-                // and a reconvergence point per pair); the dummy words sit in 32 different banks
-                if (MULTICLS) {
-                    k += (r2[u] >= e1) ? 1u : 0u;
-                    unsigned row;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(sh.cptab_a + (mi + (uint32_t)cj[u]) * 4u));
-                    ha[u] = k < nb ? sh.hist_a + (row * nb + k) * 4u : dummy_a;
-                } else {
-                    unsigned a = sh.hist_a + k * 4u;
-                    a += (r2[u] >= e1) ? 4u : 0u;
-                    ha[u] = a < hist_end ? a : dummy_a;
+                for (int u = 0; u < 4; ++u) {
+                    r2c[u] = r2n[u];
+                    cjc[u] = cjn[u];
                 }
             }
+            return;
+        }
+#pragma unroll 1
+        for (int j0 = 0; j0 < nj; j0 += 4) {
+            double r2[4];
+            int cj[4];
+            direct_eval4<MULTICLS, VAR>(ja + (unsigned)j0 * 16u, xi, yi, zi, S, hx, hy, hz, r2, cj);
+            bool any = false;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(ha[u]) : "memory");
+            for (int u = 0; u < 4; ++u) {
+                bool hit = __double2hiint(r2[u]) <= rc_hi;   // superset of rsq < rcut2; edge[nbins] <= rcut2 settles it
+                if (TRI) {
+                    hit = hit && (j0 + u > lane);
+                    if (!hit) r2[u] = INFINITY;              // the lower triangle of the self chunk never counts
+                }
+                any = any || hit;
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+            direct_bin4<MULTICLS>(db, r2, cj);
         }
         return;
     }
@@ -1587,6 +1642,15 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         p.hist = (unsigned long long *)c.hist_out;
         p.edges_in_smem = edges_in_smem;
         p.inv_ddr_biased = p.inv_ddr * (1.0f - 1.0f / 262144.0f);
+        {
+            // expected share of hits among the evaluated pairs: cutoff sphere / (box of a 32-point group dilated by the cutoff)
+            const double vol = c.box[0] * c.box[1] * c.box[2];
+            const double side = cbrt(32.0 * vol / (double)c.n_a), rc = sqrt(c.rcut2);
+            const double dil = side * side * side + 6.0 * side * side * rc + 3.0 * M_PI * side * rc * rc + 4.0 / 3.0 * M_PI * rc * rc * rc;
+            const double hit_share = vol > 0 ? (4.0 / 3.0 * M_PI * rc * rc * rc) / dil : 0.0;
+            p.pipeline = hit_share > 0.08 ? 1 : 0;
+            if (const char *e = getenv("MDP_PAIR_PIPELINE")) p.pipeline = atoi(e) ? 1 : 0;   // A/B measurements
+        }
         p.rin2 = c.rin2;
         p.rout2 = c.rout2;
         p.shell_mode = c.shell_mode;
