@@ -746,6 +746,12 @@ __host__ __device__ constexpr size_t warp_region_bytes(bool meta)
     return 2 * RING * sizeof(double2) + QCAP * sizeof(double) + (meta ? QCAP * sizeof(uint2) : 0);
 }
 
+// shared-memory bytes of the edge table: nbins + 1 (lo, hi) pairs, or direct binning's nbins + 33 plain edges
+__host__ __device__ constexpr size_t edge_region_bytes(int nbins)
+{
+    return (size_t)(nbins + 1) * 16 > (size_t)(nbins + 34) * 8 ? (size_t)(nbins + 1) * 16 : (size_t)(nbins + 34) * 8;
+}
+
 template <int MODE, bool MULTICLS>
 __device__ __forceinline__ void drain(const PairParams &p, const Shared &sh, int lane, int m, const double *qr,
                                       const uint2 *qm, int base, int frame)
@@ -863,7 +869,7 @@ __device__ __forceinline__ double image_r2(double ax, double ay, double az, cons
 
 // ---- direct binning (MODE_HIST_DIRECT) ---------------------------------------------------------------------
 struct DirectBin {
-    unsigned nb, edges_a, hist_a, cptab_a, dummy_a, hist_end;
+    unsigned nb, kmax, edges_a, hist_a, cptab_a, dummy_a;
     uint32_t mi;
     float inv;
 };
@@ -891,9 +897,9 @@ __device__ __forceinline__ void direct_eval4(unsigned a0, double xi, double yi, 
 // MUFU.SQRT -> one FFMA.RM whose multiplier is biased DOWN by 2^-18 (more than the fp32 error of the estimate, less
 // than 0.02 bin for nbins <= 4096) with the 2^23 trick, so that k_est = floor(x') is the reference bin or the one
 // below it -> ONE exact fp64 compare against edge[k_est + 1] (mdp_bin_edges: bin(rsq) >= k <=> rsq >= edge[k]) ->
-// unpredicated shared-memory increment.  Misses (final bin == nbins) increment a per-lane dummy word behind the
-// histogram: ptxas wraps every predicated shared atomic in its own branch region (4 extra instructions and a
-// reconvergence point per pair); the dummy words sit in 32 different banks.
+// unpredicated shared-memory increment.  Misses never reach a histogram word: ptxas wraps every predicated shared
+// atomic in its own branch region (4 extra instructions and a reconvergence point per pair), so they increment words
+// nobody reads instead -- see the two cases in the body (10 instructions per pair single-row, 13 multi-class).
 template <bool MULTICLS>
 __device__ __forceinline__ void direct_bin4(const DirectBin &db, const double (&r2)[4], const int (&cj)[4])
 {
@@ -904,18 +910,22 @@ __device__ __forceinline__ void direct_bin4(const DirectBin &db, const double (&
         float sq;
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(f));
         unsigned k = __float_as_uint(__fmaf_rd(sq, db.inv, 12582912.0f)) - 0x4b400000u;   // floor(sq*inv), 2^23 trick
-        k = k < db.nb ? k : db.nb;
+        k = k < db.kmax ? k : db.kmax;
         double e1;
         lds_f64(e1, db.edges_a + k * 8u + 8u);
         if (MULTICLS) {
+            // kmax = nbins: misses (final bin == nbins) increment a per-lane dummy word behind the histogram
             k += (r2[u] >= e1) ? 1u : 0u;
             unsigned row;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(db.cptab_a + (db.mi + (uint32_t)cj[u]) * 4u));
             ha[u] = k < db.nb ? db.hist_a + (row * db.nb + k) * 4u : db.dummy_a;
         } else {
+            // kmax = nbins + lane: the single-row histogram is followed by 32 scratch words and the edge table by 33
+            // +inf entries, so a miss needs no select of its own -- it lands in scratch word nbins + lane (its own bank,
+            // like its edge load), which is never zeroed, read or flushed
             unsigned a = db.hist_a + k * 4u;
             a += (r2[u] >= e1) ? 4u : 0u;
-            ha[u] = a < db.hist_end ? a : db.dummy_a;
+            ha[u] = a;
         }
     }
 #pragma unroll
@@ -942,25 +952,30 @@ __device__ __forceinline__ void chunk_loop(const PairParams &p, const Shared &sh
         db.edges_a = sh.edges_a;
         db.hist_a = sh.hist_a;
         db.cptab_a = sh.cptab_a;
+        db.kmax = MULTICLS ? db.nb : db.nb + (unsigned)lane;
         db.dummy_a = sh.hist_a + (unsigned)(p.nrows * p.nbins + lane) * 4u;
-        db.hist_end = sh.hist_a + db.nb * 4u;
         db.mi = mi;
         if (!TRI && p.pipeline) {
-            double r2c[4];
-            int cjc[4];
-            direct_eval4<MULTICLS, VAR>(ja, xi, yi, zi, S, hx, hy, hz, r2c, cjc);
+            // ping-pong over two register sets (no copies, nothing evaluated twice): round r+1 is evaluated in the
+            // same basic block as round r is binned
+            const int R = nj >> 2;
+            double r2a[4], r2b[4];
+            int cja[4], cjb[4];
+            direct_eval4<MULTICLS, VAR>(ja, xi, yi, zi, S, hx, hy, hz, r2a, cja);
+            int r = 1;
 #pragma unroll 1
-            for (int j0 = 0; j0 < nj; j0 += 4) {
-                const int jn = j0 + 4 < nj ? j0 + 4 : j0;   // the last round re-evaluates itself (unused)
-                double r2n[4];
-                int cjn[4];
-                direct_eval4<MULTICLS, VAR>(ja + (unsigned)jn * 16u, xi, yi, zi, S, hx, hy, hz, r2n, cjn);
-                direct_bin4<MULTICLS>(db, r2c, cjc);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    r2c[u] = r2n[u];
-                    cjc[u] = cjn[u];
-                }
+            for (; r + 1 < R; r += 2) {
+                direct_eval4<MULTICLS, VAR>(ja + (unsigned)r * 64u, xi, yi, zi, S, hx, hy, hz, r2b, cjb);
+                direct_bin4<MULTICLS>(db, r2a, cja);
+                direct_eval4<MULTICLS, VAR>(ja + (unsigned)r * 64u + 64u, xi, yi, zi, S, hx, hy, hz, r2a, cja);
+                direct_bin4<MULTICLS>(db, r2b, cjb);
+            }
+            if (r < R) {
+                direct_eval4<MULTICLS, VAR>(ja + (unsigned)r * 64u, xi, yi, zi, S, hx, hy, hz, r2b, cjb);
+                direct_bin4<MULTICLS>(db, r2a, cja);
+                direct_bin4<MULTICLS>(db, r2b, cjb);
+            } else {
+                direct_bin4<MULTICLS>(db, r2a, cja);
             }
             return;
         }
@@ -1084,7 +1099,7 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
     unsigned char *sp = smem_raw + (size_t)NWARP * warp_region_bytes(META);
     Shared sh;
     double2 *edges_s = reinterpret_cast<double2 *>(sp);
-    if (MODE != MODE_LIST && p.edges_in_smem) sp += (size_t)(p.nbins + 1) * sizeof(double2);
+    if (MODE != MODE_LIST && p.edges_in_smem) sp += edge_region_bytes(p.nbins);
     int *cptab_s = reinterpret_cast<int *>(sp);
     if (MULTICLS) sp += (size_t)((p.ncp * 4 + 15) & ~15);
     sh.hist = reinterpret_cast<unsigned int *>(sp);
@@ -1097,9 +1112,9 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
     const int nhist = MODE == MODE_LIST ? 0 : p.nrows * p.nbins;
     if (MODE != MODE_LIST) {
         if (MODE == MODE_HIST_DIRECT) {
-            // plain edge table e[0..nbins+1] (e[nbins+1] = +inf) in the space the edge pairs would take
+            // plain edge table e[0..nbins+32] (+inf beyond e[nbins]) in the space reserved for the edge pairs
             double *e1 = reinterpret_cast<double *>(edges_s);
-            for (int k = tid; k <= p.nbins + 1; k += blockDim.x) e1[k] = p.edges2[k].x;
+            for (int k = tid; k <= p.nbins + 32; k += blockDim.x) e1[k] = k <= p.nbins ? p.edges2[k].x : INFINITY;
         } else if (p.edges_in_smem) {
             for (int k = tid; k <= p.nbins; k += blockDim.x) edges_s[k] = p.edges2[k];
         }
@@ -1494,7 +1509,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
     int edges_in_smem = 0;
     if (hist_mode) {
         const size_t hist_bytes = (size_t)nrows * c.nbins * 4;
-        const size_t edge_bytes = (size_t)(c.nbins + 1) * sizeof(double2);
+        const size_t edge_bytes = edge_region_bytes(c.nbins);
         if (multicls) smem += (size_t)((ncp * 4 + 15) & ~15);
         const size_t cap = std::min<size_t>(ctx->smem_optin, (216 / CTAS_PER_SM) * 1024);   // keep CTAS_PER_SM CTAs per SM
         MDP_REQUIRE(smem + hist_bytes + 128 <= ctx->smem_optin,
@@ -1505,7 +1520,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
             edges_in_smem = 1;
             smem += edge_bytes;
         }
-        smem += hist_bytes + 128;   // + one dummy word per lane (direct binning sends misses there)
+        smem += hist_bytes + 128;   // + one scratch word per lane (direct binning sends misses there)
     }
 
     // sub-batching over frames so that scratch stays bounded
