@@ -1205,59 +1205,64 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
             double2 jxy = make_double2(0.0, 0.0), jzw = jxy, nxy = jxy, nzw = jxy;
 #pragma unroll 1
             while (true) {
-                if (!nvalid) {
-                    // fetch: next needed chunk of the row into the "next" registers
+                // promote the prefetched chunk and fetch its successor in the same round; the first round of a unit has
+                // nothing to promote yet and takes a second pass
 #pragma unroll 1
-                    while (needmask == 0u && t0 < tend) {
-                        const unsigned int it = t0 + (unsigned)(lane >> 3);
-                        const int cj = lane & 7;
-                        tbl = it < tend ? (int)(p.items[it] & 0x3fffffu) : -1;
-                        bool need = false;
-                        code = 0;
-                        if (tbl >= 0 && !(SYMM && tbl == ta && cj < wi)) {
-                            const float4 *gb4 = gbB + ((int64_t)tbl * GPT + cj) * 2;
-                            const float4 blo = gb4[0], bhi = gb4[1];
-                            const float gb[6] = {blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z};
-                            if (TRICL) {
-                                TriConst<DirF32> TC;
-                                TC.set(p.box + f * 6);
-                                need = tri_box_test<DirF32>(ga, gb, TC, rcut2_up, code);
-                            } else {
-                                need = chunk_test_f32(ga, gb, AX, AY, AZ, rcut2_up, code);
-                            }
-                            if (p.nocull) {
-                                need = !(ga[0] > ga[3] || gb[0] > gb[3]);
-                                code = TRICL ? TRI_MIXED : (AX_MIXED | (AX_MIXED << 2) | (AX_MIXED << 4));
-                            }
-                        }
-                        needmask = __ballot_sync(0xffffffffu, need);
-                        t0 += 4;
-                    }
-                    if (needmask) {
-                        const int l = __ffs(needmask) - 1;
-                        needmask &= needmask - 1;
-                        const int tb = __shfl_sync(0xffffffffu, tbl, l);
-                        ncode = __shfl_sync(0xffffffffu, code, l);
-                        nself = SYMM && tb == ta && (l & 7) == wi;
-                        const double2 *jsrc = rB + ((int64_t)tb * GPT + (l & 7)) * GREC;
-                        nxy = __ldg(&jsrc[lane]);
-                        nzw = __ldg(&jsrc[32 + lane]);
-                        nvalid = true;
-                    }
-                }
-                int run_n = 0, run_base = 0, run_code = cur;
-                bool run_tri = false;
-                if (!cvalid) {
-                    if (nvalid) {
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (!cvalid && nvalid) {
                         cvalid = true;
                         nvalid = false;
                         ccode = ncode;
                         cself = nself;
                         jxy = nxy;
                         jzw = nzw;
-                        continue;
                     }
-                    if (tail == head) break;
+                    if (!nvalid) {
+                        // fetch: next needed chunk of the row into the "next" registers
+#pragma unroll 1
+                        while (needmask == 0u && t0 < tend) {
+                            const unsigned int it = t0 + (unsigned)(lane >> 3);
+                            const int cj = lane & 7;
+                            tbl = it < tend ? (int)(p.items[it] & 0x3fffffu) : -1;
+                            bool need = false;
+                            code = 0;
+                            if (tbl >= 0 && !(SYMM && tbl == ta && cj < wi)) {
+                                const float4 *gb4 = gbB + ((int64_t)tbl * GPT + cj) * 2;
+                                const float4 blo = gb4[0], bhi = gb4[1];
+                                const float gb[6] = {blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z};
+                                if (TRICL) {
+                                    TriConst<DirF32> TC;
+                                    TC.set(p.box + f * 6);
+                                    need = tri_box_test<DirF32>(ga, gb, TC, rcut2_up, code);
+                                } else {
+                                    need = chunk_test_f32(ga, gb, AX, AY, AZ, rcut2_up, code);
+                                }
+                                if (p.nocull) {
+                                    need = !(ga[0] > ga[3] || gb[0] > gb[3]);
+                                    code = TRICL ? TRI_MIXED : (AX_MIXED | (AX_MIXED << 2) | (AX_MIXED << 4));
+                                }
+                            }
+                            needmask = __ballot_sync(0xffffffffu, need);
+                            t0 += 4;
+                        }
+                        if (needmask) {
+                            const int l = __ffs(needmask) - 1;
+                            needmask &= needmask - 1;
+                            const int tb = __shfl_sync(0xffffffffu, tbl, l);
+                            ncode = __shfl_sync(0xffffffffu, code, l);
+                            nself = SYMM && tb == ta && (l & 7) == wi;
+                            const double2 *jsrc = rB + ((int64_t)tb * GPT + (l & 7)) * GREC;
+                            nxy = __ldg(&jsrc[lane]);
+                            nzw = __ldg(&jsrc[32 + lane]);
+                            nvalid = true;
+                        }
+                    }
+                    if (cvalid || !nvalid) break;
+                }
+                int run_n = 0, run_base = 0, run_code = cur;
+                bool run_tri = false;
+                if (!cvalid) {
+                    if (tail == head) break;   // nothing prefetched either (a prefetched chunk was promoted above)
                     run_n = -1;   // end of the unit: flush
                 } else if ((cself || ccode != cur) && tail != head) {
                     run_n = -1;   // flush first; the chunk is looked at again in the next round
