@@ -611,70 +611,98 @@ def bench_green_kubo(args, torch, dist, ops, ctx, dev, world, rank):
 def bench_residence(args, torch, dist, ops, ctx, dev, world, rank):
     """C5 shape (SURVEY 8d): 2 000 cations and 62 666 water oxygens in a 126 A cubic box, T frames of a random walk;
     residence shell r <= 3.0 A.  (i) neighbour search mdp_pair_list (cations x oxygens per frame, the pair engine in list
-    mode), (ii) time bitmasks of the ever-neighbour pairs, (iii) survival counts cnt[tau] = sum_p popc(m_p & m_p >> tau).
-    Central atoms are split over the ranks."""
-    ncat_all, nox, L = 2_000, 62_666, 126.0
+    mode) on this rank's block of FRAMES, (ii) the entries are routed to the rank owning the central atom
+    (dist.exchange_rows: all-to-all over NVLink), (iii) time bitmasks of the ever-neighbour pairs and survival counts
+    cnt[tau] = sum_p popc(m_p & m_p >> tau) for this rank's CENTRAL ATOMS, (iv) int64 all-reduce of cnt."""
+    from mdproptools_b200 import dist as mdist
+    ncat, nox, L = 2_000, 62_666, 126.0
     T = args.res_frames
-    c0, c1 = (rank * ncat_all) // world, ((rank + 1) * ncat_all) // world
-    ncat = c1 - c0
+    t0, t1 = (rank * T) // world, ((rank + 1) * T) // world
+    Tl = t1 - t0
     g = torch.Generator(device="cuda")
     g.manual_seed(SEED + 300)
-    cat = torch.empty((T, 3, ncat), dtype=torch.float64, device=dev)
-    ox = torch.empty((T, 3, nox), dtype=torch.float64, device=dev)
-    pc = torch.rand((3, ncat_all), generator=g, dtype=torch.float64, device=dev)[:, c0:c1] * L
+    cat = torch.empty((Tl, 3, ncat), dtype=torch.float64, device=dev)
+    ox = torch.empty((Tl, 3, nox), dtype=torch.float64, device=dev)
+    pc = torch.rand((3, ncat), generator=g, dtype=torch.float64, device=dev) * L
     po = torch.rand((3, nox), generator=g, dtype=torch.float64, device=dev) * L
     CH = 250
-    for f0 in range(0, T, CH):          # random walk, sigma = 0.15 A per frame, wrapped
-        k = min(CH, T - f0)
+    for f0 in range(0, T, CH):          # random walk, sigma = 0.15 A per frame, wrapped; every rank walks all T frames
+        k = min(CH, T - f0)             # (same seed) and keeps its own block
         sc = torch.randn((k, 3, ncat), generator=g, dtype=torch.float64, device=dev).mul_(0.15).cumsum_(0)
         so = torch.randn((k, 3, nox), generator=g, dtype=torch.float64, device=dev).mul_(0.15).cumsum_(0)
-        cat[f0:f0 + k] = torch.remainder(pc + sc, L)
-        ox[f0:f0 + k] = torch.remainder(po + so, L)
+        a0, a1 = max(f0, t0), min(f0 + k, t1)
+        if a1 > a0:
+            cat[a0 - t0:a1 - t0] = torch.remainder(pc + sc[a0 - f0:a1 - f0], L)
+            ox[a0 - t0:a1 - t0] = torch.remainder(po + so[a0 - f0:a1 - f0], L)
         pc, po = pc + sc[-1], po + so[-1]
         del sc, so
-    boxes = np.tile(np.array([L, L, L]), (T, 1))
+    boxes = np.tile(np.array([L, L, L]), (Tl, 1))
     FB = 500                              # frames per search call
 
     def search():
         parts = []
-        for f0 in range(0, T, FB):
+        for f0 in range(0, Tl, FB):
             lst, _ = ops.pair_list(cat[f0:f0 + FB], ox[f0:f0 + FB], boxes[f0:f0 + FB], 0.0, 9.0, 1, capacity=16 * ncat * FB)
-            lst[:, 0] += f0
+            lst[:, 0] += t0 + f0
             parts.append(lst)
-        return torch.cat(parts)
+        return torch.cat(parts) if parts else torch.zeros((0, 3), dtype=torch.int32, device=dev)
 
-    lst = search()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    lst = search()
-    e1.record()
-    torch.cuda.synchronize()
-    ms_search = e0.elapsed_time(e1)
     holder = {}
 
-    def corr():
-        holder["cnt"], holder["P"] = ops.bitmask_autocorr_from_list(lst, nox, T)
+    def step():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record()
+        lst = search()
+        e[1].record()
+        if world > 1:
+            lst = mdist.exchange_rows(lst, mdist.owner_of_rows(lst[:, 1], ncat, world))
+        e[2].record()
+        holder["cnt"], holder["P"] = ops.bitmask_autocorr_from_list(lst.contiguous(), nox, T)
+        if world > 1:
+            dist.all_reduce(holder["cnt"], op=dist.ReduceOp.SUM)
+        e[3].record()
+        torch.cuda.synchronize()
+        holder["entries"] = int(lst.shape[0])
+        return [e[i].elapsed_time(e[i + 1]) for i in range(3)]
 
-    ms_c, kms_c, kn_c = _timed(ctx, torch, 6, corr, 3)
-    P, cnt = holder["P"], holder["cnt"]
+    step()
+    ms_search, ms_x, ms_c = step()
+    lst = None
+    holder2 = {}
+    ent = torch.tensor([holder["entries"], holder["P"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ent, op=dist.ReduceOp.SUM)
+    entries_all, P_all = int(ent[0].item()), int(ent[1].item())
+
+    # kernel time of the popcount correlation alone (this rank's central atoms), for the roofline
+    lst_local = search()
+    if world > 1:
+        lst_local = mdist.exchange_rows(lst_local, mdist.owner_of_rows(lst_local[:, 1], ncat, world))
+    lst_local = lst_local.contiguous()
+
+    def corr():
+        holder2["cnt"], holder2["P"] = ops.bitmask_autocorr_from_list(lst_local, nox, T)
+
+    _, kms_c, kn_c = _timed(ctx, torch, 6, corr, 3)
+    P = holder2["P"]
+    cnt = holder["cnt"]
     W = (T + 63) // 64
     words = P * sum(W - (tau >> 6) for tau in range(T))            # 64-bit AND+POPC per (pair, lag, word)
     gpop = words / (kms_c * 1e-3) / 1e9
     peak = 148 * 16 * 1.965 / 2                                     # POPC runs at 16 lanes/clk/SM; popcll = 2 POPC
-    t = torch.tensor([ms_search + ms_c], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_search + ms_x + ms_c, ms_search, ms_x, ms_c], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms, ms_search, ms_x, ms_c = (float(v) for v in t.tolist())
     return {
-        "metric": "residence_pair_evals_per_s", "value": ncat_all * nox * T / (total_ms * 1e-3), "unit": "pair-evals/s",
-        "config": {"workload": f"C5 shape: {ncat_all} cations x {nox} water O x {T} frames, shell r <= 3.0 A, search + bitmask "
-                               f"survival correlation at all {T} lags; central atoms x{world}"},
-        "ms_per_step": total_ms, "search_ms": ms_search, "correlation_ms": ms_c, "neighbour_entries": int(lst.shape[0]),
-        "ever_neighbour_pairs": P, "cnt0": int(cnt[0].item()),
+        "metric": "residence_pair_evals_per_s", "value": ncat * nox * T / (total_ms * 1e-3), "unit": "pair-evals/s",
+        "config": {"workload": f"C5 shape: {ncat} cations x {nox} water O x {T} frames, shell r <= 3.0 A, search + bitmask "
+                               f"survival correlation at all {T} lags; search: frames x{world}, correlation: central atoms x{world}"},
+        "ms_per_step": total_ms, "search_ms": ms_search, "exchange_ms": ms_x, "correlation_ms": ms_c,
+        "neighbour_entries": entries_all, "ever_neighbour_pairs": P_all, "cnt0": int(cnt[0].item()),
         "roofline": {"bound": "int", "achieved": gpop, "peak": peak, "unit": "G popc64/s", "frac": gpop / peak, "traffic": None,
-                     "note": "k_bitmask_autocorr only; one 64-bit AND + POPC per (pair, lag, word); peak = nominal XU rate "
-                             "16 POPC/clk/SM x 148 SMs x 1965 MHz / 2 (popcll = 2 POPC)"},
+                     "note": "k_bitmask_autocorr only (this rank's central atoms); one 64-bit AND + POPC per (pair, lag, word); "
+                             "peak = nominal XU rate 16 POPC/clk/SM x 148 SMs x 1965 MHz / 2 (popcll = 2 POPC)"},
     }
 
 

@@ -1,10 +1,12 @@
 """Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on GPUs, gloo in the CPU tests).
 
 The hot path shards naturally: frames for RDF / CN / clusters / hydration / flux, atoms for MSD,
-channels for the ACFs, central atoms for residence time.  Each API call does ONE small collective after all
-local work: integer histograms are summed with an int64 all-reduce (order independent -> bit exact), fp64
-partial sums with an fp64 all-reduce.  Without an initialised process group everything degenerates to a
-single rank.
+channels for the ACFs; residence time shards its neighbour search by frames and its survival correlation by
+central atoms.  Each API call does ONE small collective after all local work: integer histograms are summed with
+an int64 all-reduce (order independent -> bit exact), fp64 partial sums with an fp64 all-reduce.  Residence time
+is the one path with a real exchange step: the (frame, central, neighbour) entries found on a rank's frames are
+routed to the rank that owns the central atom (``exchange_rows``: all-to-all over NVLink with NCCL, an all-gather
+based equivalent with gloo).  Without an initialised process group everything degenerates to a single rank.
 """
 from __future__ import annotations
 
@@ -45,6 +47,15 @@ def owner_of(i: int, n: int, w: int | None = None) -> int:
     return i // (base + 1) if i < cut else rem + (i - cut) // max(base, 1)
 
 
+def owner_of_rows(idx: torch.Tensor, n: int, w: int | None = None) -> torch.Tensor:
+    """Vectorised ``owner_of``: rank owning each unit index of ``idx`` under ``shard_range``'s block partition."""
+    w = world_size() if w is None else w
+    base, rem = divmod(n, w)
+    cut = rem * (base + 1)
+    idx = idx.to(torch.int64)
+    return torch.where(idx < cut, idx // (base + 1), rem + (idx - cut) // max(base, 1))
+
+
 def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     """In-place SUM all-reduce (int64 or float64); no-op on a single rank."""
     d = _dist()
@@ -57,3 +68,49 @@ def barrier():
     d = _dist()
     if d and d.get_world_size() > 1:
         d.barrier()
+
+
+def all_reduce_max_(t: torch.Tensor) -> torch.Tensor:
+    d = _dist()
+    if d and d.get_world_size() > 1:
+        d.all_reduce(t, op=d.ReduceOp.MAX)
+    return t
+
+
+def exchange_rows(rows: torch.Tensor, dest: torch.Tensor) -> torch.Tensor:
+    """Route row i of ``rows`` [M, C] to rank ``dest[i]``; returns the rows addressed to this rank, grouped by source
+    rank and in their original order within a source.  Every rank must call it (M may be 0).
+
+    NCCL: one all_to_all_single of the per-destination counts and one of the rows (variable splits).  Backends
+    without all-to-all (gloo, CPU tests): every rank all-gathers the destination-sorted rows, padded to the longest
+    contribution, and keeps its own slices.
+    """
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return rows
+    w, me = d.get_world_size(), d.get_rank()
+    rows = rows.contiguous()
+    dest = dest.to(torch.int64)
+    order = torch.argsort(dest, stable=True)
+    srt = rows.index_select(0, order)
+    send = torch.bincount(dest, minlength=w)
+    if d.get_backend() == "nccl":
+        recv = torch.empty_like(send)
+        d.all_to_all_single(recv, send)
+        send_l, recv_l = send.tolist(), recv.tolist()
+        out = torch.empty((sum(recv_l),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        d.all_to_all_single(out, srt, output_split_sizes=recv_l, input_split_sizes=send_l)
+        return out
+    counts = [torch.empty_like(send) for _ in range(w)]
+    d.all_gather(counts, send)
+    counts = torch.stack(counts).cpu()                      # [source, destination]
+    longest = int(counts.sum(dim=1).max().item())
+    pad = torch.zeros((longest,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    pad[: srt.shape[0]] = srt
+    gathered = [torch.empty_like(pad) for _ in range(w)]
+    d.all_gather(gathered, pad)
+    parts = []
+    for s_ in range(w):
+        off = int(counts[s_, :me].sum().item())
+        parts.append(gathered[s_][off: off + int(counts[s_, me].item())])
+    return torch.cat(parts, dim=0)

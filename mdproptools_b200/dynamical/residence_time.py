@@ -10,7 +10,10 @@ Here: loop 1 is one rectangular neighbour-list call per batch of frames (mdp_pai
 indicators of the pairs that are ever neighbours become per-pair time bitmasks, and loop 2 is the exact
 integer count  cnt[tau] = sum_pairs popcount(m & (m >> tau))  (mdp_bitmask_autocorr); the floats are formed
 at the very end:  C(tau) = (cnt[tau] / (T - tau)) / (N_k N_l),  C /= C(0).
-Central atoms are split over ranks; cnt is merged with one int64 all-reduce (exact).
+Multi-GPU: the search is split by FRAMES (rank r parses and searches frames r, r + w, ...: sorting the neighbour
+set of every frame is the expensive part and does not shrink with the central set), the entries are routed to the
+rank that owns their central atom (dist.exchange_rows, all-to-all over NVLink), the correlation is split by
+CENTRAL ATOMS (a pair's time bitmask never crosses ranks) and cnt is merged with one int64 all-reduce (exact).
 
 Divergence: with ``num_mols=None`` the reference crashes (it feeds 4-column rows to ``_calc_rsq(..., 0)``);
 here the plain ``type`` column is used in that case.
@@ -57,18 +60,16 @@ class ResidenceTime:
         altered = bool(self.num_mols and self.num_atoms_per_mol)
         R = len(self.relation_matrix)
         lists = [[] for _ in range(R)]
-        times = []
         rows_k, rows_l = [None] * R, [None] * R
-        w = dist.world_size()
-        frame_base = 0
-        dev = None
-        for batch in FrameBatches(self.filename, want):
+        w, me = dist.world_size(), dist.rank()
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        own = {}                                # global frame index -> timestep of the frames searched here
+        batches = FrameBatches(self.filename, want, frame_select=(lambda i: i % w == me) if w > 1 else None)
+        for batch in batches:
             d = batch.wait()
-            dev = d.device
             host = batch.host.numpy()
-            F = len(batch.metas)
             for k, meta in enumerate(batch.metas):
-                times.append(meta.timestep * self.dt)
+                own[meta.index] = meta.timestep
                 # altered types are derived from the id column of the id-sorted frame (:80-90)
                 typ = calc_atom_type_ids(host[k, 0], self.num_mols, self.num_atoms_per_mol) if altered else host[k, 1]
                 for kl in range(R):
@@ -80,35 +81,46 @@ class ResidenceTime:
                         raise ValueError("atom types change between frames; residence time needs a fixed pair set")
             xyz = d[:, 2:5, :]
             boxes = np.array([m.box.lattice_lengths() for m in batch.metas])        # (:79)
+            fidx = torch.tensor([m.index for m in batch.metas], dtype=torch.int32, device=d.device)
             for kl in range(R):
                 a, b = self.relation_matrix[kl]
                 ra, rb = rows_k[kl], rows_l[kl]
-                lo, hi = dist.shard_range(len(ra))
-                if hi <= lo or len(rb) == 0:
+                if len(ra) == 0 or len(rb) == 0:
                     continue
-                xa = xyz.index_select(2, torch.from_numpy(ra[lo:hi]).to(dev)).contiguous()
-                xb = xyz.index_select(2, torch.from_numpy(rb).to(dev)).contiguous()
+                xa = xyz.index_select(2, torch.from_numpy(ra).to(d.device)).contiguous()
+                xb = xyz.index_select(2, torch.from_numpy(rb).to(d.device)).contiguous()
                 lst, _ = ops.pair_list(xa, xb, boxes, self.r_cut[kl][0] ** 2, self.r_cut[kl][1] ** 2, shell_mode=1,
                                        exclude_same_index=False)
                 if len(lst):
                     lst = lst.clone()
-                    lst[:, 1] += lo
                     if a == b:                                                   # h[idx] = False (:103-104)
                         lst = lst[lst[:, 1] != lst[:, 2]]
-                    lst[:, 0] += frame_base
+                    lst[:, 0] = fidx[lst[:, 0].long()]                           # batch-local -> trajectory frame index
                     lists[kl].append(lst)
-            frame_base += F
-        T = frame_base
+        T = batches.total_frames or 0
         if T == 0:
             raise ValueError(f"no dump frames found for {self.filename!r}")
+        # every rank needs every frame's time and the sizes of the two sets (a rank may have had no frame at all)
+        tt = torch.zeros((T,), dtype=torch.int64, device=dev)
+        for idx, ts in own.items():
+            tt[idx] = ts
+        nkl = torch.tensor([[len(rows_k[kl]), len(rows_l[kl])] if rows_k[kl] is not None else [0, 0] for kl in range(R)],
+                           dtype=torch.int64, device=dev).reshape(R, 2)
+        if w > 1:
+            dist.all_reduce_sum_(tt)
+            dist.all_reduce_max_(nkl)
+        times = [float(v) * self.dt for v in tt.cpu().numpy()]
+        nkl = nkl.cpu().numpy()
         correlation = {"Time (ps)": times}
         for kl in range(R):
             a, b = self.relation_matrix[kl]
             atom_pair = f"{a}-{b}"
-            n_k, n_l = len(rows_k[kl]), len(rows_l[kl])
-            if lists[kl]:
-                lst = torch.cat(lists[kl], dim=0).contiguous()
-                cnt, _ = ops.bitmask_autocorr_from_list(lst, n_l, T)
+            n_k, n_l = int(nkl[kl, 0]), int(nkl[kl, 1])
+            lst = torch.cat(lists[kl], dim=0) if lists[kl] else torch.zeros((0, 3), dtype=torch.int32, device=dev)
+            if w > 1:
+                lst = dist.exchange_rows(lst, dist.owner_of_rows(lst[:, 1], n_k, w))
+            if len(lst):
+                cnt, _ = ops.bitmask_autocorr_from_list(lst.contiguous(), n_l, T)
             else:
                 cnt = torch.zeros((T,), dtype=torch.int64, device=dev)
             if w > 1:

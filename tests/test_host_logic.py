@@ -267,6 +267,18 @@ lo, hi = dist.shard_range(11)
 x = torch.zeros(11, dtype=torch.float64); x[lo:hi] = 1.0
 dist.all_reduce_sum_(x)
 assert x.sum().item() == 11
+# residence time: (frame, central, neighbour) entries found on a rank's frames go to the owner of the central atom
+n_cent = 7
+rng = np.random.default_rng(5)
+full = np.stack([rng.integers(0, 9, 40), rng.integers(0, n_cent, 40), rng.integers(0, 30, 40)], axis=1).astype(np.int32)
+mine_rows = torch.from_numpy(full[full[:, 0] % 2 == r])
+got = dist.exchange_rows(mine_rows, dist.owner_of_rows(mine_rows[:, 1], n_cent, 2))
+lo, hi = dist.shard_range(n_cent)
+want = full[(full[:, 1] >= lo) & (full[:, 1] < hi)]
+assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
+assert all(dist.owner_of(i, n_cent, 2) == int(dist.owner_of_rows(torch.tensor([i]), n_cent, 2)) for i in range(n_cent))
+empty = dist.exchange_rows(torch.zeros((0, 3), dtype=torch.int32), torch.zeros((0,), dtype=torch.int64))
+assert empty.shape == (0, 3)
 d.destroy_process_group()
 print("rank", r, "ok")
 """
