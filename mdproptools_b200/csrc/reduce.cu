@@ -380,74 +380,154 @@ __global__ void __launch_bounds__(RB) k_seg_static(const double *__restrict__ ma
     qsum[s] = qs;
 }
 
-// grid (nblocks over segments [s0,s1) of one molecule type, nframes).  A CTA owns RB consecutive molecules, i.e. one
-// contiguous atom range (molecule membership is positional).  Thread-per-atom, coalesced: the three
-// velocity components (streamed once from HBM) times the atom's mass (L2-resident) go to shared memory in tiles of
-// FLUX_TILE atoms; thread-per-molecule then adds its own atoms from shared memory in atom order, as the reference
-// does.  (A thread-per-molecule gather straight from global touches 32 sectors per warp load and is L1-throughput
-// bound at half the HBM rate.)
-constexpr int FLUX_TILE = 1536;
-__global__ void __launch_bounds__(RB) k_charge_flux(const double *__restrict__ vel, int64_t n, const double *__restrict__ mass,
-                                                    const double *__restrict__ wsum, const double *__restrict__ qsum,
-                                                    const int32_t *__restrict__ seg_off, int64_t s0, int64_t s1,
-                                                    double vel_scale, double q_scale, double *__restrict__ partial, int nchunks)
+// A chunk = FLUX_B consecutive molecules of one molecule type = one contiguous atom range (molecule membership is
+// positional).  Grid (nchunks, frame lanes), sized to the resident CTA slots (2 per SM): a CTA keeps ITS
+// chunk -- every per-molecule quantity (atom range, mass, charge) is loaded once -- and walks the frames lane, lane + L, ...
+// The three velocity rows of the range (streamed once from HBM) and its masses (L2-resident) arrive in shared memory as
+// four TMA bulk copies (cp.async.bulk + mbarrier transaction count) per tile of FLUX_TILE atoms, double buffered: the
+// copies of the next frame's tile are in flight while one thread per (component, molecule) adds m*v of its own atoms from
+// the current tile in atom order, as the reference does.  History: a thread-per-molecule gather straight from global is
+// L1-throughput bound (3.5 TB/s); staging through registers with one tile per CTA serialised every CTA's loads behind
+// its barriers (4.7 TB/s); per-thread 8-byte cp.async saturated the LSU queue (3.8 TB/s); persistent CTAs walking
+// (chunk, frame) items re-read the per-molecule metadata from global for every item, on the critical path (4.2-4.9 TB/s).
+// Bulk copies need 16-byte aligned addresses and sizes: each row is copied from its address rounded down to 16 bytes
+// (shift sh = 0 or 1 element, applied when the tile is read) with its length rounded up -- at most one neighbouring
+// element on either side, which lies inside the same 16-byte granule of the caller's allocation.
+constexpr int FLUX_B = 128;
+constexpr int FLUX_TILE = 1408;                 // atoms per tile; 4 rows x (1408 + 2) x 8 B = 45 KB per stage
+constexpr int FLUX_ROW = FLUX_TILE + 2;         // + shift + round-up
+constexpr int FLUX_STAGES = 2;                  // 90 KB per CTA: two CTAs per SM
+constexpr int FLUX_T = 3 * FLUX_B;              // threads: one per (component, molecule), component-major
+constexpr size_t FLUX_SMEM = (size_t)FLUX_STAGES * 4 * FLUX_ROW * sizeof(double);
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
-    __shared__ double sm[32];
-    __shared__ double sv[3][FLUX_TILE];
-    const int f = blockIdx.y;
-    const int64_t sfirst = s0 + (int64_t)blockIdx.x * blockDim.x;
-    const int64_t slast = sfirst + blockDim.x < s1 ? sfirst + blockDim.x : s1;   // one past my CTA's last molecule
-    const int64_t s = sfirst + threadIdx.x;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+
+// the four rows of one tile [t0, t0 + cnt) of frame f -> stage buffer; returns the element shifts packed 1 bit per row
+__device__ __forceinline__ void flux_issue(const double *vel, const double *mass, int64_t n, int f, int t0, int cnt, unsigned buf,
+                                           unsigned bar)
+{
+    const double *rows[4] = {vel + (int64_t)f * 3 * n + t0, vel + (int64_t)f * 3 * n + n + t0, vel + (int64_t)f * 3 * n + 2 * n + t0,
+                             mass + t0};
+    unsigned bytes[4], total = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const unsigned sh = (unsigned)(((uintptr_t)rows[r] >> 3) & 1u);
+        bytes[r] = (((unsigned)cnt + sh + 1u) & ~1u) * 8u;
+        total += bytes[r];
+    }
+    mbar_expect_tx(bar, total);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const unsigned sh = (unsigned)(((uintptr_t)rows[r] >> 3) & 1u);
+        bulk_g2s(buf + (unsigned)(r * FLUX_ROW * 8), rows[r] - sh, bytes[r], bar);
+    }
+}
+
+__global__ void __launch_bounds__(FLUX_T) k_charge_flux(const double *__restrict__ vel, int64_t n, const double *__restrict__ mass,
+                                                        const double *__restrict__ wsum, const double *__restrict__ qsum,
+                                                        const int32_t *__restrict__ seg_off, int64_t s0, int64_t s1, int nframes,
+                                                        double vel_scale, double q_scale, double *__restrict__ partial, int nchunks)
+{
+    extern __shared__ __align__(128) double fs[];   // [FLUX_STAGES][4][FLUX_ROW]: vx, vy, vz, mass
+    __shared__ __align__(8) unsigned long long bars[FLUX_STAGES];
+    __shared__ double sm[2][3][FLUX_B / 32];
+    const unsigned fs_a = (unsigned)__cvta_generic_to_shared(fs);
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(bars);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int comp = tid / FLUX_B, mol = tid - comp * FLUX_B, wc = mol >> 5;   // component (warp uniform), molecule, warp of the component
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < FLUX_STAGES; ++k) mbar_init(bar_a + 8u * k, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // my chunk and my molecule: loaded once
+    const int chunk = blockIdx.x;
+    const int64_t sfirst = s0 + (int64_t)chunk * FLUX_B;
+    const int64_t slast = sfirst + FLUX_B < s1 ? sfirst + FLUX_B : s1;
+    const int64_t s = sfirst + mol;
     const int A0 = seg_off[sfirst], A1 = seg_off[slast];
     const bool mine = s < s1;
     const int b = mine ? seg_off[s] : A1, e = mine ? seg_off[s + 1] : A1;
-    const double *v = vel + (int64_t)f * 3 * n;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int t0 = A0; t0 < A1; t0 += FLUX_TILE) {
-        const int cnt = A1 - t0 < FLUX_TILE ? A1 - t0 : FLUX_TILE;
-        // all 18 loads of a thread are issued before anything depends on them (memory-level parallelism: the tile is
-        // only 36 KB, the CTA has nothing else in flight)
-        double r[3][FLUX_TILE / RB], mm[FLUX_TILE / RB];
-#pragma unroll
-        for (int k = 0; k < FLUX_TILE / RB; ++k) {
-            const int i = threadIdx.x + k * RB;
-            const bool ok = i < cnt;
-            const double *pv = v + t0 + (ok ? i : 0);
-            r[0][k] = ld_stream1(pv);
-            r[1][k] = ld_stream1(pv + n);
-            r[2][k] = ld_stream1(pv + 2 * n);
-            mm[k] = mass[t0 + (ok ? i : 0)];
+    const double ws = mine ? wsum[s] : 1.0;
+    const double qsi = mine ? __dmul_rn(qsum[s], q_scale) : 0.0;
+    const int shm_par = (int)(((uintptr_t)mass >> 3) & 1);
+
+    // producer cursor (the tile whose copies are issued next), advanced identically by every thread
+    int pf = blockIdx.y, pt0 = A0;
+    unsigned issued = 0, consumed = 0;
+    auto produce = [&]() {
+        if (A1 <= A0 || pf >= nframes) return;
+        const int cnt = A1 - pt0 < FLUX_TILE ? A1 - pt0 : FLUX_TILE;
+        if (tid == 0) {
+            const unsigned st = issued % FLUX_STAGES;
+            flux_issue(vel, mass, n, pf, pt0, cnt, fs_a + st * (unsigned)(4 * FLUX_ROW * 8), bar_a + 8u * st);
         }
-        __syncthreads();   // previous tile fully consumed
-#pragma unroll
-        for (int k = 0; k < FLUX_TILE / RB; ++k) {
-            const int i = threadIdx.x + k * RB;
-            if (i < cnt) {
-                sv[0][i] = __dmul_rn(r[0][k], mm[k]);
-                sv[1][i] = __dmul_rn(r[1][k], mm[k]);
-                sv[2][i] = __dmul_rn(r[2][k], mm[k]);
-            }
+        ++issued;
+        pt0 += cnt;
+        if (pt0 >= A1) {
+            pt0 = A0;
+            pf += gridDim.y;
         }
+    };
+#pragma unroll 1
+    for (int k = 0; k < FLUX_STAGES - 1; ++k) produce();
+
+    int item_k = 0;
+    for (int f = blockIdx.y; f < nframes; f += gridDim.y, ++item_k) {
+        double acc = 0.0;
+        const int64_t rowoff = (int64_t)f * 3 * n + (int64_t)comp * n;
+        for (int t0 = A0; t0 < A1; t0 += FLUX_TILE) {
+            const int cnt = A1 - t0 < FLUX_TILE ? A1 - t0 : FLUX_TILE;
+            produce();   // the stage it overwrites was released by the barrier that ended the previous tile
+            const unsigned st = consumed % FLUX_STAGES;
+            mbar_wait(bar_a + 8u * st, (consumed / FLUX_STAGES) & 1u);
+            ++consumed;
+            const double *tv = fs + (size_t)st * 4 * FLUX_ROW + comp * FLUX_ROW + (((uintptr_t)(vel + rowoff + t0) >> 3) & 1);
+            const double *tm = fs + (size_t)st * 4 * FLUX_ROW + 3 * FLUX_ROW + ((shm_par + t0) & 1);
+            const int lo = (b > t0 ? b : t0) - t0, hi = (e < t0 + cnt ? e : t0 + cnt) - t0;
+#pragma unroll 4
+            for (int i = lo; i < hi; ++i) acc = __dadd_rn(acc, __dmul_rn(tv[i], tm[i]));
+            if (t0 + cnt < A1) __syncthreads();   // tile consumed (the last tile's barrier is the one of the CTA sum)
+        }
+        double j = mine ? __dmul_rn(__dmul_rn(acc / ws, vel_scale), qsi) : 0.0;
+        // deterministic CTA sum per component with a single barrier (fixed shuffle tree, fixed warp order)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) j = __dadd_rn(j, __shfl_xor_sync(0xffffffffu, j, o));
+        double(*smk)[FLUX_B / 32] = sm[item_k & 1];
+        if (lane == 0) smk[comp][wc] = j;
         __syncthreads();
-        const int lo = b > t0 ? b : t0, hi = e < t0 + cnt ? e : t0 + cnt;
-        for (int a = lo; a < hi; ++a) {
-            a0 = __dadd_rn(a0, sv[0][a - t0]);
-            a1 = __dadd_rn(a1, sv[1][a - t0]);
-            a2 = __dadd_rn(a2, sv[2][a - t0]);
+        if (tid < 3) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < FLUX_B / 32; ++k) r = __dadd_rn(r, smk[tid][k]);
+            partial[((int64_t)f * nchunks + chunk) * 3 + tid] = r;
         }
-    }
-    double j[3] = {0, 0, 0};
-    if (mine) {
-        const double ws = wsum[s];
-        const double qsi = __dmul_rn(qsum[s], q_scale);
-        j[0] = __dmul_rn(__dmul_rn(a0 / ws, vel_scale), qsi);
-        j[1] = __dmul_rn(__dmul_rn(a1 / ws, vel_scale), qsi);
-        j[2] = __dmul_rn(__dmul_rn(a2 / ws, vel_scale), qsi);
-    }
-    const double r0 = block_sum(j[0], sm), r1 = block_sum(j[1], sm), r2 = block_sum(j[2], sm);
-    if (threadIdx.x == 0) {
-        double *o = partial + ((int64_t)f * nchunks + blockIdx.x) * 3;
-        o[0] = r0; o[1] = r1; o[2] = r2;
     }
 }
 
@@ -611,7 +691,7 @@ int mdp_charge_flux(mdp_ctx *ctx, int nframes, int64_t n, const double *vel, con
     MDP_REQUIRE(nframes > 0 && nframes <= 65535 && n > 0 && nseg > 0 && ngroups > 0, "mdp_charge_flux: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     MDP_CUDA(cudaSetDevice(ctx->device));
-    const int max_chunks = (int)ceil_div<int64_t>(nseg, RB) + 1;
+    const int max_chunks = (int)ceil_div<int64_t>(nseg, FLUX_B) + ngroups;
     int rc = ctx->arena_reserve((size_t)nframes * max_chunks * 24 + (size_t)nseg * 16 + 8192);
     if (rc) return rc;
     ctx->arena_reset();
@@ -627,10 +707,15 @@ int mdp_charge_flux(mdp_ctx *ctx, int nframes, int64_t n, const double *vel, con
     for (int g = 0; g < ngroups; ++g) {
         const int64_t s0 = group_seg_off[g], s1 = group_seg_off[g + 1];
         MDP_REQUIRE(s0 >= 0 && s1 > s0 && s1 <= nseg, "mdp_charge_flux: bad molecule-type range");
-        const int nchunks = (int)ceil_div<int64_t>(s1 - s0, RB);
-        dim3 grid(nchunks, nframes);
+        const int nchunks = (int)ceil_div<int64_t>(s1 - s0, FLUX_B);
+        // frame lanes: fill the resident CTA slots (2 per SM) without exceeding them (a partial second wave would double the time)
+        const int slots = ctx->sm_count * 2;
+        const int lanes = std::max(1, std::min(nframes, slots / std::max(1, std::min(nchunks, slots))));
+        dim3 grid((unsigned)nchunks, (unsigned)lanes);
+        MDP_CUDA(cudaFuncSetAttribute((const void *)k_charge_flux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLUX_SMEM));
         cudaEvent_t tk = ctx->timer_begin(4, st);
-        k_charge_flux<<<grid, RB, 0, st>>>(vel, n, mass, wsum, qsum, seg_off, s0, s1, vel_scale, q_scale, partial, nchunks);
+        k_charge_flux<<<grid, FLUX_T, FLUX_SMEM, st>>>(vel, n, mass, wsum, qsum, seg_off, s0, s1, nframes, vel_scale, q_scale, partial,
+                                                       nchunks);
         ctx->timer_end(tk, st);
         MDP_LAUNCHED(ctx);
         k_flux_finish<<<nframes, 96, 0, st>>>(partial, nchunks, g, ngroups, out, out_stride, frame0);
