@@ -54,19 +54,28 @@ __global__ void __launch_bounds__(XC_THREADS) k_xcorr(const double *__restrict__
             sa[pad8(i)] = t < T ? ac[t] : 0.0;   // zero padding == the reference's zero-padded FFT
         }
         __syncthreads();
-        const int s0 = ts * XC_SUB;
+        // s0, l0 and the step s are multiples of 8, so the skewed index is affine inside an octet:
+        // pad8(base + j) = pad8(base) + j + (j >> 3) for base % 8 == 0 -- the loads below take immediate offsets
+        const double *pa = sa + pad8(ts * XC_SUB + l0);     // window elements of step s: pa[k], k = 0..7; next octet at pa[9..]
+        const double2 *pb = reinterpret_cast<const double2 *>(sb + ts * XC_SUB);
         double win[XC_LPT];
 #pragma unroll
-        for (int k = 0; k < XC_LPT - 1; ++k) win[k] = sa[pad8(s0 + l0 + k)];
+        for (int k = 0; k < XC_LPT - 1; ++k) win[k] = pa[k];
 #pragma unroll 1
-        for (int s = 0; s < XC_SUB; s += XC_LPT) {
+        for (int s = 0; s < XC_SUB; s += XC_LPT, pa += XC_LPT + 1, pb += XC_LPT / 2) {
+            double bv[XC_LPT];
+#pragma unroll
+            for (int u = 0; u < XC_LPT; u += 2) {
+                const double2 t = pb[u >> 1];
+                bv[u] = t.x;
+                bv[u + 1] = t.y;
+            }
 #pragma unroll
             for (int u = 0; u < XC_LPT; ++u) {
                 // window element for lag l0+k at step s+u is a[s0+s+u + l0+k]; rotate by renaming
-                win[(u + XC_LPT - 1) % XC_LPT] = sa[pad8(s0 + s + u + l0 + XC_LPT - 1)];
-                const double bv = sb[s0 + s + u];
+                win[(u + XC_LPT - 1) % XC_LPT] = pa[u + XC_LPT - 1 + ((u + XC_LPT - 1) >> 3)];
 #pragma unroll
-                for (int k = 0; k < XC_LPT; ++k) acc[k] = fma(win[(u + k) % XC_LPT], bv, acc[k]);
+                for (int k = 0; k < XC_LPT; ++k) acc[k] = fma(win[(u + k) % XC_LPT], bv[u], acc[k]);
             }
         }
     }

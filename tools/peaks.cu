@@ -20,17 +20,24 @@
 constexpr int ITERS = 4096;
 constexpr int CHAINS = 8;
 
-template <int MODE>   // 0: DADD+DMUL unfused alternating, 1: DFMA
+template <int MODE>   // 0: DADD+DMUL unfused alternating, 1: DFMA (two uniform operands), 2: DFMA with three register operands
 __global__ void __launch_bounds__(256) k_fp64(double *out, double a, double b)
 {
-    double v[CHAINS];
+    double v[CHAINS], w[CHAINS];
 #pragma unroll
-    for (int k = 0; k < CHAINS; ++k) v[k] = a + threadIdx.x * 1e-9 + k;
+    for (int k = 0; k < CHAINS; ++k) {
+        v[k] = a + threadIdx.x * 1e-9 + k;
+        w[k] = b * (threadIdx.x + k + 1);
+    }
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int k = 0; k < CHAINS; ++k) {
-            if (MODE == 0) {
+            if (MODE == 2) {
+                // the correlation kernels' shape: accumulator += window[k'] * broadcast value, all three in registers
+                v[k] = fma(w[(k + 1) % CHAINS], w[0], v[k]);
+                v[k] = fma(w[(k + 3) % CHAINS], w[1], v[k]);
+            } else if (MODE == 0) {
                 v[k] = __dadd_rn(v[k], b);
                 v[k] = __dmul_rn(v[k], a);
             } else {
@@ -103,6 +110,7 @@ int main()
     const double ops = (double)blocks * 256 * ITERS * CHAINS * 2;
     float t0 = time_ms([&] { k_fp64<0><<<blocks, 256>>>(d_out, 1.0000001, 1e-7); }, 5);
     float t1 = time_ms([&] { k_fp64<1><<<blocks, 256>>>(d_out, 1.0000001, 1e-7); }, 5);
+    float t2 = time_ms([&] { k_fp64<2><<<blocks, 256>>>(d_out, 1.0000001, 1e-7); }, 5);
     // sustained: repeat for ~2 s to see the clock settle under the power cap
     float t0s = 0;
     {
@@ -129,6 +137,7 @@ int main()
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_mhz\": %d,\n", prop.name, sms, prop.clockRate / 1000);
     printf(" \"fp64_unfused_tflops_burst\": %.3f, \"fp64_unfused_tflops_sustained\": %.3f, \"fp64_fma_tflops_burst\": %.3f,\n",
            ops / t0 * 1e-9, ops / t0s * 1e-9, 2 * ops / t1 * 1e-9);
+    printf(" \"fp64_fma_3reg_tflops_burst\": %.3f,\n", 2 * ops / t2 * 1e-9);
     printf(" \"smem_atomic_gops_400bins\": %.2f, \"smem_atomic_gops_6000bins\": %.2f,\n",
            (double)sms * 4 * 256 * aiters / ta * 1e-6, (double)sms * 4 * 256 * aiters / ta2 * 1e-6);
     printf(" \"stream_read_gbs\": %.1f,\n", bytes / tr * 1e-6);
