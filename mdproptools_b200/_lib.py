@@ -168,8 +168,19 @@ def dptr(a: np.ndarray):
     return a.ctypes.data_as(POINTER(c_double))
 
 
+_EDGES: dict = {}
+
+
 def bin_edges(ddr: float, nb: int) -> np.ndarray:
-    """Host-only: exact rsq thresholds of bin(rsq) = int(sqrt(rsq)/ddr) (rdf_cn.py:68,85)."""
-    e = np.empty(nb + 1, dtype=np.float64)
-    check(lib().mdp_bin_edges(float(ddr), int(nb), dptr(e)), "mdp_bin_edges")
+    """Host-only: exact rsq thresholds of bin(rsq) = int(sqrt(rsq)/ddr) (rdf_cn.py:68,85).  Cached per (ddr, nb); the
+    returned array is read-only."""
+    key = (float(ddr), int(nb))
+    e = _EDGES.get(key)
+    if e is None:
+        e = np.empty(nb + 1, dtype=np.float64)
+        check(lib().mdp_bin_edges(float(ddr), int(nb), dptr(e)), "mdp_bin_edges")
+        e.setflags(write=False)
+        if len(_EDGES) > 64:
+            _EDGES.clear()
+        _EDGES[key] = e
     return e

@@ -559,20 +559,29 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
     num_bins, radii = _num_bins(r_cut, bin_size)
     num_relations = len(partial_relations[0])
     relation_matrix = np.asarray(partial_relations).transpose()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    batches = iter(ArrayBatches(pos, batch_frames, dev))          # the copy of the first batch starts now, under the host prep
+    first = next(batches, None)
     types = np.asarray(types)
-    cmap = _ClassMap(list(partial_relations[0]) + list(partial_relations[1]), present_types=np.unique(types.astype(np.int64)))
+    at_all = _value_counts(types)                                 # one pass over the types serves the class map too
+    cmap = _ClassMap(list(partial_relations[0]) + list(partial_relations[1]), present_types=list(at_all))
     weights = _sym_weights(cmap, relation_matrix, with_full=True)
     edges = bin_edges(bin_size, num_bins)
     rcut2 = _rcut_sq(r_cut)
     flags = _mic_flags(mic)
     boxes = np.broadcast_to(np.asarray(box_lengths, dtype=np.float64), (T, 6 if flags else 3))
     static_types = types.ndim == 1
-    dev = torch.device("cuda", torch.cuda.current_device())
     if static_types:
         cls_static = torch.from_numpy(cmap.classes_of(types)).to(dev)
-        at_static = _value_counts(types)
+        at_static = at_all
     out = torch.empty((T, 1 + num_relations, num_bins), dtype=torch.int64, device=dev)
-    for f0, f1, x in ArrayBatches(pos, batch_frames, dev):       # copy of batch k+1 overlaps the kernels of batch k
+
+    def _all_batches():
+        if first is not None:
+            yield first
+            yield from batches
+
+    for f0, f1, x in _all_batches():                             # copy of batch k+1 overlaps the kernels of batch k
         cls = cls_static if static_types else torch.from_numpy(np.stack([cmap.classes_of(t) for t in types[f0:f1]])).to(dev)
         hist = ops.pair_hist(x, cls, cmap.ncls, boxes[f0:f1], rcut2, edges, bin_size, flags=flags)
         out[f0:f1] = ops.hist_reduce(hist, weights)

@@ -292,3 +292,25 @@ def test_two_rank_gloo_merge(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2
+
+
+def test_utilities_mirror_reference_import_paths(tmp_path):
+    """mdproptools.utilities.{log,fluctuations,plots} resolve under the same names; the fluctuation statistics are
+    pandas describe()'s mean / std (fluctuations.py:43)."""
+    import pandas as pd
+
+    from mdproptools_b200.io import log as io_log
+    from mdproptools_b200.utilities import fluctuations, log, plots
+
+    assert log.concat_log is io_log.concat_log and callable(plots.set_axis)
+    rng = np.random.default_rng(3)
+    df = pd.DataFrame({"Step": np.arange(50) * 100, "Press": rng.normal(1.0, 40.0, 50)})
+    want = df["Press"].describe().loc[["mean", "std"]].to_dict()
+    got = fluctuations.fluctuation_stats(df, "Press")
+    assert got["mean"] == pytest.approx(want["mean"], rel=1e-14) and got["std"] == pytest.approx(want["std"], rel=1e-14)
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        return
+    mean, std = fluctuations.plot_fluctuations(df, "Press", "P", "press.png", working_dir=str(tmp_path))
+    assert (tmp_path / "press.png").exists() and mean == got["mean"] and std == got["std"]
