@@ -208,6 +208,17 @@ int mdp_bitmask_autocorr(mdp_ctx *ctx, int64_t npairs, int nwords, int64_t T, co
 int mdp_ols_sums(mdp_ctx *ctx, int ncol, int64_t T, const double *t, const double *y, int64_t i0, int64_t i1,
                  double *out, void *stream);
 
+/* ---- number density along one axis (structural/number_density.py:30-154) ---------------------------
+ * Per frame: {min, max} of coord over the atoms with key == surface_key (:77-83), then for every target key the histogram
+ * of trunc(((x - min) - (max - min)) / bin_size) over atoms with x - min < dist (dist > 0, :88-99) or of
+ * trunc((x - min) / bin_size) over atoms with x - min > dist (dist < 0, :100-110).  Negative indices wrap as numpy's do;
+ * indices outside [-nbins, nbins) (an IndexError in the reference) are dropped.  target_keys is a HOST array.
+ * coord, key = DEVICE [F][N]; counts_out = DEVICE uint64 [F][ntargets][nbins]; minmax_out = DEVICE [F][2] (NaN when a frame
+ * has no surface atom, in which case its counts are zero). */
+int mdp_axis_density(mdp_ctx *ctx, int nframes, int64_t n, const double *coord, const double *key, double surface_key,
+                     int ntargets, const double *target_keys, double dist_from_interface, double bin_size, int nbins,
+                     uint64_t *counts_out, double *minmax_out, void *stream);
+
 /* ---- LAMMPS dump reader (replaces pymatgen parse_lammps_dumps at rdf_cn.py:176 etc.) ---------------
  * HOST-side, multi-threaded.  Parses one frame of dump text into SoA doubles scattered by id
  * (row id-1 <- the reference's sort_values("id"), rdf_cn.py:191-192).

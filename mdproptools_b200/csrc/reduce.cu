@@ -568,6 +568,86 @@ __global__ void __launch_bounds__(RB) k_ols_sums(const double *__restrict__ t, c
     }
 }
 
+// ---- number density along one axis (structural/number_density.py:30-154) -------------------------------
+// Pass 1: min and max of the coordinate over the atoms whose key (type or altered id) equals the surface key, per frame
+// (number_density.py:77-83).  Doubles are ordered through the usual monotone map to uint64 so that atomicMin/Max work.
+__device__ __forceinline__ unsigned long long ord_enc(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_dec(unsigned long long u)
+{
+    const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+__global__ void __launch_bounds__(RB) k_axis_minmax(const double *__restrict__ coord, const double *__restrict__ key, int64_t n,
+                                                    double surface_key, unsigned long long *__restrict__ mm)
+{
+    const int f = blockIdx.y;
+    const double *c = coord + (int64_t)f * n, *k = key + (int64_t)f * n;
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (k[i] == surface_key) {
+            const unsigned long long e = ord_enc(c[i]);
+            lo = e < lo ? e : lo;
+            hi = e > hi ? e : hi;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (lo != ~0ull) atomicMin(&mm[f * 2 + 0], lo);
+        if (hi != 0ull) atomicMax(&mm[f * 2 + 1], hi);
+    }
+}
+
+// Pass 2: per target key, the 1-D histogram of ((x - min) - range) / bin_size truncated towards zero (positive
+// dist_from_interface, atoms with x - min < dist) or of (x - min) / bin_size (negative, atoms with x - min > dist), in the
+// reference's operation order (:84-110).  A negative index k counts in bin nbins + k, as numpy's negative indexing does
+// (:99); indices outside [-nbins, nbins) -- an IndexError in the reference -- are dropped.
+constexpr int AXD_MAX_TARGETS = 32;
+struct AxisTargets {
+    double key[AXD_MAX_TARGETS];
+    int n;
+};
+__global__ void __launch_bounds__(RB) k_axis_hist(const double *__restrict__ coord, const double *__restrict__ key, int64_t n,
+                                                  const unsigned long long *__restrict__ mm, AxisTargets tg, double dist,
+                                                  double bin_size, int nbins, unsigned long long *__restrict__ out,
+                                                  double *__restrict__ mm_out)
+{
+    const int f = blockIdx.y;
+    const double *c = coord + (int64_t)f * n, *k = key + (int64_t)f * n;
+    const bool have = mm[f * 2 + 0] != ~0ull;
+    const double mn = have ? ord_dec(mm[f * 2 + 0]) : __longlong_as_double(0x7ff8000000000000ll);
+    const double mx = have ? ord_dec(mm[f * 2 + 1]) : __longlong_as_double(0x7ff8000000000000ll);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        mm_out[f * 2 + 0] = mn;
+        mm_out[f * 2 + 1] = mx;
+    }
+    if (!have) return;   // no surface atom in this frame: the reference's min() is NaN and every comparison fails
+    const double range = __dsub_rn(mx, mn);
+    unsigned long long *o = out + (int64_t)f * tg.n * nbins;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = __dsub_rn(c[i], mn);
+        const bool sel = dist > 0.0 ? x < dist : x > dist;
+        if (!sel) continue;
+        const double b = dist > 0.0 ? __dsub_rn(x, range) : x;
+        const double q = __ddiv_rn(b, bin_size);
+        if (!(q > -2147483648.0 && q < 2147483648.0)) continue;
+        int kb = (int)q;                      // truncation towards zero, as ndarray.astype(int)
+        if (kb < 0) kb += nbins;
+        if (kb < 0 || kb >= nbins) continue;
+        const double ki = k[i];
+        for (int t = 0; t < tg.n; ++t)
+            if (ki == tg.key[t]) atomicAdd(&o[(int64_t)t * nbins + kb], 1ull);
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -733,6 +813,44 @@ int mdp_ols_sums(mdp_ctx *ctx, int ncol, int64_t T, const double *t, const doubl
     k_ols_sums<<<ncol, RB, 0, (cudaStream_t)stream>>>(t, y, T, i0, i1, out);
     MDP_LAUNCHED(ctx);
     return mdp_check_launch("k_ols_sums");
+}
+
+int mdp_axis_density(mdp_ctx *ctx, int nframes, int64_t n, const double *coord, const double *key, double surface_key,
+                     int ntargets, const double *target_keys, double dist_from_interface, double bin_size, int nbins,
+                     uint64_t *counts_out, double *minmax_out, void *stream)
+{
+    MDP_REQUIRE(ctx && coord && key && target_keys && counts_out && minmax_out, "mdp_axis_density: NULL argument");
+    MDP_REQUIRE(nframes > 0 && nframes <= 65535 && n > 0 && nbins > 0 && bin_size > 0.0 && dist_from_interface != 0.0,
+                "mdp_axis_density: bad sizes");
+    MDP_REQUIRE(ntargets > 0 && ntargets <= AXD_MAX_TARGETS, "mdp_axis_density: 1..%d target types per call", AXD_MAX_TARGETS);
+    cudaStream_t st = (cudaStream_t)stream;
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->arena_reserve((size_t)nframes * 16 + 4096);
+    if (rc) return rc;
+    ctx->arena_reset();
+    unsigned long long *mm = (unsigned long long *)ctx->arena_take((size_t)nframes * 16);
+    if (!mm) {
+        mdp_set_error("internal: scratch arena exhausted (axis density)");
+        return MDP_ERR_OOM;
+    }
+    // {min, max} in the ordered encoding: min starts at all ones, max at zero
+    std::vector<unsigned long long> init((size_t)nframes * 2);
+    for (int f = 0; f < nframes; ++f) {
+        init[2 * f] = ~0ull;
+        init[2 * f + 1] = 0ull;
+    }
+    MDP_CUDA(cudaMemcpyAsync(mm, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
+    MDP_CUDA(cudaMemsetAsync(counts_out, 0, (size_t)nframes * ntargets * nbins * 8, st));
+    AxisTargets tg;
+    tg.n = ntargets;
+    for (int t = 0; t < ntargets; ++t) tg.key[t] = target_keys[t];
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(n, RB), 4 * ctx->sm_count), nframes);
+    k_axis_minmax<<<grid, RB, 0, st>>>(coord, key, n, surface_key, mm);
+    MDP_LAUNCHED(ctx);
+    k_axis_hist<<<grid, RB, 0, st>>>(coord, key, n, mm, tg, dist_from_interface, bin_size, nbins,
+                                     (unsigned long long *)counts_out, minmax_out);
+    MDP_LAUNCHED(ctx);
+    return mdp_check_launch("k_axis_hist");
 }
 
 } // extern "C"

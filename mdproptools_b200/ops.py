@@ -252,3 +252,18 @@ def ols_sums(t, y, i0=0, i1=None):
     out = torch.empty((C, 3), dtype=torch.float64, device=t.device)
     check(lib().mdp_ols_sums(ctx.handle, C, T, ptr(t), ptr(y), int(i0), i1, ptr(out), stream_ptr()), "mdp_ols_sums")
     return out
+
+
+def axis_density(coord, key, surface_key, target_keys, dist_from_interface, bin_size, nbins):
+    """mdp_axis_density: coord, key float64 [F, N] -> (counts int64 [F, ntargets, nbins], minmax float64 [F, 2])."""
+    coord = _f64(coord, "coord")
+    key = _f64(key, "key")
+    F, n = coord.shape
+    tk = np.ascontiguousarray(target_keys, dtype=np.float64)
+    ctx = Context.get(coord.device.index)
+    counts = torch.empty((F, len(tk), nbins), dtype=torch.int64, device=coord.device)
+    mm = torch.empty((F, 2), dtype=torch.float64, device=coord.device)
+    check(lib().mdp_axis_density(ctx.handle, F, n, ptr(coord), ptr(key), float(surface_key), len(tk), _lib.dptr(tk),
+                                 float(dist_from_interface), float(bin_size), int(nbins), ptr(counts), ptr(mm), stream_ptr()),
+          "mdp_axis_density")
+    return counts, mm

@@ -23,6 +23,8 @@ import tempfile
 import time
 
 import numpy as np
+import pandas as pd
+from unittest import mock
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -162,6 +164,69 @@ def make_water_box(work, ncat=6, nwat=150, nframes=3, L=18.0):
                 f.write(f"{a} {t} {x:.6g} {y:.6g} {z:.6g} \n")
     _tar_dir(d, os.path.join(GOLD, "water_box.tar.gz"))
     return d, [ncat, nwat], [1, 3]
+
+
+def make_slab_box(work, nframes=2, L=(10.0, 11.0, 14.0)):
+    """A 2 A surface slab (type 1) at z in [3, 5] with a two-species fluid (molecules of 2 atoms: types 2, 3) below and
+    above it; ids contiguous (slab first), rows shuffled.  Fixture for calc_number_density."""
+    d = os.path.join(work, "slab")
+    os.makedirs(d)
+    rng = np.random.default_rng(20261021)
+    nsurf, nmol = 40, 120
+    surf = np.column_stack([rng.uniform(0, L[0], nsurf), rng.uniform(0, L[1], nsurf), rng.uniform(3.0, 5.0, nsurf)])
+    zf = np.where(rng.uniform(size=nmol) < 0.25, rng.uniform(0.0, 3.0, nmol), rng.uniform(5.0, 13.0, nmol))
+    mol = np.column_stack([rng.uniform(0, L[0], nmol), rng.uniform(0, L[1], nmol), zf])
+    for fr in range(nframes):
+        surf = surf + rng.normal(0, 0.02, surf.shape)
+        mol = mol + rng.normal(0, 0.1, mol.shape)
+        rows, aid = [], 1
+        for p in surf:
+            rows.append((aid, 1, *p)); aid += 1
+        for p in mol:
+            rows.append((aid, 2, *p)); aid += 1
+            rows.append((aid, 3, *(p + rng.normal(0, 0.5, 3)))); aid += 1
+        order = rng.permutation(len(rows))
+        with open(os.path.join(d, f"dump.slab.{fr * 500}.dump"), "w") as f:
+            f.write(f"ITEM: TIMESTEP\n{fr * 500}\nITEM: NUMBER OF ATOMS\n{len(rows)}\n")
+            f.write("ITEM: BOX BOUNDS pp pp pp\n" + "".join(f"0.0000000000000000e+00 {l:.16e}\n" for l in L))
+            f.write("ITEM: ATOMS id type x y z \n")
+            for k in order:
+                a, t, x, y, z = rows[k]
+                f.write(f"{a} {t} {x:.6g} {y:.6g} {z:.6g} \n")
+    _tar_dir(d, os.path.join(GOLD, "slab_box.tar.gz"))
+    return d, [nsurf, nmol], [1, 2]
+
+
+def run_number_density(slab_dir, num_mols, num_atoms, out):
+    """The reference function needs numpy < 1.24 (np.int, :50; np.product, :118); both aliases are restored for the call --
+    the reference source itself is untouched."""
+    if not hasattr(np, "int"):
+        np.int = int
+    if not hasattr(np, "product"):
+        np.product = np.prod
+    from mdproptools.structural.number_density import calc_number_density as _cnd
+
+    def calc_number_density(*a, **k):
+        # pandas >= 3 (copy-on-write) hands out read-only ``Series.values``; the reference does ``b -= dist_range`` on the
+        # values of a boolean-filtered (hence already copied) Series (:89-96), so a writable copy is what old pandas gave it
+        orig = pd.Series.values
+        with mock.patch.object(pd.Series, "values", property(lambda self: np.array(orig.fget(self)))):
+            return _cnd(*a, **k)
+
+    tmp = tempfile.mkdtemp()
+    for f in glob.glob(os.path.join(slab_dir, "*.dump")):
+        shutil.copy(f, tmp)
+    df = calc_number_density("dump.slab.*.dump", 1, [2, 3, 1], 0.5, 8.0, "z", working_dir=tmp, save_mode=False)
+    out["nd_pos"] = df.values; out["nd_pos_cols"] = np.array(list(df.columns))
+    df = calc_number_density("dump.slab.*.dump", 1, [2, 3], 0.5, -20.0, "z", working_dir=tmp, save_mode=False)
+    out["nd_neg"] = df.values
+    # altered ids: slab atoms -> 1, molecule atoms -> 2 and 3 by position in the molecule (rdf_cn.py:197-215)
+    df = calc_number_density("dump.slab.*.dump", 1, [3, 2], 0.25, 6.0, "z", num_mols=num_mols, num_atoms_per_mol=num_atoms,
+                             working_dir=tmp, save_mode=False)
+    out["nd_alt"] = df.values
+    df = calc_number_density("dump.slab.*.dump", 1, [2], 0.5, 12.0, "x", working_dir=tmp, save_mode=False)
+    out["nd_x"] = df.values
+    out["nd_num_mols"] = np.array(num_mols); out["nd_num_atoms"] = np.array(num_atoms)
 
 
 # ------------------------------------------------------------------------------------------
@@ -371,7 +436,8 @@ def main():
     mini_dir, mini_num_mols = make_mini_traj(work)
     visc_dir = make_visc_logs(work)
     water_dir, w_mols, w_atoms = make_water_box(work)
-    which = sys.argv[1:] or ["structural", "clusters", "unique", "dynamical", "hydration"]
+    slab_dir, s_mols, s_atoms = make_slab_box(work)
+    which = sys.argv[1:] or ["structural", "clusters", "unique", "dynamical", "hydration", "density"]
     if "structural" in which:
         out = {}
         run_structural(sample_dir, out)
@@ -388,6 +454,10 @@ def main():
         out = {}
         run_hydration(water_dir, w_mols, w_atoms, out)
         np.savez_compressed(os.path.join(GOLD, "ref_hydration.npz"), **out)
+    if "density" in which:
+        out = {}
+        run_number_density(slab_dir, s_mols, s_atoms, out)
+        np.savez_compressed(os.path.join(GOLD, "ref_number_density.npz"), **out)
     print("done")
 
 

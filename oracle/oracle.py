@@ -428,6 +428,45 @@ def atomic_rdf(frames, r_cut, bin_size, partial_relations, num_mols=None, num_at
     return (out, counts) if return_counts else out
 
 
+def number_density(frames, surface_atom, atom_types, bin_size, dist_from_interface, axis, num_mols=None,
+                   num_atoms_per_mol=None, return_counts=False):
+    """calc_number_density (structural/number_density.py:30-154) on a list of Frames -> float64[nb, 1+R] like df.values.
+    Same operation order: shift by the surface minimum (:84), side selection (:88-110), ``b -= dist_range`` for a positive
+    distance (:96), ``(b / bin_size).astype(int)`` (:97), ``rho_part[i][k] += 1`` with numpy's negative-index wrap (:99);
+    indices outside [-nb, nb) (IndexError in the reference) are dropped."""
+    nb = int(abs(dist_from_interface) / bin_size)
+    radii = (np.arange(nb) + 0.5) * bin_size
+    R = len(atom_types)
+    total = np.zeros((R, nb))
+    counts = []
+    for fr in frames:
+        c = fr.sorted_by_id()
+        key = calc_atom_type(c["id"], num_mols, num_atoms_per_mol) if (num_mols and num_atoms_per_mol) else c["type"]
+        x = np.asarray(c[axis], dtype=np.float64)
+        surf = x[key == surface_atom]
+        cnt = np.zeros((R, nb), dtype=np.int64)
+        if len(surf):
+            mn, mx = surf.min(), surf.max()
+            rng_ = mx - mn
+            xs = x - mn
+            for i, j in enumerate(atom_types):
+                if dist_from_interface > 0:
+                    b = xs[(key == j) & (xs < dist_from_interface)] - rng_
+                else:
+                    b = xs[(key == j) & (xs > dist_from_interface)]
+                k = (b / bin_size).astype(int)
+                k = np.where(k < 0, k + nb, k)
+                k = k[(k >= 0) & (k < nb)]
+                np.add.at(cnt[i], k, 1)
+        counts.append(cnt)
+        lengths = dict(zip("xyz", fr.lattice_lengths))
+        area = np.prod([lengths[a] for a in lengths if a != axis])
+        total += cnt.astype(np.float64) / (area * bin_size)
+    total = total / len(frames)
+    out = np.vstack((radii, total)).transpose()
+    return (out, counts) if return_counts else out
+
+
 def atomic_cn(frames, r_cuts, partial_relations, num_mols=None, num_atoms_per_mol=None, nthreads=0):
     """calc_atomic_cn (rdf_cn.py:533-651) -> float64[R]."""
     rel = np.asarray(partial_relations).transpose()

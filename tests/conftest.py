@@ -44,6 +44,18 @@ def water_dir(tmp_path_factory):
 
 
 @pytest.fixture(scope="session")
+def slab_dir(tmp_path_factory):
+    """surface slab + two-species fluid, 2 frames (oracle/gen_golden.py make_slab_box)"""
+    return _extract("slab_box.tar.gz", tmp_path_factory)
+
+
+@pytest.fixture(scope="session")
+def gold_density():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "ref_number_density.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
 def gold_structural():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "ref_structural.npz"), allow_pickle=False)

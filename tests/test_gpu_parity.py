@@ -360,6 +360,55 @@ def test_hydration_golden(water_dir, gold_hydration, tmp_path):
     assert os.path.exists(tmp_path / "angles_df.csv")
 
 
+def test_number_density_golden(slab_dir, gold_density, tmp_path):
+    """calc_number_density through the public API against the unmodified reference's DataFrames (bit-identical)."""
+    import shutil
+    from mdproptools_b200.structural.number_density import calc_number_density
+    for f in os.listdir(slab_dir):
+        shutil.copy(os.path.join(slab_dir, f), tmp_path)
+    g = gold_density
+    wd = str(tmp_path)
+    df = calc_number_density("dump.slab.*.dump", 1, [2, 3, 1], 0.5, 8.0, "z", working_dir=wd)
+    assert list(df.columns) == list(g["nd_pos_cols"]) and np.array_equal(df.values, g["nd_pos"])
+    assert os.path.exists(tmp_path / "number_density.csv")
+    df = calc_number_density("dump.slab.*.dump", 1, [2, 3], 0.5, -20.0, "z", working_dir=wd, save_mode=False)
+    assert np.array_equal(df.values, g["nd_neg"])
+    df = calc_number_density("dump.slab.*.dump", 1, [3, 2], 0.25, 6.0, "z", num_mols=g["nd_num_mols"].tolist(),
+                             num_atoms_per_mol=g["nd_num_atoms"].tolist(), working_dir=wd, save_mode=False)
+    assert np.array_equal(df.values, g["nd_alt"])
+    df = calc_number_density("dump.slab.*.dump", 1, [2], 0.5, 12.0, "x", working_dir=wd, save_mode=False)
+    assert np.array_equal(df.values, g["nd_x"])
+
+
+def test_axis_density_kernel_vs_oracle_random(ops):
+    """mdp_axis_density on seeded random frames (sizes around the block size, a frame without surface atoms, indices that
+    fall outside [-nbins, nbins)) against the numpy definition."""
+    rng = np.random.default_rng(11)
+    for n, dist, bs in [(1, 5.0, 0.5), (255, 6.0, 0.25), (4097, -9.0, 0.5), (20000, 3.0, 0.1)]:
+        F = 3
+        x = rng.uniform(-4, 12, (F, n))
+        key = rng.integers(1, 5, (F, n)).astype(np.float64)
+        key[1][key[1] == 1.0] = 2.0                      # frame 1 has no surface atom
+        nb = int(abs(dist) / bs)
+        counts, mm = ops.axis_density(_dev(x), _dev(key), 1.0, [2.0, 4.0, 2.0], dist, bs, nb)
+        counts, mm = counts.cpu().numpy(), mm.cpu().numpy()
+        for f in range(F):
+            surf = x[f][key[f] == 1.0]
+            want = np.zeros((3, nb), dtype=np.int64)
+            if len(surf):
+                mn, mx = surf.min(), surf.max()
+                assert mm[f, 0] == mn and mm[f, 1] == mx
+                xs = x[f] - mn
+                for i, j in enumerate([2.0, 4.0, 2.0]):
+                    b = xs[(key[f] == j) & (xs < dist)] - (mx - mn) if dist > 0 else xs[(key[f] == j) & (xs > dist)]
+                    k = (b / bs).astype(int)
+                    k = np.where(k < 0, k + nb, k)
+                    np.add.at(want[i], k[(k >= 0) & (k < nb)], 1)
+            else:
+                assert np.isnan(mm[f]).all()
+            assert np.array_equal(counts[f], want), (n, dist, f)
+
+
 # ------------------------------------------------------------------------------------------------
 # dynamical API vs golden outputs of the reference
 # ------------------------------------------------------------------------------------------------

@@ -247,3 +247,17 @@ def test_triclinic_image_is_the_nearest_image_within_half_the_cell_width():
     x, y, z = rng.uniform(0, 25, (3, 2000))
     assert np.array_equal(O.calc_rsq_tri((3.0, 4.0, 5.0), x, y, z, (25.0, 25.0, 25.0, 0, 0, 0)),
                           O.calc_rsq((3.0, 4.0, 5.0), x, y, z, (25.0, 25.0, 25.0)))
+
+
+def test_number_density_oracle_vs_reference(slab_dir, gold_density):
+    """calc_number_density (number_density.py:30-154): positive and negative distance, altered ids, another axis; the
+    reference output is reproduced to the last bit (integer counts, same division order)."""
+    frames = list(O.read_dumps(os.path.join(slab_dir, "dump.slab.*.dump")))
+    assert len(frames) == 2
+    g = gold_density
+    assert np.array_equal(O.number_density(frames, 1, [2, 3, 1], 0.5, 8.0, "z"), g["nd_pos"])
+    assert np.array_equal(O.number_density(frames, 1, [2, 3], 0.5, -20.0, "z"), g["nd_neg"])
+    assert np.array_equal(O.number_density(frames, 1, [3, 2], 0.25, 6.0, "z", num_mols=g["nd_num_mols"].tolist(),
+                                           num_atoms_per_mol=g["nd_num_atoms"].tolist()), g["nd_alt"])
+    assert np.array_equal(O.number_density(frames, 1, [2], 0.5, 12.0, "x"), g["nd_x"])
+    assert g["nd_pos"][:, 1:].sum() > 0 and g["nd_neg"][:, 1:].sum() > 0
