@@ -207,18 +207,27 @@ __device__ __forceinline__ void mw_tile(const double *__restrict__ A, const doub
 #pragma unroll 1
     for (int s = 0; s < MW_TT; s += MW_LB) {
         if (EDGE && s >= steps) break;
+        // Validity is uniform over the warp (lane = atom): a block of MW_LB origins whose every (origin, lag) pair lies
+        // inside the chunk and the trajectory takes the unpredicated body even in an edge tile; only the one or two
+        // blocks that straddle the end pay for the per-pair test.
+        const bool partial = EDGE && (s + MW_LB > steps || npair0 - (s + MW_LB - 1) - l0 < MW_LB);
+        if (partial) {
 #pragma unroll
-        for (int u = 0; u < MW_LB; ++u) {
-            win[(u + MW_LB - 1) % MW_LB] = B[(s + u + l0 + MW_LB - 1) * 32 + lane];
-            const double a = A[(s + u) * 32 + lane];
-            if (EDGE) {
+            for (int u = 0; u < MW_LB; ++u) {
+                win[(u + MW_LB - 1) % MW_LB] = B[(s + u + l0 + MW_LB - 1) * 32 + lane];
+                const double a = A[(s + u) * 32 + lane];
                 const int64_t kmax = (s + u < steps) ? npair0 - (s + u) - l0 : 0;
 #pragma unroll
                 for (int k = 0; k < MW_LB; ++k) {
                     const double d = win[(u + k) % MW_LB] - a;
                     if (k < kmax) acc[k] = fma(d, d, acc[k]);
                 }
-            } else {
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < MW_LB; ++u) {
+                win[(u + MW_LB - 1) % MW_LB] = B[(s + u + l0 + MW_LB - 1) * 32 + lane];
+                const double a = A[(s + u) * 32 + lane];
 #pragma unroll
                 for (int k = 0; k < MW_LB; ++k) {
                     const double d = win[(u + k) % MW_LB] - a;
