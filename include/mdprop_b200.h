@@ -232,6 +232,12 @@ int64_t mdp_dump_scan(const char *text, int64_t len, int64_t *offsets, int64_t m
 int mdp_dump_header(const char *text, int64_t len, double *header_out, char *columns_out, int columns_cap);
 int mdp_dump_parse(const char *text, int64_t len, const char *const *want, int nwant, double *out,
                    int64_t out_stride, double *header_out, int nthreads);
+/* A batch of frames in one call: frame f goes to out + f*frame_stride ([nwant][out_stride]) and headers_out + 16*f.
+ * With many frames every worker thread parses whole frames (rows go straight to out[slot][id-1] while the ids are a
+ * permutation of 1..natoms, else that frame takes mdp_dump_parse's ranking path); with fewer frames than half the
+ * threads each frame is split over all threads as in mdp_dump_parse. */
+int mdp_dump_parse_batch(int nframes, const char *const *texts, const int64_t *lens, const char *const *want, int nwant,
+                         double *out, int64_t frame_stride, int64_t out_stride, double *headers_out, int nthreads);
 
 #ifdef __cplusplus
 }

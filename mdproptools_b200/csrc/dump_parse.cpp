@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <numeric>
 #include <string>
@@ -53,9 +54,77 @@ inline const char *token_end(const char *p, const char *end)
     return p;
 }
 
-bool parse_double(const char *b, const char *e, double &v)
+// Decimal -> double.  Fast path (Clinger): a decimal significand w <= 2^53 and a power of ten |q| <= 22 are both exact
+// doubles, so ONE correctly rounded IEEE multiplication or division gives the correctly rounded result -- the same
+// double std::from_chars / strtod / Python float() return.  LAMMPS writes %g (6 significant digits) unless told
+// otherwise, so practically every token of a dump takes this path; everything else (more digits, big exponents,
+// inf/nan, malformed text) goes to std::from_chars.
+const double P10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                        1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+inline bool parse_double(const char *b, const char *e, double &v)
 {
     if (b < e && *b == '+') ++b;
+    const char *p = b;
+    bool neg = false;
+    if (p < e && *p == '-') {
+        neg = true;
+        ++p;
+    }
+    uint64_t w = 0;
+    int nd = 0, q = 0;          // significant digits taken into w, decimal exponent
+    bool any = false, ok = true;
+    while (p < e && (unsigned)(*p - '0') < 10u) {
+        any = true;
+        if (w || *p != '0') {
+            if (nd < 19) {
+                w = w * 10 + (unsigned)(*p - '0');
+                ++nd;
+            } else {
+                ok = false;
+            }
+        }
+        ++p;
+    }
+    if (p < e && *p == '.') {
+        ++p;
+        while (p < e && (unsigned)(*p - '0') < 10u) {
+            any = true;
+            if (w || *p != '0') {
+                if (nd < 19) {
+                    w = w * 10 + (unsigned)(*p - '0');
+                    ++nd;
+                } else {
+                    ok = false;
+                }
+            }
+            --q;
+            ++p;
+        }
+    }
+    if (any && ok && p < e && (*p == 'e' || *p == 'E')) {
+        const char *r = p + 1;
+        bool eneg = false;
+        if (r < e && (*r == '-' || *r == '+')) {
+            eneg = *r == '-';
+            ++r;
+        }
+        int ex = 0, ne = 0;
+        while (r < e && (unsigned)(*r - '0') < 10u && ne < 6) {
+            ex = ex * 10 + (*r - '0');
+            ++ne;
+            ++r;
+        }
+        if (ne == 0 || ne >= 6) ok = false;
+        q += eneg ? -ex : ex;
+        p = r;
+    }
+    if (any && ok && p == e && w <= (1ull << 53) && q >= -22 && q <= 22) {
+        double d = (double)w;
+        d = q < 0 ? d / P10[-q] : d * P10[q];
+        v = neg ? -d : d;
+        return true;
+    }
     auto r = std::from_chars(b, e, v);
     return r.ec == std::errc() && r.ptr == e;
 }
@@ -194,6 +263,96 @@ int parse_rows(const char *p, const char *end, int64_t row0, int64_t nrows, cons
     return 0;
 }
 
+// column selection shared by the single-frame and the batch entry points
+int select_columns(const Header &h, const char *const *want, int nwant, std::vector<int> &colsel, int &id_col)
+{
+    const int ncols = (int)h.cols.size();
+    colsel.assign(ncols, -1);
+    id_col = -1;
+    for (int c = 0; c < ncols; ++c)
+        if (h.cols[c] == "id") id_col = c;
+    for (int k = 0; k < nwant; ++k) {
+        int found = -1;
+        for (int c = 0; c < ncols; ++c)
+            if (h.cols[c] == want[k]) found = c;
+        if (found < 0) {
+            mdp_set_error("dump: column '%s' not present in the dump file", want[k]);
+            return -4;
+        }
+        if (colsel[found] >= 0) {
+            mdp_set_error("mdp_dump_parse: column '%s' requested twice", want[k]);
+            return -2;
+        }
+        colsel[found] = k;
+    }
+    return 0;
+}
+
+// One frame on the calling thread, rows written straight to their id-sorted place (out[slot][id - 1]) while the ids are a
+// permutation of 1..natoms -- the usual case; returns 1 when they are not (the caller then takes the general path, which
+// ranks the ids), 0 on success, < 0 on error.  `seen` is scratch of natoms bytes.
+int parse_frame_fused(const Header &h, const char *end, const std::vector<int> &colsel, int id_col, int nwant, double *out,
+                      int64_t out_stride, std::vector<unsigned char> &seen)
+{
+    const int64_t n = h.natoms;
+    if (id_col < 0) return 1;
+    const int ncols = (int)colsel.size();
+    int last_needed = id_col;
+    for (int c = 0; c < ncols; ++c)
+        if (colsel[c] >= 0 && c > last_needed) last_needed = c;
+    seen.assign((size_t)n, 0);
+    double rowv[64];
+    if (nwant > 64) return 1;
+    const char *p = h.atoms_begin;
+    int64_t r = 0;
+    while (r < n) {
+        if (p >= end) {
+            mdp_set_error("dump: frame announces %lld atoms but holds %lld rows", (long long)n, (long long)r);
+            return -4;
+        }
+        const char *le = next_line(p, end);
+        const char *q = skip_ws(p, le);
+        if (q >= le || *q == '\n') {   // blank line
+            p = le;
+            continue;
+        }
+        long long idv = 0;
+        for (int c = 0; c <= last_needed; ++c) {
+            q = skip_ws(q, le);
+            const char *te = token_end(q, le);
+            if (te == q) {
+                mdp_set_error("dump: row %lld has fewer than %d columns", (long long)r, ncols);
+                return -4;
+            }
+            const int slot = colsel[c];
+            if (c == id_col) {
+                auto rr = std::from_chars(q, te, idv);
+                if (rr.ec != std::errc()) {
+                    double dv;
+                    if (!parse_double(q, te, dv)) {
+                        mdp_set_error("dump: bad id '%.*s'", (int)(te - q), q);
+                        return -4;
+                    }
+                    idv = (long long)dv;
+                }
+            }
+            if (slot >= 0) {
+                if (!parse_double(q, te, rowv[slot])) {
+                    mdp_set_error("dump: cannot parse '%.*s' in row %lld column %d", (int)(te - q), q, (long long)r, c);
+                    return -4;
+                }
+            }
+            q = te;
+        }
+        if (idv < 1 || idv > n || seen[idv - 1]) return 1;
+        seen[idv - 1] = 1;
+        for (int k = 0; k < nwant; ++k) out[(int64_t)k * out_stride + (idv - 1)] = rowv[k];
+        ++r;
+        p = le;
+    }
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -255,25 +414,12 @@ int mdp_dump_parse(const char *text, int64_t len, const char *const *want, int n
         mdp_set_error("mdp_dump_parse: out_stride %lld < natoms %lld", (long long)out_stride, (long long)n);
         return -2;
     }
-    const int ncols = (int)h.cols.size();
-    std::vector<int> colsel(ncols, -1);
+    std::vector<int> colsel;
     int id_col = -1;
-    for (int c = 0; c < ncols; ++c)
-        if (h.cols[c] == "id") id_col = c;
-    for (int k = 0; k < nwant; ++k) {
-        int found = -1;
-        for (int c = 0; c < ncols; ++c)
-            if (h.cols[c] == want[k]) found = c;
-        if (found < 0) {
-            mdp_set_error("dump: column '%s' not present in the dump file", want[k]);
-            return -4;
-        }
-        if (colsel[found] >= 0) {
-            mdp_set_error("mdp_dump_parse: column '%s' requested twice", want[k]);
-            return -2;
-        }
-        colsel[found] = k;
-    }
+    rc = select_columns(h, want, nwant, colsel, id_col);
+    if (rc) return rc;
+    const int ncols = (int)colsel.size();
+    (void)ncols;
 
     const char *begin = h.atoms_begin, *end = text + len;
     // stop at the next frame if the buffer holds more than one
@@ -367,6 +513,67 @@ int mdp_dump_parse(const char *text, int64_t len, const char *const *want, int n
         for (int64_t r = 0; r < n; ++r) dst[dest[r]] = src[r];
     }
     if (header_out) fill_header_out(h, header_out, contiguous);
+    return 0;
+}
+
+int mdp_dump_parse_batch(int nframes, const char *const *texts, const int64_t *lens, const char *const *want, int nwant,
+                         double *out, int64_t frame_stride, int64_t out_stride, double *headers_out, int nthreads)
+{
+    if (nframes <= 0 || !texts || !lens || !want || !out || nwant <= 0) {
+        mdp_set_error("mdp_dump_parse_batch: bad argument");
+        return -2;
+    }
+    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    // few frames: every frame uses all threads (rows split over threads); many frames: one frame per thread at a time
+    if (nframes * 2 < nthreads || nthreads == 1) {
+        for (int f = 0; f < nframes; ++f) {
+            int rc = mdp_dump_parse(texts[f], lens[f], want, nwant, out + (size_t)f * frame_stride, out_stride,
+                                    headers_out ? headers_out + (size_t)f * 16 : nullptr, nthreads);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    const int nt = std::min(nthreads, nframes);
+    std::atomic<int> next(0), failed(0);
+    std::vector<int> rcs(nt, 0);
+    std::vector<std::string> errs(nt);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() {
+            std::vector<unsigned char> seen;
+            std::vector<int> colsel;
+            while (!failed.load(std::memory_order_relaxed)) {
+                const int f = next.fetch_add(1);
+                if (f >= nframes) break;
+                double *o = out + (size_t)f * frame_stride;
+                double *ho = headers_out ? headers_out + (size_t)f * 16 : nullptr;
+                Header h;
+                int rc = parse_header(texts[f], lens[f], h);
+                int id_col = -1;
+                if (!rc && out_stride < h.natoms) {
+                    mdp_set_error("mdp_dump_parse_batch: out_stride %lld < natoms %lld", (long long)out_stride, (long long)h.natoms);
+                    rc = -2;
+                }
+                if (!rc) rc = select_columns(h, want, nwant, colsel, id_col);
+                if (!rc) {
+                    rc = parse_frame_fused(h, texts[f] + lens[f], colsel, id_col, nwant, o, out_stride, seen);
+                    if (rc == 0 && ho) fill_header_out(h, ho, true);
+                    if (rc == 1) rc = mdp_dump_parse(texts[f], lens[f], want, nwant, o, out_stride, ho, 1);   // general path
+                }
+                if (rc) {
+                    rcs[t] = rc;
+                    errs[t] = mdp_last_error();
+                    failed.store(1);
+                    break;
+                }
+            }
+        });
+    for (auto &x : th) x.join();
+    for (int t = 0; t < nt; ++t)
+        if (rcs[t]) {
+            mdp_set_error("%s", errs[t].c_str());
+            return rcs[t];
+        }
     return 0;
 }
 

@@ -99,6 +99,36 @@ def parse_frame(buf: bytes, want, nthreads: int = 0, out: np.ndarray | None = No
     return DumpFrame(int(hdr[0]), natoms, box, columns, {w: out[k, :natoms] for k, w in enumerate(want)})
 
 
+def _frame_from_header(hdr, natoms, columns, want, out):
+    tric = hdr[11] != 0.0
+    box = Box([[hdr[2], hdr[3]], [hdr[4], hdr[5]], [hdr[6], hdr[7]]], [hdr[8], hdr[9], hdr[10]] if tric else None)
+    return DumpFrame(int(hdr[0]), natoms, box, columns, {w: out[k, :natoms] for k, w in enumerate(want)})
+
+
+def parse_frames(bufs, want, out: np.ndarray, nthreads: int = 0) -> list:
+    """Parse a batch of frames' text (equal atom counts) in ONE native call into ``out`` [F, len(want), N] (float64,
+    C-contiguous; pinned memory recommended).  Frames are spread over the host threads (mdp_dump_parse_batch)."""
+    L = _lib.lib()
+    F = len(bufs)
+    want = list(want)
+    assert out.dtype == np.float64 and out.flags.c_contiguous and out.ndim == 3 and out.shape[0] >= F and out.shape[1] >= len(want)
+    columns = frame_columns(bufs[0])
+    missing = [w for w in want if w not in columns]
+    if missing:
+        raise KeyError(f"column(s) {missing} not in dump file (has {columns})")
+    texts = (ctypes.c_char_p * F)(*bufs)
+    lens = (ctypes.c_int64 * F)(*[len(b) for b in bufs])
+    names = (ctypes.c_char_p * len(want))(*[w.encode() for w in want])
+    hdrs = (ctypes.c_double * (16 * F))()
+    _lib.check(L.mdp_dump_parse_batch(F, texts, lens, names, len(want), out.ctypes.data_as(ctypes.c_void_p),
+                                      out.shape[1] * out.shape[2], out.shape[2], hdrs, int(nthreads)), "mdp_dump_parse_batch")
+    frames = []
+    for f in range(F):
+        h = hdrs[16 * f:16 * f + 16]
+        frames.append(_frame_from_header(h, int(h[1]), columns, want, out[f]))
+    return frames
+
+
 def iter_frame_buffers(pattern: str):
     """Yield the raw text of every frame, in pymatgen's order."""
     L = _lib.lib()

@@ -65,15 +65,31 @@ class FrameBatches:
 
     def _produce(self, q: "queue.Queue"):
         try:
+            import ctypes
+
+            from .. import _lib
+
             copy_stream = torch.cuda.Stream(device=self.device) if self.to_device else None
-            metas, host, fill = [], None, 0
             C = len(self.columns)
+            pending = []                     # (trajectory index, frame text) of the batch being collected
+            cur_n, cap = None, 0
+            # pinned staging buffers are reused round-robin: a buffer comes up again only after prefetch + 2 newer batches
+            # have been handed over, i.e. after the consumer has asked for the batch that followed it
+            ring, ring_k = [None] * (self.prefetch + 3), 0
 
             def flush():
-                nonlocal metas, host, fill
-                if not metas:
+                nonlocal pending, ring_k
+                if not pending:
                     return
-                h = host[:fill]
+                F = len(pending)
+                slot = ring_k % len(ring)
+                ring_k += 1
+                buf = ring[slot]
+                if buf is None or buf.shape[1:] != (C, cur_n) or buf.shape[0] < F:
+                    buf = ring[slot] = torch.empty((max(F, cap), C, cur_n), dtype=torch.float64, pin_memory=self.cuda)
+                h = buf[:F]
+                frames = _dump.parse_frames([b for _, b in pending], self.columns, h.numpy(), self.nthreads)
+                metas = [FrameMeta(idx, fr.timestep, fr.natoms, fr.box) for (idx, _), fr in zip(pending, frames)]
                 dev, ev = None, None
                 if self.to_device:
                     with torch.cuda.stream(copy_stream):
@@ -81,27 +97,23 @@ class FrameBatches:
                         ev = torch.cuda.Event()
                         ev.record(copy_stream)
                 q.put(Batch(metas, self.columns, h, dev, ev))
-                metas, host, fill = [], None, 0
+                pending = []
 
             idx = -1
+            hdr = (ctypes.c_double * 16)()
             for buf in _dump.iter_frame_buffers(self.pattern):
                 idx += 1
                 if self.frame_select is not None and not self.frame_select(idx):
                     continue
-                # peek at natoms to size / reuse the staging buffer
-                import ctypes
-                from .. import _lib
-                hdr = (ctypes.c_double * 16)()
+                # peek at natoms: a batch holds frames of one size
                 _lib.check(_lib.lib().mdp_dump_header(buf, len(buf), hdr, None, 0), "mdp_dump_header")
                 n = int(hdr[1])
-                if host is not None and (host.shape[2] != n or fill == host.shape[0]):
+                if pending and (n != cur_n or len(pending) >= cap):
                     flush()
-                if host is None:
-                    F = max(1, min(self.max_batch_frames, self.max_batch_bytes // max(1, C * n * 8)))
-                    host = torch.empty((F, C, n), dtype=torch.float64, pin_memory=self.cuda)
-                fr = _dump.parse_frame(buf, self.columns, self.nthreads, out=host[fill].numpy())
-                metas.append(FrameMeta(idx, fr.timestep, fr.natoms, fr.box))
-                fill += 1
+                if not pending:
+                    cur_n = n
+                    cap = max(1, min(self.max_batch_frames, self.max_batch_bytes // max(1, C * n * 8)))
+                pending.append((idx, buf))
             self.total_frames = idx + 1
             flush()
             q.put(None)
