@@ -706,30 +706,54 @@ def bench_residence(args, torch, dist, ops, ctx, dev, world, rank):
     }
 
 
-def bench_dump_parse(reps=5):
-    """the native LAMMPS dump reader (csrc/dump_parse.cpp) on one C2-sized frame of text
-    (100 000 atoms, columns id type x y z, ids shuffled), all host threads, into an id-sorted SoA float64 buffer."""
+def bench_dump_parse(reps=3, batch=32):
+    """the native LAMMPS dump reader (csrc/dump_parse.cpp) on C2-sized frames of text (100 000 atoms,
+    columns id type x y z, ids shuffled), all host threads, into id-sorted SoA float64 buffers.  `value` is the pipeline's
+    mode: a batch of frames per native call (one frame per thread), numbers written as LAMMPS writes them by default (%g);
+    the single-frame call (rows of one frame split over the threads) and 17-digit text (every token misses the exact
+    fast path and goes to std::from_chars) are reported beside it."""
     from mdproptools_b200.io import dump as D
     rng = np.random.default_rng(SEED + 400)
     n = N_ATOMS
     ids = rng.permutation(n) + 1
     xyz = rng.uniform(0.0, LBOX, (n, 3))
-    lines = ["ITEM: TIMESTEP", "1000", "ITEM: NUMBER OF ATOMS", str(n), "ITEM: BOX BOUNDS pp pp pp",
-             f"0.0 {LBOX!r}", f"0.0 {LBOX!r}", f"0.0 {LBOX!r}", "ITEM: ATOMS id type x y z"]
-    lines += [f"{i} 1 {x!r} {y!r} {z!r}" for i, (x, y, z) in zip(ids.tolist(), xyz.tolist())]
-    buf = ("\n".join(lines) + "\n").encode()
-    out = np.empty((5, n), dtype=np.float64)
+    head = ["ITEM: TIMESTEP", "1000", "ITEM: NUMBER OF ATOMS", str(n), "ITEM: BOX BOUNDS pp pp pp",
+            f"0.0 {LBOX!r}", f"0.0 {LBOX!r}", f"0.0 {LBOX!r}", "ITEM: ATOMS id type x y z"]
     want = ["id", "type", "x", "y", "z"]
-    fr = D.parse_frame(buf, want, 0, out)
-    ok = bool(np.array_equal(fr.data["x"], xyz[np.argsort(ids), 0]))
-    t = time.perf_counter()
-    for _ in range(reps):
-        D.parse_frame(buf, want, 0, out)
-    dt = (time.perf_counter() - t) / reps
-    return {"metric": "dump_parse_MB_per_s", "value": len(buf) / dt / 1e6, "unit": "MB/s", "atoms_per_s": n / dt,
-            "ms_per_frame": dt * 1e3, "bytes_per_frame": len(buf), "threads": os.cpu_count(), "round_trip_exact": ok,
-            "note": "host-side parser (text -> id-sorted SoA fp64, strtod-exact); the reference reads the same text through "
-                    "pandas.read_csv + sort_values at ~24 MB/s (SURVEY 8f)"}
+    order = np.argsort(ids)
+
+    def text(fmt):
+        return ("\n".join(head + [("%d 1 " + fmt + " " + fmt + " " + fmt) % (i, x, y, z)
+                                  for i, (x, y, z) in zip(ids.tolist(), xyz.tolist())]) + "\n").encode()
+
+    res = {}
+    ok = True
+    for name, fmt in (("g", "%g"), ("repr17", "%.17g")):
+        buf = text(fmt)
+        expect = np.array([float(fmt % v) for v in xyz[order, 0]])
+        out = np.empty((batch, 5, n), dtype=np.float64)
+        D.parse_frames([buf] * batch, want, out, 0)
+        ok = ok and bool(np.array_equal(out[0, 2], expect) and np.array_equal(out[batch - 1, 2], expect))
+        t = time.perf_counter()
+        for _ in range(reps):
+            D.parse_frames([buf] * batch, want, out, 0)
+        dt_b = (time.perf_counter() - t) / (reps * batch)
+        D.parse_frame(buf, want, 0, out[0])
+        ok = ok and bool(np.array_equal(out[0, 2], expect))
+        t = time.perf_counter()
+        for _ in range(reps):
+            D.parse_frame(buf, want, 0, out[0])
+        dt_s = (time.perf_counter() - t) / reps
+        res[name] = (len(buf), dt_b, dt_s)
+    nb, dt_b, dt_s = res["g"]
+    nb17, dt_b17, dt_s17 = res["repr17"]
+    return {"metric": "dump_parse_MB_per_s", "value": nb / dt_b / 1e6, "unit": "MB/s", "atoms_per_s": n / dt_b,
+            "ms_per_frame": dt_b * 1e3, "bytes_per_frame": nb, "frames_per_call": batch, "threads": os.cpu_count(),
+            "single_frame_MB_per_s": nb / dt_s / 1e6, "single_frame_atoms_per_s": n / dt_s,
+            "repr17_MB_per_s": nb17 / dt_b17 / 1e6, "repr17_atoms_per_s": n / dt_b17, "repr17_bytes_per_frame": nb17,
+            "round_trip_exact": ok,
+            "note": "host-side parser (text -> id-sorted SoA fp64, correctly rounded = strtod/float()); the reference reads the same "
+                    "text through pandas.read_csv + sort_values at ~24 MB/s (SURVEY 8f)"}
 
 
 def main():

@@ -226,6 +226,10 @@ int parse_rows(const char *p, const char *end, int64_t row0, int64_t nrows, cons
     const int ncols = (int)colsel.size();
     for (int64_t r = 0; r < nrows; ++r) {
         const char *le = next_line(p, end);
+        while (p < end && skip_ws(p, le) >= le - (le > p && le[-1] == '\n' ? 1 : 0)) {   // blank line (pandas skips them too)
+            p = le;
+            le = next_line(p, end);
+        }
         const char *q = p;
         for (int c = 0; c < ncols; ++c) {
             q = skip_ws(q, le);
@@ -301,7 +305,9 @@ int parse_frame_fused(const Header &h, const char *end, const std::vector<int> &
     for (int c = 0; c < ncols; ++c)
         if (colsel[c] >= 0 && c > last_needed) last_needed = c;
     seen.assign((size_t)n, 0);
-    double rowv[64];
+    constexpr int PIPE = 16;
+    double rowv[64], ring[PIPE * 64];
+    long long ring_id[PIPE];
     if (nwant > 64) return 1;
     const char *p = h.atoms_begin;
     int64_t r = 0;
@@ -346,9 +352,22 @@ int parse_frame_fused(const Header &h, const char *end, const std::vector<int> &
         }
         if (idv < 1 || idv > n || seen[idv - 1]) return 1;
         seen[idv - 1] = 1;
-        for (int k = 0; k < nwant; ++k) out[(int64_t)k * out_stride + (idv - 1)] = rowv[k];
+        // the destinations are random (4 MB per frame, one line per column): ask for the lines now, store the row PIPE rows later
+        for (int k = 0; k < nwant; ++k) __builtin_prefetch(out + (int64_t)k * out_stride + (idv - 1), 1, 0);
+        const int slot_r = (int)(r % PIPE);
+        if (r >= PIPE) {
+            const double *ov = ring + (size_t)slot_r * nwant;
+            const long long od = ring_id[slot_r];
+            for (int k = 0; k < nwant; ++k) out[(int64_t)k * out_stride + od] = ov[k];
+        }
+        ring_id[slot_r] = idv - 1;
+        for (int k = 0; k < nwant; ++k) ring[(size_t)slot_r * nwant + k] = rowv[k];
         ++r;
         p = le;
+    }
+    for (int64_t t = r > PIPE ? r - PIPE : 0; t < r; ++t) {
+        const int slot_r = (int)(t % PIPE);
+        for (int k = 0; k < nwant; ++k) out[(int64_t)k * out_stride + ring_id[slot_r]] = ring[(size_t)slot_r * nwant + k];
     }
     return 0;
 }

@@ -72,6 +72,49 @@ def test_native_parser_matches_oracle_reader(sample_dir, mini_dir):
                 assert np.array_equal(g.data[k], c[k]), k
 
 
+def test_batch_parser_equals_single_frame_parser(sample_dir):
+    """mdp_dump_parse_batch (one frame per thread, rows written straight to id - 1) against mdp_dump_parse, which the
+    previous test pins to the oracle reader: real sample frames, sizes around the store pipeline depth, ids that are not
+    a permutation of 1..N (ranking path), blank lines, number spellings on and off the exact fast path, and errors."""
+    from mdproptools_b200.io import dump as D
+    want = ["id", "type", "x", "y", "z"]
+    bufs = [open(os.path.join(sample_dir, f), "rb").read() for f in sorted(os.listdir(sample_dir)) if f.endswith(".dump")]
+    n = D.parse_frame(bufs[0], want).natoms
+    out = np.full((len(bufs) * 6, len(want), n), np.nan)
+    frames = D.parse_frames(bufs * 6, want, out, nthreads=4)          # 12 frames >= threads / 2: frame-parallel mode
+    for k, fr in enumerate(frames):
+        ref = D.parse_frame(bufs[k % len(bufs)], want, nthreads=1)
+        assert fr.timestep == ref.timestep and fr.box.lattice_lengths() == ref.box.lattice_lengths()
+        for c in want:
+            assert np.array_equal(fr.data[c], ref.data[c]), (k, c)
+    rng = np.random.default_rng(2)
+    spell = [lambda v: repr(float(v)), lambda v: "%g" % v, lambda v: "%.17g" % v, lambda v: "%+.3e" % v, lambda v: "%.12f" % v,
+             lambda v: ("%f" % v).rstrip("0"), lambda v: "%.25f" % v, lambda v: "%dE0" % int(v)]
+    for nn, shift, blank in [(1, 0, False), (15, 0, False), (16, 0, True), (17, 0, False), (33, 0, False), (64, 5, False),
+                             (200, 0, True)]:
+        ids = rng.permutation(nn) + 1 + shift
+        xyz = rng.normal(0, 30, (nn, 3))
+        rows = ["%d %d %s %s %s" % (i, 1 + i % 3, spell[i % 8](x), spell[(i + 3) % 8](y), spell[(i + 5) % 8](z))
+                for i, (x, y, z) in zip(ids.tolist(), xyz.tolist())]
+        if blank:
+            rows.insert(len(rows) // 2, "   ")
+        txt = ("ITEM: TIMESTEP\n7\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n0 9\n0 9\n0 9\nITEM: ATOMS id type x y z\n"
+               % nn + "\n".join(rows) + "\n").encode()
+        ref = D.parse_frame(txt, want, nthreads=1)
+        py = np.array([[float(t) for t in r.split()] for r in rows if r.strip()])
+        py = py[np.argsort(py[:, 0], kind="stable")]
+        out = np.full((8, 5, nn), np.nan)
+        for fr in D.parse_frames([txt] * 8, want, out, nthreads=4):
+            for k, c in enumerate(want):
+                assert np.array_equal(fr.data[c], ref.data[c]) and np.array_equal(fr.data[c], py[:, k]), (nn, c)
+    bad = txt.replace(b" 1 ", b" x ", 1)
+    with pytest.raises(RuntimeError):
+        D.parse_frames([txt, bad] * 4, want, np.empty((8, 5, nn)), nthreads=4)
+    short = txt[: txt.rstrip().rfind(b"\n") + 1]
+    with pytest.raises(RuntimeError):
+        D.parse_frames([short] * 8, want, np.empty((8, 5, nn)), nthreads=4)
+
+
 def test_parser_multiframe_triclinic_and_ragged(tmp_path):
     from mdproptools_b200.io import dump as D
     rng = np.random.default_rng(0)
