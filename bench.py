@@ -138,11 +138,13 @@ def measured_peaks():
 
 def ncu_traffic(name, scale=1.0):
     """DRAM bytes (read + write) of one launch of kernel `name` from the committed ncu --set full summary
-    (profiles/r01e_k_<name>.txt, written by tools/ncu_summary.py), times `scale` when the bench launch is that much larger
+    (the newest profiles/rNNx_k_<name>.txt, written by tools/ncu_summary.py), times `scale` when the bench launch is that much larger
     than the captured one (traffic is linear in the number of frames for every kernel here).  None when absent."""
-    path = os.path.join(ROOT, "profiles", f"r01e_k_{name}.txt")
-    if not os.path.exists(path):
+    import glob as _g
+    cands = sorted(_g.glob(os.path.join(ROOT, "profiles", f"r*_k_{name}.txt")))   # newest round last (r01a < r01b < ...)
+    if not cands:
         return None
+    path = cands[-1]
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     total = 0.0
     for ln in open(path):
@@ -398,7 +400,7 @@ def run_gpu(args):
                          "step_ms": ms / args.steps},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                      "traffic": ncu_traffic("pair", F / 16.0), "peak_source": peak_src,
-                     "traffic_note": "dram bytes of the 16-frame launch captured in profiles/r01e_k_pair.txt (55 MB = the sorted "
+                     "traffic_note": "dram bytes of the 16-frame launch captured in the newest profiles/r*_k_pair.txt (55 MB = the sorted "
                                      "records read once), scaled to this launch's frames; irrelevant to an FP64/issue-bound kernel",
                      "note": f"pair kernel only; achieved = evaluated pair-evals x {FLOPS_PER_PAIR} unfused fp64 flops / "
                              f"CUDA-event kernel time; nominal-pair equivalent = {nominal_tflops:.1f} TFLOP/s "
@@ -419,6 +421,7 @@ def run_gpu(args):
         out["residence"] = res
     if not args.skip_cpu:
         out["dump_parse"] = bench_dump_parse()
+        out["rdf_from_files"] = bench_rdf_from_files(torch, frames, nominal_per_step / F)
     _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -704,6 +707,49 @@ def bench_residence(args, torch, dist, ops, ctx, dev, world, rank):
                      "note": "k_bitmask_autocorr only (this rank's central atoms); one 64-bit AND + POPC per (pair, lag, word); "
                              "peak = nominal XU rate 16 POPC/clk/SM x 148 SMs x 1965 MHz / 2 (popcll = 2 POPC)"},
     }
+
+
+def bench_rdf_from_files(torch, frames, nominal_pairs_per_frame, nfiles=16):
+    """The call a user of the reference makes: calc_atomic_rdf on LAMMPS dump FILES (C2 frames written as text with
+    LAMMPS' default %g, ids shuffled) -> page cache -> native parser (a batch of frames per call, one frame per host
+    thread) -> pinned SoA -> H2D on the copy stream -> pair engine -> D2H -> per-frame normalisation -> DataFrame."""
+    import shutil
+    import tempfile
+    from mdproptools_b200.structural import rdf_cn
+    d = tempfile.mkdtemp(prefix="mdp_bench_dumps_")
+    try:
+        rng = np.random.default_rng(SEED + 500)
+        host = frames[:nfiles].cpu().numpy()
+        xy, xz, yz = TILT
+        nbytes = 0
+        for f in range(host.shape[0]):
+            ids = rng.permutation(N_ATOMS) + 1
+            x, y, z = host[f][:, ids - 1]
+            body = "\n".join(["%d 1 %g %g %g" % t for t in zip(ids.tolist(), x.tolist(), y.tolist(), z.tolist())])
+            xlo, xhi = min(0.0, xy, xz, xy + xz), LBOX + max(0.0, xy, xz, xy + xz)
+            ylo, yhi = min(0.0, yz), LBOX + max(0.0, yz)
+            txt = (f"ITEM: TIMESTEP\n{f * 1000}\nITEM: NUMBER OF ATOMS\n{N_ATOMS}\nITEM: BOX BOUNDS xy xz yz pp pp pp\n"
+                   f"{xlo!r} {xhi!r} {xy!r}\n{ylo!r} {yhi!r} {xz!r}\n0.0 {LBOX!r} {yz!r}\nITEM: ATOMS id type x y z\n" + body + "\n")
+            nbytes += len(txt)
+            with open(os.path.join(d, f"dump.c2.{f * 1000}.dump"), "w") as fh:
+                fh.write(txt)
+        pat = os.path.join(d, "dump.c2.*.dump")
+        rdf_cn.calc_atomic_rdf(R_CUT, BIN, 1, [39.948], [[1], [1]], pat, save_mode=False)
+        torch.cuda.synchronize()
+        reps = 3
+        t = time.perf_counter()
+        for _ in range(reps):
+            df = rdf_cn.calc_atomic_rdf(R_CUT, BIN, 1, [39.948], [[1], [1]], pat, save_mode=False)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t) / reps
+        T = host.shape[0]
+        return {"metric": "rdf_pair_evals_per_s", "value": nominal_pairs_per_frame * T / dt, "unit": "pair-evals/s",
+                "frames": T, "ms_per_frame": dt / T * 1e3, "text_MB_per_s": nbytes / dt / 1e6, "text_bytes": nbytes,
+                "g_full_max": float(df["g_full(r)"].max()),
+                "api": "rdf_cn.calc_atomic_rdf(filename=<dump files>) -- the reference's own entry point (rdf_cn.py:385)",
+                "note": "text is %g (6 significant digits) as LAMMPS writes by default; files are read from the page cache"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def bench_dump_parse(reps=3, batch=32):

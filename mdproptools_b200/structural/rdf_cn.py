@@ -90,7 +90,14 @@ def calc_atom_type_ids(ids, num_mols, num_atoms):
 
 
 def _value_counts(typ):
-    u, c = np.unique(np.asarray(typ).astype(np.int64), return_counts=True)
+    """{type: count}, keys ascending.  Types are small non-negative integers in practice: one bincount pass instead of
+    np.unique's sort (this runs once per frame on the host, next to a pair kernel that takes 0.16 ms per frame)."""
+    t = np.asarray(typ).astype(np.int64)
+    if t.size and t.min() >= 0 and t.max() < (1 << 20):
+        c = np.bincount(t)
+        u = np.flatnonzero(c)
+        return dict(zip(u.tolist(), c[u].tolist()))
+    u, c = np.unique(t, return_counts=True)
     return dict(zip(u.tolist(), c.tolist()))
 
 
@@ -208,9 +215,16 @@ class _ClassMap:
 
     def classes_of(self, typ: np.ndarray) -> np.ndarray:
         t = np.asarray(typ).astype(np.int64)
-        cls = np.full(t.shape, self.other, dtype=np.int32)
-        for ty, k in self.index.items():
-            cls[t == ty] = k
+        if t.size and t.min() >= 0 and t.max() < (1 << 20):      # one table lookup instead of a mask per named type
+            lut = np.full(int(t.max()) + 1, self.other, dtype=np.int32)
+            for ty, k in self.index.items():
+                if 0 <= ty < len(lut):
+                    lut[ty] = k
+            cls = lut[t]
+        else:
+            cls = np.full(t.shape, self.other, dtype=np.int32)
+            for ty, k in self.index.items():
+                cls[t == ty] = k
         if not self.has_other and (cls < 0).any():
             raise ValueError("a frame contains atom types that were absent from the first frame")
         return cls
