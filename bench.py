@@ -709,7 +709,7 @@ def bench_residence(args, torch, dist, ops, ctx, dev, world, rank):
     }
 
 
-def bench_rdf_from_files(torch, frames, nominal_pairs_per_frame, nfiles=16):
+def bench_rdf_from_files(torch, frames, nominal_pairs_per_frame, nfiles=32):
     """The call a user of the reference makes: calc_atomic_rdf on LAMMPS dump FILES (C2 frames written as text with
     LAMMPS' default %g, ids shuffled) -> page cache -> native parser (a batch of frames per call, one frame per host
     thread) -> pinned SoA -> H2D on the copy stream -> pair engine -> D2H -> per-frame normalisation -> DataFrame."""

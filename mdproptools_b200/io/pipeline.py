@@ -49,7 +49,7 @@ class FrameBatches:
     across ranks and for ``get_clusters(frame=...)``); frames outside it are skipped without being parsed.
     """
 
-    def __init__(self, pattern, columns, max_batch_bytes=192 << 20, max_batch_frames=256, to_device=True, device=None,
+    def __init__(self, pattern, columns, max_batch_bytes=64 << 20, max_batch_frames=256, to_device=True, device=None,
                  frame_select=None, nthreads=0, prefetch=2):
         self.pattern = pattern
         self.columns = list(columns)
