@@ -369,9 +369,12 @@ def run_gpu(args):
     gk = None if args.skip_gk else bench_green_kubo(args, torch, dist, ops, ctx, dev, world, rank)
     res = None if args.skip_residence else bench_residence(args, torch, dist, ops, ctx, dev, world, rank)
 
+    # every rank leaves the process group here: what follows on rank 0 (CPU baselines, host parser, the file-based leg)
+    # is single-process work and must not meet a collective whose peers are gone
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return 0
 
     peaks = measured_peaks()
@@ -423,8 +426,6 @@ def run_gpu(args):
         out["dump_parse"] = bench_dump_parse()
         out["rdf_from_files"] = bench_rdf_from_files(torch, frames, nominal_per_step / F)
     _emit(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 
