@@ -267,6 +267,49 @@ int parse_rows(const char *p, const char *end, int64_t row0, int64_t nrows, cons
     return 0;
 }
 
+// Token at q (no leading blanks) scanned and converted in one pass: digits are consumed as they are read and the token
+// must end at a blank / line end for the exact fast path to apply; anything else re-scans the token and defers to
+// parse_double.  Returns the end of the token, nullptr when the token is empty or malformed.
+inline const char *parse_token(const char *q, const char *le, double &v)
+{
+    const char *p = q;
+    bool neg = false;
+    if (p < le && (*p == '-' || *p == '+')) {
+        neg = *p == '-';
+        ++p;
+    }
+    uint64_t w = 0;
+    int nd = 0, sc = 0;
+    const char *d0 = p;
+    while (p < le && (unsigned)(*p - '0') < 10u) {
+        w = w * 10 + (unsigned)(*p - '0');
+        nd += (w != 0);
+        ++p;
+    }
+    bool any = p > d0;
+    if (p < le && *p == '.') {
+        ++p;
+        const char *f0 = p;
+        while (p < le && (unsigned)(*p - '0') < 10u) {
+            w = w * 10 + (unsigned)(*p - '0');
+            nd += (w != 0);
+            ++p;
+        }
+        sc = (int)(f0 - p);
+        any = any || p > f0;
+    }
+    // w may have wrapped when nd > 19; nd <= 19 guarantees it has not
+    if (any && nd <= 19 && w <= (1ull << 53) && sc >= -22 && (p == le || *p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) {
+        double d = (double)w;
+        if (sc) d /= P10[-sc];
+        v = neg ? -d : d;
+        return p;
+    }
+    const char *te = token_end(q, le);
+    if (te == q || !parse_double(q, te, v)) return nullptr;
+    return te;
+}
+
 // column selection shared by the single-frame and the batch entry points
 int select_columns(const Header &h, const char *const *want, int nwant, std::vector<int> &colsel, int &id_col)
 {
@@ -325,29 +368,32 @@ int parse_frame_fused(const Header &h, const char *end, const std::vector<int> &
         long long idv = 0;
         for (int c = 0; c <= last_needed; ++c) {
             q = skip_ws(q, le);
-            const char *te = token_end(q, le);
-            if (te == q) {
-                mdp_set_error("dump: row %lld has fewer than %d columns", (long long)r, ncols);
-                return -4;
-            }
             const int slot = colsel[c];
-            if (c == id_col) {
-                auto rr = std::from_chars(q, te, idv);
-                if (rr.ec != std::errc()) {
-                    double dv;
-                    if (!parse_double(q, te, dv)) {
-                        mdp_set_error("dump: bad id '%.*s'", (int)(te - q), q);
-                        return -4;
-                    }
-                    idv = (long long)dv;
-                }
-            }
-            if (slot >= 0) {
-                if (!parse_double(q, te, rowv[slot])) {
-                    mdp_set_error("dump: cannot parse '%.*s' in row %lld column %d", (int)(te - q), q, (long long)r, c);
+            if (slot < 0 && c != id_col) {          // unwanted column: only find its end
+                const char *te = token_end(q, le);
+                if (te == q) {
+                    mdp_set_error("dump: row %lld has fewer than %d columns", (long long)r, ncols);
                     return -4;
                 }
+                q = te;
+                continue;
             }
+            double v;
+            const char *te = parse_token(q, le, v);
+            if (!te) {
+                const char *t2 = token_end(q, le);
+                if (t2 == q)
+                    mdp_set_error("dump: row %lld has fewer than %d columns", (long long)r, ncols);
+                else
+                    mdp_set_error("dump: cannot parse '%.*s' in row %lld column %d", (int)(t2 - q), q, (long long)r, c);
+                return -4;
+            }
+            if (c == id_col) {
+                // ids are integers; a spelling like 1e3 or 12.0 goes through the double, as in the general path
+                if (!(v >= -9.2e18 && v <= 9.2e18)) return 1;
+                idv = (long long)v;
+            }
+            if (slot >= 0) rowv[slot] = v;
             q = te;
         }
         if (idv < 1 || idv > n || seen[idv - 1]) return 1;
