@@ -76,6 +76,7 @@ class FrameBatches:
             # pinned staging buffers are reused round-robin: a buffer comes up again only after prefetch + 2 newer batches
             # have been handed over, i.e. after the consumer has asked for the batch that followed it
             ring, ring_k = [None] * (self.prefetch + 3), 0
+            ring_ev = [None] * len(ring)     # H2D copy that last read each buffer: complete before the buffer is refilled
 
             def flush():
                 nonlocal pending, ring_k
@@ -85,6 +86,9 @@ class FrameBatches:
                 slot = ring_k % len(ring)
                 ring_k += 1
                 buf = ring[slot]
+                if ring_ev[slot] is not None:
+                    ring_ev[slot].synchronize()
+                    ring_ev[slot] = None
                 if buf is None or buf.shape[1:] != (C, cur_n) or buf.shape[0] < F:
                     buf = ring[slot] = torch.empty((max(F, cap), C, cur_n), dtype=torch.float64, pin_memory=self.cuda)
                 h = buf[:F]
@@ -96,6 +100,7 @@ class FrameBatches:
                         dev = h.to(self.device or "cuda", non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(copy_stream)
+                    ring_ev[slot] = ev
                 q.put(Batch(metas, self.columns, h, dev, ev))
                 pending = []
 

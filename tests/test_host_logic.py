@@ -115,6 +115,46 @@ def test_batch_parser_equals_single_frame_parser(sample_dir):
         D.parse_frames([short] * 8, want, np.empty((8, 5, nn)), nthreads=4)
 
 
+def test_frame_batches_pipeline_on_host(tmp_path):
+    """FrameBatches without a device: batching by atom count and by the frame cap, frame_select (rank sharding), global
+    frame indices, total_frames, and the pinned-buffer ring -- more batches than ring slots, with a deliberately slow
+    consumer, must still hand every batch over intact."""
+    import time as _t
+    from mdproptools_b200.io import dump as D
+    from mdproptools_b200.io.pipeline import FrameBatches
+    rng = np.random.default_rng(4)
+    sizes = [7] * 9 + [5] * 3 + [7] * 11
+    p = tmp_path / "traj.dump"
+    with open(p, "w") as f:
+        for t, n in enumerate(sizes):
+            ids = rng.permutation(n) + 1
+            xyz = rng.normal(0, 5, (n, 3))
+            f.write(f"ITEM: TIMESTEP\n{t * 5}\nITEM: NUMBER OF ATOMS\n{n}\nITEM: BOX BOUNDS pp pp pp\n0 9\n0 9\n0 9\n")
+            f.write("ITEM: ATOMS id type x y z\n")
+            for i, (x, y, z) in zip(ids, xyz):
+                f.write(f"{i} {1 + i % 2} {x:.6g} {y:.6g} {z:.6g}\n")
+    want = ["id", "type", "x", "y", "z"]
+    ref = list(D.read_dumps(str(p), want, nthreads=1))
+    assert len(ref) == len(sizes)
+    for sel in (None, lambda i: i % 2 == 1):
+        fb = FrameBatches(str(p), want, max_batch_frames=2, to_device=False, frame_select=sel, prefetch=2)
+        seen = []
+        for batch in fb:
+            assert batch.dev is None and batch.ready is None
+            n = batch.metas[0].natoms
+            assert all(m.natoms == n for m in batch.metas) and len(batch.metas) <= 2
+            _t.sleep(0.01)                               # the producer runs ahead and cycles through its ring meanwhile
+            host = batch.host.numpy()
+            assert host.shape == (len(batch.metas), len(want), n)
+            for k, m in enumerate(batch.metas):
+                assert m.timestep == ref[m.index].timestep
+                for c, name in enumerate(want):
+                    assert np.array_equal(host[k, c], ref[m.index].data[name]), (m.index, name)
+                seen.append(m.index)
+        assert fb.total_frames == len(sizes)
+        assert seen == [i for i in range(len(sizes)) if sel is None or sel(i)]
+
+
 def test_parser_multiframe_triclinic_and_ragged(tmp_path):
     from mdproptools_b200.io import dump as D
     rng = np.random.default_rng(0)
