@@ -35,7 +35,12 @@ class Batch:
 
     def wait(self):
         if self.ready is not None:
-            torch.cuda.current_stream().wait_event(self.ready)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self.ready)
+            if self.dev is not None:
+                # the batch was allocated under the copy stream: tell the caching allocator that this stream reads it too,
+                # so that the block is not handed to a later copy while kernels queued here are still using it
+                self.dev.record_stream(cur)
         return self.dev
 
     def col(self, name):
