@@ -239,6 +239,18 @@ int mdp_dump_parse(const char *text, int64_t len, const char *const *want, int n
 int mdp_dump_parse_batch(int nframes, const char *const *texts, const int64_t *lens, const char *const *want, int nwant,
                          double *out, int64_t frame_stride, int64_t out_stride, double *headers_out, int nthreads);
 
+/* EXPERIMENTAL, opt-in (FrameBatches(device_parse=True)); the default pipeline parses on the host.
+ * Device-side parse of the atom rows of nframes frames whose bytes are already in device memory: rows are placed by id
+ * (out[f][slot][id-1]) with the exact fast path the host parser uses (dump_line.h).  begin/end = DEVICE int64 [nframes]:
+ * byte offsets into text of the first row / one past the last row of each frame; longest = max(end - begin);
+ * colsel = HOST int[ncols], output slot of file column c or -1.  seen = DEVICE uint32 [nframes][ceil(natoms/32)] scratch
+ * and status = DEVICE uint64 [nframes][2] = {rows parsed, flags}, both zeroed by the call: a frame is valid iff rows ==
+ * natoms and flags == 0; any other frame must be re-parsed with mdp_dump_parse (nothing is approximated on the device).
+ * Uses no scratch of the context (safe next to other calls of the same context on another stream). */
+int mdp_dump_parse_device(mdp_ctx *ctx, int nframes, const char *text, const int64_t *begin, const int64_t *end,
+                          int64_t longest, int64_t natoms, int ncols, const int *colsel, int id_col, int nwant, double *out,
+                          int64_t frame_stride, int64_t out_stride, uint32_t *seen, uint64_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,8 @@ _PROTOS = {
     "mdp_dump_header": (c_int, [c_char_p, c_int64, POINTER(c_double), c_char_p, c_int]),
     "mdp_dump_parse": (c_int, [c_char_p, c_int64, POINTER(c_char_p), c_int, c_void_p, c_int64, POINTER(c_double),
                                c_int]),
+    "mdp_dump_parse_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                      POINTER(c_int), c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "mdp_dump_parse_batch": (c_int, [c_int, POINTER(c_char_p), POINTER(c_int64), POINTER(c_char_p), c_int, c_void_p, c_int64,
                                      c_int64, POINTER(c_double), c_int]),
 }

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/mdprop_b200.h"
+#include "dump_line.h"
 
 void mdp_set_error(const char *fmt, ...);
 
@@ -42,25 +43,14 @@ inline const char *next_line(const char *p, const char *end)
     return nl ? nl + 1 : end;
 }
 
-inline const char *skip_ws(const char *p, const char *end)
-{
-    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
-    return p;
-}
-
-inline const char *token_end(const char *p, const char *end)
-{
-    while (p < end && *p != ' ' && *p != '\t' && *p != '\n' && *p != '\r') ++p;
-    return p;
-}
+inline const char *skip_ws(const char *p, const char *end) { return mdp_skip_ws(p, end); }
+inline const char *token_end(const char *p, const char *end) { return mdp_token_end(p, end); }
 
 // Decimal -> double.  Fast path (Clinger): a decimal significand w <= 2^53 and a power of ten |q| <= 22 are both exact
 // doubles, so ONE correctly rounded IEEE multiplication or division gives the correctly rounded result -- the same
 // double std::from_chars / strtod / Python float() return.  LAMMPS writes %g (6 significant digits) unless told
 // otherwise, so practically every token of a dump takes this path; everything else (more digits, big exponents,
 // inf/nan, malformed text) goes to std::from_chars.
-const double P10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
-                        1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
 
 inline bool parse_double(const char *b, const char *e, double &v)
 {
@@ -121,7 +111,7 @@ inline bool parse_double(const char *b, const char *e, double &v)
     }
     if (any && ok && p == e && w <= (1ull << 53) && q >= -22 && q <= 22) {
         double d = (double)w;
-        d = q < 0 ? d / P10[-q] : d * P10[q];
+        d = q < 0 ? d / mdp_pow10(-q) : d * mdp_pow10(q);
         v = neg ? -d : d;
         return true;
     }
@@ -267,44 +257,11 @@ int parse_rows(const char *p, const char *end, int64_t row0, int64_t nrows, cons
     return 0;
 }
 
-// Token at q (no leading blanks) scanned and converted in one pass: digits are consumed as they are read and the token
-// must end at a blank / line end for the exact fast path to apply; anything else re-scans the token and defers to
-// parse_double.  Returns the end of the token, nullptr when the token is empty or malformed.
+// Token at q (no leading blanks): the exact one-pass fast path shared with the device parser (dump_line.h), else the
+// token is re-scanned and handed to parse_double.  Returns the end of the token, nullptr when it is empty or malformed.
 inline const char *parse_token(const char *q, const char *le, double &v)
 {
-    const char *p = q;
-    bool neg = false;
-    if (p < le && (*p == '-' || *p == '+')) {
-        neg = *p == '-';
-        ++p;
-    }
-    uint64_t w = 0;
-    int nd = 0, sc = 0;
-    const char *d0 = p;
-    while (p < le && (unsigned)(*p - '0') < 10u) {
-        w = w * 10 + (unsigned)(*p - '0');
-        nd += (w != 0);
-        ++p;
-    }
-    bool any = p > d0;
-    if (p < le && *p == '.') {
-        ++p;
-        const char *f0 = p;
-        while (p < le && (unsigned)(*p - '0') < 10u) {
-            w = w * 10 + (unsigned)(*p - '0');
-            nd += (w != 0);
-            ++p;
-        }
-        sc = (int)(f0 - p);
-        any = any || p > f0;
-    }
-    // w may have wrapped when nd > 19; nd <= 19 guarantees it has not
-    if (any && nd <= 19 && w <= (1ull << 53) && sc >= -22 && (p == le || *p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) {
-        double d = (double)w;
-        if (sc) d /= P10[-sc];
-        v = neg ? -d : d;
-        return p;
-    }
+    if (const char *p = mdp_parse_fast(q, le, &v)) return p;
     const char *te = token_end(q, le);
     if (te == q || !parse_double(q, te, v)) return nullptr;
     return te;

@@ -55,7 +55,7 @@ class FrameBatches:
     """
 
     def __init__(self, pattern, columns, max_batch_bytes=64 << 20, max_batch_frames=256, to_device=True, device=None,
-                 frame_select=None, nthreads=0, prefetch=2):
+                 frame_select=None, nthreads=0, prefetch=2, device_parse=None):
         self.pattern = pattern
         self.columns = list(columns)
         self.max_batch_bytes = int(max_batch_bytes)
@@ -67,6 +67,14 @@ class FrameBatches:
         self.nthreads = nthreads
         self.prefetch = prefetch
         self.total_frames = None   # known once iteration has finished
+        # EXPERIMENTAL, off by default: ship the TEXT to the device and parse it there (csrc/dump_device.cu); frames the
+        # device parser refuses (numbers off the exact fast path, irregular ids) are re-parsed by the host parser
+        if device_parse is None:
+            import os
+            device_parse = os.environ.get("MDP_DEVICE_PARSE", "0") not in ("", "0")
+        self.device_parse = bool(device_parse) and self.to_device
+        self.device_parsed_frames = 0
+        self.host_reparsed_frames = 0
 
     def _produce(self, q: "queue.Queue"):
         try:
@@ -97,6 +105,14 @@ class FrameBatches:
                 if buf is None or buf.shape[1:] != (C, cur_n) or buf.shape[0] < F:
                     buf = ring[slot] = torch.empty((max(F, cap), C, cur_n), dtype=torch.float64, pin_memory=self.cuda)
                 h = buf[:F]
+                if self.device_parse:
+                    got = self._flush_device([b for _, b in pending], [i for i, _ in pending], h, copy_stream)
+                    if got is not None:
+                        metas, dev, ev = got
+                        ring_ev[slot] = ev
+                        q.put(Batch(metas, self.columns, h, dev, ev))
+                        pending = []
+                        return
                 frames = _dump.parse_frames([b for _, b in pending], self.columns, h.numpy(), self.nthreads)
                 metas = [FrameMeta(idx, fr.timestep, fr.natoms, fr.box) for (idx, _), fr in zip(pending, frames)]
                 dev, ev = None, None
@@ -129,6 +145,67 @@ class FrameBatches:
             q.put(None)
         except BaseException as exc:  # noqa: BLE001 - forwarded to the consumer
             q.put(exc)
+
+    def _flush_device(self, bufs, indices, h, copy_stream):
+        """Device parse of one batch (EXPERIMENTAL): text -> pinned bytes -> H2D -> k_dump_rows -> D2H of the parsed SoA
+        into ``h`` (the consumers read types and ids on the host).  Returns (metas, dev, event), or None when the batch
+        does not qualify (no id column, too many columns) and the host parser should take it."""
+        import ctypes
+
+        from .. import _lib, ops
+
+        cols = _dump.frame_columns(bufs[0])
+        want = self.columns
+        if "id" not in cols or any(w not in cols for w in want) or len(want) > 16:
+            return None
+        colsel = [want.index(c) if c in want else -1 for c in cols]
+        if max([cols.index("id")] + [k for k, v in enumerate(colsel) if v >= 0]) >= 64:
+            return None
+        F, C, n = h.shape
+        hdr = (ctypes.c_double * 16)()
+        metas, begin, end, off = [], [], [], 0
+        for idx, b in zip(indices, bufs):
+            _lib.check(_lib.lib().mdp_dump_header(b, len(b), hdr, None, 0), "mdp_dump_header")
+            tric = hdr[11] != 0.0
+            box = _dump.Box([[hdr[2], hdr[3]], [hdr[4], hdr[5]], [hdr[6], hdr[7]]], [hdr[8], hdr[9], hdr[10]] if tric else None)
+            metas.append(FrameMeta(idx, int(hdr[0]), int(hdr[1]), box))
+            a = b.find(b"ITEM: ATOMS")
+            begin.append(off + b.find(b"\n", a) + 1)
+            end.append(off + len(b))
+            off += len(b)
+        text = torch.empty((off,), dtype=torch.uint8, pin_memory=True)
+        tv = text.numpy()
+        pos = 0
+        for b in bufs:
+            tv[pos:pos + len(b)] = np.frombuffer(b, dtype=np.uint8)
+            pos += len(b)
+        device = self.device or torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.stream(copy_stream):
+            text_d = text.to(device, non_blocking=True)
+            begin_d = torch.tensor(begin, dtype=torch.int64).to(device)
+            end_d = torch.tensor(end, dtype=torch.int64).to(device)
+            dev = torch.empty((F, C, n), dtype=torch.float64, device=device)
+            seen = torch.empty((F, (n + 31) // 32), dtype=torch.int32, device=device)
+            status = torch.empty((F, 2), dtype=torch.int64, device=device)
+            ops.dump_parse_device(text_d, begin_d, end_d, max(e - b0 for b0, e in zip(begin, end)), n, len(cols), colsel,
+                                  cols.index("id"), dev, seen, status, stream=copy_stream)
+            st = status.cpu()                                   # synchronises the copy stream: the parse has finished
+            redo = [f for f in range(F) if int(st[f, 0]) != n or int(st[f, 1]) != 0]
+            good = [f for f in range(F) if f not in set(redo)]
+            if not redo:
+                h.copy_(dev, non_blocking=True)
+            else:
+                for f in good:
+                    h[f].copy_(dev[f], non_blocking=True)
+            for f in redo:                                      # nothing is approximated: the host parser decides
+                _dump.parse_frame(bufs[f], want, self.nthreads, out=h[f].numpy())
+                dev[f].copy_(h[f], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        copy_stream.synchronize()                               # h is complete before the batch is handed over
+        self.device_parsed_frames += len(good)
+        self.host_reparsed_frames += len(redo)
+        return metas, dev, ev
 
     def __iter__(self):
         q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)

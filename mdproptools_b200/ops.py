@@ -267,3 +267,16 @@ def axis_density(coord, key, surface_key, target_keys, dist_from_interface, bin_
                                  float(dist_from_interface), float(bin_size), int(nbins), ptr(counts), ptr(mm), stream_ptr()),
           "mdp_axis_density")
     return counts, mm
+
+
+def dump_parse_device(text, begin, end, longest, natoms, ncols, colsel, id_col, out, seen, status, stream=None):
+    """mdp_dump_parse_device (EXPERIMENTAL, opt-in): text uint8 [bytes], begin/end int64 [F] byte offsets of each frame's
+    rows, out float64 [F, nwant, N], seen int32 [F, ceil(N/32)] scratch, status int64 [F, 2] = (rows parsed, flags) --
+    all on the device.  Enqueued on ``stream`` (default: the current stream); the caller checks ``status``."""
+    F, nwant, stride = out.shape
+    cs = (c_int * int(ncols))(*[int(v) for v in colsel])
+    ctx = Context.get(out.device.index)
+    sp = stream_ptr() if stream is None else ctypes.c_void_p(stream.cuda_stream)
+    check(lib().mdp_dump_parse_device(ctx.handle, F, ptr(text), ptr(begin), ptr(end), int(longest), int(natoms), int(ncols), cs,
+                                      int(id_col), nwant, ptr(out), nwant * stride, stride, ptr(seen), ptr(status), sp),
+          "mdp_dump_parse_device")

@@ -409,6 +409,37 @@ def test_axis_density_kernel_vs_oracle_random(ops):
             assert np.array_equal(counts[f], want), (n, dist, f)
 
 
+@pytest.mark.skipif(os.environ.get("MDP_TEST_DEVICE_PARSE", "0") in ("", "0"),
+                    reason="the device dump parser is opt-in and not yet validated on hardware (set MDP_TEST_DEVICE_PARSE=1)")
+def test_device_dump_parser_matches_host_parser(sample_dir, tmp_path):
+    """FrameBatches(device_parse=True) against the default host-parsed pipeline: same device batches, same host copies,
+    same metadata -- on the real sample frames and on a file whose second frame the device parser must refuse (an
+    exponent spelling), which the pipeline answers with the host parser."""
+    import torch
+    from mdproptools_b200.io.pipeline import FrameBatches
+    want = ["id", "type", "x", "y", "z", "q"]
+    pat = os.path.join(sample_dir, "dump.nvt.*.dump")
+    ref = list(FrameBatches(pat, want, device_parse=False))
+    fb = FrameBatches(pat, want, device_parse=True)
+    got = list(fb)
+    assert fb.device_parsed_frames == sum(len(b.metas) for b in ref) and fb.host_reparsed_frames == 0
+    for a, b in zip(got, ref):
+        assert [m.timestep for m in a.metas] == [m.timestep for m in b.metas]
+        assert [m.box.lattice_lengths() for m in a.metas] == [m.box.lattice_lengths() for m in b.metas]
+        assert torch.equal(a.wait(), b.wait()) and torch.equal(a.host, b.host)
+    p = tmp_path / "two.dump"
+    rows = ["%d 1 %g %g %g" % (i + 1, 0.5 * i, 1.25 * i, 2.0 * i) for i in range(40)]
+    body = "\n".join(rows) + "\n"
+    head = "ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n40\nITEM: BOX BOUNDS pp pp pp\n0 9\n0 9\n0 9\nITEM: ATOMS id type x y z\n"
+    p.write_text(head % 0 + body + head % 10 + body.replace("1.25 ", "1.25e0 ", 1))
+    ref = list(FrameBatches(str(p), ["id", "x", "y", "z"], device_parse=False))
+    fb = FrameBatches(str(p), ["id", "x", "y", "z"], device_parse=True)
+    got = list(fb)
+    assert (fb.device_parsed_frames, fb.host_reparsed_frames) == (1, 1)
+    for a, b in zip(got, ref):
+        assert torch.equal(a.wait(), b.wait()) and torch.equal(a.host, b.host)
+
+
 # ------------------------------------------------------------------------------------------------
 # dynamical API vs golden outputs of the reference
 # ------------------------------------------------------------------------------------------------

@@ -155,6 +155,94 @@ def test_frame_batches_pipeline_on_host(tmp_path):
         assert seen == [i for i in range(len(sizes)) if sel is None or sel(i)]
 
 
+def _atoms_section(buf: bytes):
+    a = buf.index(b"ITEM: ATOMS")
+    return buf.index(b"\n", a) + 1
+
+
+def test_device_parser_body_on_host(sample_dir, tmp_path):
+    """The body of the (opt-in) device dump parser, mdp_parse_chunk of csrc/dump_rows.h, run on the host for every
+    (frame, chunk) in both orders against the host parser: real sample frames (20 columns, 8 wanted), generated frames
+    with row lengths around the 64-byte chunk size, CRLF and blank lines; and its refusals -- tokens off the exact fast
+    path, short rows, duplicate / out-of-range ids, a wrong row count -- which the caller answers with the host parser."""
+    import ctypes
+    from mdproptools_b200.io import dump as D
+    so = tmp_path / "dump_rows_host.so"
+    src = os.path.join(ROOT, "tests", "native", "dump_rows_host.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-fno-fast-math", "-o", str(so), src], check=True)
+    emu = ctypes.CDLL(str(so)).emulate_dump_rows
+    LL, I = ctypes.c_longlong, ctypes.c_int
+
+    def run(bufs, want, reverse):
+        cols = D.frame_columns(bufs[0])
+        n = int(bufs[0].split(b"\n")[3])                            # the line after ITEM: NUMBER OF ATOMS
+        text = b"".join(bufs)
+        begin, end, off = [], [], 0
+        for b in bufs:
+            begin.append(off + _atoms_section(b))
+            end.append(off + len(b))
+            off += len(b)
+        colsel = [want.index(c) if c in want else -1 for c in cols]
+        F = len(bufs)
+        out = np.full((F, len(want), n), np.nan)
+        seen = np.zeros((F, (n + 31) // 32), dtype=np.uint32)
+        status = np.zeros((F, 2), dtype=np.uint64)
+        rc = emu(I(F), text, (LL * F)(*begin), (LL * F)(*end), LL(n), I(len(cols)), (I * len(cols))(*colsel), I(cols.index("id")),
+                 I(len(want)), out.ctypes.data_as(ctypes.c_void_p), LL(len(want) * n), LL(n), seen.ctypes.data_as(ctypes.c_void_p),
+                 status.ctypes.data_as(ctypes.c_void_p), I(1 if reverse else 0))
+        assert rc == 0
+        return out, status, n
+
+    want = ["id", "type", "x", "y", "z", "fx", "q", "iz"]
+    bufs = [open(os.path.join(sample_dir, f), "rb").read() for f in sorted(os.listdir(sample_dir)) if f.endswith(".dump")]
+    for reverse in (False, True):
+        out, status, n = run(bufs, want, reverse)
+        assert status[:, 0].tolist() == [n] * len(bufs) and status[:, 1].tolist() == [0] * len(bufs)
+        for f, b in enumerate(bufs):
+            ref = D.parse_frame(b, want, nthreads=1)
+            for k, c in enumerate(want):
+                assert np.array_equal(out[f, k], ref.data[c]), (f, c)
+
+    rng = np.random.default_rng(8)
+    head = "ITEM: TIMESTEP\n3\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n0 9\n0 9\n0 9\nITEM: ATOMS id type x y z extra\n"
+    fmts = ["%.3f", "%.6g", "%.10f", "%.12f", "%d.", "%.1f"]
+    for nn, eol, pad in [(1, "\n", 0), (3, "\n", 40), (50, "\r\n", 0), (200, "\n", 17), (333, "\n", 64), (64, "\n", 128)]:
+        ids = rng.permutation(nn) + 1
+        xyz = rng.normal(0, 40, (nn, 3))
+        rows = []
+        for i, (x, y, z) in zip(ids.tolist(), xyz.tolist()):
+            f1, f2, f3 = fmts[i % 6], fmts[(i + 2) % 6], fmts[(i + 4) % 6]
+            rows.append(" " * (i % 3) + "%d %d %s %s  %s %s" % (i, 1 + i % 4, f1 % x, f2 % y, f3 % z, "p" * (pad + 1 + i % 5)))
+        rows.insert(nn // 2, "  ")                                   # a blank line
+        buf = ((head % nn).replace("\n", eol) + eol.join(rows) + eol).encode()
+        if nn == 3:
+            buf = buf.rstrip()                                        # last row without a line end
+        want5 = ["x", "id", "z", "type", "y"]
+        ref = D.parse_frame(buf, want5, nthreads=1)
+        for reverse in (False, True):
+            out, status, n = run([buf, buf], want5, reverse)
+            assert status.tolist() == [[nn, 0], [nn, 0]], (nn, status)
+            for k, c in enumerate(want5):
+                assert np.array_equal(out[0, k], ref.data[c]) and np.array_equal(out[1, k], ref.data[c]), (nn, c)
+
+    good = ((head % 4) + "1 1 0.5 1.5 2.5 a\n2 1 0.25 1 2 a\n3 2 7 8 9 a\n4 2 1 1 1 a\n").encode()
+    cases = {
+        "exponent": (good.replace(b"0.25", b"2.5e-1"), 1),            # DPF_SLOW_TOKEN
+        "digits": (good.replace(b"0.25", b"0.12345678901234567890123"), 1),
+        "nan": (good.replace(b"0.25", b"nan"), 1),
+        "short row": (good.replace(b"3 2 7 8 9 a", b"3 2 7"), 2),      # DPF_BAD_ROW
+        "duplicate id": (good.replace(b"4 2 1 1 1", b"3 2 1 1 1"), 4),  # DPF_BAD_ID
+        "id out of range": (good.replace(b"4 2 1 1 1", b"9 2 1 1 1"), 4),
+    }
+    for name, (buf, flag) in cases.items():
+        _, status, _ = run([good, buf], ["id", "x", "y", "z"], False)
+        assert status[0].tolist() == [4, 0], name
+        assert int(status[1, 1]) & flag, (name, status)
+    fewer = good[: good.rstrip().rfind(b"\n") + 1]                    # 3 rows where the header announces 4
+    _, status, _ = run([fewer], ["id", "x"], False)
+    assert status[0].tolist() == [3, 0]                              # rows != natoms: the caller rejects the frame
+
+
 def test_parser_multiframe_triclinic_and_ragged(tmp_path):
     from mdproptools_b200.io import dump as D
     rng = np.random.default_rng(0)
