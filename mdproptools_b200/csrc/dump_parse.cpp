@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <atomic>
 #include <charconv>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -292,28 +293,24 @@ int select_columns(const Header &h, const char *const *want, int nwant, std::vec
     return 0;
 }
 
-// One frame on the calling thread, rows written straight to their id-sorted place (out[slot][id - 1]) while the ids are a
-// permutation of 1..natoms -- the usual case; returns 1 when they are not (the caller then takes the general path, which
-// ranks the ids), 0 on success, < 0 on error.  `seen` is scratch of natoms bytes.
-int parse_frame_fused(const Header &h, const char *end, const std::vector<int> &colsel, int id_col, int nwant, double *out,
-                      int64_t out_stride, std::vector<unsigned char> &seen)
+// Rows written straight to their id-sorted place (out[slot][id - 1]) while the ids are a permutation of 1..natoms -- the
+// usual case.  Parses the first `nrows` non-blank rows of [p, end); `seen` is a bitmap of natoms bits shared by every
+// thread working on the frame (ATOMIC) or private to the caller.  Returns 0 on success, 1 when an id is out of range or
+// occurs twice (the caller then takes the general path, which ranks the ids), < 0 on error.
+template <bool ATOMIC>
+int parse_rows_fused(const char *p, const char *end, int64_t row0, int64_t nrows, int64_t n, const std::vector<int> &colsel,
+                     int id_col, int nwant, double *out, int64_t out_stride, std::atomic<uint32_t> *seen)
 {
-    const int64_t n = h.natoms;
-    if (id_col < 0) return 1;
+    if (id_col < 0 || nwant > 64) return 1;
     const int ncols = (int)colsel.size();
     int last_needed = id_col;
     for (int c = 0; c < ncols; ++c)
         if (colsel[c] >= 0 && c > last_needed) last_needed = c;
-    seen.assign((size_t)n, 0);
-    constexpr int PIPE = 16;
-    double rowv[64], ring[PIPE * 64];
-    long long ring_id[PIPE];
-    if (nwant > 64) return 1;
-    const char *p = h.atoms_begin;
+    double rowv[64];
     int64_t r = 0;
-    while (r < n) {
+    while (r < nrows) {
         if (p >= end) {
-            mdp_set_error("dump: frame announces %lld atoms but holds %lld rows", (long long)n, (long long)r);
+            mdp_set_error("dump: frame announces %lld atoms but holds %lld rows", (long long)n, (long long)(row0 + r));
             return -4;
         }
         const char *le = next_line(p, end);
@@ -329,7 +326,7 @@ int parse_frame_fused(const Header &h, const char *end, const std::vector<int> &
             if (slot < 0 && c != id_col) {          // unwanted column: only find its end
                 const char *te = token_end(q, le);
                 if (te == q) {
-                    mdp_set_error("dump: row %lld has fewer than %d columns", (long long)r, ncols);
+                    mdp_set_error("dump: row %lld has fewer than %d columns", (long long)(row0 + r), ncols);
                     return -4;
                 }
                 q = te;
@@ -340,39 +337,57 @@ int parse_frame_fused(const Header &h, const char *end, const std::vector<int> &
             if (!te) {
                 const char *t2 = token_end(q, le);
                 if (t2 == q)
-                    mdp_set_error("dump: row %lld has fewer than %d columns", (long long)r, ncols);
+                    mdp_set_error("dump: row %lld has fewer than %d columns", (long long)(row0 + r), ncols);
                 else
-                    mdp_set_error("dump: cannot parse '%.*s' in row %lld column %d", (int)(t2 - q), q, (long long)r, c);
+                    mdp_set_error("dump: cannot parse '%.*s' in row %lld column %d", (int)(t2 - q), q, (long long)(row0 + r), c);
                 return -4;
             }
             if (c == id_col) {
-                // ids are integers; a spelling like 1e3 or 12.0 goes through the double, as in the general path
+                // ids are integers; a spelling like 1e3 or 12.0 goes through the double
                 if (!(v >= -9.2e18 && v <= 9.2e18)) return 1;
                 idv = (long long)v;
             }
             if (slot >= 0) rowv[slot] = v;
             q = te;
         }
-        if (idv < 1 || idv > n || seen[idv - 1]) return 1;
-        seen[idv - 1] = 1;
-        // the destinations are random (4 MB per frame, one line per column): ask for the lines now, store the row PIPE rows later
-        for (int k = 0; k < nwant; ++k) __builtin_prefetch(out + (int64_t)k * out_stride + (idv - 1), 1, 0);
-        const int slot_r = (int)(r % PIPE);
-        if (r >= PIPE) {
-            const double *ov = ring + (size_t)slot_r * nwant;
-            const long long od = ring_id[slot_r];
-            for (int k = 0; k < nwant; ++k) out[(int64_t)k * out_stride + od] = ov[k];
+        if (idv < 1 || idv > n) return 1;
+        const uint32_t bit = 1u << ((idv - 1) & 31);
+        std::atomic<uint32_t> &word = seen[(idv - 1) >> 5];
+        if (ATOMIC) {
+            if (word.fetch_or(bit, std::memory_order_relaxed) & bit) return 1;
+        } else {
+            const uint32_t o = word.load(std::memory_order_relaxed);
+            if (o & bit) return 1;
+            word.store(o | bit, std::memory_order_relaxed);
         }
-        ring_id[slot_r] = idv - 1;
-        for (int k = 0; k < nwant; ++k) ring[(size_t)slot_r * nwant + k] = rowv[k];
+        for (int k = 0; k < nwant; ++k) out[(int64_t)k * out_stride + (idv - 1)] = rowv[k];
         ++r;
         p = le;
     }
-    for (int64_t t = r > PIPE ? r - PIPE : 0; t < r; ++t) {
-        const int slot_r = (int)(t % PIPE);
-        for (int k = 0; k < nwant; ++k) out[(int64_t)k * out_stride + ring_id[slot_r]] = ring[(size_t)slot_r * nwant + k];
-    }
     return 0;
+}
+
+struct SeenBits {
+    std::unique_ptr<std::atomic<uint32_t>[]> w;
+    size_t words = 0;
+    std::atomic<uint32_t> *reset(int64_t n)
+    {
+        const size_t need = (size_t)(n + 31) / 32;
+        if (need > words) {
+            w.reset(new std::atomic<uint32_t>[need]);
+            words = need;
+        }
+        for (size_t k = 0; k < need; ++k) w[k].store(0, std::memory_order_relaxed);
+        return w.get();
+    }
+};
+
+// one frame on the calling thread
+int parse_frame_fused(const Header &h, const char *end, const std::vector<int> &colsel, int id_col, int nwant, double *out,
+                      int64_t out_stride, SeenBits &seen)
+{
+    return parse_rows_fused<false>(h.atoms_begin, end, 0, h.natoms, h.natoms, colsel, id_col, nwant, out, out_stride,
+                                   seen.reset(h.natoms));
 }
 
 } // namespace
@@ -484,10 +499,41 @@ int mdp_dump_parse(const char *text, int64_t len, const char *const *want, int n
         return -4;
     }
 
-    std::vector<double> vals((size_t)nwant * n);
-    std::vector<long long> ids((size_t)n, 0);
     std::vector<int> rcs(nthreads, 0);
     std::vector<std::string> errs(nthreads);
+    if (id_col >= 0) {
+        // usual case, ids a permutation of 1..natoms: every thread places its rows itself (shared atomic bitmap); no
+        // staging copy, no serial pass
+        SeenBits seen;
+        std::atomic<uint32_t> *bits = seen.reset(n);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() {
+                const int64_t r0 = row0[t];
+                const int64_t nr = std::min<int64_t>(rows[t], std::max<int64_t>(0, n - r0));
+                if (nr <= 0) return;
+                rcs[t] = parse_rows_fused<true>(cut[t], cut[t + 1], r0, nr, n, colsel, id_col, nwant, out, out_stride, bits);
+                if (rcs[t] < 0) errs[t] = mdp_last_error();
+            });
+        for (auto &x : th) x.join();
+        bool irregular = false;
+        for (int t = 0; t < nthreads; ++t) {
+            if (rcs[t] < 0) {
+                mdp_set_error("%s", errs[t].c_str());
+                return rcs[t];
+            }
+            irregular = irregular || rcs[t] == 1;
+        }
+        if (!irregular) {
+            if (header_out) fill_header_out(h, header_out, true);
+            return 0;
+        }
+        std::fill(rcs.begin(), rcs.end(), 0);
+    }
+
+    // general path: values in file order, then ranked by id
+    std::vector<double> vals((size_t)nwant * n);
+    std::vector<long long> ids((size_t)n, 0);
     {
         std::vector<std::thread> th;
         for (int t = 0; t < nthreads; ++t)
@@ -562,7 +608,7 @@ int mdp_dump_parse_batch(int nframes, const char *const *texts, const int64_t *l
     std::vector<std::thread> th;
     for (int t = 0; t < nt; ++t)
         th.emplace_back([&, t]() {
-            std::vector<unsigned char> seen;
+            SeenBits seen;
             std::vector<int> colsel;
             while (!failed.load(std::memory_order_relaxed)) {
                 const int f = next.fetch_add(1);
