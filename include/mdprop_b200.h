@@ -202,6 +202,13 @@ int mdp_bitmask_fill(mdp_ctx *ctx, int64_t nentries, const int32_t *list, int64_
 int mdp_bitmask_autocorr(mdp_ctx *ctx, int64_t npairs, int nwords, int64_t T, const uint64_t *masks,
                          uint64_t *cnt_out, void *stream);
 
+/* EXPERIMENTAL, opt-in (MDP_SURVIVAL_RUNS=1): the same counts as mdp_bitmask_autocorr -- cnt_out accumulates, bit for bit
+ * the same integers -- from the RUNS of each pair's bitmask: a pair with k runs costs 4*k(k+1)/2 integer updates of a
+ * second-difference array instead of T^2/128 word operations (csrc/survival_runs.h).  T is limited by the shared-memory
+ * array (about 25 000 frames). */
+int mdp_survival_runs(mdp_ctx *ctx, int64_t npairs, int nwords, int64_t T, const uint64_t *masks, uint64_t *cnt_out,
+                      void *stream);
+
 /* ---- OLS through the origin (diffusion.py:323-329) -------------------------------------------------
  * out[c] = {sum t*t, sum t*y_c, sum y_c*y_c} over rows i0..i1-1; the host forms slope, bse, R2.
  * t = DEVICE [T], y = DEVICE [ncol][T], out = DEVICE [ncol][3]. */

@@ -61,6 +61,7 @@ _PROTOS = {
     "mdp_cumtrapz": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_double, c_double, c_int, c_void_p, c_void_p]),
     "mdp_bitmask_fill": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mdp_bitmask_autocorr": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mdp_survival_runs": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "mdp_axis_density": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_double, c_int, POINTER(c_double), c_double,
                                  c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "mdp_ols_sums": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

@@ -221,6 +221,12 @@ def cumtrapz(y, dx, scale=1.0, leading_zero=True):
     return out
 
 
+def survival_runs_enabled() -> bool:
+    import os
+
+    return os.environ.get("MDP_SURVIVAL_RUNS", "0") not in ("", "0")
+
+
 def bitmask_autocorr_from_list(lst, n_b, T):
     """Neighbour list (frame, ia, ib) -> integer survival counts cnt[tau] (int64 [T]) and the number of ever-neighbour pairs."""
     ctx = Context.get(lst.device.index)
@@ -235,6 +241,10 @@ def bitmask_autocorr_from_list(lst, n_b, T):
     lst = lst.contiguous()
     check(lib().mdp_bitmask_fill(ctx.handle, lst.shape[0], ptr(lst), int(n_b), ptr(ukeys), P, W, ptr(masks),
                                  stream_ptr()), "mdp_bitmask_fill")
+    if survival_runs_enabled() and T * 8 + 32768 <= 200 * 1024:
+        # EXPERIMENTAL, off by default: the same integers from the runs of each mask (csrc/survival.cu)
+        check(lib().mdp_survival_runs(ctx.handle, P, W, T, ptr(masks), ptr(cnt), stream_ptr()), "mdp_survival_runs")
+        return cnt, P
     step = 65535 * 64
     for p0 in range(0, P, step):
         m = masks[p0:p0 + step]

@@ -409,6 +409,29 @@ def test_axis_density_kernel_vs_oracle_random(ops):
             assert np.array_equal(counts[f], want), (n, dist, f)
 
 
+@pytest.mark.skipif(os.environ.get("MDP_TEST_SURVIVAL_RUNS", "0") in ("", "0"),
+                    reason="the run-based survival kernel is opt-in and not yet validated on hardware (set MDP_TEST_SURVIVAL_RUNS=1)")
+def test_survival_runs_kernel_equals_popcount_kernel(ops, monkeypatch):
+    """mdp_survival_runs against mdp_bitmask_autocorr (itself pinned to the oracle) on the same neighbour lists: dense
+    random indicators (many runs, some pairs beyond the run buffer) and persistent ones; several trajectory lengths."""
+    import torch
+    rng = np.random.default_rng(21)
+    for T, na, nb, kind in [(130, 6, 40, "dense"), (1000, 10, 60, "walk"), (2600, 4, 30, "dense"), (5000, 12, 50, "walk")]:
+        if kind == "dense":
+            h = rng.uniform(size=(T, na, nb)) < 0.5
+        else:
+            walk = np.cumsum(rng.normal(0, 0.3, (T, na, nb)), axis=0) + rng.normal(0, 1.5, (na, nb))
+            h = np.abs(walk) < 1.0
+        f, a, b = np.nonzero(h)
+        lst = torch.from_numpy(np.stack([f, a, b], axis=1).astype(np.int32)).cuda()
+        monkeypatch.setenv("MDP_SURVIVAL_RUNS", "0")
+        ref, P = ops.bitmask_autocorr_from_list(lst, nb, T)
+        monkeypatch.setenv("MDP_SURVIVAL_RUNS", "1")
+        got, P2 = ops.bitmask_autocorr_from_list(lst, nb, T)
+        assert P == P2 and torch.equal(ref, got), (T, kind)
+        assert np.array_equal(got.cpu().numpy(), O.survival_counts(h.reshape(T, -1).astype(np.uint8)))
+
+
 @pytest.mark.skipif(os.environ.get("MDP_TEST_DEVICE_PARSE", "0") in ("", "0"),
                     reason="the device dump parser is opt-in and not yet validated on hardware (set MDP_TEST_DEVICE_PARSE=1)")
 def test_device_dump_parser_matches_host_parser(sample_dir, tmp_path):

@@ -243,6 +243,49 @@ def test_device_parser_body_on_host(sample_dir, tmp_path):
     assert status[0].tolist() == [3, 0]                              # rows != natoms: the caller rejects the frame
 
 
+def test_survival_counts_from_runs_on_host(tmp_path):
+    """The run-based survival correlation (csrc/survival_runs.h: run extraction from the time bitmask + four
+    second-difference updates per run pair + two prefix sums) against the oracle's direct sum: random indicators of
+    every density, runs touching both ends, trajectories that are / are not a multiple of 64 frames, empty and full
+    masks.  Integer counts, equal bit for bit."""
+    import ctypes
+    so = tmp_path / "survival_runs_host.so"
+    src = os.path.join(ROOT, "tests", "native", "survival_runs_host.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(so), src], check=True)
+    emu = ctypes.CDLL(str(so)).emulate_survival_runs
+    emu.restype = ctypes.c_int
+    rng = np.random.default_rng(12)
+
+    def check(h, cap=None):
+        T, P = h.shape
+        W = (T + 63) // 64
+        bits = np.zeros((P, W * 64), dtype=np.uint8)
+        bits[:, :T] = h.T
+        masks = np.packbits(bits.reshape(P, W, 64), axis=2, bitorder="little").view(np.uint64).reshape(P, W)
+        masks = np.ascontiguousarray(masks)
+        cnt = np.zeros(T, dtype=np.int64)
+        k = emu(masks.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(P), ctypes.c_int(W), ctypes.c_longlong(T),
+                ctypes.c_int(cap or T // 2 + 2), cnt.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(cnt, O.survival_counts(h)), (T, P)
+        return k
+
+    for T in (1, 2, 63, 64, 65, 127, 128, 200, 321, 1023, 1025, 2500):
+        for dens in (0.02, 0.3, 0.5, 0.9):
+            check((rng.uniform(size=(T, 7)) < dens).astype(np.uint8))
+        # persistent neighbours: long runs with a few flips, as a residence shell produces them
+        walk = np.cumsum(rng.normal(0, 0.4, (T, 9)), axis=0) + rng.normal(0, 1, 9)
+        check((np.abs(walk) < 1.0).astype(np.uint8))
+        check(np.zeros((T, 2), dtype=np.uint8))
+        check(np.ones((T, 3), dtype=np.uint8))
+        edge = np.zeros((T, 4), dtype=np.uint8)
+        edge[0, 0] = 1; edge[T - 1, 1] = 1; edge[0, 2] = edge[T - 1, 2] = 1; edge[T // 2:, 3] = 1
+        check(edge)
+    assert check((np.arange(300)[:, None] % 2 == 0).astype(np.uint8)) == 150      # alternating bits: T/2 runs
+    # a run buffer that is too small for some pairs: those take the word route (AND-shift-popcount), the sum is the same
+    for T in (64, 129, 500):
+        assert check((rng.uniform(size=(T, 11)) < 0.5).astype(np.uint8), cap=8) > 8
+
+
 def test_parser_multiframe_triclinic_and_ragged(tmp_path):
     from mdproptools_b200.io import dump as D
     rng = np.random.default_rng(0)
