@@ -135,6 +135,14 @@ int mdp_pair_list(mdp_ctx *ctx, int nframes,
                   const double *box, double rin2, double rout2, int shell_mode, int exclude_same_index,
                   int32_t *list_out, double *rsq_out, int64_t capacity, int64_t *count_out, int flags, void *stream);
 
+/* EXPERIMENTAL, opt-in (MDP_SHELL_GRID=1): the entries mdp_pair_list returns (same arguments, orthogonal cell, no rsq
+ * output), found through a cell grid over a SMALL set A (n_a <= 4096) held in shared memory while B is streamed once
+ * (csrc/shell_grid.h).  Returns 0, or 1 when the grid does not apply (n_a too large, or the outer radius exceeds a third
+ * of a box length in some frame): the caller then uses mdp_pair_list. */
+int mdp_shell_search(mdp_ctx *ctx, int nframes, int64_t n_a, const double *xyz_a, int64_t n_b, const double *xyz_b,
+                     const double *box, double rin2, double rout2, int shell_mode, int exclude_same_index,
+                     int32_t *list_out, int64_t capacity, int64_t *count_out, void *stream);
+
 /* ---- segmented (per-molecule) reductions ------------------------------------------------------
  * calc_com (com_mols.py:5-62) / _define_mol_cols (rdf_cn.py:218-241): for each segment s (molecule;
  * atoms seg_off[s]..seg_off[s+1]-1 in id order) out[c][s] = sum_a w[a]*attr[c][a] / sum_a w[a],

@@ -109,6 +109,20 @@ def pair_list(xyz_a, xyz_b, box, r_in2, r_out2, shell_mode, exclude_same_index=F
     ctx = Context.get(xyz_a.device.index)
     box = _host_box(box, F, flags)
     cap = int(capacity or max(1 << 16, 64 * na * F))
+    if shell_grid_enabled() and not want_rsq and flags == 0 and na <= 4096 and 8 * na <= nb_:
+        # EXPERIMENTAL, off by default: small set A against a large set B through a cell grid over A (csrc/shell.cu)
+        while True:
+            lst = torch.empty((cap, 3), dtype=torch.int32, device=xyz_a.device)
+            cnt = torch.zeros((1,), dtype=torch.int64, device=xyz_a.device)
+            rc = lib().mdp_shell_search(ctx.handle, F, na, ptr(xyz_a), nb_, ptr(xyz_b), _lib.dptr(box), float(r_in2), float(r_out2),
+                                        int(shell_mode), 1 if exclude_same_index else 0, ptr(lst), cap, ptr(cnt), stream_ptr())
+            if rc == 1:
+                break                      # the grid does not apply (radius above a third of the box): general engine below
+            check(rc, "mdp_shell_search")
+            m = int(cnt.item())
+            if m <= cap:
+                return lst[:m], None
+            cap = int(m * 1.1) + 1024
     while True:
         lst = torch.empty((cap, 3), dtype=torch.int32, device=xyz_a.device)
         rsq = torch.empty((cap,), dtype=torch.float64, device=xyz_a.device) if want_rsq else None
@@ -219,6 +233,12 @@ def cumtrapz(y, dx, scale=1.0, leading_zero=True):
     check(lib().mdp_cumtrapz(ctx.handle, R, T, ptr(y), float(dx), float(scale), 1 if leading_zero else 0, ptr(out),
                              stream_ptr()), "mdp_cumtrapz")
     return out
+
+
+def shell_grid_enabled() -> bool:
+    import os
+
+    return os.environ.get("MDP_SHELL_GRID", "0") not in ("", "0")
 
 
 def survival_runs_enabled() -> bool:

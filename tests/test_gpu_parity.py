@@ -409,6 +409,30 @@ def test_axis_density_kernel_vs_oracle_random(ops):
             assert np.array_equal(counts[f], want), (n, dist, f)
 
 
+@pytest.mark.skipif(os.environ.get("MDP_TEST_SHELL_GRID", "0") in ("", "0"),
+                    reason="the small-set shell search is opt-in and not yet validated on hardware (set MDP_TEST_SHELL_GRID=1)")
+def test_shell_grid_search_equals_pair_list(ops, monkeypatch):
+    """mdp_shell_search against mdp_pair_list (itself pinned to the oracle): same set of (frame, ia, ib) entries for
+    wrapped and unwrapped coordinates, both shell modes, per-frame boxes; and the automatic fallback when the radius
+    exceeds a third of the box."""
+    rng = np.random.default_rng(41)
+    F, na, nb = 6, 150, 4000
+    Ls = np.stack([rng.uniform(20, 26, F), rng.uniform(19, 24, F), rng.uniform(22, 27, F)], axis=1)
+    a = rng.uniform(0, 1, (F, 3, na)) * Ls[:, :, None]
+    b = rng.uniform(0, 1, (F, 3, nb)) * Ls[:, :, None]
+    b[3:] += rng.integers(-2, 3, (F - 3, 3, nb)) * Ls[3:, :, None]            # unwrapped in the later frames
+
+    def entries(flag, r_in, r_out, mode):
+        monkeypatch.setenv("MDP_SHELL_GRID", flag)
+        lst, _ = ops.pair_list(_dev(a), _dev(b), Ls, r_in ** 2, r_out ** 2, mode)
+        return sorted(map(tuple, lst.cpu().numpy().tolist()))
+
+    for r_in, r_out, mode in [(0.0, 3.0, 1), (1.0, 4.5, 1), (0.0, 3.0, 0)]:
+        ref, got = entries("0", r_in, r_out, mode), entries("1", r_in, r_out, mode)
+        assert len(ref) > 0 and ref == got, (r_in, r_out, mode)
+    assert entries("1", 0.0, 9.0, 1) == entries("0", 0.0, 9.0, 1)               # 9 A > L/3: falls back to the engine
+
+
 @pytest.mark.skipif(os.environ.get("MDP_TEST_SURVIVAL_RUNS", "0") in ("", "0"),
                     reason="the run-based survival kernel is opt-in and not yet validated on hardware (set MDP_TEST_SURVIVAL_RUNS=1)")
 def test_survival_runs_kernel_equals_popcount_kernel(ops, monkeypatch):

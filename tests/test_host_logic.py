@@ -286,6 +286,64 @@ def test_survival_counts_from_runs_on_host(tmp_path):
         assert check((rng.uniform(size=(T, 11)) < 0.5).astype(np.uint8), cap=8) > 8
 
 
+def test_shell_grid_search_on_host(tmp_path):
+    """The small-set neighbour search (csrc/shell_grid.h: periodic cell grid over A as a conservative filter, the
+    reference's own rsq arithmetic as the test) against the oracle's all-pairs shell mask: wrapped and unwrapped
+    coordinates, points on the box faces, pairs planted exactly on the shell radii, radii close to a third of the box,
+    both shell modes, same-set exclusion.  Every pair is found exactly once."""
+    import ctypes
+    so = tmp_path / "shell_grid_host.so"
+    src = os.path.join(ROOT, "tests", "native", "shell_grid_host.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(so), src], check=True)
+    emu = ctypes.CDLL(str(so)).emulate_shell_grid
+    emu.restype = ctypes.c_int
+    D = ctypes.c_double
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    rng = np.random.default_rng(31)
+
+    def check(A, B, L, r_in, r_out, mode, same):
+        A = [np.ascontiguousarray(v, dtype=np.float64) for v in A]
+        B = [np.ascontiguousarray(v, dtype=np.float64) for v in B]
+        na, nb = len(A[0]), len(B[0])
+        out = np.zeros((na, nb), dtype=np.uint8)
+        Lc = np.asarray(L, dtype=np.float64)
+        rc = emu(dp(A[0]), dp(A[1]), dp(A[2]), na, dp(B[0]), dp(B[1]), dp(B[2]), nb, dp(Lc), D(O.rcut_sq(r_in)), D(O.rcut_sq(r_out)),
+                 mode, 1 if same else 0, out.ctypes.data_as(ctypes.c_void_p))
+        if rc != 0:
+            return False
+        if mode:
+            want = O.shell_mask(A[0], A[1], A[2], B[0], B[1], B[2], L, r_in, r_out, same)
+        else:
+            rsq = np.stack([O.calc_rsq([A[0][i], A[1][i], A[2][i]], B[0], B[1], B[2], L) for i in range(na)])
+            want = (rsq < O.rcut_sq(r_out)).astype(np.uint8)
+            if same:
+                want[np.arange(min(na, nb)), np.arange(min(na, nb))] = 0
+        assert np.array_equal(out, want), (na, nb, L, r_out, mode)
+        return True
+
+    L = (21.0, 19.5, 23.25)
+    for na, nb in [(1, 50), (40, 900), (300, 300), (7, 5000)]:
+        a = rng.uniform(0, 1, (3, na)) * np.asarray(L)[:, None]
+        b = rng.uniform(0, 1, (3, nb)) * np.asarray(L)[:, None]
+        for r_in, r_out in [(0.0, 3.0), (1.5, 4.0), (0.0, 6.4)]:              # 6.4: three cells on the short axis
+            assert check(a, b, L, r_in, r_out, 1, False)
+            assert check(a, b, L, r_in, r_out, 0, False)
+        # unwrapped coordinates (several box lengths away, both signs) and a shifted origin
+        shift_a = rng.integers(-3, 4, (3, na)) * np.asarray(L)[:, None]
+        shift_b = rng.integers(-3, 4, (3, nb)) * np.asarray(L)[:, None]
+        assert check(a + shift_a + 100.0, b + shift_b + 100.0, L, 0.0, 3.0, 1, False)
+    # same set, self pairs excluded (residence_time.py:103-104)
+    a = rng.uniform(0, 1, (3, 400)) * np.asarray(L)[:, None]
+    assert check(a, a, L, 0.0, 3.5, 1, True) and check(a, a, L, 0.0, 3.5, 0, True)
+    # points on the faces and pairs planted exactly at the radii (<= r_out counts in shell mode, < r_out does not in mode 0)
+    a = np.array([[0.0, 21.0, 10.5, 0.0], [0.0, 0.0, 19.5, 9.75], [0.0, 23.25, 0.0, 23.25]])
+    b = np.concatenate([a + np.array([[3.0], [0.0], [0.0]]), a - np.array([[0.0], [3.0], [0.0]]),
+                        a + np.array([[0.0], [0.0], [1.5]]), a + 1e-13, rng.uniform(0, 20, (3, 50))], axis=1)
+    assert check(a, b, L, 1.5, 3.0, 1, False) and check(a, b, L, 0.0, 3.0, 0, False)
+    # a radius beyond a third of the shortest box length: the grid does not apply
+    assert not check(a, b, L, 0.0, 7.0, 1, False)
+
+
 def test_parser_multiframe_triclinic_and_ragged(tmp_path):
     from mdproptools_b200.io import dump as D
     rng = np.random.default_rng(0)
