@@ -196,6 +196,11 @@ int mdp_charge_flux(mdp_ctx *ctx, int nframes, int64_t n, const double *vel, con
  * nlags <= T lags are produced (out row stride = nlags). */
 int mdp_xcorr_unbiased(mdp_ctx *ctx, int nchan, int64_t T, const double *a, const double *b, int64_t nlags,
                        double *out, void *stream);
+/* EXPERIMENTAL, opt-in (MDP_XCORR_FFT=1): the same correlation through a radix-2 Stockham FFT in fp64 (csrc/fft_corr.h) --
+ * N log N instead of T^2/2, for the 10^6..10^7-step series of a viscosity run; agrees with mdp_xcorr_unbiased to the
+ * round-off of an FFT (~1e-15 of max|C| times log2 N), which is how the reference computes it.  Same arguments. */
+int mdp_xcorr_fft(mdp_ctx *ctx, int nchan, int64_t T, const double *a, const double *b, int64_t nlags, double *out,
+                  void *stream);
 /* cumulative trapezoid along rows (conductivity.py:231 with leading zero, viscosity.py:151 without):
  * in = DEVICE [nrows][T]; out = DEVICE [nrows][T] if leading_zero else [nrows][T-1]; out = scale*integral. */
 int mdp_cumtrapz(mdp_ctx *ctx, int nrows, int64_t T, const double *in, double dx, double scale,

@@ -15,9 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmdprop_b200.so")
 
-CU_SOURCES = ["ctx.cu", "pair.cu", "reduce.cu", "corr.cu", "dump_device.cu", "survival.cu", "shell.cu"]
+CU_SOURCES = ["ctx.cu", "pair.cu", "reduce.cu", "corr.cu", "dump_device.cu", "survival.cu", "shell.cu", "fftcorr.cu"]
 CPP_SOURCES = ["dump_parse.cpp"]
-HEADERS = ["common.cuh", "dump_line.h", "dump_rows.h", "survival_runs.h", "shell_grid.h", os.path.join("..", "..", "include", "mdprop_b200.h")]
+HEADERS = ["common.cuh", "dump_line.h", "dump_rows.h", "survival_runs.h", "shell_grid.h", "fft_corr.h", os.path.join("..", "..", "include", "mdprop_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -221,6 +221,10 @@ def xcorr_unbiased(a, b, nlags=None):
     nlags = T if nlags is None else int(nlags)
     ctx = Context.get(a.device.index)
     out = torch.empty((C, nlags), dtype=torch.float64, device=a.device)
+    if xcorr_fft_enabled():
+        # EXPERIMENTAL, off by default: N log N through a Stockham FFT (csrc/fftcorr.cu)
+        check(lib().mdp_xcorr_fft(ctx.handle, C, T, ptr(a), ptr(b), nlags, ptr(out), stream_ptr()), "mdp_xcorr_fft")
+        return out
     check(lib().mdp_xcorr_unbiased(ctx.handle, C, T, ptr(a), ptr(b), nlags, ptr(out), stream_ptr()), "mdp_xcorr_unbiased")
     return out
 
@@ -233,6 +237,12 @@ def cumtrapz(y, dx, scale=1.0, leading_zero=True):
     check(lib().mdp_cumtrapz(ctx.handle, R, T, ptr(y), float(dx), float(scale), 1 if leading_zero else 0, ptr(out),
                              stream_ptr()), "mdp_cumtrapz")
     return out
+
+
+def xcorr_fft_enabled() -> bool:
+    import os
+
+    return os.environ.get("MDP_XCORR_FFT", "0") not in ("", "0")
 
 
 def shell_grid_enabled() -> bool:

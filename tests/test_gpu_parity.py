@@ -409,6 +409,27 @@ def test_axis_density_kernel_vs_oracle_random(ops):
             assert np.array_equal(counts[f], want), (n, dist, f)
 
 
+@pytest.mark.skipif(os.environ.get("MDP_TEST_XCORR_FFT", "0") in ("", "0"),
+                    reason="the FFT correlation is opt-in and not yet validated on hardware (set MDP_TEST_XCORR_FFT=1)")
+def test_xcorr_fft_equals_direct_kernel(ops, monkeypatch):
+    """mdp_xcorr_fft against mdp_xcorr_unbiased and the oracle's long-double direct sum: 1e-10 of max|C| (north star)."""
+    import torch
+    rng = np.random.default_rng(61)
+    for C, T, nlags in [(1, 1, 1), (3, 9, 9), (4, 1000, 1000), (2, 4097, 1500), (5, 50000, 50000)]:
+        a = np.cumsum(rng.normal(0, 1, (C, T)), axis=1) * 0.05 + rng.normal(0, 1, (C, T))
+        b = a.copy()
+        b[C // 2:] = rng.normal(0, 2, (C - C // 2, T))
+        monkeypatch.setenv("MDP_XCORR_FFT", "0")
+        ref = ops.xcorr_unbiased(_dev(a), _dev(b), nlags).cpu().numpy()
+        monkeypatch.setenv("MDP_XCORR_FFT", "1")
+        got = ops.xcorr_unbiased(_dev(a), _dev(b), nlags).cpu().numpy()
+        for c in range(C):
+            scale = np.abs(ref[c]).max() + 1e-300
+            assert np.abs(got[c] - ref[c]).max() / scale < 1e-10, (C, T, c)
+            if T <= 5000:
+                assert np.abs(got[c] - O.xcorr_direct(a[c], b[c])[:nlags]).max() / scale < 1e-10
+
+
 @pytest.mark.skipif(os.environ.get("MDP_TEST_SHELL_GRID", "0") in ("", "0"),
                     reason="the small-set shell search is opt-in and not yet validated on hardware (set MDP_TEST_SHELL_GRID=1)")
 def test_shell_grid_search_equals_pair_list(ops, monkeypatch):

@@ -344,6 +344,37 @@ def test_shell_grid_search_on_host(tmp_path):
     assert not check(a, b, L, 0.0, 7.0, 1, False)
 
 
+def test_fft_correlation_on_host(tmp_path):
+    """The FFT route of the unbiased correlation (csrc/fft_corr.h: Stockham radix-2 butterflies, both spectra from one
+    transform of a + i*b, second transform of the conjugated cross spectrum) against the oracle's long-double direct sum
+    and the reference's numpy-FFT form: cross- and auto-correlation, lengths around powers of two, fewer lags than
+    steps.  Tolerance: the north star's 1e-10 of max|C| (observed ~1e-15)."""
+    import ctypes
+    so = tmp_path / "fft_corr_host.so"
+    src = os.path.join(ROOT, "tests", "native", "fft_corr_host.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(so), src], check=True)
+    emu = ctypes.CDLL(str(so)).emulate_fft_xcorr
+    emu.restype = ctypes.c_int
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    rng = np.random.default_rng(51)
+    worst = 0.0
+    for T in (1, 2, 3, 7, 8, 9, 100, 255, 256, 257, 1000, 4097):
+        for same in (False, True):
+            a = np.cumsum(rng.normal(0, 1, T)) * 0.1 + rng.normal(0, 1, T)
+            b = a if same else rng.normal(0, 2, T) + 0.5
+            for nlags in sorted({T, max(1, T // 3)}):
+                out = np.empty(nlags)
+                emu(dp(a), dp(b), ctypes.c_longlong(T), ctypes.c_longlong(nlags), dp(out))
+                want = O.xcorr_direct(a, b)[:nlags]
+                scale = np.abs(want).max() + 1e-300
+                err = np.abs(out - want).max() / scale
+                worst = max(worst, err)
+                assert err < 1e-10, (T, same, nlags, err)
+                if T > 1:
+                    assert np.abs(out - O.correlate_fft(a, b)[:nlags]).max() / scale < 1e-10
+    assert worst < 1e-12
+
+
 def test_parser_multiframe_triclinic_and_ragged(tmp_path):
     from mdproptools_b200.io import dump as D
     rng = np.random.default_rng(0)
