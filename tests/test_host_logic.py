@@ -115,6 +115,39 @@ def test_batch_parser_equals_single_frame_parser(sample_dir):
         D.parse_frames([short] * 8, want, np.empty((8, 5, nn)), nthreads=4)
 
 
+def test_parser_numbers_equal_python_float():
+    """Every spelling the parser accepts must give the double Python's float() gives (correctly rounded): random decimal
+    strings around the limits of the exact fast path -- 1 to 25 digits, the point anywhere, exponents from -30 to 30,
+    signs, leading zeros -- through both entry points (rows of one frame split over threads / one frame per thread)."""
+    from mdproptools_b200.io import dump as D
+    rng = np.random.default_rng(77)
+    toks = []
+    for _ in range(30000):
+        nd = int(rng.integers(1, 26))
+        digits = "".join(rng.choice(list("0123456789"), nd))
+        pos = int(rng.integers(0, nd + 1))
+        body = digits[:pos] + ("." if rng.uniform() < 0.8 else "") + digits[pos:] if pos < nd or rng.uniform() < 0.5 else digits + "."
+        if body in (".", ""):
+            body = "0."
+        if body.startswith(".") and rng.uniform() < 0.3:
+            body = "0" + body
+        if rng.uniform() < 0.35:
+            body += rng.choice(["e", "E"]) + rng.choice(["", "+", "-"]) + str(int(rng.integers(0, 31)))
+        toks.append(rng.choice(["", "-", "+"]) + ("000" if rng.uniform() < 0.05 else "") + body)
+    toks += ["0", "-0", "-0.0", "9007199254740992", "9007199254740993", "9007199254740993.", "0.000000000000000000000001",
+             "1e22", "1e23", "1e-22", "1e-23", "123456789012345678901234567890", "4.9e-324", "1.7976931348623157e308"]
+    n = len(toks)
+    want = np.array([float(t) for t in toks])
+    txt = ("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n0 1\n0 1\n0 1\nITEM: ATOMS id x\n" % n
+           + "\n".join("%d %s" % (i + 1, t) for i, t in enumerate(toks)) + "\n").encode()
+    for nthreads in (1, 3):
+        got = D.parse_frame(txt, ["id", "x"], nthreads=nthreads).data["x"]
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), toks[int(np.flatnonzero(got.view(np.uint64) != want.view(np.uint64))[0])]
+    out = np.empty((8, 2, n))
+    for fr in D.parse_frames([txt] * 8, ["id", "x"], out, nthreads=4):
+        assert np.array_equal(fr.data["x"].view(np.uint64), want.view(np.uint64))
+
+
 def test_frame_batches_pipeline_on_host(tmp_path):
     """FrameBatches without a device: batching by atom count and by the frame cap, frame_select (rank sharding), global
     frame indices, total_frames, and the pinned-buffer ring -- more batches than ring slots, with a deliberately slow
