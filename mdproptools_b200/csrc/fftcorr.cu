@@ -1,5 +1,5 @@
-// fftcorr.cu -- unbiased time correlation through a radix-2 Stockham FFT (EXPERIMENTAL, opt-in: MDP_XCORR_FFT=1; the
-// default is the direct fp64 sum k_xcorr of corr.cu).
+// fftcorr.cu -- unbiased time correlation through a radix-2 Stockham FFT (the default for series of >= 2048 steps,
+// ops.XCORR_FFT_MIN_T; shorter ones and MDP_XCORR_FFT=0 take the direct fp64 sum k_xcorr of corr.cu).
 //
 // Same result as mdp_xcorr_unbiased (Conductivity.correlate conductivity.py:97-114, Viscosity.autocorrelate
 // viscosity.py:86-120) to the round-off of an FFT -- which is how the reference itself computes it -- at N log N instead of

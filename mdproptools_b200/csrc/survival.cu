@@ -1,5 +1,5 @@
-// survival.cu -- residence-time survival counts from the RUNS of the pair bitmasks (EXPERIMENTAL, opt-in:
-// MDP_SURVIVAL_RUNS=1; the default is the AND-shift-popcount kernel of corr.cu).
+// survival.cu -- residence-time survival counts from the RUNS of the pair bitmasks (the default since its
+// first hardware run in round 2; MDP_SURVIVAL_RUNS=0 selects the AND-shift-popcount kernel of corr.cu).
 //
 // Replaces the same loop as mdp_bitmask_autocorr (residence_time.py:112-143).  Method and proof of equality in
 // survival_runs.h: a pair whose indicator consists of k runs costs 4 * k(k+1)/2 integer updates of a second-difference

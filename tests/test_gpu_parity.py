@@ -409,8 +409,6 @@ def test_axis_density_kernel_vs_oracle_random(ops):
             assert np.array_equal(counts[f], want), (n, dist, f)
 
 
-@pytest.mark.skipif(os.environ.get("MDP_TEST_XCORR_FFT", "0") in ("", "0"),
-                    reason="the FFT correlation is opt-in and not yet validated on hardware (set MDP_TEST_XCORR_FFT=1)")
 def test_xcorr_fft_equals_direct_kernel(ops, monkeypatch):
     """mdp_xcorr_fft against mdp_xcorr_unbiased and the oracle's long-double direct sum: 1e-10 of max|C| (north star)."""
     import torch
@@ -430,8 +428,6 @@ def test_xcorr_fft_equals_direct_kernel(ops, monkeypatch):
                 assert np.abs(got[c] - O.xcorr_direct(a[c], b[c])[:nlags]).max() / scale < 1e-10
 
 
-@pytest.mark.skipif(os.environ.get("MDP_TEST_SHELL_GRID", "0") in ("", "0"),
-                    reason="the small-set shell search is opt-in and not yet validated on hardware (set MDP_TEST_SHELL_GRID=1)")
 def test_shell_grid_search_equals_pair_list(ops, monkeypatch):
     """mdp_shell_search against mdp_pair_list (itself pinned to the oracle): same set of (frame, ia, ib) entries for
     wrapped and unwrapped coordinates, both shell modes, per-frame boxes; and the automatic fallback when the radius
@@ -454,8 +450,6 @@ def test_shell_grid_search_equals_pair_list(ops, monkeypatch):
     assert entries("1", 0.0, 9.0, 1) == entries("0", 0.0, 9.0, 1)               # 9 A > L/3: falls back to the engine
 
 
-@pytest.mark.skipif(os.environ.get("MDP_TEST_SURVIVAL_RUNS", "0") in ("", "0"),
-                    reason="the run-based survival kernel is opt-in and not yet validated on hardware (set MDP_TEST_SURVIVAL_RUNS=1)")
 def test_survival_runs_kernel_equals_popcount_kernel(ops, monkeypatch):
     """mdp_survival_runs against mdp_bitmask_autocorr (itself pinned to the oracle) on the same neighbour lists: dense
     random indicators (many runs, some pairs beyond the run buffer) and persistent ones; several trajectory lengths."""
@@ -477,8 +471,6 @@ def test_survival_runs_kernel_equals_popcount_kernel(ops, monkeypatch):
         assert np.array_equal(got.cpu().numpy(), O.survival_counts(h.reshape(T, -1).astype(np.uint8)))
 
 
-@pytest.mark.skipif(os.environ.get("MDP_TEST_DEVICE_PARSE", "0") in ("", "0"),
-                    reason="the device dump parser is opt-in and not yet validated on hardware (set MDP_TEST_DEVICE_PARSE=1)")
 def test_device_dump_parser_matches_host_parser(sample_dir, tmp_path):
     """FrameBatches(device_parse=True) against the default host-parsed pipeline: same device batches, same host copies,
     same metadata -- on the real sample frames and on a file whose second frame the device parser must refuse (an
@@ -696,7 +688,8 @@ def test_segment_com_kernel(ops):
 
 
 @pytest.mark.parametrize("T", [1, 2, 127, 128, 129, 2048, 5000])
-def test_xcorr_kernel_vs_long_double(ops, T):
+def test_xcorr_kernel_vs_long_double(ops, T, monkeypatch):
+    monkeypatch.setenv("MDP_XCORR_FFT", "0")      # the direct kernel (series of >= 2048 steps take the FFT route by default)
     rng = np.random.default_rng(T)
     a = rng.normal(0, 1, (3, T))
     b = rng.normal(0, 1, (3, T))
