@@ -4,15 +4,19 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (N>1: launched by torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPU
 
-Workload (BASELINE.json configs[1], "C2"): synthetic LJ-like fluid, 100 000 atoms per frame, triclinic cell
-(lx=ly=lz=167.19 A, xy=0.2lx, xz=0.1lx, yz=-0.15ly), all-pair RDF with r_cut = 20 A, bin = 0.05 A (400 bins),
-minimum image as the reference applies it (orthogonal wrap with the lattice lengths).  One *step* is one pass of
-the RDF hot path over a batch of FRAMES_PER_STEP frames resident in HBM (154 MB of coordinates > the 126 MB L2,
-so no L2 flush is needed between steps).  The headline metric is RDF pair-evaluations per second, counted
-NOMINALLY as frames x N(N-1)/2 (what the reference's loop evaluates); the kernel actually evaluates only the
-tile/chunk pairs that survive the bounding-box test, that number is reported beside it and is what the FP64
-roofline fraction is computed from.  The same JSON line carries the second half of the BASELINE metric, MSD
-atom-frames/s (config C3 shape: 1 000 000 atoms, a resident chunk of frames), with its HBM roofline.
+Workload (BASELINE.json configs[1], "C2", at its full size): synthetic LJ-like fluid, 100 000 atoms per frame,
+1 000 frames, triclinic cell (lx=ly=lz=167.19 A, xy=0.2lx, xz=0.1lx, yz=-0.15ly), all-pair RDF with r_cut = 20 A,
+bin = 0.05 A (400 bins), minimum image as the reference applies it (orthogonal wrap with the lattice lengths).
+One *step* is one pass of the RDF hot path over the WHOLE trajectory, resident in HBM (2.4 GB of coordinates, far
+larger than the 126 MB L2, so no L2 flush is needed between steps); with N GPUs the frames are split in contiguous
+blocks (STRONG scaling: the job is the same 1 000 frames at every N) and the per-frame integer histograms are
+all-gathered.  The headline metric is RDF pair-evaluations per second, counted NOMINALLY as frames x N(N-1)/2 (what
+the reference's loop evaluates); the kernel actually evaluates only the pairs that survive the bounding-box tests,
+that number is reported beside it and is what the roofline fraction is computed from.  The run checks itself: the GPU
+histogram of frame 0 must equal the oracle's brute-force histogram bit for bit (`parity_frame0`), at N > 1 rank 0
+recomputes frames of the other ranks' blocks (`nrank_equals_1rank`), and `hist_sha256` of all 1 000 per-frame
+histograms is the same string at every N.  The same JSON line carries the second half of the BASELINE metric, MSD
+atom-frames/s (config C3), and the C4/C5 legs, each with its own roofline.
 """
 from __future__ import annotations
 
@@ -36,11 +40,11 @@ TILT = (0.20 * LBOX, 0.10 * LBOX, -0.15 * LBOX)
 R_CUT = 20
 BIN = 0.05
 NBINS = 400
-FRAMES_PER_STEP = 64
+FRAMES_TOTAL = 1000            # C2 as BASELINE.json states it: 100k atoms x 1k frames
 SEED = 20261017
 FLOPS_PER_PAIR = 11            # 3 sub, 3 minimum-image add, 3 mul, 2 add, unfused
 MSD_ATOMS = 1_000_000
-MSD_FRAMES = 256               # resident chunk: 256 x 24 MB = 6.1 GB
+MSD_FRAMES = 10_000            # C3 as BASELINE.json states it: 1M atoms x 10k frames (240 GB; walked in resident 30 GB chunks)
 MSD_BYTES_PER_ATOM_FRAME = 24
 
 
@@ -49,9 +53,11 @@ def lattice_lengths():
     return (LBOX, float(np.sqrt(xy * xy + LBOX * LBOX)), float(np.sqrt(xz * xz + yz * yz + LBOX * LBOX)))
 
 
-def make_frames(nframes, seed, xp):
+def make_frames(nframes, seed, xp, keep=None):
     """C2 generator: simple-cubic lattice sites (first N of 47^3) in fractional coordinates, jitter,
-    per-frame Gaussian steps of 0.05 A, wrapped into the triclinic cell.  xp = torch (device) or numpy (host)."""
+    per-frame Gaussian steps of 0.05 A, wrapped into the triclinic cell.  xp = "cuda" (device) or "cpu" (host).
+    The trajectory is one random walk, so a rank that owns frames keep=[lo, hi) walks frames 0..hi-1 and keeps its block
+    (same seed on every rank: the union over the ranks is the one 1000-frame trajectory whatever the rank count)."""
     import torch
     g = torch.Generator(device="cuda" if xp == "cuda" else "cpu")
     g.manual_seed(seed)
@@ -63,13 +69,15 @@ def make_frames(nframes, seed, xp):
     inv = torch.linalg.inv(cell)
     cart = cell.T @ frac                                           # r = sx a + sy b + sz c
     cart = cart + (torch.rand((3, N_ATOMS), generator=g, dtype=torch.float64, device=dev) - 0.5) * 2 * 0.3 * 3.405
-    out = torch.empty((nframes, 3, N_ATOMS), dtype=torch.float64, device=dev)
-    for f in range(nframes):
+    lo, hi = keep if keep is not None else (0, nframes)
+    out = torch.empty((hi - lo, 3, N_ATOMS), dtype=torch.float64, device=dev)
+    for f in range(hi):
         cart = cart + torch.randn((3, N_ATOMS), generator=g, dtype=torch.float64, device=dev) * 0.05
         s = inv.T @ cart
         s = s - torch.floor(s)
         cart = cell.T @ s
-        out[f] = cart
+        if f >= lo:
+            out[f - lo] = cart
     return out
 
 
@@ -157,6 +165,34 @@ def ncu_traffic(name, scale=1.0):
 # ------------------------------------------------------------------------------------------------
 # CPU legs (oracle port; the only place bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """Threads the CPU legs use: every core this process may run on.  Passed to the oracle explicitly -- torchrun
+    exports OMP_NUM_THREADS=1 to its workers, which made the round-1 reference arm single-threaded at N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_rdf_frame0(host_frame):
+    """The exact oracle histogram of one whole C2 frame (reference wrap with the lattice lengths): int64 [NBINS] = rdf_full
+    of rdf_cn.py:85-86 (2 per in-cutoff pair).  ~2 s on 16 threads; bench.py compares the GPU histogram of the same frame
+    with it bit for bit (`parity_frame0`)."""
+    from oracle import oracle as O
+    x, y, z = host_frame
+    full, _ = O.rdf_loop(np.ones(N_ATOMS), x, y, z, np.array([[1, 1]]), lattice_lengths(), R_CUT, BIN, NBINS,
+                         nthreads=host_threads())
+    return np.asarray(full).astype(np.int64)
+
+
+def cpu_rdf_frame0_triclinic(host_frame):
+    from oracle import oracle as O
+    x, y, z = host_frame
+    full, _ = O.rdf_loop_tri(np.ones(N_ATOMS), x, y, z, np.array([[1, 1]]), (LBOX, LBOX, LBOX) + TILT, R_CUT, BIN, NBINS,
+                             nthreads=host_threads())
+    return np.asarray(full).astype(np.int64)
+
+
 def cpu_rdf_sample(target_seconds, host_frame=None):
     """The reference's pair loop (oracle/oracle.c restatement of rdf_cn.py:35-97) on a bounded sample of the C2
     workload: the first n_sub atoms of one frame against all N atoms (n_sub x N pair evaluations, same
@@ -167,12 +203,12 @@ def cpu_rdf_sample(target_seconds, host_frame=None):
     L = lattice_lengths()
     x, y, z = host_frame
     ones = np.ones(N_ATOMS)
-    cores = O.max_threads()
+    cores = host_threads()
     rel = np.array([[1, 1]])
 
     def run(n_sub):
         t = time.perf_counter()
-        O.rdf_rect(ones[:n_sub], x[:n_sub], y[:n_sub], z[:n_sub], ones, x, y, z, rel, L, R_CUT, BIN, NBINS, nthreads=0)
+        O.rdf_rect(ones[:n_sub], x[:n_sub], y[:n_sub], z[:n_sub], ones, x, y, z, rel, L, R_CUT, BIN, NBINS, nthreads=cores)
         return time.perf_counter() - t
 
     run(64)                                            # warm-up (thread pool, page faults)
@@ -197,6 +233,18 @@ def cpu_msd_sample(target_seconds):
     return n * T / dt, 1, f"numpy restatement of diffusion.py:207-218 on {n} atoms x {T} frames ({dt:.2f} s/pass)"
 
 
+WORKLOAD = "C2: LJ fluid 100k atoms/frame x 1000 frames, triclinic cell, all-pair RDF r_cut=20 bin=0.05 (400 bins)"
+
+
+def headline_config(world, T_total):
+    """The `config` object of BOTH arms (the driver compares them key by key)."""
+    return {"workload": WORKLOAD, "frames_total": T_total, "atoms_per_frame": N_ATOMS,
+            "mic": "reference (orthogonal wrap with lattice lengths)",
+            "pair_evals": "nominal: frames*N(N-1)/2, what the reference's loop evaluates",
+            "l2_policy": "inputs larger than L2 (2.4 MB of coordinates per frame, every frame read once per step)",
+            "parallelism": f"frames x{world}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -215,10 +263,10 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": "rdf_pair_evals_per_s", "value": value, "unit": "pair-evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: LJ fluid 100k atoms/frame, triclinic cell, all-pair RDF r_cut=20 bin=0.05 (400 bins)",
-                   "note": "reference algorithm (brute-force pair loop, oracle/oracle.c port of rdf_cn.py:35-97) on host cores; "
-                           "each step is a bounded sample"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": headline_config(args.gpus, args.frames),
+        "note": "reference algorithm (brute-force pair loop, oracle/oracle.c port of rdf_cn.py:35-97) on all host cores; "
+                "each step is a bounded sample of one frame of the same trajectory (per-unit throughput)",
         "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": descr},
         "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -244,26 +292,25 @@ def run_gpu(args):
     from mdproptools_b200.dynamical.diffusion import Diffusion
     from mdproptools_b200.structural import rdf_cn
 
+    from mdproptools_b200 import dist as mdist
     dev = torch.device("cuda", local)
     ctx = Context.get(local)
-    F = args.frames_per_step
+    # STRONG scaling: the whole C2 trajectory (T_total frames, default 1000) is one job; rank r owns the contiguous block
+    # shard_range(T_total) of its frames.  One step = one pass of the RDF hot path over all T_total frames.
+    T_total = args.frames
+    lo, hi = mdist.shard_range(T_total, rank, world)
+    F = hi - lo
     L = lattice_lengths()
     boxes = np.tile(np.asarray(L), (F, 1))
     edges = bin_edges(BIN, NBINS)
     rcut2 = float(R_CUT ** 2)
     weights = np.array([[2], [2]], dtype=np.int32)            # g_full and the single like relation 1-1
-    frames = make_frames(F, SEED + rank, "cuda")                 # resident in HBM before the timed region
-    merged = torch.zeros((world * F, 2, NBINS), dtype=torch.int64, device=dev)
+    frames = make_frames(T_total, SEED, "cuda", keep=(lo, hi))   # resident in HBM before the timed region
 
     def step():
         hist = ops.pair_hist(frames, None, 1, boxes, rcut2, edges, BIN)
         red = ops.hist_reduce(hist, weights)
-        if world > 1:
-            merged.zero_()
-            merged[rank * F:(rank + 1) * F] = red
-            dist.all_reduce(merged)
-            return merged
-        return red
+        return mdist.all_gather_blocks(red, T_total)             # [T_total, 2, NBINS] on every rank (exact integers)
 
     def barrier():
         if world > 1:
@@ -274,11 +321,40 @@ def run_gpu(args):
         out = step()
     barrier()
     stats = ctx.pair_stats()
-    evaluated_per_step = stats["pair_evals"]
-    nominal_per_step = F * N_ATOMS * (N_ATOMS - 1) // 2
-    # sanity: a uniform fluid has N(N-1)/2 * (4/3 pi rc^3)/V pairs inside the cutoff (V = |det cell| = L^3 here,
-    # but the reference-mode wrap uses the lattice lengths, so only the order of magnitude is checked)
-    in_cut = int(out[rank * F if world > 1 else 0, 0].sum().item()) // 2
+    st = torch.tensor([stats["pair_evals"], stats.get("exact_path_pairs", 0)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(st)
+    evaluated_per_step, exact_per_step = int(st[0].item()), int(st[1].item())
+    nominal_per_step = T_total * N_ATOMS * (N_ATOMS - 1) // 2
+    in_cut = int(out[0, 0].sum().item()) // 2
+    import hashlib
+    hist_sha = hashlib.sha256(out.cpu().numpy().astype(np.int64).tobytes()).hexdigest()   # same at every N: N-rank == 1-rank
+
+    # ---- parity at headline scale: frame 0 of the trajectory against the exact oracle histogram (brute force on the host
+    # cores), bit for bit; and, at N > 1, rank 0 recomputes the first frame of every other rank's block from its own walk
+    parity = {"parity_frame0": None}
+    if rank == 0 and not args.skip_cpu:
+        f0_host = make_frames(1, SEED, "cpu")[0].numpy()
+        same_input = bool(np.array_equal(f0_host, frames[0].cpu().numpy()))    # host and device generators agree bit for bit?
+        src = frames[0:1] if same_input else torch.from_numpy(f0_host[None]).to(dev)
+        g0 = ops.hist_reduce(ops.pair_hist(src.contiguous(), None, 1, boxes[:1], rcut2, edges, BIN), weights)[0, 0].cpu().numpy()
+        want = cpu_rdf_frame0(f0_host)
+        parity = {"parity_frame0": bool(np.array_equal(g0, want)), "parity_frame0_pairs_in_cutoff": int(want.sum()) // 2,
+                  "parity_frame0_input": "frame 0 of the benchmarked trajectory" if same_input else
+                                         "frame 0 regenerated on the host (device and host RNG streams differ)"}
+        if same_input:
+            parity["parity_frame0_in_step_output"] = bool(np.array_equal(out[0, 0].cpu().numpy(), want))
+    if world > 1:
+        # N-rank == 1-rank on hardware: rank 0 walks the trajectory itself up to the first frame of each other block
+        firsts = sorted({mdist.shard_range(T_total, r, world)[0] for r in range(1, world)})
+        ok = True
+        if rank == 0:
+            for fidx in firsts[: args.nrank_checks]:
+                fr = make_frames(T_total, SEED, "cuda", keep=(fidx, fidx + 1))
+                mine = ops.hist_reduce(ops.pair_hist(fr, None, 1, boxes[:1], rcut2, edges, BIN), weights)[0]
+                ok = ok and bool(torch.equal(mine, out[fidx]))
+            parity["nrank_equals_1rank_frames"] = firsts[: args.nrank_checks]
+            parity["nrank_equals_1rank"] = ok
 
     ctx.timing(True)
     ctx.timing_read(0), ctx.timing_read(1)
@@ -302,7 +378,8 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = world * nominal_per_step * args.steps / (ms * 1e-3)
+    value = nominal_per_step * args.steps / (ms * 1e-3)
+    evaluated_local = stats["pair_evals"]
 
     # ---- the same workload with the general triclinic image (mic="triclinic": true nearest image in the tilted cell;
     # an extension, the reference wraps tilted cells as if they were orthogonal)
@@ -320,6 +397,10 @@ def run_gpu(args):
         barrier()
         ev_t = ctx.pair_stats()["pair_evals"]
         in_cut_t = int(out_t[0, 0].sum().item()) // 2
+        if rank == 0 and parity.get("parity_frame0") is not None:
+            gt = ops.hist_reduce(ops.pair_hist(src.contiguous(), None, 1, cells[:1], rcut2, edges, BIN, flags=PAIR_TRICLINIC),
+                                 weights)[0, 0].cpu().numpy()
+            parity["parity_frame0_triclinic"] = bool(np.array_equal(gt, cpu_rdf_frame0_triclinic(f0_host)))
         ctx.timing(True)
         ctx.timing_read(0), ctx.timing_read(1)
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -336,30 +417,33 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_t = float(tt.item())
-        tric = {"value": world * nominal_per_step * args.steps / (ms_t * 1e-3), "unit": "pair-evals/s",
+        tric = {"value": nominal_per_step * args.steps / (ms_t * 1e-3), "unit": "pair-evals/s",
                 "ms_per_step": ms_t / args.steps, "pair_kernel_ms_per_step": pair_ms_t / args.steps,
-                "evaluated_pair_evals_per_step": ev_t, "pairs_in_cutoff_frame0": in_cut_t,
-                "achieved_tflops_11_per_pair": ev_t * FLOPS_PER_PAIR / (pair_ms_t / max(pair_n_t, 1) * 1e-3) / 1e12,
+                "evaluated_pair_evals_per_step_rank0": ev_t, "pairs_in_cutoff_frame0": in_cut_t,
+                "achieved_tflops_11_per_pair": ev_t * FLOPS_PER_PAIR * args.steps / (pair_ms_t * 1e-3) / 1e12,
                 "mic": "triclinic (sequential z,y,x single shift of the restricted triclinic cell; oracle-defined extension)"}
 
     # ---- end to end through the public array API: pinned host frames -> H2D -> kernels -> D2H -> normalised g(r)
+    # (every rank streams ITS block of the trajectory from its own pinned buffer; the integer histograms are all-gathered and
+    # every rank normalises all T_total frames, as a user of the API on N GPUs would get it)
     host = torch.empty((F, 3, N_ATOMS), dtype=torch.float64, pin_memory=True)
     host.copy_(frames)
     rel = [[1], [1]]
     types = np.ones(N_ATOMS)
     for _ in range(2):
-        rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=16)
+        rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=16, frame_range=(lo, hi, T_total))
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(4, args.steps)
+    e2e_steps = max(3, min(args.steps, 6))
     for _ in range(e2e_steps):
-        rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=16)
+        df_e2e = rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=16, frame_range=(lo, hi, T_total))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * nominal_per_step * e2e_steps / float(te.item())
+    e2e_value = nominal_per_step * e2e_steps / float(te.item())
+    del host
 
     # ---- MSD (second half of the BASELINE metric), C3 shape: 1M atoms, resident chunk of frames
     msd = None
@@ -383,33 +467,34 @@ def run_gpu(args):
     if not fp64_peak:
         fp64_peak = 148 * 64 * 1.965e9 / 1e12            # nominal: 64 DP lanes/SM, unfused = 1 flop/lane/clk
         peak_src = "nominal 148 SMs x 64 FP64 lanes x 1965 MHz, unfused (no measured FP64 peak on file yet)"
-    pair_ms_per_launch = pair_ms / max(pair_n, 1)
-    achieved = evaluated_per_step * FLOPS_PER_PAIR / (pair_ms_per_launch * 1e-3) / 1e12
-    nominal_tflops = nominal_per_step * FLOPS_PER_PAIR / (pair_ms_per_launch * 1e-3) / 1e12
+    # roofline of the dominant kernel on rank 0: its evaluated pairs x 11 flops over its CUDA-event kernel time (all launches
+    # of the timed region: a 1000-frame call is cut into sub-batches that fit the scratch arena)
+    achieved = evaluated_local * FLOPS_PER_PAIR * args.steps / (pair_ms * 1e-3) / 1e12
+    nominal_tflops = (F * N_ATOMS * (N_ATOMS - 1) // 2) * FLOPS_PER_PAIR * args.steps / (pair_ms * 1e-3) / 1e12
+    frames_per_launch = F * args.steps / max(pair_n, 1)
     cpu_rate, cores, sample = cpu_rdf_sample(10.0) if not args.skip_cpu else (None, None, "skipped")
     out = {
         "metric": "rdf_pair_evals_per_s", "value": value, "unit": "pair-evals/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: LJ fluid 100k atoms/frame, triclinic cell, all-pair RDF r_cut=20 bin=0.05 (400 bins)",
-                   "frames_per_step_per_gpu": F, "mic": "reference (orthogonal wrap with lattice lengths)",
-                   "l2_policy": f"inputs larger than L2 ({F * 3 * N_ATOMS * 8 / 1e6:.0f} MB of coordinates per step)",
-                   "pair_evals": "nominal frames*N(N-1)/2; evaluated_pair_evals counts what the kernel executed after "
-                                 "bounding-box culling", "parallelism": f"frames x{world}"},
+        "config": headline_config(world, T_total),
+        "frames_per_gpu": F, "hist_sha256": hist_sha, **parity,
         "evaluated_pair_evals_per_step": evaluated_per_step, "nominal_pair_evals_per_step": nominal_per_step,
+        "exact_path_pairs_per_step": exact_per_step,
         "pairs_in_cutoff_frame0": in_cut,
         "gpu_launches": launches,
         "kernel_share": {"pair_kernel_ms_per_step": pair_ms / args.steps, "prep_ms_per_step": prep_ms / args.steps,
                          "step_ms": ms / args.steps},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                     "traffic": ncu_traffic("pair", F / 16.0), "peak_source": peak_src,
+                     "traffic": ncu_traffic("pair", frames_per_launch / 16.0), "peak_source": peak_src,
                      "traffic_note": "dram bytes of the 16-frame launch captured in the newest profiles/r*_k_pair.txt (55 MB = the sorted "
                                      "records read once), scaled to this launch's frames; irrelevant to an FP64/issue-bound kernel",
                      "note": f"pair kernel only; achieved = evaluated pair-evals x {FLOPS_PER_PAIR} unfused fp64 flops / "
                              f"CUDA-event kernel time; nominal-pair equivalent = {nominal_tflops:.1f} TFLOP/s "
                              f"({nominal_tflops / fp64_peak:.2f} of peak) because culling skips work the reference does"},
-        "e2e": {"value": e2e_value, "unit": "pair-evals/s", "h2d_bytes_per_step": F * 3 * N_ATOMS * 8,
-                "d2h_bytes_per_step": F * 2 * NBINS * 8, "api": "rdf_cn.calc_atomic_rdf_from_arrays (pinned host frames)"},
+        "e2e": {"value": e2e_value, "unit": "pair-evals/s", "h2d_bytes_per_step": T_total * 3 * N_ATOMS * 8,
+                "d2h_bytes_per_step": world * T_total * 2 * NBINS * 8, "g_full_max": float(df_e2e["g_full(r)"].max()),
+                "api": "rdf_cn.calc_atomic_rdf_from_arrays (pinned host frames, frame blocks over the ranks)"},
         "clocks": clk,
         "cpu_baseline": {"value": cpu_rate, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample},
     }
@@ -424,57 +509,85 @@ def run_gpu(args):
         out["residence"] = res
     if not args.skip_cpu:
         out["dump_parse"] = bench_dump_parse()
-        out["rdf_from_files"] = bench_rdf_from_files(torch, frames, nominal_per_step / F)
+        out["rdf_from_files"] = bench_rdf_from_files(torch, frames, N_ATOMS * (N_ATOMS - 1) // 2)
     _emit(json.dumps(out))
+    bad = [k for k in ("parity_frame0", "parity_frame0_in_step_output", "parity_frame0_triclinic", "nrank_equals_1rank")
+           if parity.get(k) is False]
+    if bad:
+        sys.stderr.write(f"PARITY FAILURE: {bad}\n")
+        return 1
     return 0
 
 
 def bench_msd(args, torch, dist, ops, ctx, dev, world, rank):
+    """C3 at its full size, STRONG scaling: 1 000 000 atoms x 10 000 frames of unwrapped fp64 coordinates (240 GB), single-origin
+    MSD (diffusion.py:207-218).  Atoms are split over the ranks; a rank walks its atoms in resident chunks of <= 125 000 atoms
+    x all frames (30 GB: one chunk per GPU at N = 8, eight chunks one after the other at N = 1, which cannot hold 240 GB).  A
+    chunk is generated on the device (untimed), then `steps` passes of the kernel over it are timed with CUDA events; the job
+    time is the sum over the rank's chunks, max over ranks.  The per-frame sums [T, 1, 4] are all-reduced (fp64)."""
     n, T = args.msd_atoms, args.msd_frames
-    g = torch.Generator(device="cuda")
-    g.manual_seed(SEED + 100 + rank)
-    traj = torch.empty((T, 3, n), dtype=torch.float64, device=dev)
-    cur = torch.rand((3, n), generator=g, dtype=torch.float64, device=dev) * 215.0
-    for f in range(T):
-        cur = cur + torch.randn((3, n), generator=g, dtype=torch.float64, device=dev) * 0.1
-        traj[f] = cur
-    ref = traj[0].contiguous()
-
-    def step():
-        sums, _ = ops.msd_single_origin(traj, ref, 1e-10)
-        if world > 1:
-            dist.all_reduce(sums)                       # atoms are split over ranks: fp64 all-reduce of [T,1,4]
-        return sums
-
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
+    nchunks = 8 * ((world + 7) // 8)
+    if nchunks % world:
+        nchunks = world
+    ca = (n + nchunks - 1) // nchunks                       # atoms per chunk
+    mine = range(rank * nchunks // world, (rank + 1) * nchunks // world)
+    steps = max(args.steps, 4)
+    total = torch.zeros((T, 1, 4), dtype=torch.float64, device=dev)
+    ms_sum, kms_sum, kn_sum = 0.0, 0.0, 0
+    traj = None
+    for c in mine:
+        a0, a1 = c * ca, min(n, (c + 1) * ca)
+        nc = a1 - a0
+        del traj
+        g = torch.Generator(device="cuda")
+        g.manual_seed(SEED + 100 + c)                       # chunk c holds the same atoms whatever the rank count
+        traj = torch.empty((T, 3, nc), dtype=torch.float64, device=dev)
+        cur = torch.rand((3, nc), generator=g, dtype=torch.float64, device=dev) * 215.0
+        TB = 250
+        for f0 in range(0, T, TB):
+            k = min(TB, T - f0)
+            blk = torch.randn((k, 3, nc), generator=g, dtype=torch.float64, device=dev).mul_(0.1).cumsum_(0).add_(cur)
+            traj[f0:f0 + k] = blk
+            cur = blk[-1].clone()
+            del blk
+        ref = traj[0].contiguous()
+        for _ in range(2):
+            sums, _ = ops.msd_single_origin(traj, ref, 1e-10)
+        torch.cuda.synchronize()
+        ctx.timing(True)
+        ctx.timing_read(2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            sums, _ = ops.msd_single_origin(traj, ref, 1e-10)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_sum += e0.elapsed_time(e1)
+        kms, kn = ctx.timing_read(2)
+        ctx.timing(False)
+        kms_sum += kms
+        kn_sum += kn
+        total += sums
     if world > 1:
-        dist.barrier()
-    ctx.timing(True)
-    ctx.timing_read(2)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    steps = max(args.steps, 10)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    kms, kn = ctx.timing_read(2)
-    ctx.timing(False)
+        dist.all_reduce(total)                              # atoms are split over ranks: fp64 all-reduce of [T,1,4]
+    msd_last = float(total[-1, 0, 0].item()) / n
+    ms = ms_sum
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = world * n * T * steps / (ms * 1e-3)
+    value = n * T * steps / (ms * 1e-3)
+    kms, kn = kms_sum, kn_sum
+    n_local = sum(min(n, (c + 1) * ca) - c * ca for c in mine)
+    nfull = n
+    n = nc                                                  # the legs below run on the last resident chunk
     # ---- windowed MSD over all time origins (north-star extension): FP64-pipe bound, 2 pipe slots (DADD + DFMA) per
     # (atom, axis, origin, lag); same C3-shaped random walk re-cut as n/4 atoms x 4T frames so that a long window fits
     allo = None
     if not args.skip_msd_window:
-        nw, Tw = n // 4, T * 4
+        nw, Tw = n, min(T, 1024)
         W = min(args.msd_window, Tw)
-        trajw = traj.view(-1)[: Tw * 3 * nw].view(Tw, 3, nw)      # any fp64 data serves the throughput measurement
+        trajw = traj[:Tw]                                         # the first Tw frames of the resident chunk
         outw = torch.zeros((W, 1, 4), dtype=torch.float64, device=dev)
         for _ in range(2):
             ops.msd_all_origins(trajw, W, 1e-10, out=outw)
@@ -505,7 +618,7 @@ def bench_msd(args, torch, dist, ops, ctx, dev, world, rank):
                                      "DADD/DMUL issue rate (tools/peaks.cu), which is also the DFMA issue rate"}}
     # end to end: pinned host frames through Diffusion.get_msd_from_arrays
     from mdproptools_b200.dynamical.diffusion import Diffusion
-    Te = min(T, 64)
+    Te = min(T, 512)
     host = torch.empty((Te, 3, n), dtype=torch.float64, pin_memory=True)
     host.copy_(traj[:Te])
     d = Diffusion(timestep=1, units="real")
@@ -517,24 +630,25 @@ def bench_msd(args, torch, dist, ops, ctx, dev, world, rank):
     for _ in range(e_reps):
         d.get_msd_from_arrays(host, steps_e, batch_frames=16)
     torch.cuda.synchronize()
-    e2e = world * n * Te * e_reps / (time.perf_counter() - t0)
+    e2e = world * n * Te * e_reps / (time.perf_counter() - t0)        # each rank streams its own atoms: PCIe lanes in parallel
     peaks = measured_peaks()
     hbm = peaks.get("hbm_gbs", 6650.0)
     src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    achieved = n * T * MSD_BYTES_PER_ATOM_FRAME / (kms / max(kn, 1) * 1e-3) / 1e9
+    achieved = n_local * T * steps * MSD_BYTES_PER_ATOM_FRAME / (kms * 1e-3) / 1e9   # this rank's bytes over its kernel time
     cpu = cpu_msd_sample(5.0) if (rank == 0 and not args.skip_cpu) else (None, None, "skipped")
     return {
-        "metric": "msd_atom_frames_per_s", "value": value, "unit": "atom-frames/s",
-        "config": {"workload": f"C3 shape: {n} atoms, resident chunk of {T} frames ({n * T * 24 / 1e9:.1f} GB, larger than L2), "
-                               "single-origin MSD (diffusion.py:207-218)", "parallelism": f"atoms x{world}"},
-        "ms_per_step": ms / steps, "steps": steps,
+        "metric": "msd_atom_frames_per_s", "value": value, "unit": "atom-frames/s", "scaling": "strong",
+        "config": {"workload": f"C3: {nfull} atoms x {T} frames ({nfull * T * 24 / 1e9:.0f} GB of fp64 coordinates), single-origin MSD "
+                               f"(diffusion.py:207-218); resident chunks of {ca} atoms x {T} frames ({ca * T * 24 / 1e9:.1f} GB, "
+                               f"generated on the device, {len(mine)} per GPU)", "parallelism": f"atoms x{world}"},
+        "ms_per_step": ms / steps, "steps": steps, "msd_last_frame": msd_last, "kernel_launches": kn,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": ncu_traffic("msd_single", n * T / (1_000_000 * 64.0)),
+                     "traffic": ncu_traffic("msd_single", n_local * T * steps / max(kn, 1) / (1_000_000 * 64.0)),
                      "peak_source": src, "note": "k_msd_single only; 24 algorithmic bytes per atom-frame; traffic = dram bytes of "
                                                  "the 64-frame launch in profiles/r01e_k_msd_single.txt (1.545 GB for 1.536 GB "
                                                  "algorithmic) scaled to this launch"},
         "e2e": {"value": e2e, "unit": "atom-frames/s", "h2d_bytes_per_step": Te * 3 * n * 8, "d2h_bytes_per_step": Te * 32,
-                "api": "Diffusion.get_msd_from_arrays (pinned host frames)"},
+                "api": f"Diffusion.get_msd_from_arrays (pinned host frames; {n} atoms x {Te} frames per rank)"},
         "cpu_baseline": {"value": cpu[0], "unit": "atom-frames/s", "cores": cpu[1], "kind": "port", "sample": cpu[2]},
         "all_origins": allo,
     }
@@ -564,22 +678,46 @@ def bench_green_kubo(args, torch, dist, ops, ctx, dev, world, rank):
     correlations of a 100 000-step series: 27 conductivity channels (3 axes x 9 ordered type pairs incl. totals) + 3
     pressure-tensor channels = 30 channels, direct sum in fp64 FMA (FP64-pipe bound: T(T+1)/2 FMAs per channel).
     Channels are split over the ranks."""
+    from mdproptools_b200 import dist as mdist
     n, nmol, per = 50_000, 5_000, 10
-    Tf = args.gk_flux_frames
+    Tf_total = args.gk_flux_frames                      # C4: 100 000 frames of velocities = 120 GB, frames split over ranks
+    f_lo, f_hi = mdist.shard_range(Tf_total, rank, world)
+    CH = 8192                                           # resident chunk: 8192 frames = 9.8 GB, generated on the device
     g = torch.Generator(device="cuda")
-    g.manual_seed(SEED + 200 + rank)
-    vel = torch.randn((Tf, 3, n), generator=g, dtype=torch.float64, device=dev) * 1e-3
     masses = torch.tensor([12.01, 1.008, 14.01, 16.0, 19.0, 32.06, 12.01, 1.008, 16.0, 19.0], dtype=torch.float64, device=dev).repeat(nmol)
     q = torch.cat([torch.full((n // 2,), 0.1, dtype=torch.float64, device=dev), torch.full((n // 2,), -0.1, dtype=torch.float64, device=dev)])
     seg_off = torch.arange(0, n + 1, per, dtype=torch.int32, device=dev)
     type_off = np.array([0, nmol // 2, nmol], dtype=np.int64)
-    out = torch.zeros((3, 2, Tf), dtype=torch.float64, device=dev)
-    # the ABI takes <= 65535 frames per call
-    ms_f, kms_f, kn_f = _timed(ctx, torch, 4, lambda: ops.charge_flux(vel, masses, q, seg_off, type_off, 1e5, 1.602e-19, out=out), 5)
+    ms_f = kms_f = 0.0
+    kn_f = 0
+    reps_f = 3
+    vel = None
+    flux_sum = 0.0
+    for c0f in range(f_lo, f_hi, CH):
+        k = min(CH, f_hi - c0f)
+        del vel
+        g.manual_seed(SEED + 200 + c0f)                 # a chunk's content depends on its first frame only
+        vel = torch.randn((k, 3, n), generator=g, dtype=torch.float64, device=dev).mul_(1e-3)
+        out = torch.zeros((3, 2, k), dtype=torch.float64, device=dev)
+        # the ABI takes <= 65535 frames per call
+        a_, b_, c_ = _timed(ctx, torch, 4, lambda: ops.charge_flux(vel, masses, q, seg_off, type_off, 1e5, 1.602e-19, out=out), reps_f)
+        ms_f += a_
+        kms_f += b_
+        kn_f += c_
+        flux_sum += float(out.abs().sum().item())
+    del vel
+    tf = torch.tensor([ms_f, flux_sum], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = tf.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tf, op=dist.ReduceOp.SUM)
+        ms_f_max, flux_sum = float(tm[0].item()), float(tf[1].item())
+    else:
+        ms_f_max = ms_f
     peaks = measured_peaks()
     hbm = peaks.get("hbm_gbs", 6650.0)
-    flux_gbs = n * Tf * 24 / (kms_f * 1e-3) / 1e9
-    del vel
+    Tf = f_hi - f_lo
+    flux_gbs = n * Tf * 24 / (kms_f * 1e-3) / 1e9 if kms_f > 0 else 0.0
     T = args.gk_steps
     C_all = 30
     c0, c1 = (rank * C_all) // world, ((rank + 1) * C_all) // world
@@ -594,18 +732,39 @@ def bench_green_kubo(args, torch, dist, ops, ctx, dev, world, rank):
     fma = C * T * (T + 1) // 2
     fma_peak = peaks.get("fp64_fma_tflops_burst", 2 * 148 * 64 * 1.965e9 / 1e12)
     ach = 2 * fma / (kms_x * 1e-3) / 1e12
+    use_fft = ops.xcorr_fft_enabled(T)
+    if use_fft:
+        # FFT route (the default at this length): HBM-bound.  Algorithmic bytes = the two input series read once and the
+        # correlation written once (24 B per channel-step); the radix-2 Stockham passes move far more (2 log2 N stages x
+        # 32 B per point of the padded transform), which is what `traffic` states
+        p2 = 1
+        while (1 << p2) < 2 * T:
+            p2 += 1
+        alg = C * T * 24
+        moved = C * (1 << p2) * 16 * 2 * (2 * p2 + 2)
+        gbs = alg / (kms_x * 1e-3) / 1e9
+        roof_x = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": moved,
+                  "note": f"mdp_xcorr_fft (all its launches: twiddles, load, 2 x {p2} radix-2 stages, cross spectrum, store); "
+                          f"algorithmic bytes = 24 B per channel-step; traffic = bytes the {2 * p2 + 2} passes move (computed, "
+                          f"not measured: {moved / 1e9:.2f} GB -> {moved / (kms_x * 1e-3) / 1e9:.0f} GB/s); the same job as a direct "
+                          f"sum costs {fma:.3g} FMAs ({ach:.0f} TFLOP/s-equivalent at this time)"}
+    else:
+        roof_x = {"bound": "fp64", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s", "frac": ach / fma_peak, "traffic": None,
+                  "note": "k_xcorr only; 2 flops per fp64 FMA, T(T+1)/2 FMAs per channel; peak = measured DFMA rate "
+                          "(tools/peaks.cu); inputs are a few MB, HBM bandwidth is not a meaningful bound here"}
     # the integral on device as well (conductivity.py:231)
     corr = ops.xcorr_unbiased(a, b)
     ms_c, _, _ = _timed(ctx, torch, 7, lambda: ops.cumtrapz(corr, 1.0, 1.0, True), 3)
     return {
         "metric": "acf_lag_products_per_s", "value": C_all * T * (T + 1) // 2 / (ms_x_max * 1e-3), "unit": "fp64 FMA/s",
-        "config": {"workload": f"C4 shape: {C_all} channels x {T} steps, unbiased correlation at every lag (direct sum), "
-                               f"channels x{world}; charge flux on {n} atoms x {Tf} resident frames ({n * Tf * 24 / 1e9:.1f} GB)"},
+        "method": "fft (radix-2 Stockham, fp64)" if use_fft else "direct sum",
+        "config": {"workload": f"C4 shape: {C_all} channels x {T} steps, unbiased correlation at every lag, "
+                               f"channels x{world}; charge flux on {n} atoms x {Tf_total} frames ({n * Tf_total * 24 / 1e9:.0f} GB, frames "
+                               f"x{world}, resident chunks of {CH} frames generated on the device)"},
         "ms_per_step": ms_x_max, "cumtrapz_ms": ms_c,
-        "roofline": {"bound": "fp64", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s", "frac": ach / fma_peak, "traffic": None,
-                     "note": "k_xcorr only; 2 flops per fp64 FMA, T(T+1)/2 FMAs per channel; peak = measured DFMA rate "
-                             "(tools/peaks.cu); inputs are a few MB, HBM bandwidth is not a meaningful bound here"},
-        "charge_flux": {"value": world * n * Tf / (ms_f * 1e-3), "unit": "atom-frames/s", "ms_per_step": ms_f,
+        "roofline": roof_x,
+        "charge_flux": {"value": n * Tf_total / (ms_f_max * 1e-3), "unit": "atom-frames/s", "ms_per_step": ms_f_max, "scaling": "strong",
+                        "abs_flux_sum": flux_sum,
                         "roofline": {"bound": "hbm", "achieved": flux_gbs, "peak": hbm, "unit": "GB/s", "frac": flux_gbs / hbm,
                                      "traffic": None, "note": "k_charge_flux only (two molecule types = two launches, each reads "
                                                               "its own molecules); 24 B per atom-frame in total"}},
@@ -809,7 +968,9 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
+    ap.add_argument("--frames", "--frames-per-step", dest="frames", type=int, default=FRAMES_TOTAL,
+                    help="frames of the C2 trajectory (the whole job; split over the GPUs)")
+    ap.add_argument("--nrank-checks", type=int, default=3, help="N>1: how many other ranks' first frames rank 0 recomputes")
     ap.add_argument("--msd-atoms", type=int, default=MSD_ATOMS)
     ap.add_argument("--msd-frames", type=int, default=MSD_FRAMES)
     ap.add_argument("--skip-msd", action="store_true")
@@ -820,7 +981,7 @@ def main():
     ap.add_argument("--skip-gk", action="store_true")
     ap.add_argument("--skip-residence", action="store_true")
     ap.add_argument("--gk-steps", type=int, default=100_000)
-    ap.add_argument("--gk-flux-frames", type=int, default=4096)
+    ap.add_argument("--gk-flux-frames", type=int, default=100_000)
     ap.add_argument("--res-frames", type=int, default=5000)
     args = ap.parse_args()
     # stdout carries exactly one JSON line (rank 0): anything a library prints there while the bench runs (NCCL's

@@ -80,7 +80,7 @@ _PROTOS = {
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 
-PAIR_NO_CULL, PAIR_NO_SORT, PAIR_TRICLINIC, PAIR_QUEUE_BINNING = 1, 2, 4, 8   # flags of mdp_pair_hist / mdp_pair_list
+PAIR_NO_CULL, PAIR_NO_SORT, PAIR_TRICLINIC, PAIR_QUEUE_BINNING, PAIR_F64 = 1, 2, 4, 8, 16   # flags of mdp_pair_hist / mdp_pair_list
 
 
 def lib() -> ctypes.CDLL:
@@ -160,7 +160,8 @@ class Context:
     def pair_stats(self) -> dict:
         out = (c_int64 * 4)()
         check(lib().mdp_ctx_pair_stats(self.handle, out), "mdp_ctx_pair_stats")
-        return {"items": int(out[0]), "nominal_tile_pairs": int(out[1]), "pair_evals": int(out[2])}
+        return {"items": int(out[0]), "nominal_tile_pairs": int(out[1]), "pair_evals": int(out[2]),
+                "exact_path_pairs": int(out[3])}    # pairs k_pair_fast settled in fp64 (0 for the all-fp64 kernel)
 
 
 def ptr(t):

@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "libmdprop_b200.so")
 
 CU_SOURCES = ["ctx.cu", "pair.cu", "reduce.cu", "corr.cu", "dump_device.cu", "survival.cu", "shell.cu", "fftcorr.cu"]
 CPP_SOURCES = ["dump_parse.cpp"]
-HEADERS = ["common.cuh", "dump_line.h", "dump_rows.h", "survival_runs.h", "shell_grid.h", "fft_corr.h", os.path.join("..", "..", "include", "mdprop_b200.h")]
+HEADERS = ["common.cuh", "pair_fast.cuh", "dump_line.h", "dump_rows.h", "survival_runs.h", "shell_grid.h", "fft_corr.h", os.path.join("..", "..", "include", "mdprop_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -54,13 +54,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc, cxx = _nvcc(), _host_cxx()
+    extra = os.environ.get("MDP_NVCC_EXTRA", "").split()          # e.g. -DMDP_FAST_CTAS=2 for A/B builds
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for s in CU_SOURCES:
         o = os.path.join(objdir, s + ".o")
-        cmd = [nvcc, "-ccbin", cxx] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc, "-ccbin", cxx] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s in CPP_SOURCES:

@@ -731,6 +731,11 @@ struct PairParams {
     unsigned long long *list_count;
     int frame0;                      // global index of the first frame of this sub-batch
     int nocull;                      // MDP_PAIR_NO_CULL: evaluate every chunk pair on the general path
+    // k_pair_fast (pair_fast.cuh): error-bound terms in bins, already times the 1.5 safety factor
+    float f_rc;                      // cutoff radius, rounded up
+    float f_c1;                      // 1.5 * sqrt(3) * 2^-24 / ddr: bins per A of coordinate error
+    float f_rel;                     // 1.5 * (nbins + 1) * RHO: the relative part
+    int f_smax;                      // most fraction bits the 2^23 trick leaves room for
 };
 
 struct Shared {
@@ -1348,6 +1353,12 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
     if (lane == 0 && my_evals) atomicAdd(&p.stats[2], my_evals * (unsigned long long)GS);
 }
 
+} // namespace
+
+#include "pair_fast.cuh"
+
+namespace {
+
 // out[f][r][b] = sum_rows w[r][row] * (cumulative ? prefix : value) hist[f][row][b]
 __global__ void __launch_bounds__(256) k_hist_reduce(const unsigned long long *__restrict__ hist, int rows, int nbins,
                                                      int nout, const int *__restrict__ wts, int cumulative,
@@ -1465,6 +1476,27 @@ static pair_kernel_t pick_kernel(bool multicls, bool symm, bool tric)
     return tric ? pick_kernel2<MODE, true>(multicls, symm) : pick_kernel2<MODE, false>(multicls, symm);
 }
 
+template <int NCTA>
+static pair_kernel_t pick_fast_n(bool multicls, bool symm, bool tric)
+{
+    if (tric) {
+        if (multicls) return symm ? k_pair_fast<true, true, true, NCTA> : k_pair_fast<true, false, true, NCTA>;
+        return symm ? k_pair_fast<false, true, true, NCTA> : k_pair_fast<false, false, true, NCTA>;
+    }
+    if (multicls) return symm ? k_pair_fast<true, true, false, NCTA> : k_pair_fast<true, false, false, NCTA>;
+    return symm ? k_pair_fast<false, true, false, NCTA> : k_pair_fast<false, false, false, NCTA>;
+}
+static int fast_ctas()
+{
+    const char *e = getenv("MDP_FAST_CTAS");   // A/B measurements: resident CTAs per SM the kernel is compiled for
+    const int v = e ? atoi(e) : FAST_CTAS_PER_SM;
+    return v == 2 ? 2 : 3;
+}
+static pair_kernel_t pick_fast(bool multicls, bool symm, bool tric)
+{
+    return fast_ctas() == 2 ? pick_fast_n<2>(multicls, symm, tric) : pick_fast_n<3>(multicls, symm, tric);
+}
+
 struct PairCall {
     int mode = MODE_HIST_UNIFORM;
     int nframes = 0;
@@ -1567,11 +1599,30 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
     // and rsq >= rcut2 must imply bin >= nbins (edge[nbins] <= rcut2), which holds whenever nbins = int(r_cut/bin_size)
     const bool direct = c.mode == MODE_HIST_UNIFORM && edges_in_smem && c.nbins <= 4096 && c.edges[c.nbins] <= c.rcut2 &&
                         !(c.flags & MDP_PAIR_QUEUE_BINNING);
-    pair_kernel_t kern = direct                        ? pick_kernel<MODE_HIST_DIRECT>(multicls, symm, tric)
+    // the fp32-filtered kernel (pair_fast.cuh) serves the uniform-bin histograms unless the caller asks for the fp64 one
+    int f_smax = 0;
+    {
+        int bits = 0;
+        while ((1 << bits) <= c.nbins + FAST_XROW) ++bits;
+        f_smax = std::min(12, 22 - bits);
+    }
+    const size_t fast_smem = NWARP * FAST_WARP_BYTES + ((sizeof(FrameConst) + 15) & ~(size_t)15) +
+                             (multicls ? (size_t)((ncp * 4 + 15) & ~15) : 0) + 32 + (size_t)nrows * (c.nbins + FAST_XROW) * 4;
+    const bool fast = c.mode == MODE_HIST_UNIFORM && !nocull && c.edges[c.nbins] <= c.rcut2 && f_smax >= 6 &&
+                      !(c.flags & (MDP_PAIR_QUEUE_BINNING | MDP_PAIR_F64)) && Bp.npad < ((int64_t)1 << 22) &&
+                      fast_smem <= ctx->smem_optin && !getenv("MDP_PAIR_F64");
+    if (fast) smem = fast_smem;
+    pair_kernel_t kern = fast                          ? pick_fast(multicls, symm, tric)
+                         : direct                      ? pick_kernel<MODE_HIST_DIRECT>(multicls, symm, tric)
                          : c.mode == MODE_HIST_UNIFORM ? pick_kernel<MODE_HIST_UNIFORM>(multicls, symm, tric)
                          : c.mode == MODE_HIST_TABLE ? pick_kernel<MODE_HIST_TABLE>(multicls, symm, tric)
                                                      : pick_kernel<MODE_LIST>(false, symm, tric);
     MDP_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = CTAS_PER_SM;
+    if (fast) {
+        MDP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, (const void *)kern, NWARP * 32, smem));
+        ctas_per_sm = std::max(1, std::min(ctas_per_sm, fast_ctas()));
+    }
 
     MDP_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), st));
 
@@ -1682,9 +1733,17 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         p.list_count = (unsigned long long *)c.list_count;
         p.frame0 = f0;
         p.nocull = nocull ? 1 : 0;
+        if (fast) {
+            const double rho = 1.0 / 4194304.0 + 3.5 / 16777216.0, safety = 1.5 * 1.02;
+            const double rcd = sqrt(c.rcut2);
+            p.f_rc = (float)(rcd * (1.0 + 1e-6));
+            p.f_c1 = (float)(safety * sqrt(3.0) / 16777216.0 / c.uniform_ddr);
+            p.f_rel = (float)(safety * (c.nbins + 1) * rho);
+            p.f_smax = f_smax;
+        }
         MDP_CUDA(cudaMemsetAsync(d_fcount, 0, (size_t)F * 4, st));
         cudaEvent_t tk = ctx->timer_begin(0, st);
-        kern<<<ctx->sm_count * CTAS_PER_SM, NWARP * 32, smem, st>>>(p);
+        kern<<<ctx->sm_count * ctas_per_sm, NWARP * 32, smem, st>>>(p);
         ctx->timer_end(tk, st);
         MDP_LAUNCHED(ctx);
         rc = mdp_check_launch("k_pair");

@@ -64,6 +64,28 @@ def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def all_gather_blocks(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Inverse of ``shard_range``: every rank holds rows [lo, hi) of an [n_total, ...] array (``local`` = those rows) and
+    gets the whole array.  One ``all_gather_into_tensor`` of blocks padded to the longest shard (at most one row of
+    padding per rank) -- the bytes on the wire are the array itself, not world_size zero-padded copies of it."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return local
+    w = d.get_world_size()
+    longest = (n_total + w - 1) // w
+    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((w * longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    d.all_gather_into_tensor(out, pad)
+    if n_total == w * longest:
+        return out
+    parts = []
+    for r in range(w):
+        lo, hi = shard_range(n_total, r, w)
+        parts.append(out[r * longest: r * longest + (hi - lo)])
+    return torch.cat(parts, dim=0)
+
+
 def barrier():
     d = _dist()
     if d and d.get_world_size() > 1:

@@ -99,20 +99,33 @@ class Conductivity:
         sel = (lambda i: i % w == r) if w > 1 else None
         batches = FrameBatches(pattern, want, frame_select=sel)
         pieces, times = [], {}
-        dev = None
+        dev = torch.device("cuda", torch.cuda.current_device())    # a rank without frames still joins the collectives
+        seg_d = torch.from_numpy(seg_off.astype(np.int32)).to(dev)
+        vs, qs = constants.VELOCITY_CONVERSION[self.units], constants.CHARGE_CONVERSION[self.units]
         for batch in batches:
             d = batch.wait()
-            dev = d.device
-            host0 = batch.host[0].numpy()
-            n = host0.shape[1]
+            host = batch.host.numpy()
+            n = host.shape[2]
             if seg_off[-1] != n:
                 raise ValueError(f"Length of values ({seg_off[-1]}) does not match length of index ({n})")
-            m_atom = atom_masses(host0[1], self.mass) if self.mass else host0[batch.col("mass")]
-            q = d[0, 2].contiguous()
+            mcol = None if self.mass else batch.col("mass")
+
+            def masses(k):
+                return atom_masses(host[k, 1], self.mass) if self.mass else host[k, mcol]
+
             vel = d[:, 3:6, :].contiguous()
-            j = ops.charge_flux(vel, torch.from_numpy(np.ascontiguousarray(m_atom)).to(dev), q,
-                                torch.from_numpy(seg_off.astype(np.int32)).to(dev), type_off,
-                                constants.VELOCITY_CONVERSION[self.units], constants.CHARGE_CONVERSION[self.units])
+            # the kernel sums each molecule's charge and mass once per call; the reference does it per frame
+            # (_conductivity.py:11-18), so one call serves the batch only when q, type and mass do not change inside it
+            # (fixed-charge force fields); fluctuating charges (QEq, polarisable models) take one call per frame
+            static = bool((host[:, 2] == host[0, 2]).all() and (host[:, 1] == host[0, 1]).all()
+                          and (mcol is None or (host[:, mcol] == host[0, mcol]).all()))
+            if static:
+                j = ops.charge_flux(vel, torch.from_numpy(np.ascontiguousarray(masses(0))).to(dev), d[0, 2].contiguous(),
+                                    seg_d, type_off, vs, qs)
+            else:
+                j = torch.cat([ops.charge_flux(vel[k:k + 1], torch.from_numpy(np.ascontiguousarray(masses(k))).to(dev),
+                                               d[k, 2].contiguous(), seg_d, type_off, vs, qs)
+                               for k in range(vel.shape[0])], dim=2)
             pieces.append(([m.index for m in batch.metas], j))
             for m in batch.metas:
                 times[m.index] = m.timestep * constants.TIME_CONVERSION[self.units] * self.timestep

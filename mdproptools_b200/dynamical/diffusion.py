@@ -310,3 +310,42 @@ class Diffusion:
             msd.loc[:, col] = msd[col] * constants.DISTANCE_CONVERSION[self.units] ** 2
         msd["Time (s)"] = full_log["Step"] * self.timestep * constants.TIME_CONVERSION[self.units]
         return msd
+
+    def get_diff_dist(self, msd_int, dump_freq, dimension=3, tao_coeff=4, plot=False, diff_names=None):
+        """Distribution of per-atom / per-molecule diffusion coefficients from the interval-averaged MSD ``msd_int`` of
+        ``get_msd_from_dump(avg_interval=True)`` (:410-516): adds the column
+        ``diff = msd / (2 * dimension * tao_coeff * dump_freq * timestep * TIME_CONVERSION)`` in place and returns the frame.
+        With ``plot`` the histograms (one panel per molecule type when a ``type`` column is present) go to
+        ``<diff_dir>/diff_dist.png``; matplotlib is imported only then."""
+        delta = dump_freq * self.timestep * constants.TIME_CONVERSION[self.units]
+        msd_int["diff"] = msd_int["msd"] / (2 * dimension * tao_coeff * delta)
+        if plot:
+            try:
+                import matplotlib
+                matplotlib.use("Agg")
+                import matplotlib.pyplot as plt
+            except ImportError as exc:
+                raise ImportError("plot=True needs matplotlib") from exc
+            if "type" in msd_int.columns:
+                groups = msd_int.groupby("type")
+                ind = diff_names or [i + 1 for i in range(len(groups))]
+                ncols = 2
+                nrows = int(np.ceil(groups.ngroups / ncols))
+                fig, axes = plt.subplots(nrows, ncols, figsize=(12, 8), squeeze=False)
+                for ax, (key, grp) in zip(axes.flatten(), groups):
+                    ax.hist(grp["diff"] * 10 ** 9, bins=max(1, int(np.sqrt(len(grp)))), density=True, edgecolor="k",
+                            label=str(ind[key - 1]))
+                    ax.legend(frameon=False)
+                    ax.set_xlabel("Diffusivity, 10^-9 (m^2/s)")
+                    ax.set_ylabel("Frequency")
+                if len(groups) % 2 != 0:
+                    fig.delaxes(ax=axes.flatten()[-1])
+            else:
+                fig, ax = plt.subplots(figsize=(8, 6))
+                ax.hist(msd_int["diff"] * 10 ** 9, bins=max(1, int(np.sqrt(len(msd_int)))), density=True, edgecolor="k")
+                ax.set_xlabel("Diffusivity, 10^-9 (m^2/s)")
+                ax.set_ylabel("Frequency")
+            fig.tight_layout()
+            fig.savefig(f"{self.diff_dir}/diff_dist.png", bbox_inches="tight", pad_inches=0.1)
+            plt.close(fig)
+        return msd_int

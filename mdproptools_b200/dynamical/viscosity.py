@@ -146,12 +146,21 @@ class Viscosity:
             plt.close(fig)
         return viscosity
 
-    def bootstrapping(self, visc_avg, num_samples, sample_size, initial_guess=[1e-10, 0.8, 1.1e4, 1.1e4], seed=None):
-        """(:382-434) resample replicates with replacement and refit; returns the list of fitted viscosities."""
-        rng = np.random.default_rng(seed)
-        visc_avg = np.asarray(visc_avg)
-        out = []
-        for _ in range(num_samples):
-            pick = rng.integers(0, len(visc_avg), size=sample_size)
-            out.append(self.fit_avg_visc(visc_avg[pick], initial_guess=initial_guess))
-        return out
+    def bootstrapping(self, visc_avg, num_replicates, tot_replicates, initial_guess=[1e-10, 0.8, 1.1e4, 1.1e4], plot=True,
+                      seed=None):
+        """(:382-434) ``tot_replicates`` bootstrap iterations, each refitting the mean of ``num_replicates`` running integrals
+        drawn WITHOUT replacement (``random.sample``, as the reference: no replicate twice within one iteration); returns
+        ``(mean viscosity, std)`` of the fitted values.  ``seed`` (an addition, trailing keyword) makes the draw reproducible;
+        None uses the global ``random`` state exactly as the reference does."""
+        import random
+        rnd = random.Random(seed) if seed is not None else random
+        idx = np.zeros((tot_replicates, num_replicates), dtype=int)
+        for i in range(tot_replicates):
+            idx[i] = rnd.sample(range(len(visc_avg)), num_replicates)
+        visc_samples = np.array(visc_avg)[idx]
+        all_visc = []
+        for ind, visc in enumerate(visc_samples):
+            print(f"Fitting viscosity sample {ind + 1} out of {len(visc_samples)}")
+            all_visc.append(self.fit_avg_visc(visc_avg=visc, initial_guess=initial_guess, plot=plot,
+                                              plot_file=f"viscosity_{ind + 1}.png"))
+        return np.average(all_visc), np.std(all_visc)

@@ -332,7 +332,7 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
 
     batches = _frame_batches(filename, ["id", "type", "x", "y", "z"])
     counts, props = {}, {}
-    device = None
+    device = torch.device("cuda", torch.cuda.current_device())   # a rank that receives no frames still joins the merge
     for batch in batches:
         dev = batch.wait()
         device = dev.device
@@ -409,7 +409,7 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
 
     batches = _frame_batches(filename, ["id", "type", "x", "y", "z"])
     counts, props = {}, {}
-    device = None
+    device = torch.device("cuda", torch.cuda.current_device())   # a rank that receives no frames still joins the merge
     for batch in batches:
         dev = batch.wait()
         device = dev.device
@@ -460,7 +460,7 @@ def _molecular_common(filename, num_types, mass, partial_relations, num_mols, nu
     mol_types_count = _value_counts(mol_type)
     batches = _frame_batches(filename, ["id", "type", "x", "y", "z"])
     counts, props = {}, {}
-    device = None
+    device = torch.device("cuda", torch.cuda.current_device())   # a rank that receives no frames still joins the merge
     for batch in batches:
         dev = batch.wait()
         device = dev.device
@@ -557,7 +557,7 @@ def calc_molecular_cn(r_cut, bin_size, num_types, mass, partial_relations, filen
 
 
 def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, partial_relations, batch_frames=64,
-                                return_counts=False, mic="reference"):
+                                return_counts=False, mic="reference", frame_range=None):
     """Array front end of :func:`calc_atomic_rdf` for trajectories that are already in memory.
 
     positions   float64 [T, 3, N] host array (numpy, or a pinned torch tensor for async copies), rows in id order
@@ -567,15 +567,27 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
     Everything else as in calc_atomic_rdf; same per-frame normalisation (rdf_cn.py:297-329, 502-521), same DataFrame.
     Frames stream through pinned staging buffers: the copy of batch k+1 overlaps the kernels of batch k.
     With ``return_counts`` the raw integer histograms [T, 1+R, nbins] (g_full row first) are returned as well.
+
+    Under an initialised process group the T frames are split in contiguous blocks over the ranks (``dist.shard_range``);
+    ``positions`` then holds either all T frames on every rank, or only this rank's block with ``frame_range=(lo, hi, T)``
+    saying which block of a T-frame trajectory it is.  The per-frame integer histograms are all-gathered (exact) and every
+    rank returns the same DataFrame.
     """
     pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, dtype=np.float64))
     T, _, N = pos.shape
+    if frame_range is not None:
+        lo, hi, T = (int(v) for v in frame_range)
+        if (lo, hi) != dist.shard_range(T) or pos.shape[0] != hi - lo:
+            raise ValueError(f"frame_range {frame_range} is not this rank's block {dist.shard_range(T)} of {T} frames")
+    else:
+        lo, hi = dist.shard_range(T)
+        pos = pos[lo:hi]
     num_bins, radii = _num_bins(r_cut, bin_size)
     num_relations = len(partial_relations[0])
     relation_matrix = np.asarray(partial_relations).transpose()
     dev = torch.device("cuda", torch.cuda.current_device())
-    batches = iter(ArrayBatches(pos, batch_frames, dev))          # the copy of the first batch starts now, under the host prep
-    first = next(batches, None)
+    batches = iter(ArrayBatches(pos, batch_frames, dev)) if hi > lo else iter(())   # (a rank beyond the last frame has no block)
+    first = next(batches, None)                                   # the copy of the first batch starts now, under the host prep
     types = np.asarray(types)
     at_all = _value_counts(types)                                 # one pass over the types serves the class map too
     cmap = _ClassMap(list(partial_relations[0]) + list(partial_relations[1]), present_types=list(at_all))
@@ -588,7 +600,7 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
     if static_types:
         cls_static = torch.from_numpy(cmap.classes_of(types)).to(dev)
         at_static = at_all
-    out = torch.empty((T, 1 + num_relations, num_bins), dtype=torch.int64, device=dev)
+    out = torch.empty((hi - lo, 1 + num_relations, num_bins), dtype=torch.int64, device=dev)
 
     def _all_batches():
         if first is not None:
@@ -596,10 +608,10 @@ def calc_atomic_rdf_from_arrays(positions, types, box_lengths, r_cut, bin_size, 
             yield from batches
 
     for f0, f1, x in _all_batches():                             # copy of batch k+1 overlaps the kernels of batch k
-        cls = cls_static if static_types else torch.from_numpy(np.stack([cmap.classes_of(t) for t in types[f0:f1]])).to(dev)
-        hist = ops.pair_hist(x, cls, cmap.ncls, boxes[f0:f1], rcut2, edges, bin_size, flags=flags)
+        cls = cls_static if static_types else torch.from_numpy(np.stack([cmap.classes_of(t) for t in types[lo + f0:lo + f1]])).to(dev)
+        hist = ops.pair_hist(x, cls, cmap.ncls, boxes[lo + f0:lo + f1], rcut2, edges, bin_size, flags=flags)
         out[f0:f1] = ops.hist_reduce(hist, weights)
-    counts = out.cpu().numpy()
+    counts = dist.all_gather_blocks(out, T).cpu().numpy()
     rdf_full_sum = np.zeros(num_bins)
     rdf_part_sum = np.zeros((num_relations, num_bins))
     den_cache = {}   # frames with the same composition and volume share their divisors (the usual NVT case: one entry)
