@@ -271,14 +271,17 @@ __device__ __forceinline__ void fast_run(const FastRunP &R, const FastExact &ex,
     for (int j0 = 0; j0 < nj; j0 += 4) {
         unsigned b[4];
         bool unc = false;
+        float jx[4], jy[4], jz[4];
+        unsigned jm[4];
+        // the four candidates first (back-to-back loads, nothing depends on the previous one), then the arithmetic
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(jx[u]), "=f"(jy[u]), "=f"(jz[u]), "=r"(jm[u])
+                         : "r"(ja + (unsigned)(j0 + u) * 16u));
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            float jx, jy, jz;
-            unsigned jm;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(jx), "=f"(jy), "=f"(jz), "=r"(jm)
-                         : "r"(ja + (unsigned)(j0 + u) * 16u));
-            float dx = xi - jx, dy = yi - jy, dz = zi - jz;
+            float dx = xi - jx[u], dy = yi - jy[u], dz = zi - jz[u];
             if (MIXED) {
                 dx = fminf(fabsf(dx), fabsf(fabsf(dx) - l32x));
                 dy = fminf(fabsf(dy), fabsf(fabsf(dy) - l32y));
@@ -292,10 +295,13 @@ __device__ __forceinline__ void fast_run(const FastRunP &R, const FastExact &ex,
             v = v < clampv ? v : clampv;
             b[u] = v;
             unc = unc || ((v & mask) == 0u);
-            unsigned a = base + ((v >> s) << 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            unsigned a = base + ((b[u] >> s) << 2);
             if (MULTICLS) {
                 unsigned row;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(R.cptab_mi_a + ((jm & 63u) << 2)));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(R.cptab_mi_a + ((jm[u] & 63u) << 2)));
                 a += row;
             }
             asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");

@@ -29,6 +29,19 @@ def sample_dir(tmp_path_factory):
 
 
 @pytest.fixture(scope="session")
+def c1_dir(tmp_path_factory):
+    """config C1 at full length: all 101 frames of the reference's data/mg_tfsi_dme, columns id type x y z xu yu zu
+    (oracle/make_c1_fixture.py; 24 MB, git-ignored, travels to the GPU box with the snapshot)"""
+    path = os.path.join(ROOT, "tests", "golden_large", "c1_frames.tar.gz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden_large/c1_frames.tar.gz is absent (python oracle/make_c1_fixture.py builds it from /root/reference)")
+    d = tmp_path_factory.mktemp("c1_frames")
+    with tarfile.open(path) as tf:
+        tf.extractall(d)
+    return str(d)
+
+
+@pytest.fixture(scope="session")
 def mini_dir(tmp_path_factory):
     return _extract("mini_traj.tar.gz", tmp_path_factory)
 

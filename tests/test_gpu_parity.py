@@ -807,3 +807,101 @@ def test_calc_atomic_rdf_triclinic_api(tmp_path):
     assert abs(a[40:, 1].mean() - 1.0) < 0.02
     with pytest.raises(ValueError):
         rdf_cn.calc_atomic_rdf(8.0, 0.05, 3, [1.0, 2.0, 3.0], rel, p, save_mode=False, mic="nearest")
+
+
+# ------------------------------------------------------------------------------------------------
+# config C1 at full length (101 frames): known answers of the UNMODIFIED reference, SURVEY.md 8(c)
+# ------------------------------------------------------------------------------------------------
+C1_REL = [[9, 9, 9, 9], [1, 4, 6, 9]]
+
+
+def _sha(df):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(df.values, dtype=np.float64).tobytes()).hexdigest()
+
+
+def test_c1_full_atomic_rdf_kat(c1_dir, tmp_path):
+    """calc_atomic_rdf over all 101 frames: the reference's DataFrame bit for bit (486 s on one core there)."""
+    from mdproptools_b200.structural.rdf_cn import calc_atomic_rdf
+    df = calc_atomic_rdf(20, 0.05, 9, MASS, C1_REL, os.path.join(c1_dir, "dump.nvt.*.dump"), path_or_buff=str(tmp_path / "rdf.csv"))
+    assert df.shape == (400, 6)
+    assert list(df.columns) == [r"r ($\AA$)", "g_full(r)", "g_9-1", "g_9-4", "g_9-6", "g_9-9"]
+    assert df.iloc[40, 1:].tolist() == [1.2618212188545432, 28.56133801821835, 0.0, 89.25671173472328, 0.0]
+    assert df.iloc[200, 1:].tolist() == [0.9977710416003582, 1.0339062617991446, 0.5995108632667641, 1.076978443654223,
+                                         1.986950289684134]
+    assert df.iloc[399, 1:].tolist() == [0.999904654025423, 1.0075979643460262, 0.9772216479509167, 0.9238303989734666,
+                                         0.992322203217268]
+    assert _sha(df) == "b418f238f5e58393edbe59e8419c8afe1053dada1af6959fa589ce88cfa9ccfc"
+
+
+def test_c1_full_atomic_cn_kat(c1_dir, tmp_path):
+    """calc_atomic_cn over all 101 frames (534 s on one core in the reference)."""
+    from mdproptools_b200.structural.rdf_cn import calc_atomic_cn
+    df = calc_atomic_cn([2.325, 4.375, 2.375, 13.0], 0.05, 9, MASS, C1_REL, os.path.join(c1_dir, "dump.nvt.*.dump"),
+                        path_or_buff=str(tmp_path / "cn.csv"))
+    got = {c: float(df[c].iloc[0]) for c in df.columns}
+    assert got["cn_9-1"] == 4.322232223222324 and got["cn_9-4"] == 1.0768076807680773
+    assert got["cn_9-6"] == 1.6762676267626753 and got["cn_9-9"] == 3.0483048304830462
+    assert _sha(df) == "0ad5461c6508bf07e42aeb21004303b189fbf2a1ed756a2a01fc4ce1b488bb1e"
+
+
+def test_c1_full_diffusion_kat(c1_dir, tmp_path):
+    """MSD + diffusion over all 101 frames: the survey's MSD values of the unmodified reference and the diffusion table
+    printed in the reference's example notebook (cell 17)."""
+    from mdproptools_b200.dynamical.diffusion import Diffusion
+    d = Diffusion(timestep=1, units="real", outputs_dir=c1_dir, diff_dir=str(tmp_path))
+    msd, msd_all = d.get_msd_from_dump("dump.nvt.*.dump", msd_type="allatom")[:2]
+    assert abs(msd["msd"].iloc[1] / 4.710123052923229e-19 - 1) < 1e-12
+    assert abs(msd["msd"].iloc[100] / 3.6239421444312684e-17 - 1) < 1e-12
+    msd, msd_all, msd_int = d.get_msd_from_dump("dump.nvt.*.dump", msd_type="com", num_mols=NUM_MOLS, num_atoms_per_mol=NUM_ATOMS,
+                                                mass=MASS, com_drift=True, avg_interval=True, tao_coeff=4)
+    assert abs(msd["msd1"].iloc[100] / 3.918949266310726e-17 - 1) < 1e-10
+    assert abs(msd["msd3"].iloc[100] / 5.32844116327746e-18 - 1) < 1e-10
+    diff = d.calc_diff(msd, diff_names=["dme", "tfsi", "mg"])
+    want = {"dme": (1.330522e-09, 2.164493e-12, 0.999735), "tfsi": (1.976415e-10, 2.162102e-12, 0.988174),
+            "mg": (1.585219e-10, 1.821829e-12, 0.986964)}
+    for name, (dv, sd, r2) in want.items():
+        row = diff.loc[name]
+        assert f"{row['diffusion (m2/s)']:.6e}" == f"{dv:.6e}", (name, row.tolist())       # all 7 printed digits
+        assert f"{row['std']:.6e}" == f"{sd:.6e}" and f"{row['R2']:.6f}" == f"{r2:.6f}", (name, row.tolist())
+    dist = d.get_diff_dist(msd_int, dump_freq=50000, dimension=3, tao_coeff=4)
+    assert "diff" in dist.columns and np.all(np.isfinite(dist["diff"].values))
+
+
+# ------------------------------------------------------------------------------------------------
+# N ranks == 1 rank under NCCL (needs >= 2 GPUs on the box; the driver's 1-GPU run skips it, tools/gpu_nrank_check.sh runs it)
+# ------------------------------------------------------------------------------------------------
+def test_nrank_equals_1rank_under_nccl(tmp_path):
+    """bench.py at reduced sizes on 1 GPU and under torchrun on 2 (and 4) GPUs: the same RDF histograms (sha256 of all
+    per-frame integer histograms), the same residence survival counts (sha256), the same MSD to 1e-12 -- frames, atoms and
+    central atoms are only re-distributed, never re-computed differently."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    small = ["--steps", "2", "--warmup", "1", "--frames", "24", "--msd-atoms", "400000", "--msd-frames", "200", "--gk-steps", "20000",
+             "--gk-flux-frames", "1000", "--res-frames", "400", "--skip-cpu", "--skip-msd-window"]
+
+    def run(n):
+        cmd = ([sys.executable, "bench.py", "--gpus", "1"] if n == 1 else
+               [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                "--master-port", str(29511 + n), "bench.py", "--gpus", str(n)]) + small
+        r = subprocess.run(cmd, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return json.loads(r.stdout.strip().splitlines()[-1])
+
+    one = run(1)
+    for n in [k for k in (2, 4) if k <= ngpu]:
+        many = run(n)
+        assert many["n_gpus"] == n and many["scaling"] == "strong"
+        assert many["hist_sha256"] == one["hist_sha256"]                                   # RDF counts: exact
+        assert many.get("nrank_equals_1rank") is True
+        assert many["residence"]["cnt_sha256"] == one["residence"]["cnt_sha256"]             # survival counts: exact
+        assert many["residence"]["neighbour_entries"] == one["residence"]["neighbour_entries"]
+        assert abs(many["msd"]["msd_last_frame"] / one["msd"]["msd_last_frame"] - 1) < 1e-12   # fp64 all-reduce order only
+        a, b = many["green_kubo"]["charge_flux"]["abs_flux_sum"], one["green_kubo"]["charge_flux"]["abs_flux_sum"]
+        assert abs(a / b - 1) < 1e-12
