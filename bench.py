@@ -517,6 +517,7 @@ def run_gpu(args):
 
     gk = None if args.skip_gk else bench_green_kubo(args, torch, dist, ops, ctx, dev, world, rank)
     res = None if args.skip_residence else bench_residence(args, torch, dist, ops, ctx, dev, world, rank)
+    c5s = None if args.skip_clusters else bench_clusters_hydration(args, torch, dist, ops, ctx, dev, world, rank)
 
     # every rank leaves the process group here: what follows on rank 0 (CPU baselines, host parser, the file-based leg)
     # is single-process work and must not meet a collective whose peers are gone
@@ -572,6 +573,8 @@ def run_gpu(args):
         out["green_kubo"] = gk
     if res:
         out["residence"] = res
+    if c5s:
+        out["clusters_hydration"] = c5s
     if not args.skip_cpu:
         out["dump_parse"] = bench_dump_parse()
         out["rdf_from_files"] = bench_rdf_from_files(torch, frames, N_ATOMS * (N_ATOMS - 1) // 2)
@@ -956,6 +959,113 @@ def bench_residence(args, torch, dist, ops, ctx, dev, world, rank):
     }
 
 
+def bench_clusters_hydration(args, torch, dist, ops, ctx, dev, world, rank):
+    """C5, the structural half: 200 000 atoms = 2 000 cations (1 atom) + 2 000 anions (5 atoms) + 62 666 three-site
+    waters (O, H, H) in a 126 A cubic box, T frames (default 5 000), molecule centres on a random walk (sigma 0.15 A per frame,
+    rigid translation).  Per frame (i) hydration: cation x water-O search inside 3.0 A + the cosine / counter epilogue
+    (mdp_hydration_count); (ii) clusters: cation x all-atom search inside 3.0 A + molecule completion and force filter
+    (mdp_cluster_members).  STRONG scaling: frames are split over the ranks; a rank walks its frames in resident chunks
+    generated on the device (coordinates + forces of 250 frames = 2.4 GB)."""
+    from mdproptools_b200 import dist as mdist
+    ncat, nan, nwat, L = 2_000, 2_000, 62_666, 126.0
+    n = ncat + 5 * nan + 3 * nwat
+    nmol = ncat + nan + nwat
+    T = args.c5_frames
+    t_lo, t_hi = mdist.shard_range(T, rank, world)
+    sizes = np.concatenate([np.full(ncat, 1), np.full(nan, 5), np.full(nwat, 3)])
+    seg_off = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
+    mol_of_atom = np.repeat(np.arange(nmol), sizes).astype(np.int32)
+    seg_d, moa_d = torch.from_numpy(seg_off).to(dev), torch.from_numpy(mol_of_atom).to(dev)
+    moa_l = moa_d.to(torch.int64)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED + 600)
+    centre0 = torch.rand((3, nmol), generator=g, dtype=torch.float64, device=dev) * L
+    intra = torch.randn((3, n), generator=g, dtype=torch.float64, device=dev) * 0.55       # fixed offsets inside a molecule
+    first = torch.from_numpy(seg_off[:-1].astype(np.int64)).to(dev)
+    intra[:, first] = 0.0                                                                   # first atom = molecule centre (O, cation)
+    cat_rows = torch.arange(ncat, device=dev)
+    o_rows = first[ncat + nan:]
+    CH = 250
+    GB = 50                                    # the walk is defined in blocks of 50 frames seeded by the block index
+    rc2 = 9.0
+    ms = {"hyd_search": 0.0, "hyd_epilogue": 0.0, "cl_search": 0.0, "cl_epilogue": 0.0}
+    tot = {"hyd_entries": 0, "oriented": 0, "cl_entries": 0, "cl_members": 0, "evaluated": 0}
+
+    def block_steps(b):
+        g.manual_seed(SEED + 700 + b)
+        return torch.randn((GB, 3, nmol), generator=g, dtype=torch.float64, device=dev).mul_(0.15).cumsum_(0)
+
+    # centre position at the start of this rank's first frame: sum of the whole blocks before it (cheap: one block at a time)
+    cur = centre0.clone()
+    for b in range(t_lo // GB):
+        cur += block_steps(b)[-1]
+    for c0 in range(t_lo, t_hi, CH):
+        k = min(CH, t_hi - c0)
+        cen = torch.empty((k, 3, nmol), dtype=torch.float64, device=dev)
+        for b in range(c0 // GB, (c0 + k - 1) // GB + 1):
+            st = block_steps(b)
+            a0, a1 = max(b * GB, c0), min((b + 1) * GB, c0 + k)
+            cen[a0 - c0:a1 - c0] = cur + st[a0 - b * GB:a1 - b * GB]
+            if a1 == (b + 1) * GB:
+                cur = cur + st[-1]
+            del st
+        xyz = torch.remainder(cen.index_select(2, moa_l) + intra, L)                      # [k, 3, n] wrapped atom coordinates
+        del cen
+        g.manual_seed(SEED + 800 + c0)
+        force = torch.randn((k, 3, n), generator=g, dtype=torch.float64, device=dev) * 60.0
+        boxes = np.tile(np.array([L, L, L]), (k, 1))
+        xa = xyz.index_select(2, cat_rows).contiguous()
+        xo = xyz.index_select(2, o_rows).contiguous()
+        xh1 = xyz.index_select(2, o_rows + 1).contiguous()
+        xh2 = xyz.index_select(2, o_rows + 2).contiguous()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        for rep in range(2):                   # first pass warms the arena, second is timed
+            ev[0].record()
+            lst_h, _ = ops.pair_list(xa, xo, boxes, 0.0, rc2, 0, capacity=8 * ncat * k)
+            ev[1].record()
+            cos, so_h, cnt_h = ops.hydration_count(lst_h, xa, xo, xh1, xh2, boxes, -0.72)
+            ev[2].record()
+            lst_c, _ = ops.pair_list(xa, xyz, boxes, 0.0, rc2, 0, capacity=24 * ncat * k)
+            ev[3].record()
+            so_c, mols, cnt_c = ops.cluster_members(lst_c, ncat, force, seg_d, moa_d, 0.043363 / 16, 0.75)
+            ev[4].record()
+        torch.cuda.synchronize()
+        evs = ctx.pair_stats()["pair_evals"]                      # of the last pair call = the cation x all-atom search
+        for name, a, b_ in (("hyd_search", 0, 1), ("hyd_epilogue", 1, 2), ("cl_search", 2, 3), ("cl_epilogue", 3, 4)):
+            ms[name] += ev[a].elapsed_time(ev[b_])
+        tot["hyd_entries"] += int(lst_h.shape[0])
+        tot["oriented"] += int(cnt_h[:, :, 1].sum().item())
+        tot["cl_entries"] += int(lst_c.shape[0])
+        tot["cl_members"] += int(cnt_c.sum().item())
+        tot["evaluated"] += evs
+        del xyz, force, xa, xo, xh1, xh2, lst_h, lst_c
+    t = torch.tensor([sum(ms.values())] + [ms[k_] for k_ in ("hyd_search", "hyd_epilogue", "cl_search", "cl_epilogue")], dtype=torch.float64,
+                     device=dev)
+    c = torch.tensor([tot[k_] for k_ in ("hyd_entries", "oriented", "cl_entries", "cl_members", "evaluated")], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c)
+    total_ms, hs, he, cs, ce = (float(v) for v in t.tolist())
+    hyd_entries, oriented, cl_entries, cl_members, evaluated = (int(v) for v in c.tolist())
+    nominal = T * ncat * (n + nwat)
+    peaks = measured_peaks()
+    pk = peaks.get("fp64_unfused_tflops_sustained") or 148 * 64 * 1.965e9 / 1e12
+    ach = evaluated * FLOPS_PER_PAIR / (cs * 1e-3) / 1e12 * (1.0 if world == 1 else 1.0 / world)
+    return {
+        "metric": "cluster_hydration_pair_evals_per_s", "value": nominal / (total_ms * 1e-3), "unit": "pair-evals/s", "scaling": "strong",
+        "config": {"workload": f"C5: {n} atoms ({ncat} cations, {nan} anions x 5, {nwat} waters x 3) x {T} frames, 126 A box; per frame "
+                               f"hydration (cation x water O inside 3.0 A + cosine/counter epilogue) and clusters (cation x all atoms "
+                               f"inside 3.0 A + molecule completion + force filter); frames x{world}, resident chunks of {CH} frames"},
+        "ms_per_step": total_ms, "hydration_search_ms": hs, "hydration_epilogue_ms": he, "cluster_search_ms": cs,
+        "cluster_epilogue_ms": ce, "hydration_entries": hyd_entries, "oriented_waters": oriented, "cluster_entries": cl_entries,
+        "cluster_member_molecules": cl_members,
+        "roofline": {"bound": "fp64", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
+                     "note": "the cation x all-atom search (k_pair in list mode, all-fp64) only: evaluated pairs x 11 unfused flops over "
+                             "its time; the search of 2 000 points against 200 000 is dominated by sorting and culling the large set, "
+                             "not by pair arithmetic -- the figure of merit is the time per frame"},
+    }
+
+
 def bench_rdf_from_files(torch, frames, nominal_pairs_per_frame, nfiles=32):
     """The call a user of the reference makes: calc_atomic_rdf on LAMMPS dump FILES (C2 frames written as text with
     LAMMPS' default %g, ids shuffled) -> page cache -> native parser (a batch of frames per call, one frame per host
@@ -1071,6 +1181,8 @@ def main():
     ap.add_argument("--gk-steps", type=int, default=100_000)
     ap.add_argument("--gk-flux-frames", type=int, default=100_000)
     ap.add_argument("--res-frames", type=int, default=5000)
+    ap.add_argument("--c5-frames", type=int, default=5000)
+    ap.add_argument("--skip-clusters", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly one JSON line (rank 0): anything a library prints there while the bench runs (NCCL's
     # version banner, for one) is sent to stderr instead

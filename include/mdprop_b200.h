@@ -139,6 +139,33 @@ int mdp_pair_list(mdp_ctx *ctx, int nframes,
                   const double *box, double rin2, double rout2, int shell_mode, int exclude_same_index,
                   int32_t *list_out, double *rsq_out, int64_t capacity, int64_t *count_out, int flags, void *stream);
 
+/* ---- epilogues of the cutoff searches (csrc/epilogue.cu) -------------------------------------------
+ * All take the neighbour list of mdp_pair_list (DEVICE int32 [m][3] = (frame, ia, ib), any order).
+ *
+ * mdp_list_group: the entries grouped by (frame, ia) -- segment s = frame * n_a + ia occupies slots
+ * seg_off[s] .. seg_off[s+1] (DEVICE int64 [nframes*n_a + 1]) -- and sorted inside a segment by `key` (DEVICE uint32 [m],
+ * or NULL for key = ib; ties by entry index).  key_out[slot] = key, perm_out[slot] = index of the entry (DEVICE, [m]).
+ * This is the row order the reference's per-central-atom pandas code produces (hydration_number.py:69-73,
+ * cluster_analysis.py:143-165). */
+int mdp_list_group(mdp_ctx *ctx, int nframes, int64_t n_a, int64_t m, const int32_t *list, const uint32_t *key,
+                   int64_t *seg_off, uint32_t *key_out, int64_t *perm_out, void *stream);
+/* get_angle (hydration_number.py:13-32) for every (frame, cation, water O) entry: cos between the minimum-image
+ * displacement cation - O (rdf_cn.py:46-55 with the frame's box, HOST double [nframes][3]) and the bisector
+ * (H1 + H2) - 2 O of raw coordinates (hydration_number.py:60-63), numpy's fp64 expression order.  cos_out = DEVICE
+ * double [m] in (frame, cation, water) order; seg_off as in mdp_list_group; counts = DEVICE int32 [nframes][n_cat][2] =
+ * (waters in range, waters with cos < threshold).  Coordinates: DEVICE double [nframes][3][n]. */
+int mdp_hydration_count(mdp_ctx *ctx, int nframes, int64_t n_cat, const double *xyz_cat, int64_t n_wat, const double *xyz_o,
+                        const double *xyz_h1, const double *xyz_h2, const double *box, int64_t m, const int32_t *list,
+                        double threshold, double *cos_out, int64_t *seg_off, int32_t *counts, void *stream);
+/* get_clusters' molecule completion and force filter (cluster_analysis.py:163-182): for every (frame, central atom) the
+ * sorted, duplicate-free molecules owning an atom of the neighbour list (ib = atom row) whose
+ * min(sum fx, sum fy, sum fz) * force_constant < max_force (sums over the molecule's atoms in atom order; force = DEVICE
+ * double [nframes][3][n_atoms]; mol_seg_off = DEVICE int32 [n_mol+1]; mol_of_atom = DEVICE int32 [n_atoms]).
+ * mol_out[seg_off[s] .. seg_off[s] + mol_count[s]) = those molecules (DEVICE uint32 [m], int32 [nframes*n_central]). */
+int mdp_cluster_members(mdp_ctx *ctx, int nframes, int64_t n_central, int64_t n_atoms, const double *force, int64_t n_mol,
+                        const int32_t *mol_seg_off, const int32_t *mol_of_atom, double force_constant, double max_force,
+                        int64_t m, const int32_t *list, int64_t *seg_off, uint32_t *mol_out, int32_t *mol_count, void *stream);
+
 /* EXPERIMENTAL, opt-in (MDP_SHELL_GRID=1): the entries mdp_pair_list returns (same arguments, orthogonal cell, no rsq
  * output), found through a cell grid over a SMALL set A (n_a <= 4096) held in shared memory while B is streamed once
  * (csrc/shell_grid.h).  Returns 0, or 1 when the grid does not apply (n_a too large, or the outer radius exceeds a third

@@ -46,6 +46,11 @@ _PROTOS = {
                               c_void_p, c_int, c_void_p]),
     "mdp_hist_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p,
                                 c_void_p]),
+    "mdp_list_group": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mdp_hydration_count": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, POINTER(c_double),
+                                    c_int64, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mdp_cluster_members": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_double, c_double,
+                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mdp_shell_search": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, POINTER(c_double), c_double, c_double,
                                  c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "mdp_pair_list": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, POINTER(c_double), c_double,

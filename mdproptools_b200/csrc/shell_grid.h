@@ -3,7 +3,7 @@
 //
 // The residence-time search (residence_time.py:100-104) asks, per frame, which of ~10^3 central atoms have which of ~10^5
 // partners inside a 3 A shell.  The general pair engine sorts BOTH sets of every frame; here only A is binned (in shared
-// memory) and B is streamed once, each B point probing the 27 cells around it.
+// memory) and B is streamed once, each B point probing the cells around it that can hold a partner (5.4 on average).
 //
 // Exactness: the grid is only a candidate filter; a candidate pair is accepted by the reference's own arithmetic
 // (_calc_rsq, rdf_cn.py:46-56: d = a - b, one shift by -sign(d)*l when |d| > l/2, rsq = (dx*dx + dy*dy) + dz*dz, unfused).
@@ -27,8 +27,14 @@ constexpr int SG_NC_MAX = 16;                     // cells per axis at most: 409
 
 struct ShellGrid {
     double origin[3], inv_w[3], len[3];           // cell coordinate of x on axis k: (x - origin[k]) * inv_w[k]
+    double rw[3];                                 // r / cell width * (1 + 1e-6) per axis, set by mdp_grid_set_radius
     int nc[3];
 };
+
+MDP_HD void mdp_grid_set_radius(ShellGrid &g, double r)
+{
+    for (int k = 0; k < 3; ++k) g.rw[k] = r * (1.0 + 1e-6) * g.inv_w[k];
+}
 
 // cells per axis for box length l and outer radius r: as many as fit with width >= r * (1 + 1e-9), at most SG_NC_MAX;
 // < 3 means "this search is not for the grid" (the caller takes the general engine)
@@ -40,14 +46,33 @@ MDP_HD int mdp_grid_cells(double l, double r)
     return n;
 }
 
+// cell of x on one axis and the position inside it: t = (x - origin) * inv_w, cell = floor(t) mod nc, frac = t - floor(t).
+// Wrapped coordinates (the usual case) take no modulo at all; anything else one integer remainder.  NaN / inf / absurd
+// magnitudes fall into cell 0 with frac 0.5 (they never pass the exact test).
+MDP_HD int mdp_grid_cell1f(double x, double origin, double inv_w, int nc, double &frac)
+{
+    const double t = (x - origin) * inv_w;
+    const double fl = floor(t);
+    frac = t - fl;
+    if (!(fl > -2.0e9 && fl < 2.0e9)) {
+        frac = 0.5;
+        return 0;
+    }
+    int c = (int)fl;
+    if ((unsigned)c >= (unsigned)nc) {
+        c += c < 0 ? nc : -nc;                    // one period off (coordinates wrapped relative to another origin): no division
+        if ((unsigned)c >= (unsigned)nc) {
+            c %= nc;
+            if (c < 0) c += nc;
+        }
+    }
+    return c;
+}
+
 MDP_HD int mdp_grid_cell1(double x, double origin, double inv_w, int nc)
 {
-    const double t = floor((x - origin) * inv_w);
-    // true modulo; |t| stays far below 2^53 for any sane coordinate, NaN / inf fall into cell 0 (they never pass the
-    // exact test)
-    double m = t - floor(t / (double)nc) * (double)nc;
-    int c = (m >= 0.0 && m < (double)nc) ? (int)m : 0;
-    return c;
+    double frac;
+    return mdp_grid_cell1f(x, origin, inv_w, nc, frac);
 }
 
 MDP_HD int mdp_grid_cell(const ShellGrid &g, double x, double y, double z)
@@ -84,29 +109,68 @@ MDP_HD bool mdp_shell_accepts(double rsq, double rin2, double rout2, int shell_m
 
 // Probe the grid with one B point: emit(ia) for every A point accepted.  cell_start[ncell + 1] and the A points sorted by
 // cell (sx, sy, sz, sidx = original index) describe the grid; ib is B's index (for exclude_same).
+//
+// Which neighbour cells can hold a partner is decided per axis from B's position INSIDE its cell: an A point in the cell
+// below is at least frac * w away (w = cell width), one in the cell above at least (1 - frac) * w, so the lower neighbour
+// is needed only when frac <= rw and the upper one only when frac >= 1 - rw, rw = r / w * (1 + 1e-6) (the margin is six
+// orders of magnitude above the rounding of t and covers an A point that sits on a cell boundary and was rounded into the
+// neighbour).  With cells two to three radii wide (2 000 ions in a 126 A box: w = 7.9 A, r = 3 A) that is 5.4 cells per
+// point on average instead of 27.
+// cand(k) for every slot k of the sorted A arrays that lies in a cell B's point can have a partner in
+template <class Cand>
+MDP_HD void mdp_shell_candidates(const ShellGrid &g, const int *cell_start, double bx, double by, double bz, const Cand cand)
+{
+    int c0[3], lo[3], hi[3];
+    const double b[3] = {bx, by, bz};
+    for (int k = 0; k < 3; ++k) {
+        double frac;
+        c0[k] = mdp_grid_cell1f(b[k], g.origin[k], g.inv_w[k], g.nc[k], frac);
+        lo[k] = frac <= g.rw[k] ? -1 : 0;
+        hi[k] = frac >= 1.0 - g.rw[k] ? 1 : 0;
+    }
+    for (int oz = lo[2]; oz <= hi[2]; ++oz) {
+        int z = c0[2] + oz;
+        z = z < 0 ? z + g.nc[2] : (z >= g.nc[2] ? z - g.nc[2] : z);
+        for (int oy = lo[1]; oy <= hi[1]; ++oy) {
+            int y = c0[1] + oy;
+            y = y < 0 ? y + g.nc[1] : (y >= g.nc[1] ? y - g.nc[1] : y);
+            for (int ox = lo[0]; ox <= hi[0]; ++ox) {
+                int x = c0[0] + ox;
+                x = x < 0 ? x + g.nc[0] : (x >= g.nc[0] ? x - g.nc[0] : x);
+                const int c = (z * g.nc[1] + y) * g.nc[0] + x;
+                for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) cand(k);
+            }
+        }
+    }
+}
+
+// the exact test of one candidate: the reference's own arithmetic decides
+MDP_HD bool mdp_shell_pair_ok(const ShellGrid &g, double ax, double ay, double az, int ia, double bx, double by, double bz, int ib,
+                              double rin2, double rout2, int shell_mode, int exclude_same)
+{
+    const double rsq = mdp_rsq_ref(ax, ay, az, bx, by, bz, g.len);
+    return mdp_shell_accepts(rsq, rin2, rout2, shell_mode) && !(exclude_same && ia == ib);
+}
+
+template <class Emit>
+struct ShellProbeCand {
+    const ShellGrid &g;
+    const double *sx, *sy, *sz;
+    const int *sidx;
+    double bx, by, bz, rin2, rout2;
+    int ib, shell_mode, exclude_same;
+    const Emit &emit;
+    MDP_HD void operator()(int k) const
+    {
+        if (mdp_shell_pair_ok(g, sx[k], sy[k], sz[k], sidx[k], bx, by, bz, ib, rin2, rout2, shell_mode, exclude_same)) emit(sidx[k]);
+    }
+};
+
 template <class Emit>
 MDP_HD void mdp_shell_probe(const ShellGrid &g, const int *cell_start, const double *sx, const double *sy, const double *sz,
                             const int *sidx, double bx, double by, double bz, int ib, double rin2, double rout2, int shell_mode,
                             int exclude_same, const Emit emit)
 {
-    const int cx = mdp_grid_cell1(bx, g.origin[0], g.inv_w[0], g.nc[0]);
-    const int cy = mdp_grid_cell1(by, g.origin[1], g.inv_w[1], g.nc[1]);
-    const int cz = mdp_grid_cell1(bz, g.origin[2], g.inv_w[2], g.nc[2]);
-    for (int oz = -1; oz <= 1; ++oz) {
-        int z = cz + oz;
-        z = z < 0 ? z + g.nc[2] : (z >= g.nc[2] ? z - g.nc[2] : z);
-        for (int oy = -1; oy <= 1; ++oy) {
-            int y = cy + oy;
-            y = y < 0 ? y + g.nc[1] : (y >= g.nc[1] ? y - g.nc[1] : y);
-            for (int ox = -1; ox <= 1; ++ox) {
-                int x = cx + ox;
-                x = x < 0 ? x + g.nc[0] : (x >= g.nc[0] ? x - g.nc[0] : x);
-                const int c = (z * g.nc[1] + y) * g.nc[0] + x;
-                for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) {
-                    const double rsq = mdp_rsq_ref(sx[k], sy[k], sz[k], bx, by, bz, g.len);
-                    if (mdp_shell_accepts(rsq, rin2, rout2, shell_mode) && !(exclude_same && sidx[k] == ib)) emit(sidx[k]);
-                }
-            }
-        }
-    }
+    mdp_shell_candidates(g, cell_start, bx, by, bz,
+                         ShellProbeCand<Emit>{g, sx, sy, sz, sidx, bx, by, bz, rin2, rout2, ib, shell_mode, exclude_same, emit});
 }

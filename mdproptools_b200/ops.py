@@ -110,7 +110,7 @@ def pair_list(xyz_a, xyz_b, box, r_in2, r_out2, shell_mode, exclude_same_index=F
     box = _host_box(box, F, flags)
     cap = int(capacity or max(1 << 16, 64 * na * F))
     if shell_grid_enabled() and not want_rsq and flags == 0 and na <= 4096 and 8 * na <= nb_:
-        # EXPERIMENTAL, off by default: small set A against a large set B through a cell grid over A (csrc/shell.cu)
+        # small set A against a large set B through a cell grid over A (csrc/shell.cu); answers 1 when it does not apply
         while True:
             lst = torch.empty((cap, 3), dtype=torch.int32, device=xyz_a.device)
             cnt = torch.zeros((1,), dtype=torch.int64, device=xyz_a.device)
@@ -134,6 +134,57 @@ def pair_list(xyz_a, xyz_b, box, r_in2, r_out2, shell_mode, exclude_same_index=F
         if m <= cap:
             return lst[:m], (rsq[:m] if want_rsq else None)
         cap = int(m * 1.1) + 1024
+
+
+def list_group(lst, n_a, nframes, key=None):
+    """mdp_list_group: neighbour list int32 [M,3] -> (seg_off int64 [nframes*n_a+1], key_out int32-as-uint32 [M], perm int64 [M]):
+    entries grouped by (frame, ia) and sorted by key (default ib) inside a group."""
+    lst = _i32(lst.contiguous(), "lst")
+    M = lst.shape[0]
+    ctx = Context.get(lst.device.index)
+    seg_off = torch.empty((nframes * n_a + 1,), dtype=torch.int64, device=lst.device)
+    okey = torch.empty((max(M, 1),), dtype=torch.int32, device=lst.device)
+    perm = torch.empty((max(M, 1),), dtype=torch.int64, device=lst.device)
+    check(lib().mdp_list_group(ctx.handle, int(nframes), int(n_a), int(M), ptr(lst), ptr(key), ptr(seg_off), ptr(okey), ptr(perm),
+                               stream_ptr()), "mdp_list_group")
+    return seg_off, okey[:M], perm[:M]
+
+
+def hydration_count(lst, xyz_cat, xyz_o, xyz_h1, xyz_h2, box, threshold=-0.72):
+    """mdp_hydration_count: -> (cos float64 [M] in (frame, cation, water) order, seg_off int64 [F*ncat+1],
+    counts int32 [F, ncat, 2] = (waters in range, waters with cos < threshold))."""
+    xyz_cat, xyz_o, xyz_h1, xyz_h2 = (_f64(t, "xyz") for t in (xyz_cat, xyz_o, xyz_h1, xyz_h2))
+    lst = _i32(lst.contiguous(), "lst")
+    F, _, ncat = xyz_cat.shape
+    nw = xyz_o.shape[2]
+    M = lst.shape[0]
+    ctx = Context.get(lst.device.index)
+    box = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(F, 3))
+    cos = torch.empty((max(M, 1),), dtype=torch.float64, device=lst.device)
+    seg_off = torch.empty((F * ncat + 1,), dtype=torch.int64, device=lst.device)
+    counts = torch.empty((F, ncat, 2), dtype=torch.int32, device=lst.device)
+    check(lib().mdp_hydration_count(ctx.handle, F, ncat, ptr(xyz_cat), nw, ptr(xyz_o), ptr(xyz_h1), ptr(xyz_h2), _lib.dptr(box), M,
+                                    ptr(lst), float(threshold), ptr(cos), ptr(seg_off), ptr(counts), stream_ptr()),
+          "mdp_hydration_count")
+    return cos[:M], seg_off, counts
+
+
+def cluster_members(lst, n_central, force, mol_seg_off, mol_of_atom, force_constant, max_force):
+    """mdp_cluster_members: -> (seg_off int64 [F*n_central+1], mols int32 [M], mol_count int32 [F*n_central]); the kept
+    molecules of segment s are mols[seg_off[s] : seg_off[s] + mol_count[s]] (sorted, unique)."""
+    force = _f64(force, "force")
+    lst = _i32(lst.contiguous(), "lst")
+    F, _, n = force.shape
+    M = lst.shape[0]
+    nmol = mol_seg_off.shape[0] - 1
+    ctx = Context.get(lst.device.index)
+    seg_off = torch.empty((F * n_central + 1,), dtype=torch.int64, device=lst.device)
+    mols = torch.empty((max(M, 1),), dtype=torch.int32, device=lst.device)
+    cnt = torch.empty((F * n_central,), dtype=torch.int32, device=lst.device)
+    check(lib().mdp_cluster_members(ctx.handle, F, int(n_central), n, ptr(force), nmol, ptr(_i32(mol_seg_off, "mol_seg_off")),
+                                    ptr(_i32(mol_of_atom, "mol_of_atom")), float(force_constant), float(max_force), M, ptr(lst),
+                                    ptr(seg_off), ptr(mols), ptr(cnt), stream_ptr()), "mdp_cluster_members")
+    return seg_off, mols[:M], cnt
 
 
 def segment_com(attr, w, seg_off, extra=None):
@@ -255,9 +306,12 @@ def xcorr_fft_enabled(T: int = XCORR_FFT_MIN_T) -> bool:
 
 
 def shell_grid_enabled() -> bool:
+    """The small-set shell search (csrc/shell.cu) is the default for n_a <= 4096 central points against a set at least 8
+    times larger (round 2 on hardware, C5: 26 ms against 47 ms for the general engine's list mode, same entries);
+    MDP_SHELL_GRID=0 selects the general engine."""
     import os
 
-    return os.environ.get("MDP_SHELL_GRID", "0") not in ("", "0")
+    return os.environ.get("MDP_SHELL_GRID", "1") not in ("", "0")
 
 
 def survival_runs_enabled() -> bool:

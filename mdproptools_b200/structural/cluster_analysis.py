@@ -3,10 +3,11 @@
 citations are lines of that file).
 
 The O(n_central x N) cutoff search of every frame (:143-161, ``_calc_rsq`` + ``rsq < r_cut**2``) runs on the
-device as one rectangular neighbour-list call per batch of frames (``mdp_pair_list``, csrc/pair.cu).  What is
-left -- completing molecules, the signed force filter (:169-182), the output ordering (:185-207), the
-re-imaging relative to the central atom (:31-44) and the .xyz writer (:213-233) -- is bookkeeping on a few
-hundred atoms per cluster and is restated here on the host in numpy.
+device as one rectangular neighbour-list call per batch of frames (``mdp_pair_list``, csrc/pair.cu), and so do
+the molecule completion and the signed force filter (:163-182): ``mdp_cluster_members`` (csrc/epilogue.cu) returns,
+per frame and central atom, the sorted molecules that own a neighbour atom and whose min(sum fx, sum fy, sum fz)
+times FORCE_CONSTANT is below ``max_force``.  What is left -- the output ordering (:185-207), the re-imaging relative
+to the central atom (:31-44) and the .xyz writer (:213-233) -- is per-cluster file output on the host.
 
 Not supported (raises): element names read from an ``element`` column of the dump (pass ``elements``).
 
@@ -116,7 +117,12 @@ def get_clusters(filename, atom_type, r_cut, num_mols, num_atoms_per_mol, full_t
         same = all(np.array_equal(per_frame[0], p) for p in per_frame[1:])
         xyz = dev[:, [ci["x"], ci["y"], ci["z"]], :].contiguous()
         groups = [(0, F)] if same else [(k, k + 1) for k in range(F)]
-        hits = [[] for _ in range(F)]
+        # per frame and central atom: the molecules that own a neighbour atom and pass the force filter, on the device
+        # (search: mdp_pair_list; molecule completion + signed-component force filter :163-182: mdp_cluster_members)
+        members = [None] * F                                         # per frame: (seg_off, mols, counts) host arrays
+        fdev = dev[:, [ci["fx"], ci["fy"], ci["fz"]], :].contiguous()
+        seg_d = torch.from_numpy(seg_off.astype(np.int32)).to(dev.device)
+        moa_d = torch.from_numpy(mol_of_atom.astype(np.int32)).to(dev.device)
         for k0, k1 in groups:
             cen = per_frame[k0]
             if len(cen) == 0:
@@ -125,26 +131,20 @@ def get_clusters(filename, atom_type, r_cut, num_mols, num_atoms_per_mol, full_t
             xa = xyz[k0:k1].index_select(2, idx).contiguous()
             boxes = np.array([batch.metas[k].box.bound_lengths() for k in range(k0, k1)])
             lst, _ = ops.pair_list(xa, xyz[k0:k1].contiguous(), boxes, 0.0, rc2, shell_mode=0)
-            lst = lst.cpu().numpy()
-            order = np.lexsort((lst[:, 2], lst[:, 1], lst[:, 0]))
-            lst = lst[order]
+            so, mols_d, cnt_d = ops.cluster_members(lst, len(cen), fdev[k0:k1].contiguous(), seg_d, moa_d, FORCE_CONSTANT, max_force)
+            so, mols_h, cnt_h = so.cpu().numpy(), mols_d.cpu().numpy(), cnt_d.cpu().numpy()
             for fidx in range(k1 - k0):
-                hits[k0 + fidx] = lst[lst[:, 0] == fidx][:, 1:]
+                members[k0 + fidx] = (so[fidx * len(cen):(fidx + 1) * len(cen)], mols_h, cnt_h[fidx * len(cen):(fidx + 1) * len(cen)])
         for k, meta in enumerate(batch.metas):
             lx, ly, lz = meta.box.bound_lengths()
-            ids = host[k, ci["id"]]
             x = np.stack([host[k, ci["x"]], host[k, ci["y"]], host[k, ci["z"]]], axis=1)
-            fsum = np.stack([np.add.reduceat(host[k, ci[c]], seg_off[:-1]) for c in ("fx", "fy", "fz")], axis=1)
-            min_force = fsum.min(axis=1) * FORCE_CONSTANT
             elem = np.array([elements.get(int(t)) for t in host[k, ci["type"]]], dtype=object)
             cen = per_frame[k]
             index = pos_of[meta.index]
             frame_number = "{}{}".format("0" * (len(str(n_sel)) - len(str(index))), index)
-            h = hits[k]
             for counter, row in enumerate(cen):
-                nb_atoms = h[h[:, 0] == counter][:, 1] if len(h) else np.zeros(0, dtype=np.int64)
-                mols = np.unique(mol_of_atom[nb_atoms])                  # sorted == (mol_type, mol_id) order
-                mols = mols[min_force[mols] < max_force]                 # signed-component force filter (:169-182)
+                so, mols_h, cnt_h = members[k]
+                mols = mols_h[so[counter]: so[counter] + cnt_h[counter]].astype(np.int64)   # sorted == (mol_type, mol_id) order
                 own = mol_of_atom[row]
                 kept_atoms = np.concatenate([np.arange(seg_off[m], seg_off[m + 1]) for m in mols]) if len(mols) else \
                     np.zeros(0, dtype=np.int64)

@@ -6,8 +6,10 @@ Per frame the reference loops over cation atoms, finds the waters (first atom of
 within ``r_cut`` with ``_calc_rsq`` (:16-19) and evaluates the cosine between the minimum-image cation->O
 displacement and the water bisector (H1 + H2 - 2 O, raw coordinates, :60-63); a water counts as oriented
 when cos < -0.72 (:32).  Here the cation x water cutoff search of all frames of a batch is one
-``mdp_pair_list`` call on the device; the cosines of the (few) in-cutoff pairs are then formed on the host
-with the reference's numpy expressions, in the reference's order (frame, cation, water).
+``mdp_pair_list`` call on the device, and so is the epilogue (``mdp_hydration_count``, csrc/epilogue.cu): the
+entries are grouped in the reference's row order (frame, cation, water), the cosines are formed in numpy's fp64
+expression order (bit-identical to the host expressions they replace), and the two counters per cation -- waters
+in range, waters with cos < -0.72 -- come back as integers.  The host only averages them.
 """
 from __future__ import annotations
 
@@ -56,26 +58,22 @@ def get_hydration_number(dump_pattern, cation_type, water_type, r_cut, alter_ato
         xb = xyz.index_select(2, torch.from_numpy(o_rows).to(dev.device)).contiguous()
         boxes = np.array([m.box.bound_lengths() for m in batch.metas])
         lst, _ = ops.pair_list(xa, xb, boxes, 0.0, rc2, shell_mode=0)
-        lst = lst.cpu().numpy()
-        lst = lst[np.lexsort((lst[:, 2], lst[:, 1], lst[:, 0]))]
+        dv = dev.device
+        xh1 = xyz.index_select(2, torch.from_numpy(h1_rows).to(dv)).contiguous()
+        xh2 = xyz.index_select(2, torch.from_numpy(h2_rows).to(dv)).contiguous()
+        cos_d, seg_off, counts = ops.hydration_count(lst, xa, xb, xh1, xh2, boxes, threshold=-0.72)
+        cos_h = cos_d.cpu().numpy()
+        off = seg_off.cpu().numpy()
+        cnt = counts.cpu().numpy().astype(np.int64)                        # [F, ncat, 2]
+        ncat = len(cat_rows)
+        if np.any(cnt[:, :, 0] == 0):
+            raise ZeroDivisionError("division by zero")                   # a cation without water in range, as the reference (:32)
+        frac = cnt[:, :, 1] / cnt[:, :, 0]
         for k, meta in enumerate(batch.metas):
-            lx, ly, lz = meta.box.bound_lengths()
-            pos = np.stack([host[k, 1], host[k, 2], host[k, 3]], axis=1)
-            hk = lst[lst[:, 0] == k]
-            ia, ib = hk[:, 1], hk[:, 2]
-            # minimum-image displacement head - water exactly as _calc_rsq forms it (rdf_cn.py:44-55)
-            d = pos[cat_rows[ia]] - pos[o_rows[ib]]
-            for c, l in enumerate((lx, ly, lz)):
-                cond = (d[:, c] > l / 2) | (d[:, c] < -l / 2)
-                d[cond, c] = d[cond, c] - np.sign(d[cond, c]) * l
-            v = (pos[h1_rows[ib]] + pos[h2_rows[ib]]) - 2 * pos[o_rows[ib]]          # (:54-55)
-            dot_prod = np.sum(d * v, axis=1)
-            cos = dot_prod / (np.linalg.norm(d, axis=1) * np.linalg.norm(v, axis=1))   # (:27-30)
             factor = 0.0
-            for a in range(len(cat_rows)):
-                ca = cos[ia == a]
-                factor += len(ca[ca < -0.72]) / len(ca)      # ZeroDivisionError when a cation has no water in range, as in the reference (:32)
-            per_frame[meta.index] = (list(cos), factor / len(cat_rows))
+            for a in range(ncat):                                          # the reference's running sum over cations (:72-73)
+                factor += float(frac[k, a])                               # (Python floats: the final sum() below is the reference's)
+            per_frame[meta.index] = (cos_h[off[k * ncat]: off[(k + 1) * ncat]].tolist(), factor / ncat)
     T = batches.total_frames or 0
     if w > 1:
         import torch.distributed as d_

@@ -25,6 +25,7 @@ extern "C" int emulate_shell_grid(const double *xa, const double *ya, const doub
         g.len[k] = len[k];
         g.inv_w[k] = (double)g.nc[k] / len[k];
     }
+    mdp_grid_set_radius(g, r);
     g.origin[0] = g.origin[1] = g.origin[2] = 0.0;
     if (na > 0) {
         g.origin[0] = xa[0];

@@ -884,7 +884,7 @@ def test_nrank_equals_1rank_under_nccl(tmp_path):
         pytest.skip("needs at least 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     small = ["--steps", "2", "--warmup", "1", "--frames", "24", "--msd-atoms", "400000", "--msd-frames", "200", "--gk-steps", "20000",
-             "--gk-flux-frames", "1000", "--res-frames", "400", "--skip-cpu", "--skip-msd-window"]
+             "--gk-flux-frames", "1000", "--res-frames", "400", "--c5-frames", "100", "--skip-cpu", "--skip-msd-window"]
 
     def run(n):
         cmd = ([sys.executable, "bench.py", "--gpus", "1"] if n == 1 else
@@ -905,3 +905,78 @@ def test_nrank_equals_1rank_under_nccl(tmp_path):
         assert abs(many["msd"]["msd_last_frame"] / one["msd"]["msd_last_frame"] - 1) < 1e-12   # fp64 all-reduce order only
         a, b = many["green_kubo"]["charge_flux"]["abs_flux_sum"], one["green_kubo"]["charge_flux"]["abs_flux_sum"]
         assert abs(a / b - 1) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# device epilogues of the cutoff searches (csrc/epilogue.cu) against numpy restatements of the reference's host code
+# ------------------------------------------------------------------------------------------------
+def _rand_list(rng, F, na, nb, m):
+    lst = np.stack([rng.integers(0, F, m), rng.integers(0, na, m), rng.integers(0, nb, m)], axis=1).astype(np.int32)
+    return np.unique(lst, axis=0)[rng.permutation(len(np.unique(lst, axis=0)))]          # distinct entries, shuffled
+
+
+def test_list_group_kernel(ops):
+    import torch
+    rng = np.random.default_rng(5)
+    for F, na, nb, m in [(1, 1, 5, 3), (4, 7, 300, 2000), (3, 50, 40, 5000), (2, 3, 10, 0)]:
+        lst = _rand_list(rng, F, na, nb, m) if m else np.zeros((0, 3), dtype=np.int32)
+        seg_off, key, perm = ops.list_group(torch.from_numpy(lst).cuda(), na, F)
+        seg_off, key, perm = seg_off.cpu().numpy(), key.cpu().numpy(), perm.cpu().numpy()
+        order = np.lexsort((lst[:, 2], lst[:, 1], lst[:, 0])) if len(lst) else np.zeros(0, dtype=np.int64)
+        assert np.array_equal(perm, order) and np.array_equal(key, lst[order, 2])
+        counts = np.bincount(lst[:, 0].astype(np.int64) * na + lst[:, 1], minlength=F * na) if len(lst) else np.zeros(F * na, dtype=np.int64)
+        assert np.array_equal(seg_off, np.concatenate(([0], np.cumsum(counts))))
+
+
+def test_hydration_count_kernel(ops):
+    """cosines bit-identical to the numpy expressions of hydration_number.py:27-30 / rdf_cn.py:46-55, counters exact."""
+    import torch
+    rng = np.random.default_rng(8)
+    F, ncat, nw = 3, 9, 120
+    L = np.array([[14.0, 15.0, 13.5], [14.2, 15.1, 13.4], [13.9, 14.8, 13.6]])
+    cat = rng.uniform(0, 1, (F, 3, ncat)) * L[:, :, None]
+    o = rng.uniform(0, 1, (F, 3, nw)) * L[:, :, None]
+    h1 = o + rng.normal(0, 0.6, o.shape)
+    h2 = o + rng.normal(0, 0.6, o.shape)
+    lst = _rand_list(rng, F, ncat, nw, 900)
+    cos, seg_off, counts = ops.hydration_count(torch.from_numpy(lst).cuda(), _dev(cat), _dev(o), _dev(h1), _dev(h2), L, -0.72)
+    cos, seg_off, counts = cos.cpu().numpy(), seg_off.cpu().numpy(), counts.cpu().numpy()
+    order = np.lexsort((lst[:, 2], lst[:, 1], lst[:, 0]))
+    f, ia, ib = lst[order].T
+    d = np.stack([cat[f, a, ia] - o[f, a, ib] for a in range(3)], axis=1)
+    for a in range(3):
+        l = L[f, a]
+        cond = (d[:, a] > l / 2) | (d[:, a] < -l / 2)
+        d[cond, a] = d[cond, a] - np.sign(d[cond, a]) * l[cond]
+    v = np.stack([(h1[f, a, ib] + h2[f, a, ib]) - 2 * o[f, a, ib] for a in range(3)], axis=1)
+    want = np.sum(d * v, axis=1) / (np.linalg.norm(d, axis=1) * np.linalg.norm(v, axis=1))
+    assert np.array_equal(cos, want)
+    seg = f.astype(np.int64) * ncat + ia
+    assert np.array_equal(counts[:, :, 0].ravel(), np.bincount(seg, minlength=F * ncat))
+    assert np.array_equal(counts[:, :, 1].ravel(), np.bincount(seg[want < -0.72], minlength=F * ncat))
+
+
+def test_cluster_members_kernel(ops):
+    """molecule completion + signed-component force filter (cluster_analysis.py:163-182) against numpy."""
+    import torch
+    rng = np.random.default_rng(9)
+    F, ncen, sizes = 3, 11, rng.integers(1, 17, 60)
+    seg_off = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
+    n, nmol = int(seg_off[-1]), len(sizes)
+    mol_of_atom = np.repeat(np.arange(nmol), sizes).astype(np.int32)
+    force = rng.normal(0, 40.0, (F, 3, n))
+    const, max_force = 0.043363 / 16, 0.05
+    lst = _rand_list(rng, F, ncen, n, 1500)
+    so, mols, cnt = ops.cluster_members(torch.from_numpy(lst).cuda(), ncen, _dev(force), torch.from_numpy(seg_off).cuda(),
+                                        torch.from_numpy(mol_of_atom).cuda(), const, max_force)
+    so, mols, cnt = so.cpu().numpy(), mols.cpu().numpy(), cnt.cpu().numpy()
+    fsum = np.stack([[np.array([force[f, a, seg_off[m]:seg_off[m + 1]].sum() for m in range(nmol)]) for a in range(3)] for f in range(F)])
+    ok = fsum.min(axis=1) * const < max_force                                   # [F, nmol]
+    assert 0 < ok.sum() < ok.size
+    for f in range(F):
+        for c in range(ncen):
+            s = f * ncen + c
+            atoms = lst[(lst[:, 0] == f) & (lst[:, 1] == c)][:, 2]
+            want = np.unique(mol_of_atom[atoms])
+            want = want[ok[f, want]]
+            assert np.array_equal(mols[so[s]: so[s] + cnt[s]], want), (f, c)

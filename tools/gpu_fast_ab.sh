@@ -12,7 +12,7 @@ for mode in fast3 fast2 f64; do
   unset MDP_PAIR_F64 MDP_FAST_CTAS
   if [ $mode = f64 ]; then export MDP_PAIR_F64=1; fi
   if [ $mode = fast2 ]; then export MDP_FAST_CTAS=2; fi
-  timeout 600 python bench.py --steps 6 --warmup 3 --frames $FR --skip-msd --skip-cpu --skip-gk --skip-residence > $OUT/bench_ab_$mode.json 2> $OUT/bench_ab_$mode.err; echo "bench $mode rc=$?"
+  timeout 600 python bench.py --steps 6 --warmup 3 --frames $FR --skip-msd --skip-cpu --skip-gk --skip-residence --skip-clusters > $OUT/bench_ab_$mode.json 2> $OUT/bench_ab_$mode.err; echo "bench $mode rc=$?"
   tail -3 $OUT/bench_ab_$mode.err
   python - <<PY
 import json
@@ -28,6 +28,6 @@ done
 unset MDP_PAIR_F64 MDP_FAST_CTAS
 if [ "${1:-}" = "ncu" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pair -s 3 -c 1 -f -o $OUT/prof_pair_fast \
-      python bench.py --steps 1 --warmup 1 --frames 16 --skip-msd --skip-cpu --skip-gk --skip-residence --skip-triclinic > $OUT/ncu_pair_fast.log 2>&1
+      python bench.py --steps 1 --warmup 1 --frames 16 --skip-msd --skip-cpu --skip-gk --skip-residence --skip-clusters --skip-triclinic > $OUT/ncu_pair_fast.log 2>&1
   echo "ncu pair rc=$?"
 fi

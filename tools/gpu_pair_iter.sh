@@ -12,7 +12,7 @@ else
   timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider --timeout 600 -k "pair or rdf or cn or bin" > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 fi
 tail -8 $OUT/pytest_gpu.log
-timeout 600 python bench.py --steps 6 --warmup 3 --skip-msd --skip-cpu --skip-gk --skip-residence > $OUT/bench_pair.json 2> $OUT/bench_pair.err; echo "bench rc=$?"
+timeout 600 python bench.py --steps 6 --warmup 3 --skip-msd --skip-cpu --skip-gk --skip-residence --skip-clusters > $OUT/bench_pair.json 2> $OUT/bench_pair.err; echo "bench rc=$?"
 tail -3 $OUT/bench_pair.err
 python - <<'PY'
 import json
@@ -25,5 +25,5 @@ except Exception as e:
     print('no bench json', e)
 PY
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pair -s 3 -c 1 -f -o $OUT/prof_pair \
-    python bench.py --steps 1 --warmup 1 --frames-per-step 16 --skip-msd --skip-cpu --skip-gk --skip-residence --skip-triclinic > $OUT/ncu_pair.log 2>&1
+    python bench.py --steps 1 --warmup 1 --frames-per-step 16 --skip-msd --skip-cpu --skip-gk --skip-residence --skip-clusters --skip-triclinic > $OUT/ncu_pair.log 2>&1
 echo "ncu pair rc=$?"
