@@ -132,6 +132,19 @@ def parse_frames(bufs, want, out: np.ndarray, nthreads: int = 0) -> list:
 _FRAME_MARK = b"ITEM: TIMESTEP"
 
 
+def _read_and_scan(fname: str):
+    """(file bytes, frame offsets) -- runs in the read-ahead threads: the read and the native frame scan (mdp_dump_scan,
+    memchr-speed) both release the GIL, so neither sits on the producer thread's critical path."""
+    buf = _read_bytes(fname)
+    cap = 64
+    while True:
+        offs = (ctypes.c_int64 * cap)()
+        n = int(_lib.lib().mdp_dump_scan(buf, len(buf), offs, cap))
+        if n <= cap:
+            return buf, list(offs[:max(n, 0)])
+        cap = n
+
+
 def _split_frames(buf: bytes):
     """Offsets of every line that starts with ``ITEM: TIMESTEP`` (bytes.find: memchr-speed, no per-line work)."""
     offs = [0] if buf.startswith(_FRAME_MARK) else []
@@ -142,7 +155,7 @@ def _split_frames(buf: bytes):
     return offs
 
 
-def iter_frame_buffers(pattern: str, readahead_bytes: int = 512 << 20, readers: int = 4):
+def iter_frame_buffers(pattern: str, readahead_bytes: int = 512 << 20, readers: int = 0):
     """Yield the raw text of every frame, in pymatgen's order.  Files are read ahead by a few threads (file reads release
     the GIL) while the caller parses, bounded by ``readahead_bytes`` of text in flight."""
     from collections import deque
@@ -151,6 +164,9 @@ def iter_frame_buffers(pattern: str, readahead_bytes: int = 512 << 20, readers: 
     files = dump_files(pattern)
     if not files:
         return
+    # read-ahead threads: three quarters of the cores (measured on the 16-core B200 host with 3 MB files: 4 readers 1.26 ms
+    # per frame end to end, 8 readers 1.09, 12 readers 0.96 -- the reads and frame scans run beside the parser's threads)
+    readers = int(os.environ.get("MDP_READERS", readers or max(4, min(16, (3 * (os.cpu_count() or 4)) // 4))))
     with ThreadPoolExecutor(max_workers=max(1, readers)) as ex:
         pending, inflight, k = deque(), 0, 0
 
@@ -161,17 +177,16 @@ def iter_frame_buffers(pattern: str, readahead_bytes: int = 512 << 20, readers: 
                     sz = os.path.getsize(files[k])
                 except OSError:
                     sz = 0
-                pending.append((ex.submit(_read_bytes, files[k]), sz))
+                pending.append((ex.submit(_read_and_scan, files[k]), sz))
                 inflight += sz
                 k += 1
 
         top_up()
         while pending:
             fut, sz = pending.popleft()
-            buf = fut.result()
+            buf, offs = fut.result()
             inflight -= sz
             top_up()
-            offs = _split_frames(buf)
             if len(offs) <= 1:
                 yield buf if not offs or offs[0] == 0 else buf[offs[0]:]
                 continue

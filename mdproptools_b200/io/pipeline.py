@@ -54,10 +54,13 @@ class FrameBatches:
     across ranks and for ``get_clusters(frame=...)``); frames outside it are skipped without being parsed.
     """
 
-    def __init__(self, pattern, columns, max_batch_bytes=64 << 20, max_batch_frames=256, to_device=True, device=None,
+    def __init__(self, pattern, columns, max_batch_bytes=256 << 20, max_batch_frames=256, to_device=True, device=None,
                  frame_select=None, nthreads=0, prefetch=2, device_parse=None):
+        import os as _os
         self.pattern = pattern
         self.columns = list(columns)
+        if _os.environ.get("MDP_BATCH_MB"):                    # tuning knob for measurements
+            max_batch_bytes = int(_os.environ["MDP_BATCH_MB"]) << 20
         self.max_batch_bytes = int(max_batch_bytes)
         self.max_batch_frames = int(max_batch_frames)
         self.cuda = torch.cuda.is_available()
