@@ -47,6 +47,14 @@ class Batch:
         return self.columns.index(name)
 
 
+def _guard_multi(source, owner):
+    """Pass (index, text) pairs through; a MultiFrameFile from a sharded read ends the stream and is recorded."""
+    try:
+        yield from source
+    except _dump.MultiFrameFile:
+        owner.multi_frame_seen = True
+
+
 class FrameBatches:
     """Iterate over a trajectory in batches of frames with equal atom count.
 
@@ -55,7 +63,7 @@ class FrameBatches:
     """
 
     def __init__(self, pattern, columns, max_batch_bytes=256 << 20, max_batch_frames=256, to_device=True, device=None,
-                 frame_select=None, nthreads=0, prefetch=2, device_parse=None):
+                 frame_select=None, nthreads=0, prefetch=2, device_parse=None, file_shard=None):
         import os as _os
         self.pattern = pattern
         self.columns = list(columns)
@@ -67,6 +75,11 @@ class FrameBatches:
         self.to_device = to_device and self.cuda
         self.device = device
         self.frame_select = frame_select
+        # file_shard=(rank, world): this rank READS only every world-th file (one frame per file assumed and checked: a file
+        # with another number of frames sets multi_frame_seen and ends the iteration; the caller then falls back to
+        # frame_select, where every rank reads everything).  total_frames = number of files.
+        self.file_shard = file_shard
+        self.multi_frame_seen = False
         self.nthreads = nthreads
         self.prefetch = prefetch
         self.total_frames = None   # known once iteration has finished
@@ -130,9 +143,14 @@ class FrameBatches:
 
             idx = -1
             hdr = (ctypes.c_double * 16)()
-            for buf in _dump.iter_frame_buffers(self.pattern):
-                idx += 1
-                if self.frame_select is not None and not self.frame_select(idx):
+            if self.file_shard is not None:
+                source = _dump.iter_frame_buffers(self.pattern, file_shard=self.file_shard)
+            else:
+                source = ((None, b) for b in _dump.iter_frame_buffers(self.pattern))
+            sharded_total = len(_dump.dump_files(self.pattern)) if self.file_shard is not None else None
+            for fidx, buf in _guard_multi(source, self):
+                idx = idx + 1 if fidx is None else fidx
+                if fidx is None and self.frame_select is not None and not self.frame_select(idx):
                     continue
                 # peek at natoms: a batch holds frames of one size
                 _lib.check(_lib.lib().mdp_dump_header(buf, len(buf), hdr, None, 0), "mdp_dump_header")
@@ -143,7 +161,7 @@ class FrameBatches:
                     cur_n = n
                     cap = max(1, min(self.max_batch_frames, self.max_batch_bytes // max(1, C * n * 8)))
                 pending.append((idx, buf))
-            self.total_frames = idx + 1
+            self.total_frames = idx + 1 if sharded_total is None else sharded_total
             flush()
             q.put(None)
         except BaseException as exc:  # noqa: BLE001 - forwarded to the consumer

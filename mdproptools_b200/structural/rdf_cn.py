@@ -308,10 +308,51 @@ def _frame_box(box, flags):
 # ------------------------------------------------------------------------------------------------
 # frame iteration shared by all entry points
 # ------------------------------------------------------------------------------------------------
+class _RetryUnsharded(Exception):
+    """Some rank met a dump file with more than one frame while reading only its share of the files."""
+
+
+_SHARD_FILES = [True]
+
+
 def _frame_batches(filename, columns):
+    """This rank's frames.  With several ranks every rank READS only every world-th file (frame index = file index for the
+    usual one-frame-per-file dumps); ``_agree_sharding`` then checks collectively that no rank met a multi-frame file --
+    otherwise the call is repeated with every rank reading everything and selecting its frames (``file_sharded``)."""
     w, r = dist.world_size(), dist.rank()
+    if w > 1 and _SHARD_FILES[0]:
+        return FrameBatches(filename, columns, file_shard=(r, w))
     sel = (lambda i: i % w == r) if w > 1 else None
     return FrameBatches(filename, columns, frame_select=sel)
+
+
+def _agree_sharding(batches, device):
+    """Call after the batch loop and before the merge collective: all ranks learn whether the sharded read held."""
+    if getattr(batches, "file_shard", None) is None:
+        return
+    flag = torch.tensor([1 if batches.multi_frame_seen else 0], dtype=torch.int64, device=device)
+    dist.all_reduce_max_(flag)
+    if int(flag.item()):
+        raise _RetryUnsharded()
+
+
+def file_sharded(fn):
+    """Decorator of the file-based entry points: run with sharded file reads, fall back (on every rank at once) when a
+    multi-frame file was met."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        try:
+            return fn(*args, **kwargs)
+        except _RetryUnsharded:
+            _SHARD_FILES[0] = False
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                _SHARD_FILES[0] = True
+
+    return wrapper
 
 
 def _merge_frames(per_frame: dict, total_frames: int, shape, device):
@@ -334,6 +375,7 @@ def _mol_segments(num_mols, num_atoms_per_mol):
 # ------------------------------------------------------------------------------------------------
 # public API
 # ------------------------------------------------------------------------------------------------
+@file_sharded
 def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols=None, num_atoms_per_mol=None,
                     path_or_buff="rdf.csv", save_mode=True, mic="reference"):
     """Full and partial atom-atom RDF; see the reference docstring (:397-452) for the arguments."""
@@ -385,6 +427,7 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
         red = ops.hist_reduce(hist, weights)                      # [F, 1+R, nb]
         for k, meta in enumerate(batch.metas):
             counts[meta.index] = red[k]
+    _agree_sharding(batches, device)
     T = batches.total_frames or 0
     if T == 0:
         raise ValueError(f"no dump frames found for {filename!r}")
@@ -420,6 +463,7 @@ def _gather_props(props: dict, total_frames: int) -> dict:
     return out
 
 
+@file_sharded
 def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols=None, num_atoms_per_mol=None,
                    path_or_buff="cn.csv", save_mode=True, mic="reference"):
     """Atom-atom coordination numbers, one cutoff per relation (:533-651)."""
@@ -470,6 +514,7 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
         red = ops.hist_reduce(hist, weights, cumulative=True)     # [F, R, nthr] cumulative over thresholds
         for k, meta in enumerate(batch.metas):
             counts[meta.index] = red[k]
+    _agree_sharding(batches, device)
     T = batches.total_frames or 0
     if T == 0:
         raise ValueError(f"no dump frames found for {filename!r}")
@@ -534,12 +579,14 @@ def _molecular_common(filename, num_types, mass, partial_relations, num_mols, nu
             res = run_pairs(xyz, torch.from_numpy(cls_a).to(device), cmap_a.ncls, com, cls_m, cmap_b.ncls, boxes, weights)
         for k, meta in enumerate(batch.metas):
             counts[meta.index] = res[k]
+    _agree_sharding(batches, device)
     T = batches.total_frames or 0
     if T == 0:
         raise ValueError(f"no dump frames found for {filename!r}")
     return counts, props, T, device, relation_matrix, num_relations
 
 
+@file_sharded
 def calc_molecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
                        path_or_buff="rdf_mol.csv", save_mode=True, _inter=False, mic="reference"):
     """Partial RDF between atoms and molecule centres of mass (:654-756)."""
@@ -566,6 +613,7 @@ def calc_molecular_rdf(r_cut, bin_size, num_types, mass, partial_relations, file
     return _save_rdf(radii, relation_matrix, path_or_buff, save_mode, rdf_part_sum)
 
 
+@file_sharded
 def calc_molecular_cn(r_cut, bin_size, num_types, mass, partial_relations, filename, num_mols, num_atoms_per_mol,
                       path_or_buff="cn_mol.csv", save_mode=True, mic="reference"):
     """Coordination numbers between atoms and molecule centres of mass (:759-854)."""

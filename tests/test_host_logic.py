@@ -615,6 +615,41 @@ assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
 assert all(dist.owner_of(i, n_cent, 2) == int(dist.owner_of_rows(torch.tensor([i]), n_cent, 2)) for i in range(n_cent))
 empty = dist.exchange_rows(torch.zeros((0, 3), dtype=torch.int32), torch.zeros((0,), dtype=torch.int64))
 assert empty.shape == (0, 3)
+# strong-scaling merge: contiguous frame blocks are all-gathered (uneven split: 7 frames over 2 ranks)
+lo, hi = dist.shard_range(7)
+blk = torch.arange(lo, hi, dtype=torch.int64).reshape(-1, 1, 1).expand(-1, 2, 3).contiguous()
+whole = dist.all_gather_blocks(blk, 7)
+assert whole.shape == (7, 2, 3) and whole[:, 1, 2].tolist() == list(range(7))
+# sharded file reads: every rank reads only its files; frame index = file index; total = number of files
+from mdproptools_b200.io.pipeline import FrameBatches
+from mdproptools_b200.structural.rdf_cn import _agree_sharding, _RetryUnsharded
+def write(path, step, n=4):
+    rows = "\n".join("%d 1 %g %g %g" % (i + 1, 0.5 * i + step, 1.0 * i, 2.0 * i) for i in range(n))
+    return "ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n0 9\n0 9\n0 9\nITEM: ATOMS id type x y z\n%s\n" % (step, n, rows)
+base = {tmp!r}
+if r == 0:
+    os.makedirs(base + "/one", exist_ok=True); os.makedirs(base + "/multi", exist_ok=True)
+    for k in range(5):
+        open(base + "/one/dump.t.%d.dump" % (k * 10), "w").write(write(None, k * 10))
+    for k in range(3):
+        open(base + "/multi/dump.t.%d.dump" % (k * 10), "w").write(write(None, k * 10) + (write(None, k * 10 + 5) if k == 1 else ""))
+d.barrier()
+fb = FrameBatches(base + "/one/dump.t.*.dump", ["id", "x"], to_device=False, file_shard=(r, 2))
+seen = {{m.index: (m.timestep, float(b.host[k, 1, 0])) for b in fb for k, m in enumerate(b.metas)}}
+assert sorted(seen) == list(range(r, 5, 2)) and fb.total_frames == 5 and not fb.multi_frame_seen
+assert all(seen[i] == (i * 10, float(i * 10)) for i in seen)
+_agree_sharding(fb, torch.device("cpu"))
+fb = FrameBatches(base + "/multi/dump.t.*.dump", ["id", "x"], to_device=False, file_shard=(r, 2))
+list(fb)
+assert fb.multi_frame_seen == (r == 1)          # file 1 holds two frames; only the rank that read it knows ...
+try:
+    _agree_sharding(fb, torch.device("cpu"))
+    raise SystemExit("no retry")
+except _RetryUnsharded:
+    pass                                         # ... and both ranks learn it
+fb = FrameBatches(base + "/multi/dump.t.*.dump", ["id", "x"], to_device=False, frame_select=lambda i: i % 2 == r)
+seen = sorted(m.index for b in fb for m in b.metas)
+assert seen == list(range(r, 4, 2)) and fb.total_frames == 4
 d.destroy_process_group()
 print("rank", r, "ok")
 """
@@ -622,7 +657,7 @@ print("rank", r, "ok")
 
 def test_two_rank_gloo_merge(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(_WORKER.format(root=ROOT))
+    script.write_text(_WORKER.format(root=ROOT, tmp=str(tmp_path)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29611", str(script)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
