@@ -5,27 +5,27 @@
 // (cluster_analysis.py:150-161, hydration_number.py:16-19, residence_time.py:100-104).
 //
 // Design (B200-first, not a translation of the row-by-row reference loop):
-//   1. per frame the point set is binned on a grid of cells ordered along a Hilbert curve by a counting sort and written out as
-//      32-byte AoS records (x, y, z, class|index), padded to 256-point tiles; every 32-point group and
-//      every tile gets an axis-aligned bounding box;
-//   2. tile pairs whose boxes cannot contain a pair inside the cutoff (under the REFERENCE's
-//      single-shift minimum image, evaluated with interval arithmetic that is exact w.r.t. the fp64
-//      operation order) are dropped when the work list is built; inside a tile pair every warp
-//      repeats the test per 32-point chunk.  The set of pairs with rsq < rcut2 is unchanged, each
-//      surviving pair's rsq is computed in the reference's unfused fp64 order, so counts are bit-exact;
-//   3. persistent CTAs (3 per SM) walk the frames of the batch (each CTA starts at a different frame);
-//      inside a frame every WARP pulls its own work items -- (32 i points, one 256-point j tile) -- from
-//      the frame's global counter, so there is no CTA barrier on the pair path (a barrier-per-tile
-//      version lost 45 % of its issue slots waiting, profiles/r01a_k_pair.txt).  Each lane keeps one i
-//      point in registers; the needed 32-point j chunks are streamed into a warp-private, double
-//      buffered shared-memory stage with cp.async (1 KB contiguous per chunk: records are stored
-//      group-blocked, [32 x (x,y)][32 x (z,meta)]).  Chunk pairs whose displacement interval lies inside
-//      [-l/2, l/2] on all axes take a path with no minimum-image work at all (8 fp64 ops / pair), the
-//      others the general path (11 fp64 ops + integer compares);
-//   4. in-cutoff pairs are compacted into a per-warp shared-memory queue (ballot + popc) and binned
-//      32 at a time at full lane utilisation: bin index from an fp32 sqrt estimate corrected against
-//      the exact fp64 edge table, then a shared-memory histogram atomic; the per-CTA histogram is
-//      flushed to the per-frame uint64 global histogram when the CTA leaves a frame (the only barrier).
+//   1. per frame the point set is binned on a grid of cells ordered along a Hilbert curve by a counting sort and written out
+//      group-blocked (32 points = one contiguous 1 KB block of double2: 32 x (x, y), then 32 x (z, class|index)), padded to
+//      256-point tiles; every 32-point group gets a float box rounded outward, every tile an fp64 box;
+//   2. tile pairs whose boxes cannot contain a pair inside the cutoff (under the REFERENCE's single-shift minimum image,
+//      evaluated with interval arithmetic that is monotone w.r.t. the fp64 operation order) are dropped when the work list
+//      is built, per tile row.  The set of pairs with rsq < rcut2 is unchanged by any culling level;
+//   3. persistent CTAs walk the frames of the batch (each starts at a different frame); inside a frame every WARP pulls
+//      units -- one 32-point i group (one point per lane) against the whole tile row of its tile -- from the frame's
+//      counter, so there is no CTA barrier on the pair path.  Chunk level: 32 lanes test 32 j-chunk boxes at a time (fp32,
+//      directed rounding) and classify the image per axis; point level: the points of a needed chunk are filtered against
+//      the i group's box; the survivors queue up in a per-warp ring and are evaluated 32 at a time;
+//   4. TWO pair kernels share all of that:
+//        k_pair_fast (pair_fast.cuh, the default for uniform bins): distances and bins in fp32 relative to the group
+//          centre, every pair within a proven error bound of a bin edge re-evaluated in the reference's fp64 arithmetic
+//          and corrected -- counts identical to the reference's, 1.6x faster than the all-fp64 kernel;
+//        k_pair (this file): the reference's unfused fp64 chain for every evaluated pair (8-14 FP64-pipe ops), direct
+//          binning (fp32 estimate + one exact fp64 edge compare) or the hit queue.  It serves table bins (coordination
+//          numbers), the neighbour list (clusters, hydration, residence searches), MDP_PAIR_F64 and every shape the fast
+//          kernel declines.
+//      The per-CTA uint32 histogram is flushed to the per-frame uint64 global histogram when the CTA leaves a frame (the
+//      only barrier) and whenever the CTA has evaluated 2^30 pairs since the last flush (overflow guard).
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
@@ -1107,6 +1107,8 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
     if (MODE != MODE_LIST && p.edges_in_smem) sp += edge_region_bytes(p.nbins);
     int *cptab_s = reinterpret_cast<int *>(sp);
     if (MULTICLS) sp += (size_t)((p.ncp * 4 + 15) & ~15);
+    unsigned int *evals_s = reinterpret_cast<unsigned int *>(sp);   // 32-pair steps since the CTA histogram was last flushed
+    sp += 16;
     sh.hist = reinterpret_cast<unsigned int *>(sp);
     sh.edges_s = edges_s;
     sh.cptab = p.cptab;
@@ -1125,6 +1127,7 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
         }
         for (int k = tid; k < nhist; k += blockDim.x) sh.hist[k] = 0u;
     }
+    if (tid == 0) *evals_s = 0u;
     if (MULTICLS) {
         for (int k = tid; k < p.ncp; k += blockDim.x) cptab_s[k] = p.cptab[k];
         sh.cptab = cptab_s;
@@ -1182,6 +1185,7 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
             unsigned int qnext = 0;
             if (lane == 0) qnext = atomicAdd(&p.counters[MODE == MODE_LIST ? 0 : f], 1u);   // prefetch the next work index
             did = true;
+            const unsigned long long unit_evals0 = my_evals;
             // One unit = one i group (32 points, one per lane) against every j tile of its tile row of the work list.
             const int ta = (int)(q >> 3), wi = (int)(q & 7u);
             const int64_t row = (int64_t)f * p.ntA + ta;
@@ -1324,6 +1328,23 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
                     head += 32;
                 }
             }
+            if (MODE != MODE_LIST) {
+                // overflow guard of the uint32 shared histogram (a frame of N >~ 90 000 points has more than 2^32 pairs and a
+                // CTA may own a whole frame): the CTA counts its 32-pair steps; the warp that crosses a multiple of 2^25
+                // steps (2^30 pairs) moves the histogram to the global one word by word with atomicExch -- race free without
+                // a barrier; a unit adds at most 32 x npad pairs (npad < 2^22: 8 warps stay below 2^31 in between)
+                const unsigned add = (unsigned)(my_evals - unit_evals0);
+                unsigned old_ = 0;
+                if (lane == 0) old_ = atomicAdd(evals_s, add);
+                old_ = __shfl_sync(0xffffffffu, old_, 0);
+                if (((old_ + add) >> 25) != (old_ >> 25)) {
+                    unsigned long long *hg = p.hist + (int64_t)frame * nhist;
+                    for (int k = lane; k < nhist; k += 32) {
+                        const unsigned int v = atomicExch(&sh.hist[k], 0u);
+                        if (v) atomicAdd(&hg[k], (unsigned long long)v);
+                    }
+                }
+            }
             q = __shfl_sync(0xffffffffu, qnext, 0);
             if (MODE == MODE_LIST) {
                 gq = q;                                   // global index; beyond this frame it ends the unit loop
@@ -1346,6 +1367,7 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
                         sh.hist[k] = 0u;
                     }
                 }
+                if (tid == 0) *evals_s = 0u;
                 __syncthreads();
             }
         }
@@ -1538,6 +1560,9 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
     if (!symm) plan_set(B, c.n_b, nosort);
     const SetPlan &Bp = symm ? A : B;
     MDP_REQUIRE(A.ntiles < (1 << 22) && Bp.ntiles < (1 << 22), "pair: too many tiles");
+    MDP_REQUIRE(!hist_mode || Bp.npad < ((int64_t)1 << 22),
+                "pair: histogram calls are limited to 2^22 points per frame and set (the overflow guard of the per-CTA uint32 "
+                "histogram assumes a work unit adds fewer than 2^27 pairs)");
 
     // shared memory budget of the pair kernel
     const bool meta = multicls || !hist_mode;
@@ -1549,15 +1574,15 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         const size_t edge_bytes = edge_region_bytes(c.nbins);
         if (multicls) smem += (size_t)((ncp * 4 + 15) & ~15);
         const size_t cap = std::min<size_t>(ctx->smem_optin, (216 / CTAS_PER_SM) * 1024);   // keep CTAS_PER_SM CTAs per SM
-        MDP_REQUIRE(smem + hist_bytes + 128 <= ctx->smem_optin,
+        MDP_REQUIRE(smem + hist_bytes + 128 + 16 <= ctx->smem_optin,
                     "pair: histogram of %d rows x %d bins does not fit in shared memory (%zu B needed); "
                     "reduce the number of distinct classes or bins per call",
                     nrows, c.nbins, smem + hist_bytes);
-        if (smem + hist_bytes + 128 + edge_bytes <= cap) {
+        if (smem + hist_bytes + 128 + 16 + edge_bytes <= cap) {
             edges_in_smem = 1;
             smem += edge_bytes;
         }
-        smem += hist_bytes + 128;   // + one scratch word per lane (direct binning sends misses there)
+        smem += hist_bytes + 128 + 16;   // + one scratch word per lane (direct binning sends misses there) + the guard counter
     }
 
     // sub-batching over frames so that scratch stays bounded

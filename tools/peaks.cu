@@ -6,6 +6,7 @@
 // Run (on the GPU box): tools/peaks > gpurun_out/peaks.json
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <string.h>
 #include <stdlib.h>
 
 #define CK(x)                                                                                   \
@@ -77,6 +78,59 @@ __global__ void __launch_bounds__(256) k_stream_read(const double2 *p, size_t n2
     if (s == 12345.678) out[0] = s;
 }
 
+// ---- accuracy of MUFU.SQRT (sqrt.approx.ftz.f32), every positive normal fp32 input: k_pair_fast's error bound
+// (csrc/pair_fast.cuh) budgets 2^-22 for it.  out[0] = max over all inputs of |approx - sqrt| / sqrt as ulps-of-2^-24, scaled.
+__global__ void __launch_bounds__(256) k_mufu_sqrt_err(unsigned long long *worst)
+{
+    // inputs: bit patterns 0x00800000 .. 0x7f7fffff (positive normals), grid-strided
+    double w = 0.0;
+    for (unsigned long long b = 0x00800000ull + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= 0x7f7fffffull;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)b);
+        float a;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(x));
+        const double exact = sqrt((double)x);
+        const double rel = fabs((double)a - exact) / exact;
+        w = rel > w ? rel : w;
+    }
+    // max-reduce through the order-preserving bit pattern of a non-negative double
+    atomicMax(worst, (unsigned long long)__double_as_longlong(w));
+}
+
+// FP32 issue rate (FFMA), and the integer POPC rate the popcount survival kernel is bounded by
+__global__ void __launch_bounds__(256) k_fp32(float *out, float a, float b)
+{
+    float v[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) v[c] = a + (float)(threadIdx.x + c);
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) v[c] = __fmaf_rn(v[c], a, b);
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) v[c] = __fmaf_rn(v[c], b, a);
+    }
+    float s = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) s += v[c];
+    if (s == 12345.678f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) k_popc(unsigned long long *out, unsigned long long a)
+{
+    unsigned long long v[CHAINS];
+    unsigned int acc = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) v[c] = a * (threadIdx.x + c + 1);
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            acc += __popcll(v[c] & (v[c] >> (it & 63)));
+            v[c] += acc;
+        }
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
 template <class F>
 float time_ms(F f, int reps)
 {
@@ -134,7 +188,22 @@ int main()
     CK(cudaMalloc(&buf, bytes));
     CK(cudaMemset(buf, 0, bytes));
     float tr = time_ms([&] { k_stream_read<<<sms * 16, 256>>>(buf, bytes / 16, d_out); }, 5);
+    // MUFU.SQRT accuracy over every positive normal fp32 input
+    unsigned long long *d_worst;
+    CK(cudaMalloc(&d_worst, 8));
+    CK(cudaMemset(d_worst, 0, 8));
+    k_mufu_sqrt_err<<<sms * 16, 256>>>(d_worst);
+    CK(cudaDeviceSynchronize());
+    unsigned long long hw = 0;
+    CK(cudaMemcpy(&hw, d_worst, 8, cudaMemcpyDeviceToHost));
+    double worst_rel;
+    memcpy(&worst_rel, &hw, 8);
+    float tf32 = time_ms([&] { k_fp32<<<blocks, 256>>>((float *)d_out, 1.0000001f, 1e-7f); }, 5);
+    float tpop = time_ms([&] { k_popc<<<blocks, 256>>>((unsigned long long *)d_out, 0x9e3779b97f4a7c15ull); }, 5);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_mhz\": %d,\n", prop.name, sms, prop.clockRate / 1000);
+    printf(" \"mufu_sqrt_max_rel_err\": %.6e, \"mufu_sqrt_max_rel_err_log2\": %.3f,\n", worst_rel, log2(worst_rel));
+    printf(" \"fp32_ffma_tflops_burst\": %.3f, \"popc64_and_shift_gops\": %.1f,\n", 2 * ops / tf32 * 1e-9,
+           (double)blocks * 256 * ITERS * CHAINS / tpop * 1e-6);
     printf(" \"fp64_unfused_tflops_burst\": %.3f, \"fp64_unfused_tflops_sustained\": %.3f, \"fp64_fma_tflops_burst\": %.3f,\n",
            ops / t0 * 1e-9, ops / t0s * 1e-9, 2 * ops / t1 * 1e-9);
     printf(" \"fp64_fma_3reg_tflops_burst\": %.3f,\n", 2 * ops / t2 * 1e-9);
