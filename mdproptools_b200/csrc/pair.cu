@@ -1108,7 +1108,7 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
     int *cptab_s = reinterpret_cast<int *>(sp);
     if (MULTICLS) sp += (size_t)((p.ncp * 4 + 15) & ~15);
     unsigned int *evals_s = reinterpret_cast<unsigned int *>(sp);   // 32-pair steps since the CTA histogram was last flushed
-    sp += 16;
+    if (MODE != MODE_LIST) sp += 16;                                // (list mode has no histogram region at all)
     sh.hist = reinterpret_cast<unsigned int *>(sp);
     sh.edges_s = edges_s;
     sh.cptab = p.cptab;
@@ -1127,7 +1127,7 @@ __global__ void __launch_bounds__(NWARP * 32, CTAS_PER_SM) k_pair(const PairPara
         }
         for (int k = tid; k < nhist; k += blockDim.x) sh.hist[k] = 0u;
     }
-    if (tid == 0) *evals_s = 0u;
+    if (MODE != MODE_LIST && tid == 0) *evals_s = 0u;
     if (MULTICLS) {
         for (int k = tid; k < p.ncp; k += blockDim.x) cptab_s[k] = p.cptab[k];
         sh.cptab = cptab_s;
