@@ -894,7 +894,7 @@ def bench_residence(args, torch, dist, ops, ctx, dev, world, rank):
         if world > 1:
             lst = mdist.exchange_rows(lst, mdist.owner_of_rows(lst[:, 1], ncat, world))
         e[2].record()
-        holder["cnt"], holder["P"] = ops.bitmask_autocorr_from_list(lst.contiguous(), nox, T)
+        holder["cnt"], holder["P"] = ops.bitmask_autocorr_from_list(lst.contiguous(), nox, T, n_a=ncat)
         if world > 1:
             dist.all_reduce(holder["cnt"], op=dist.ReduceOp.SUM)
         e[3].record()
@@ -918,7 +918,7 @@ def bench_residence(args, torch, dist, ops, ctx, dev, world, rank):
     lst_local = lst_local.contiguous()
 
     def corr():
-        holder2["cnt"], holder2["P"] = ops.bitmask_autocorr_from_list(lst_local, nox, T)
+        holder2["cnt"], holder2["P"] = ops.bitmask_autocorr_from_list(lst_local, nox, T, n_a=ncat)
 
     _, kms_c, kn_c = _timed(ctx, torch, 6, corr, 3)
     P = holder2["P"]

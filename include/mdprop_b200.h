@@ -149,6 +149,11 @@ int mdp_pair_list(mdp_ctx *ctx, int nframes,
  * cluster_analysis.py:143-165). */
 int mdp_list_group(mdp_ctx *ctx, int nframes, int64_t n_a, int64_t m, const int32_t *list, const uint32_t *key,
                    int64_t *seg_off, uint32_t *key_out, int64_t *perm_out, void *stream);
+/* The distinct (ia, ib) pairs of a neighbour list as sorted keys ia * n_b + ib (residence_time.py:100-111 needs one
+ * indicator series per ever-neighbour pair): keys_out = DEVICE int64 [capacity], count_out = DEVICE int64 (total found; only
+ * `capacity` are written).  A bitmap over the n_a * n_b possible pairs + a popcount scan, no sort. */
+int mdp_unique_pair_keys(mdp_ctx *ctx, int64_t m, const int32_t *list, int64_t n_a, int64_t n_b, int64_t *keys_out,
+                         int64_t capacity, int64_t *count_out, void *stream);
 /* get_angle (hydration_number.py:13-32) for every (frame, cation, water O) entry: cos between the minimum-image
  * displacement cation - O (rdf_cn.py:46-55 with the frame's box, HOST double [nframes][3]) and the bisector
  * (H1 + H2) - 2 O of raw coordinates (hydration_number.py:60-63), numpy's fp64 expression order.  cos_out = DEVICE

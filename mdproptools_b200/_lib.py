@@ -46,6 +46,7 @@ _PROTOS = {
                               c_void_p, c_int, c_void_p]),
     "mdp_hist_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p,
                                 c_void_p]),
+    "mdp_unique_pair_keys": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "mdp_list_group": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mdp_hydration_count": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, POINTER(c_double),
                                     c_int64, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),

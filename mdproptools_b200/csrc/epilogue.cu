@@ -284,9 +284,94 @@ __global__ void __launch_bounds__(EB) k_seg_unique(const int64_t *__restrict__ o
     ucount[s] = (int32_t)(w - b);
 }
 
+// ---- unique (ia, ib) pairs of a neighbour list, sorted by key = ia * n_b + ib ------------------------------------------------
+// (what the residence-time correlation needs before it can build one time bitmask per ever-neighbour pair,
+// residence_time.py:100-111).  One bit per possible pair (n_a * n_b / 8 bytes: 16 MB for 2 000 x 62 666), set by the entries;
+// the set bits are then enumerated in order by a popcount scan -- no sort.
+__global__ void __launch_bounds__(EB) k_pk_set(const int32_t *__restrict__ list, int64_t m, int64_t n_b, uint32_t *__restrict__ bits)
+{
+    const int64_t e = (int64_t)blockIdx.x * EB + threadIdx.x;
+    if (e >= m) return;
+    const int64_t key = (int64_t)list[e * 3 + 1] * n_b + list[e * 3 + 2];
+    atomicOr(&bits[key >> 5], 1u << (key & 31));
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_pk_tile_sums(const uint32_t *__restrict__ bits, int64_t nwords, unsigned long long *__restrict__ tsum)
+{
+    __shared__ unsigned long long ws[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) {
+        const int64_t i = base + (int64_t)k * SCAN_T + threadIdx.x;
+        if (i < nwords) s += __popc(bits[i]);
+    }
+    unsigned long long total;
+    block_excl_scan(s, ws, total);
+    if (threadIdx.x == 0) tsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_pk_emit(const uint32_t *__restrict__ bits, int64_t nwords, const unsigned long long *__restrict__ tsum,
+                                                    int64_t *__restrict__ keys, int64_t cap)
+{
+    __shared__ unsigned long long ws[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER;
+    uint32_t v[SCAN_PER];
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) {
+        v[k] = base + k < nwords ? bits[base + k] : 0u;
+        s += __popc(v[k]);
+    }
+    unsigned long long total;
+    unsigned long long run = tsum[blockIdx.x] + block_excl_scan(s, ws, total);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) {
+        uint32_t w = v[k];
+        while (w) {
+            const int b = __ffs(w) - 1;
+            w &= w - 1;
+            if ((int64_t)run < cap) keys[run] = (base + k) * 32 + b;
+            ++run;
+        }
+    }
+}
+
 } // namespace
 
 extern "C" {
+
+int mdp_unique_pair_keys(mdp_ctx *ctx, int64_t m, const int32_t *list, int64_t n_a, int64_t n_b, int64_t *keys_out, int64_t capacity,
+                         int64_t *count_out, void *stream)
+{
+    MDP_REQUIRE(ctx && count_out && (m == 0 || (list && keys_out)), "mdp_unique_pair_keys: NULL argument");
+    MDP_REQUIRE(m >= 0 && n_a > 0 && n_b > 0 && n_a * n_b <= ((int64_t)1 << 36), "mdp_unique_pair_keys: bad sizes (n_a * n_b <= 2^36)");
+    cudaStream_t st = (cudaStream_t)stream;
+    MDP_CUDA(cudaSetDevice(ctx->device));
+    const int64_t nwords = ceil_div<int64_t>(n_a * n_b, 32);
+    const int64_t ntiles = ceil_div<int64_t>(nwords, SCAN_TILE);
+    int rc = ctx->arena_reserve(align256((size_t)nwords * 4) + align256((size_t)ntiles * 8) + 4096);
+    if (rc) return rc;
+    ctx->arena_reset();
+    uint32_t *bits = (uint32_t *)ctx->arena_take((size_t)nwords * 4);
+    unsigned long long *tsum = (unsigned long long *)ctx->arena_take((size_t)ntiles * 8);
+    if (!bits || !tsum) {
+        mdp_set_error("internal: scratch arena exhausted (unique pair keys)");
+        return MDP_ERR_OOM;
+    }
+    MDP_CUDA(cudaMemsetAsync(bits, 0, (size_t)nwords * 4, st));
+    if (m > 0) {
+        k_pk_set<<<(unsigned)ceil_div<int64_t>(m, EB), EB, 0, st>>>(list, m, n_b, bits);
+        MDP_LAUNCHED(ctx);
+    }
+    k_pk_tile_sums<<<(unsigned)ntiles, SCAN_T, 0, st>>>(bits, nwords, tsum);
+    MDP_LAUNCHED(ctx);
+    k_scan_tiles<<<1, 1024, 0, st>>>(tsum, ntiles, count_out);
+    MDP_LAUNCHED(ctx);
+    k_pk_emit<<<(unsigned)ntiles, SCAN_T, 0, st>>>(bits, nwords, tsum, keys_out, capacity);
+    MDP_LAUNCHED(ctx);
+    return mdp_check_launch("k_pk_emit");
+}
 
 int mdp_list_group(mdp_ctx *ctx, int nframes, int64_t n_a, int64_t m, const int32_t *list, const uint32_t *key, int64_t *seg_off,
                    uint32_t *key_out, int64_t *perm_out, void *stream)

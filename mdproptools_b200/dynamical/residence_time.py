@@ -120,7 +120,7 @@ class ResidenceTime:
             if w > 1:
                 lst = dist.exchange_rows(lst, dist.owner_of_rows(lst[:, 1], n_k, w))
             if len(lst):
-                cnt, _ = ops.bitmask_autocorr_from_list(lst.contiguous(), n_l, T)
+                cnt, _ = ops.bitmask_autocorr_from_list(lst.contiguous(), n_l, T, n_a=n_k)
             else:
                 cnt = torch.zeros((T,), dtype=torch.int64, device=dev)
             if w > 1:

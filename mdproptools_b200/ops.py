@@ -322,14 +322,28 @@ def survival_runs_enabled() -> bool:
     return os.environ.get("MDP_SURVIVAL_RUNS", "1") not in ("", "0")
 
 
-def bitmask_autocorr_from_list(lst, n_b, T):
+def unique_pair_keys(lst, n_a, n_b):
+    """mdp_unique_pair_keys: the distinct (ia, ib) of a neighbour list as sorted int64 keys ia * n_b + ib."""
+    lst = _i32(lst.contiguous(), "lst")
+    M = lst.shape[0]
+    ctx = Context.get(lst.device.index)
+    cap = max(M, 1)
+    keys = torch.empty((cap,), dtype=torch.int64, device=lst.device)
+    cnt = torch.zeros((1,), dtype=torch.int64, device=lst.device)
+    check(lib().mdp_unique_pair_keys(ctx.handle, M, ptr(lst), int(n_a), int(n_b), ptr(keys), cap, ptr(cnt), stream_ptr()),
+          "mdp_unique_pair_keys")
+    return keys[: int(cnt.item())]
+
+
+def bitmask_autocorr_from_list(lst, n_b, T, n_a=None):
     """Neighbour list (frame, ia, ib) -> integer survival counts cnt[tau] (int64 [T]) and the number of ever-neighbour pairs."""
     ctx = Context.get(lst.device.index)
     cnt = torch.zeros((T,), dtype=torch.int64, device=lst.device)
     if lst.shape[0] == 0:
         return cnt, 0
-    keys = lst[:, 1].to(torch.int64) * int(n_b) + lst[:, 2].to(torch.int64)
-    ukeys = torch.unique(keys)   # sorted; plumbing only (the pair set is tiny next to the search)
+    lst = lst.contiguous()
+    n_a = int(n_a) if n_a is not None else int(lst[:, 1].max().item()) + 1
+    ukeys = unique_pair_keys(lst, n_a, int(n_b))                # sorted distinct (ia, ib) keys: bitmap + popcount scan, no sort
     P = int(ukeys.shape[0])
     W = (T + 63) // 64
     masks = torch.zeros((P, W), dtype=torch.int64, device=lst.device)

@@ -980,3 +980,13 @@ def test_cluster_members_kernel(ops):
             want = np.unique(mol_of_atom[atoms])
             want = want[ok[f, want]]
             assert np.array_equal(mols[so[s]: so[s] + cnt[s]], want), (f, c)
+
+
+def test_unique_pair_keys_kernel(ops):
+    import torch
+    rng = np.random.default_rng(12)
+    for na, nb, m in [(1, 1, 1), (7, 33, 500), (40, 1000, 20000), (3, 5, 0)]:
+        lst = np.stack([rng.integers(0, 50, m), rng.integers(0, na, m), rng.integers(0, nb, m)], axis=1).astype(np.int32)
+        got = ops.unique_pair_keys(torch.from_numpy(lst).cuda(), na, nb).cpu().numpy()
+        want = np.unique(lst[:, 1].astype(np.int64) * nb + lst[:, 2])
+        assert np.array_equal(got, want)
