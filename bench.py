@@ -253,6 +253,7 @@ def reference_numba_sample(host_frame, n_sub=8000):
         return None
     import multiprocessing as mp
     cores = host_threads()
+    n_sub = min(n_sub, N_ATOMS // max(cores, 1))            # one disjoint slice per core
     x, y, z = host_frame
     data = np.column_stack([np.ones(N_ATOMS), x, y, z])
     _REF_STATE.update(data=data, rel=np.array([[1, 1]], dtype=np.int64), L=tuple(lattice_lengths()))
@@ -538,6 +539,20 @@ def run_gpu(args):
     achieved = evaluated_local * FLOPS_PER_PAIR * args.steps / (pair_ms * 1e-3) / 1e12
     nominal_tflops = (F * N_ATOMS * (N_ATOMS - 1) // 2) * FLOPS_PER_PAIR * args.steps / (pair_ms * 1e-3) / 1e12
     frames_per_launch = F * args.steps / max(pair_n, 1)
+    # what actually bounds k_pair_fast: instruction issue.  Warp instructions per 32 evaluated pairs from the committed ncu
+    # capture (profiles/r02a_k_pair_fast_meta.json) x this run's evaluated pairs / its kernel time, against 4 schedulers x
+    # 148 SMs x 1 instruction per clock
+    issue = None
+    try:
+        meta = json.load(open(os.path.join(ROOT, "profiles", "r02a_k_pair_fast_meta.json")))
+        wi = meta["warp_instr_per_32_pairs"] if not os.environ.get("MDP_PAIR_F64") else meta["all_fp64_kernel"]["warp_instr_per_32_pairs"]
+        ips = evaluated_local / 32.0 * wi * args.steps / (pair_ms * 1e-3)
+        ipk = 148 * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6
+        issue = {"bound": "issue slots", "achieved": ips, "peak": ipk, "unit": "warp-instr/s", "frac": ips / ipk,
+                 "warp_instr_per_32_pairs": wi, "source": "instruction count per evaluated pair from profiles/r02a_k_pair_fast.txt "
+                 "(smsp__inst_executed.sum; issue slots 83.7 % busy under ncu), scaled to this run"}
+    except Exception:
+        pass
     cpu_rate, cores, sample = cpu_rdf_sample(10.0) if not args.skip_cpu else (None, None, "skipped")
     out = {
         "metric": "rdf_pair_evals_per_s", "value": value, "unit": "pair-evals/s", "n_gpus": world, "steps": args.steps,
@@ -552,11 +567,17 @@ def run_gpu(args):
         "kernel_share": {"pair_kernel_ms_per_step": pair_ms / args.steps, "prep_ms_per_step": prep_ms / args.steps,
                          "step_ms": ms / args.steps},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                     "traffic": ncu_traffic("pair", frames_per_launch / 16.0), "peak_source": peak_src,
-                     "traffic_note": "dram bytes of the 16-frame launch captured in the newest profiles/r*_k_pair.txt (55 MB = the sorted "
-                                     "records read once), scaled to this launch's frames; irrelevant to an FP64/issue-bound kernel",
-                     "note": f"pair kernel only; achieved = evaluated pair-evals x {FLOPS_PER_PAIR} unfused fp64 flops / "
-                             f"CUDA-event kernel time; nominal-pair equivalent = {nominal_tflops:.1f} TFLOP/s "
+                     "traffic": ncu_traffic("pair_fast", frames_per_launch / 16.0), "peak_source": peak_src,
+                     "traffic_note": "dram bytes of the 16-frame launch captured in the newest profiles/r*_k_pair_fast.txt (56 MB = the "
+                                     "sorted records read once), scaled to this launch's frames; irrelevant to an issue-bound kernel",
+                     "kernel": "k_pair_fast" if not os.environ.get("MDP_PAIR_F64") else "k_pair (all fp64)",
+                     "issue": issue,
+                     "note": f"pair kernel only; achieved = evaluated pair-evals x {FLOPS_PER_PAIR} unfused fp64 flops (the ALGORITHMIC "
+                             f"cost of a pair in the reference, SURVEY 8d) / CUDA-event kernel time, against the measured unfused FP64 "
+                             f"rate.  k_pair_fast does that arithmetic in fp32 (6 FP32-pipe instructions per pair, fp64 only for the "
+                             f"{exact_per_step / max(evaluated_per_step, 1):.2%} of pairs within the proven error bound of a bin edge), so "
+                             f"the fraction says how fast the kernel is relative to an ideal all-fp64 one, not how busy the FP64 pipe is; "
+                             f"what bounds it is instruction issue (`issue`).  Nominal-pair equivalent = {nominal_tflops:.1f} TFLOP/s "
                              f"({nominal_tflops / fp64_peak:.2f} of peak) because culling skips work the reference does"},
         "e2e": {"value": e2e_value, "unit": "pair-evals/s", "h2d_bytes_per_step": T_total * 3 * N_ATOMS * 8,
                 "d2h_bytes_per_step": world * T_total * 2 * NBINS * 8, "g_full_max": float(df_e2e["g_full(r)"].max()),
