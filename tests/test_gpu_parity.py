@@ -990,3 +990,73 @@ def test_unique_pair_keys_kernel(ops):
         got = ops.unique_pair_keys(torch.from_numpy(lst).cuda(), na, nb).cpu().numpy()
         want = np.unique(lst[:, 1].astype(np.int64) * nb + lst[:, 2])
         assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------
+# k_pair_fast (fp32 filter + fp64 exact path) against k_pair (all fp64) and the oracle over awkward geometries
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["dense", "tiny_cell", "unwrapped", "far_from_origin", "nosort", "many_bins", "coarse_bins", "rect",
+                                  "clustered", "multiframe", "huge_groups"])
+def test_pair_fast_equals_f64_kernel_and_oracle(ops, case):
+    """The fp32-filtered kernel must give the integers of the all-fp64 kernel (and of the oracle) whatever the geometry:
+    box-sized groups (MDP_PAIR_NO_SORT: the error bound collapses the fraction bits and almost every pair takes the exact
+    path), cells smaller than twice the cutoff (MIXED image everywhere), coordinates many box lengths outside the cell,
+    coordinates 10^5 A from the origin, thousands of bins, a handful of bins, rectangular sets, tightly clustered points
+    (many pairs on identical distances), per-frame boxes."""
+    import torch
+    from mdproptools_b200._lib import PAIR_F64, PAIR_NO_SORT, bin_edges
+    rng = np.random.default_rng(abs(hash(case)) % (2 ** 31))
+    n, L, rc, ddr, flags, ncls = 3000, np.array([44.0, 41.0, 39.0]), 9.0, 0.05, 0, 2
+    F = 1
+    if case == "tiny_cell":
+        n, L, rc = 900, np.array([13.0, 12.5, 14.0]), 6.2
+    if case == "many_bins":
+        ddr = 0.0025                                 # 3600 bins
+    if case == "coarse_bins":
+        ddr = 1.5
+    if case == "multiframe":
+        F = 3
+    Ls = np.stack([L * (1.0 + 0.01 * f) for f in range(F)])
+    pos = rng.uniform(0, 1, (F, 3, n)) * Ls[:, :, None]
+    if case == "unwrapped":
+        pos += rng.integers(-3, 4, (F, 3, n)) * Ls[:, :, None]
+    if case == "far_from_origin":
+        pos += 1.0e5
+    if case == "clustered":
+        centres = rng.uniform(0, 1, (F, 3, 30)) * Ls[:, :, None]
+        pos = centres[:, :, rng.integers(0, 30, n)] + np.round(rng.normal(0, 0.8, (F, 3, n)), 1)   # lattice-like offsets: many ties
+    if case == "nosort":
+        flags = PAIR_NO_SORT
+    if case == "huge_groups":
+        # caller order + points thousands of box lengths apart: group boxes 10^5 A wide, the error bound exceeds a bin and the
+        # kernel must route (nearly) everything it evaluates through the exact path
+        flags = PAIR_NO_SORT
+        pos += rng.integers(-3000, 3001, (F, 3, n)) * Ls[:, :, None]
+        pos[:, :, : n // 2] = rng.uniform(0, 1, (F, 3, n // 2)) * Ls[:, :, None]          # half of them in the home cell: real hits
+    typ = rng.integers(1, ncls + 1, n).astype(np.float64)
+    cls = torch.from_numpy((typ - 1).astype(np.int32)).cuda()
+    nb = int(rc / ddr)
+    edges = bin_edges(ddr, nb)
+    kw = {}
+    if case == "rect":
+        m = 700
+        posb = rng.uniform(0, 1, (F, 3, m)) * Ls[:, :, None]
+        typb = rng.integers(1, ncls + 1, m).astype(np.float64)
+        kw = dict(xyz_b=_dev(posb), cls_b=torch.from_numpy((typb - 1).astype(np.int32)).cuda(), ncls_b=ncls)
+    fast = ops.pair_hist(_dev(pos), cls, ncls, Ls, O.rcut_sq(rc), edges, ddr, flags=flags, **kw)
+    stats = Context_stats()
+    slow = ops.pair_hist(_dev(pos), cls, ncls, Ls, O.rcut_sq(rc), edges, ddr, flags=flags | PAIR_F64, **kw)
+    assert torch.equal(fast, slow), case
+    assert stats["pair_evals"] > 0
+    if case == "huge_groups":
+        assert stats["exact_path_pairs"] > 100 * 945             # (the well-sorted cases settle ~1e3 pairs in fp64)
+    # and the oracle, frame 0 (symmetric cases: full histogram = sum over class pairs x 2)
+    if case != "rect":
+        full, _ = O.rdf_loop(typ, pos[0, 0], pos[0, 1], pos[0, 2], np.array([[1, 1]]), tuple(Ls[0]), rc, ddr, nb, nthreads=0)
+        assert np.array_equal(fast[0].sum(dim=0).cpu().numpy() * 2, full)
+
+
+def Context_stats():
+    from mdproptools_b200._lib import Context
+    import torch
+    return Context.get(torch.cuda.current_device()).pair_stats()
