@@ -735,6 +735,7 @@ struct PairParams {
     float f_rc;                      // cutoff radius, rounded up
     float f_c1;                      // 1.5 * sqrt(3) * 2^-24 / ddr: bins per A of coordinate error
     float f_rel;                     // 1.5 * (nbins + 1) * RHO: the relative part
+    float f_rc2t;                    // point-filter threshold: rcut2 rounded up, times (1 + 2^-18) rounded up
     int f_smax;                      // most fraction bits the 2^23 trick leaves room for
 };
 
@@ -1765,6 +1766,7 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
             p.f_c1 = (float)(safety * sqrt(3.0) / 16777216.0 / c.uniform_ddr);
             p.f_rel = (float)(safety * (c.nbins + 1) * rho);
             p.f_smax = f_smax;
+            p.f_rc2t = nextafterf(nextafterf((float)c.rcut2, INFINITY) * (1.0f + 1.0f / 262144.0f), INFINITY);
         }
         MDP_CUDA(cudaMemsetAsync(d_fcount, 0, (size_t)F * 4, st));
         cudaEvent_t tk = ctx->timer_begin(0, st);

@@ -42,6 +42,10 @@ namespace {
 #define MDP_FAST_CTAS 3
 #endif
 constexpr int FAST_CTAS_PER_SM = MDP_FAST_CTAS;
+#ifndef MDP_FAST_UNROLL
+#define MDP_FAST_UNROLL 4
+#endif
+constexpr int FU = MDP_FAST_UNROLL;           // candidates per round of the pair loop (ring runs are padded to a multiple of it)
 constexpr int FRING = 64;                     // candidate ring: float4 entries per warp
 constexpr int FQ_CAP = 64;                    // undecided-pair queue: entries per warp
 constexpr unsigned FMAGIC_BITS = 0x4b400000u; // bits of 12582912.0f = 1.5 * 2^23
@@ -136,10 +140,12 @@ constexpr size_t FW_RING = 0, FW_XQ = FW_RING + FRING * 16, FW_JST = FW_XQ + FQ_
 static_assert(FAST_WARP_BYTES % 16 == 0, "warp region must keep 16-byte alignment");
 
 struct FrameConst {
-    float ax[3][4];        // per axis: l_dn, l_up, h_dn, h_up
+    float ax[3][4];        // per axis: l_dn, l_up, h_dn, h_up   (read as float4: keep at offset 0, 16-byte aligned)
     float l32[3];          // fl32(l): the MIXED variant's shift
     float lmax_up;
     double cell[6];        // lx, ly, lz, xy, xz, yz
+    const double2 *rB;     // records of set B of the current frame (kept here: the pointer is needed once per chunk, and
+                           // re-deriving it from the parameter block costs a 64-bit multiply chain in an issue-bound loop)
 };
 
 struct FastShared {
@@ -258,29 +264,30 @@ struct FastRunP {               // per-unit constants of the pair loop
     float xi, yi, zi;           // my i point relative to the group centre
 };
 
-// nj (a multiple of 4) queued candidates at shared address ja against my i point.  MIXED: min(|d|, ||d| - l|) per axis on
+// nj (a multiple of FU) queued candidates at shared address ja against my i point.  MIXED: min(|d|, ||d| - l|) per axis on
 // unshifted candidates (l32*).  TRI: the self chunk, only j > lane counts.
 template <bool MULTICLS, bool TRICL, bool MIXED, bool TRI>
 __device__ __forceinline__ void fast_run(const FastRunP &R, const FastExact &ex, const unsigned ja, const int nj,
-                                         const float l32x, const float l32y, const float l32z, const int lane, int &qn, uint2 *xq)
+                                         const float l32x, const float l32y, const float l32z, const int lane, int &qn, uint2 *xq,
+                                         unsigned &uex)
 {
     const float inv_s = R.inv_s, xi = R.xi, yi = R.yi, zi = R.zi;
     const unsigned mask = R.mask, clampv = R.clampv, base = R.base;
     const int s = R.s;
 #pragma unroll 1
-    for (int j0 = 0; j0 < nj; j0 += 4) {
-        unsigned b[4];
+    for (int j0 = 0; j0 < nj; j0 += FU) {
+        unsigned b[FU];
         bool unc = false;
-        float jx[4], jy[4], jz[4];
-        unsigned jm[4];
+        float jx[FU], jy[FU], jz[FU];
+        unsigned jm[FU];
         // the four candidates first (back-to-back loads, nothing depends on the previous one), then the arithmetic
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < FU; ++u)
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(jx[u]), "=f"(jy[u]), "=f"(jz[u]), "=r"(jm[u])
                          : "r"(ja + (unsigned)(j0 + u) * 16u));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < FU; ++u) {
             float dx = xi - jx[u], dy = yi - jy[u], dz = zi - jz[u];
             if (MIXED) {
                 dx = fminf(fabsf(dx), fabsf(fabsf(dx) - l32x));
@@ -297,7 +304,7 @@ __device__ __forceinline__ void fast_run(const FastRunP &R, const FastExact &ex,
             unc = unc || ((v & mask) == 0u);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < FU; ++u) {
             unsigned a = base + ((b[u] >> s) << 2);
             if (MULTICLS) {
                 unsigned row;
@@ -309,7 +316,7 @@ __device__ __forceinline__ void fast_run(const FastRunP &R, const FastExact &ex,
         if (__any_sync(0xffffffffu, unc)) {
             const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {   // unrolled: b[] stays in registers; the candidate's w is re-read from the ring
+            for (int u = 0; u < FU; ++u) {   // unrolled: b[] stays in registers; the candidate's w is re-read from the ring
                 unsigned jm;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(jm) : "r"(ja + (unsigned)(j0 + u) * 16u + 12u));
                 bool f = (b[u] & mask) == 0u && jm < FAST_PADMETA;
@@ -319,6 +326,7 @@ __device__ __forceinline__ void fast_run(const FastRunP &R, const FastExact &ex,
                 const int c = __popc(m);
                 if (qn + c > FQ_CAP) {
                     __syncwarp();
+                    uex += (unsigned)qn;
                     fast_settle<MULTICLS, TRICL>(ex.nb, ex.edges2, ex.nclsB, ex.hist, ex.cptab, lane, qn, xq, ex.rAg, ex.rB, ex.cell);
                     qn = 0;
                 }
@@ -329,16 +337,16 @@ __device__ __forceinline__ void fast_run(const FastRunP &R, const FastExact &ex,
     }
 }
 
-// the ring holds n pending candidates from `base`: pad to a multiple of 4 and evaluate them (uniform-image variant)
+// the ring holds n pending candidates from `base`: pad to a multiple of FU and evaluate them (uniform-image variant)
 template <bool MULTICLS, bool TRICL>
 __device__ __forceinline__ void fast_flush(const FastRunP &R, const FastExact &ex, float4 *ring, unsigned ring_a, int head, int tail,
-                                           int lane, int &qn, uint2 *xq)
+                                           int lane, int &qn, uint2 *xq, unsigned &uex)
 {
     const int n = tail - head;
-    const int np = (n + 3) & ~3;
+    const int np = (n + FU - 1) & ~(FU - 1);
     if (lane < np - n) ring[(tail + lane) & (FRING - 1)] = make_float4(FAST_PAD, 0.f, 0.f, __uint_as_float(FAST_PADMETA));
     __syncwarp();
-    fast_run<MULTICLS, TRICL, false, false>(R, ex, ring_a + (unsigned)(head & 32) * 16u, np, 0.f, 0.f, 0.f, lane, qn, xq);
+    fast_run<MULTICLS, TRICL, false, false>(R, ex, ring_a + (unsigned)(head & 32) * 16u, np, 0.f, 0.f, 0.f, lane, qn, xq, uex);
     __syncwarp();
 }
 
@@ -349,7 +357,7 @@ template <bool MULTICLS, bool TRICL>
 __device__ __forceinline__ unsigned fast_special(int f_smax, float inv_ddr, const FastRunP &R, const FastExact &ex, const FrameConst *fc,
                                                  float4 *ring, unsigned ring_a, float jx, float jy, float jz, unsigned jmeta, bool self,
                                                  bool mixed, float extx, float exty, float extz, float rc2t, float e15m,
-                                                 unsigned hist_a, int lane, int &qn, uint2 *xq)
+                                                 unsigned hist_a, int lane, int &qn, uint2 *xq, unsigned &uex)
 {
     int n = 32;
     if (self) {
@@ -361,13 +369,13 @@ __device__ __forceinline__ unsigned fast_special(int f_smax, float inv_ddr, cons
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (ok) ring[__popc(m & ((1u << lane) - 1u))] = make_float4(jx, jy, jz, __uint_as_float(jmeta));
         const int c = __popc(m);
-        n = (c + 3) & ~3;
+        n = (c + FU - 1) & ~(FU - 1);
         if (lane < n - c) ring[c + lane] = make_float4(FAST_PAD, 0.f, 0.f, __uint_as_float(FAST_PADMETA));
     }
     __syncwarp();
     if (n > 0) {
         if (!mixed) {
-            fast_run<MULTICLS, TRICL, false, true>(R, ex, ring_a, n, 0.f, 0.f, 0.f, lane, qn, xq);    // (only the self chunk gets here)
+            fast_run<MULTICLS, TRICL, false, true>(R, ex, ring_a, n, 0.f, 0.f, 0.f, lane, qn, xq, uex);    // (only the self chunk gets here)
         } else if (!TRICL) {
             const FastBin fbM = make_fastbin(e15m, f_smax, inv_ddr, (unsigned)ex.nb, lane, hist_a);
             FastRunP RM = R;
@@ -377,9 +385,9 @@ __device__ __forceinline__ unsigned fast_special(int f_smax, float inv_ddr, cons
             RM.base = fbM.base;
             RM.s = fbM.s;
             if (self)
-                fast_run<MULTICLS, TRICL, true, true>(RM, ex, ring_a, n, fc->l32[0], fc->l32[1], fc->l32[2], lane, qn, xq);
+                fast_run<MULTICLS, TRICL, true, true>(RM, ex, ring_a, n, fc->l32[0], fc->l32[1], fc->l32[2], lane, qn, xq, uex);
             else
-                fast_run<MULTICLS, TRICL, true, false>(RM, ex, ring_a, n, fc->l32[0], fc->l32[1], fc->l32[2], lane, qn, xq);
+                fast_run<MULTICLS, TRICL, true, false>(RM, ex, ring_a, n, fc->l32[0], fc->l32[1], fc->l32[2], lane, qn, xq, uex);
         }
     }
     __syncwarp();
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
     }
     int qn = 0;
     const float rcut2_up = __double2float_ru(p.rcut2);
-    const float rc2t = __fmul_ru(rcut2_up, 1.0f + 1.0f / 262144.0f);   // point filter: covers the fp32 rounding of its own sums
+    const float rc2t = p.f_rc2t;   // point filter threshold: rcut2 rounded up x (1 + 2^-18), covers the fp32 rounding of its own sums
     const int F = p.nframes;
     const int fstart = (int)(((long long)blockIdx.x * F) / gridDim.x);
     const unsigned int nunits = (unsigned int)p.ntA * GPT;
@@ -457,6 +465,7 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
             fc->cell[threadIdx.x - 3] = cell[threadIdx.x - 3];
         } else if (threadIdx.x == 9) {
             fc->lmax_up = __double2float_ru(fmax(fmax(cell[0], cell[1]), cell[2]));
+            fc->rB = p.recB + (int64_t)f * p.npadB * 2;
         }
         __syncthreads();
         const int frame = p.frame0 + f;
@@ -587,7 +596,7 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
                     nself = SYMM && tb == ta && (l & 7) == wi;
                     const unsigned cidx = (unsigned)tb * GPT + (unsigned)(l & 7);
                     nbase = cidx * GS;
-                    const double2 *jsrc = rB + (int64_t)cidx * GREC + lane;
+                    const double2 *jsrc = fc->rB + (size_t)(cidx * GREC + (unsigned)lane);
                     const unsigned dst = wp_a + (unsigned)FW_JST + stage * 1024u + (unsigned)lane * 16u;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(jsrc) : "memory");
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(jsrc + 32) : "memory");
@@ -631,10 +640,15 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
                     } else {
                         mixed = ((ccode & (ccode >> 1)) & 0x15) != 0;
                         // j relative to the group centre: subtraction of (g - S) in fp64, ONE rounding to fp32
-                        const int sel = mixed ? 0 : ccode;
-                        jx = __double2float_rn(__dsub_rn(jxy.x, gs[sel & 3]));
-                        jy = __double2float_rn(__dsub_rn(jxy.y, gs[3 + ((sel >> 2) & 3)]));
-                        jz = __double2float_rn(__dsub_rn(jzw.x, gs[6 + ((sel >> 4) & 3)]));
+                        if (ccode == 0 || mixed) {           // the common case (no image shift anywhere): fixed table slots
+                            jx = __double2float_rn(__dsub_rn(jxy.x, gs[0]));
+                            jy = __double2float_rn(__dsub_rn(jxy.y, gs[3]));
+                            jz = __double2float_rn(__dsub_rn(jzw.x, gs[6]));
+                        } else {
+                            jx = __double2float_rn(__dsub_rn(jxy.x, gs[ccode & 3]));
+                            jy = __double2float_rn(__dsub_rn(jxy.y, gs[3 + ((ccode >> 2) & 3)]));
+                            jz = __double2float_rn(__dsub_rn(jzw.x, gs[6 + ((ccode >> 4) & 3)]));
+                        }
                     }
                     if (jpad) {
                         jx = FAST_PAD;
@@ -645,13 +659,13 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
                     } else if (cself || mixed) {
                         // rare: the triangular self chunk / a chunk pair without a uniform image (small cells)
                         if (tail != head) {
-                            uev += (unsigned)((tail - head + 3) & ~3);
-                            fast_flush<MULTICLS, TRICL>(R, ex, ring, wp_a + (unsigned)FW_RING, head, tail, lane, qn, xq);
+                            uev += (unsigned)((tail - head + FU - 1) & ~(FU - 1));
+                            fast_flush<MULTICLS, TRICL>(R, ex, ring, wp_a + (unsigned)FW_RING, head, tail, lane, qn, xq, uex);
                         }
                         head = 0;
                         tail = 0;
                         uev += fast_special<MULTICLS, TRICL>(p.f_smax, p.inv_ddr, R, ex, fc, ring, wp_a + (unsigned)FW_RING, jx, jy, jz, jmeta, cself, mixed, extx, exty,
-                                                             extz, rc2t, e15m, hist_a, lane, qn, xq);
+                                                             extz, rc2t, e15m, hist_a, lane, qn, xq, uex);
                     } else {
                         const float bx = fmaxf(fabsf(jx) - extx, 0.f), by = fmaxf(fabsf(jy) - exty, 0.f), bz = fmaxf(fabsf(jz) - extz, 0.f);
                         const bool ok = __fmaf_rn(bz, bz, __fmaf_rn(by, by, bx * bx)) < rc2t && !jpad;
@@ -662,7 +676,7 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
                             __syncwarp();
                             uev += 32u;
                             fast_run<MULTICLS, TRICL, false, false>(R, ex, wp_a + (unsigned)FW_RING + (unsigned)(head & 32) * 16u, 32, 0.f, 0.f, 0.f,
-                                                                    lane, qn, xq);
+                                                                    lane, qn, xq, uex);
                             __syncwarp();
                             head += 32;
                         }
@@ -677,8 +691,8 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             if (tail != head) {
-                uev += (unsigned)((tail - head + 3) & ~3);
-                fast_flush<MULTICLS, TRICL>(R, ex, ring, wp_a + (unsigned)FW_RING, head, tail, lane, qn, xq);
+                uev += (unsigned)((tail - head + FU - 1) & ~(FU - 1));
+                fast_flush<MULTICLS, TRICL>(R, ex, ring, wp_a + (unsigned)FW_RING, head, tail, lane, qn, xq, uex);
             }
             if (qn > 0) {
                 uex += (unsigned)qn;

@@ -1060,3 +1060,25 @@ def Context_stats():
     from mdproptools_b200._lib import Context
     import torch
     return Context.get(torch.cuda.current_device()).pair_stats()
+
+
+def test_atomic_rdf_from_arrays_equals_file_api(sample_dir, tmp_path):
+    """calc_atomic_rdf_from_arrays (the in-memory front end bench.py's e2e number goes through) against calc_atomic_rdf on the
+    same frames: identical DataFrames, through the vectorised normalisation (one composition, one volume) and through the
+    per-frame loop (a trajectory whose box changes)."""
+    from mdproptools_b200.io import dump as D
+    from mdproptools_b200.structural.rdf_cn import calc_atomic_rdf, calc_atomic_rdf_from_arrays
+    pat = os.path.join(sample_dir, "dump.nvt.*.dump")
+    want = calc_atomic_rdf(20, 0.05, 9, MASS, C1_REL, pat, save_mode=False)
+    frames = list(D.read_dumps(pat, ["id", "type", "x", "y", "z"]))
+    pos = np.stack([np.stack([f.data["x"], f.data["y"], f.data["z"]]) for f in frames])
+    typ = frames[0].data["type"]
+    L = frames[0].box.lattice_lengths()
+    got, counts = calc_atomic_rdf_from_arrays(pos, typ, L, 20, 0.05, C1_REL, return_counts=True)
+    assert np.array_equal(got.values, want.values) and list(got.columns) == list(want.columns)
+    assert counts.shape == (len(frames), 5, 400)
+    # box changing from frame to frame: the per-frame normalisation loop; compare with the two single-frame results averaged
+    Ls = np.stack([np.asarray(L), np.asarray(L) * 1.001])
+    got2 = calc_atomic_rdf_from_arrays(pos, typ, Ls, 20, 0.05, C1_REL)
+    one = [calc_atomic_rdf_from_arrays(pos[k:k + 1], typ, Ls[k], 20, 0.05, C1_REL).values for k in range(2)]
+    assert np.array_equal(got2.values[:, 1:], (one[0][:, 1:] + one[1][:, 1:]) / 2)
