@@ -47,6 +47,39 @@ class Batch:
         return self.columns.index(name)
 
 
+class _ProducerStopped(BaseException):
+    """Raised inside the producer thread when the consumer has gone away."""
+
+
+class _StoppableQueue:
+    """queue.Queue whose put() gives up (raises _ProducerStopped in the producer) once stop() was called."""
+
+    def __init__(self, maxsize):
+        self._q = queue.Queue(maxsize=maxsize)
+        self._stop = threading.Event()
+
+    def put(self, item):
+        while True:
+            if self._stop.is_set():
+                raise _ProducerStopped()
+            try:
+                self._q.put(item, timeout=0.05)
+                return
+            except queue.Full:
+                continue
+
+    def get(self):
+        return self._q.get()
+
+    def stop(self):
+        self._stop.set()
+        try:
+            while True:                       # drain: a producer blocked in put() gets its slot and then sees the flag
+                self._q.get_nowait()
+        except queue.Empty:
+            pass
+
+
 def _guard_multi(source, owner):
     """Pass (index, text) pairs through; a MultiFrameFile from a sharded read ends the stream and is recorded."""
     try:
@@ -164,8 +197,13 @@ class FrameBatches:
             self.total_frames = idx + 1 if sharded_total is None else sharded_total
             flush()
             q.put(None)
+        except _ProducerStopped:
+            return                        # the consumer left; nothing to forward
         except BaseException as exc:  # noqa: BLE001 - forwarded to the consumer
-            q.put(exc)
+            try:
+                q.put(exc)
+            except _ProducerStopped:
+                pass
 
     def _flush_device(self, bufs, indices, h, copy_stream):
         """Device parse of one batch (EXPERIMENTAL): text -> pinned bytes -> H2D -> k_dump_rows -> D2H of the parsed SoA
@@ -229,17 +267,23 @@ class FrameBatches:
         return metas, dev, ev
 
     def __iter__(self):
-        q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
+        q: "queue.Queue" = _StoppableQueue(self.prefetch)
         th = threading.Thread(target=self._produce, args=(q,), daemon=True)
         th.start()
-        while True:
-            item = q.get()
-            if item is None:
-                break
-            if isinstance(item, BaseException):
-                raise item
-            yield item
-        th.join()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            # the consumer may leave early (an exception in its loop body, a generator that is dropped): tell the producer to
+            # stop, unblock its pending put, and wait for it -- otherwise the thread would sit in q.put() for ever, holding
+            # the pinned staging ring, the device batches and the read-ahead pool
+            q.stop()
+            th.join()
 
 
 class ArrayBatches:

@@ -685,3 +685,25 @@ def test_utilities_mirror_reference_import_paths(tmp_path):
         return
     mean, std = fluctuations.plot_fluctuations(df, "Press", "P", "press.png", working_dir=str(tmp_path))
     assert (tmp_path / "press.png").exists() and mean == got["mean"] and std == got["std"]
+
+
+def test_frame_batches_producer_stops_when_the_consumer_leaves(tmp_path):
+    """A consumer that raises (or drops the generator) mid-iteration must not leave the producer thread blocked in q.put()
+    with its pinned buffers: FrameBatches.__iter__ stops and joins it."""
+    import threading
+    from mdproptools_b200.io.pipeline import FrameBatches
+    rows = "\n".join("%d 1 %g %g %g" % (i + 1, 0.5 * i, 1.0 * i, 2.0 * i) for i in range(50))
+    for k in range(40):
+        (tmp_path / f"dump.s.{k}.dump").write_text(
+            f"ITEM: TIMESTEP\n{k}\nITEM: NUMBER OF ATOMS\n50\nITEM: BOX BOUNDS pp pp pp\n0 9\n0 9\n0 9\nITEM: ATOMS id type x y z\n{rows}\n")
+    before = threading.active_count()
+    fb = FrameBatches(str(tmp_path / "dump.s.*.dump"), ["id", "x"], to_device=False, max_batch_frames=2, prefetch=1)
+    with pytest.raises(RuntimeError):
+        for n, batch in enumerate(fb):
+            if n == 2:
+                raise RuntimeError("consumer gives up")
+    it = iter(FrameBatches(str(tmp_path / "dump.s.*.dump"), ["id", "x"], to_device=False, max_batch_frames=2, prefetch=1))
+    next(it)
+    it.close()                                           # generator dropped after one batch
+    assert threading.active_count() <= before            # both producer threads were joined
+    assert sum(len(b.metas) for b in FrameBatches(str(tmp_path / "dump.s.*.dump"), ["id", "x"], to_device=False)) == 40
