@@ -131,12 +131,13 @@ __device__ __forceinline__ float mixed_axis_lb(float a, float e, float l_dn, flo
 // per warp:  ring   float4[FRING]        candidates (x, y, z relative to the group centre, w = sorted j position [<< 6 | class])
 //            xq     uint2[FQ_CAP]        undecided pairs: (w of the candidate, lane << 16 | bin already incremented)
 //            jst    double2[2][64]       two staged j chunks (1 KB each, filled by cp.async one chunk ahead of their use)
-//            gs     double[3][3]         g - S for the three uniform image classes of each axis (0: none, 1: j + l, 2: j - l)
+//            gs     double[3][3]         g - S for the three uniform image classes of each axis (0: none, 1: j + l, 2: j - l);
+//                   double[27][3]        triclinic: g - S for the 27 image vectors (index ex + 3 ey + 9 ez, e = 0 / 1 / 2 for k = 0 / +1 / -1)
 //            ga     float[8]             box of the i group (lo.xyz, -, hi.xyz, -), for the chunk-level test
 // per CTA:   fc     FrameConst           box lengths of the current frame in the forms the tests need
 //            cptab, evals, totals, hist
 constexpr size_t FW_RING = 0, FW_XQ = FW_RING + FRING * 16, FW_JST = FW_XQ + FQ_CAP * 8, FW_GS = FW_JST + 2 * 1024,
-                 FW_GA = FW_GS + 80, FAST_WARP_BYTES = FW_GA + 32;
+                 FW_GA = FW_GS + 656, FAST_WARP_BYTES = FW_GA + 32;
 static_assert(FAST_WARP_BYTES % 16 == 0, "warp region must keep 16-byte alignment");
 
 struct FrameConst {
@@ -246,6 +247,19 @@ __device__ __noinline__ void fast_exact_chunk(int nb, const double2 *__restrict_
             atomicAdd(&hist[(row >> 2) + k], 1u);
         }
     }
+}
+
+// triclinic chunk-level test, out of line (scalar arguments): its 27-image enumeration needs ~40 registers of its own, which
+// inlined would be taken from the pair loop of the whole kernel.  Returns code | need << 8.
+__device__ __noinline__ int fast_tri_chunk_test(float a0, float a1, float a2, float a3, float a4, float a5, float b0, float b1, float b2,
+                                                float b3, float b4, float b5, const double *cell, float rcut2_up)
+{
+    const float a[6] = {a0, a1, a2, a3, a4, a5}, b[6] = {b0, b1, b2, b3, b4, b5};
+    TriConst<DirF32> TC;
+    TC.set(cell);
+    int code = 0;
+    const bool need = tri_box_test<DirF32>(a, b, TC, rcut2_up, code);
+    return code | (need ? 256 : 0);
 }
 
 struct FastExact {              // what the exact path needs (per unit); all warp-uniform
@@ -522,7 +536,17 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
                     gas[0] = alo;
                     gas[1] = ahi;
                 }
-                if (lane < 9) {
+                if (TRICL) {
+                    if (lane < 27) {
+                        // gs[t][axis] = g - S(image vector t): S = (kx lx + ky xy + kz xz, ky ly + kz yz, kz lz)
+                        const int ez = lane / 9, r9 = lane - ez * 9, ey = r9 / 3, ex3 = r9 - ey * 3;
+                        const double kx = tri_dec(ex3, 1.0), ky = tri_dec(ey, 1.0), kz = tri_dec(ez, 1.0);
+                        const double *c6 = fc->cell;
+                        gs[lane * 3 + 0] = __dsub_rn((double)gcx, __dadd_rn(__dadd_rn(__dmul_rn(kx, c6[0]), __dmul_rn(ky, c6[3])), __dmul_rn(kz, c6[4])));
+                        gs[lane * 3 + 1] = __dsub_rn((double)gcy, __dadd_rn(__dmul_rn(ky, c6[1]), __dmul_rn(kz, c6[5])));
+                        gs[lane * 3 + 2] = __dsub_rn((double)gcz, __dmul_rn(kz, c6[2]));
+                    }
+                } else if (lane < 9) {
                     // gs[axis][cls] = g - S(cls): the j point's coordinate relative to the centre is X_j - gs (one DADD)
                     const int a = lane / 3, c = lane - a * 3;
                     const double g = (double)(a == 0 ? gcx : (a == 1 ? gcy : gcz));
@@ -575,9 +599,10 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
                         const float4 alo = gas[0], ahi = gas[1];
                         const float ga[6] = {alo.x, alo.y, alo.z, ahi.x, ahi.y, ahi.z};
                         if (TRICL) {
-                            TriConst<DirF32> TC;
-                            TC.set(fc->cell);
-                            need = tri_box_test<DirF32>(ga, gb, TC, rcut2_up, code);
+                            const int rcode = fast_tri_chunk_test(ga[0], ga[1], ga[2], ga[3], ga[4], ga[5], gb[0], gb[1], gb[2], gb[3], gb[4], gb[5],
+                                                                  fc->cell, rcut2_up);
+                            need = (rcode & 256) != 0;
+                            code = rcode & 255;
                         } else {
                             const float4 a0 = *reinterpret_cast<const float4 *>(fc->ax[0]), a1 = *reinterpret_cast<const float4 *>(fc->ax[1]),
                                          a2 = *reinterpret_cast<const float4 *>(fc->ax[2]);
@@ -625,17 +650,10 @@ __global__ void __launch_bounds__(NWARP * 32, NCTA) k_pair_fast(const PairParams
                             skip = true;
                             jx = jy = jz = 0.f;
                         } else {
-                            double gx = gs[0], gy = gs[3], gz = gs[6];
-                            if (ccode != 0) {
-                                const double kx = tri_dec(ccode & 3, 1.0), ky = tri_dec((ccode >> 2) & 3, 1.0), kz = tri_dec((ccode >> 4) & 3, 1.0);
-                                const double *c6 = fc->cell;
-                                gx = __dsub_rn(gx, __dadd_rn(__dadd_rn(__dmul_rn(kx, c6[0]), __dmul_rn(ky, c6[3])), __dmul_rn(kz, c6[4])));
-                                gy = __dsub_rn(gy, __dadd_rn(__dmul_rn(ky, c6[1]), __dmul_rn(kz, c6[5])));
-                                gz = __dsub_rn(gz, __dmul_rn(kz, c6[2]));
-                            }
-                            jx = __double2float_rn(__dsub_rn(jxy.x, gx));
-                            jy = __double2float_rn(__dsub_rn(jxy.y, gy));
-                            jz = __double2float_rn(__dsub_rn(jzw.x, gz));
+                            const int t3 = ((ccode & 3) + 3 * ((ccode >> 2) & 3) + 9 * ((ccode >> 4) & 3)) * 3;
+                            jx = __double2float_rn(__dsub_rn(jxy.x, gs[t3]));
+                            jy = __double2float_rn(__dsub_rn(jxy.y, gs[t3 + 1]));
+                            jz = __double2float_rn(__dsub_rn(jzw.x, gs[t3 + 2]));
                         }
                     } else {
                         mixed = ((ccode & (ccode >> 1)) & 0x15) != 0;
