@@ -830,17 +830,21 @@ def bench_green_kubo(args, torch, dist, ops, ctx, dev, world, rank):
     use_fft = ops.xcorr_fft_enabled(T)
     if use_fft:
         # FFT route (the default at this length): HBM-bound.  Algorithmic bytes = the two input series read once and the
-        # correlation written once (24 B per channel-step); the radix-2 Stockham passes move far more (2 log2 N stages x
-        # 32 B per point of the padded transform), which is what `traffic` states
+        # correlation written once (24 B per channel-step); the Stockham passes (three stages each) move more: per point of
+        # the padded transform 32 B per inner pass, which is what `traffic` states
         p2 = 1
         while (1 << p2) < 2 * T:
             p2 += 1
+        passes = -(-p2 // 3)
         alg = C * T * 24
-        moved = C * (1 << p2) * 16 * 2 * (2 * p2 + 2)
+        npts = C * (1 << p2)
+        # transform 1: first pass reads the series (16 B per step) and writes 16 B per point, the others 32 B; cross
+        # spectrum 48 B (two reads, one write); transform 2: 32 B per pass, the last one reads 16 B and writes the lags
+        moved = C * T * 16 + npts * 16 + npts * 32 * (passes - 1) + npts * 48 + npts * 32 * (passes - 1) + npts * 16 + C * T * 8
         gbs = alg / (kms_x * 1e-3) / 1e9
         roof_x = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": moved,
-                  "note": f"mdp_xcorr_fft (all its launches: twiddles, load, 2 x {p2} radix-2 stages, cross spectrum, store); "
-                          f"algorithmic bytes = 24 B per channel-step; traffic = bytes the {2 * p2 + 2} passes move (computed, "
+                  "note": f"mdp_xcorr_fft (all its launches: twiddles, 2 x {passes} passes of three radix-2 stages, cross spectrum); "
+                          f"algorithmic bytes = 24 B per channel-step; traffic = bytes the {2 * passes + 1} passes move (computed, "
                           f"not measured: {moved / 1e9:.2f} GB -> {moved / (kms_x * 1e-3) / 1e9:.0f} GB/s); the same job as a direct "
                           f"sum costs {fma:.3g} FMAs ({ach:.0f} TFLOP/s-equivalent at this time)"}
     else:
@@ -852,7 +856,7 @@ def bench_green_kubo(args, torch, dist, ops, ctx, dev, world, rank):
     ms_c, _, _ = _timed(ctx, torch, 7, lambda: ops.cumtrapz(corr, 1.0, 1.0, True), 3)
     return {
         "metric": "acf_lag_products_per_s", "value": C_all * T * (T + 1) // 2 / (ms_x_max * 1e-3), "unit": "fp64 FMA/s",
-        "method": "fft (radix-2 Stockham, fp64)" if use_fft else "direct sum",
+        "method": "fft (Stockham, three radix-2 stages per pass, fp64)" if use_fft else "direct sum",
         "config": {"workload": f"C4 shape: {C_all} channels x {T} steps, unbiased correlation at every lag, "
                                f"channels x{world}; charge flux on {n} atoms x {Tf_total} frames ({n * Tf_total * 24 / 1e9:.0f} GB, frames "
                                f"x{world}, resident chunks of {CH} frames generated on the device)"},
@@ -964,11 +968,23 @@ def bench_residence(args, torch, dist, ops, ctx, dev, world, rank):
         roof_r = {"bound": "int", "achieved": gpop, "peak": peak, "unit": "G popc64/s", "frac": gpop / peak, "traffic": None,
                   "note": "k_bitmask_autocorr only (this rank's central atoms); one 64-bit AND + POPC per (pair, lag, word); "
                           "peak = nominal XU rate 16 POPC/clk/SM x 148 SMs x 1965 MHz / 2 (popcll = 2 POPC)"}
+    # the neighbour search alone (this rank's frames): HBM-bound by design, both coordinate sets read once
+    roof_s = None
+    if ops.shell_grid_enabled():
+        _, kms_s, kn_s = _timed(ctx, torch, 0, search, 2)
+        alg_s = Tl * (ncat + nox) * 24
+        hbm = measured_peaks().get("hbm_gbs", 6650.0)
+        gbs_s = alg_s / (kms_s * 1e-3) / 1e9 if kms_s > 0 else 0.0
+        roof_s = {"bound": "hbm", "achieved": gbs_s, "peak": hbm, "unit": "GB/s", "frac": gbs_s / hbm, "traffic": None,
+                  "note": f"k_shell_grid only ({kn_s} launches of {FB} frames, {kms_s:.3f} ms for this rank's {Tl} frames); algorithmic "
+                          "bytes = 24 B per atom and frame of both sets; the kernel is issue-bound (cell walk + exact fp64 test per "
+                          "candidate: profiles/*_k_shell_grid.txt), HBM is the floor it is compared with"}
     t = torch.tensor([ms_search + ms_x + ms_c, ms_search, ms_x, ms_c], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, ms_search, ms_x, ms_c = (float(v) for v in t.tolist())
     return {
+        "search_roofline": roof_s,
         "metric": "residence_pair_evals_per_s", "value": ncat * nox * T / (total_ms * 1e-3), "unit": "pair-evals/s",
         "config": {"workload": f"C5 shape: {ncat} cations x {nox} water O x {T} frames, shell r <= 3.0 A, search + bitmask "
                                f"survival correlation at all {T} lags; search: frames x{world}, correlation: central atoms x{world}"},

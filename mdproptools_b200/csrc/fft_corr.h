@@ -1,5 +1,5 @@
-// fft_corr.h -- unbiased time correlation through a radix-2 Stockham FFT in fp64 (host/device shared bodies of the
-// kernels in fftcorr.cu; exercised on the host by tests/native/fft_corr_host.cpp).
+// fft_corr.h -- unbiased time correlation through a Stockham FFT in fp64: radix-2 butterflies, three stages per pass
+// (host/device shared bodies of the kernels in fftcorr.cu; exercised on the host by tests/native/fft_corr_host.cpp).
 //
 // out[tau] = (sum_{t < T - tau} a[t + tau] * b[t]) / (T - tau)       (conductivity.py:97-114, viscosity.py:86-120)
 //
@@ -59,6 +59,66 @@ MDP_HD void mdp_fft_butterfly(const mdp_c64 *x, mdp_c64 *y, const mdp_c64 *W, lo
     r.im = d.re * w.im + d.im * w.re;
     y[k + 2 * j * m] = s;
     y[k + 2 * j * m + m] = r;
+}
+
+// 2^R butterflies of R consecutive stages t .. t+R-1 in registers: one pass over the data instead of R.  Thread i
+// (0 <= i < n >> R) owns the points i + q * (n >> R); after every stage the two results of a butterfly stay in the
+// registers of its two inputs, and the positions they WOULD have in the Stockham array are carried along (pos[]), so the
+// arithmetic is, operation for operation, that of R calls of mdp_fft_butterfly -- bit-identical results (checked on the
+// host by tests/native/fft_corr_host.cpp).  in(pos) reads a point, out(pos, v) writes one: the first pass of a transform
+// can read the real series directly and the last one can write the normalised correlation (fftcorr.cu).
+// Requires t + R <= log2 n.
+template <int R, class In, class Out>
+MDP_HD void mdp_fft_radix_pass(const In in, const Out out, const mdp_c64 *W, long long i, int t, long long n)
+{
+    constexpr int Q = 1 << R;
+    mdp_c64 v[Q];
+    long long pos[Q];
+    const long long step = n >> R;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < Q; ++q) {
+        pos[q] = i + q * step;
+        v[q] = in(pos[q]);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int s = 0; s < R; ++s) {
+        const int ts = t + s, h = Q >> (s + 1);
+        const long long ms = 1ll << ts;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int a = 0; a < Q; ++a) {
+            if (a & h) continue;
+            const int b = a + h;                           // pos[b] == pos[a] + n/2: the butterfly of index pos[a]
+            const long long k = pos[a] & (ms - 1), j = pos[a] >> ts;
+            const mdp_c64 w = W[j << ts];
+            const mdp_c64 c0 = v[a], c1 = v[b];
+            mdp_c64 sum, d, r;
+            sum.re = c0.re + c1.re;
+            sum.im = c0.im + c1.im;
+            d.re = c0.re - c1.re;
+            d.im = c0.im - c1.im;
+            r.re = d.re * w.re - d.im * w.im;
+            r.im = d.re * w.im + d.im * w.re;
+            v[a] = sum;
+            v[b] = r;
+            pos[a] = k + 2 * j * ms;
+            pos[b] = pos[a] + ms;
+        }
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < Q; ++q) out(pos[q], v[q]);
+}
+
+MDP_HD int mdp_fft_pass_radix(int t, int p)               // stages fused by the pass that starts at stage t: 3, then what is left
+{
+    return p - t >= 3 ? 3 : p - t;
 }
 
 // element k (0 <= k < n) of conj(P), P = A * conj(B), from the spectrum Z of z = a + i*b

@@ -13,47 +13,23 @@
 
 namespace {
 
-constexpr int SG_THREADS = 512;
 constexpr int SG_MAX_A = 4096;
 
-constexpr int SG_WQ = 384;                      // candidate queue of a warp: (lane << 16 | slot) entries per tile of 32 B points
-constexpr int SG_WSTAGE = 128;                  // entries a warp stages in shared memory before one global append
+constexpr int SG_WQ = 192;                      // candidate queue of a warp: (lane << 16 | slot) entries, drained when it could overflow
+constexpr int SG_WSTAGE = 96;                   // entries a warp stages in shared memory before one global append
+constexpr unsigned SG_FULL = 0xffffffffu;
 
-// Hits are staged per WARP in shared memory (one shared atomic each) and appended to the global list with ONE global atomic
-// per ~100 entries: a global atomic per hit serialises on the list counter (35 M hits for the C5 residence search -- that,
-// not the probing, was most of the 70 ms of the first hardware run), and a per-CTA stage needs a barrier per tile of B.
-struct ListEmit {
-    int32_t *list;
-    unsigned long long *count;
-    long long capacity;
-    int frame, ib;
-    int2 *stage;                 // this warp's SG_WSTAGE entries
-    unsigned int *nstage;        // this warp's fill count
-    __device__ __forceinline__ void operator()(int ia) const
-    {
-        const unsigned int p = atomicAdd(nstage, 1u);
-        if (p < (unsigned)SG_WSTAGE) {
-            stage[p] = make_int2(ia, ib);
-            return;
-        }
-        const unsigned long long pos = atomicAdd(count, 1ull);        // stage full (a tile with an unusual number of hits)
-        if ((long long)pos < capacity) {
-            list[pos * 3 + 0] = frame;
-            list[pos * 3 + 1] = ia;
-            list[pos * 3 + 2] = ib;
-        }
-    }
-};
-
-// the warp appends its staged entries to the global list (all lanes call)
+// Hits are staged per WARP in shared memory and appended to the global list with ONE global atomic per ~64..96 entries: a
+// global atomic per hit serialises on the list counter (35 M hits for the C5 residence search -- that, not the probing,
+// was most of the 70 ms of the first hardware run), and a per-CTA stage needs a barrier per tile of B.
+// The warp appends its n staged entries to the global list (all lanes call, n uniform).
 __device__ __forceinline__ void warp_flush(int32_t *list, unsigned long long *count, long long capacity, int frame, const int2 *stage,
-                                           unsigned int *nstage, int lane)
+                                           unsigned int n, int lane)
 {
     __syncwarp();
-    const unsigned int n = *nstage < (unsigned)SG_WSTAGE ? *nstage : (unsigned)SG_WSTAGE;
     unsigned long long base = 0;
     if (lane == 0 && n) base = atomicAdd(count, (unsigned long long)n);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    base = __shfl_sync(SG_FULL, base, 0);
     for (unsigned int k = lane; k < n; k += 32) {
         const unsigned long long pos = base + k;
         if ((long long)pos < capacity) {
@@ -63,58 +39,91 @@ __device__ __forceinline__ void warp_flush(int32_t *list, unsigned long long *co
         }
     }
     __syncwarp();
-    if (lane == 0) *nstage = 0u;
+}
+
+// The nq queued candidates of the warp's current tile of 32 B points, one per lane and round, through the reference's own
+// fp64 test; accepted ones go to the warp's stage by ballot compaction (nst = entries staged, uniform).
+__device__ __forceinline__ void shell_drain(const ShellGrid &g, const double *sx, const double *sy, const double *sz, const int *sidx,
+                                            const double *wb, const unsigned int *wq, unsigned int nq, long long jbase, double rin2,
+                                            double rout2, int shell_mode, int exclude_same, int32_t *list, unsigned long long *count,
+                                            long long capacity, int frame, int2 *wst, unsigned int &nst, int lane)
+{
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
+    for (unsigned int q0 = 0; q0 < nq; q0 += 32) {
+        const unsigned int q = q0 + lane;
+        bool ok = false;
+        int ia = 0, ib = 0;
+        if (q < nq) {
+            const unsigned int e = wq[q];
+            const int bl = (int)(e >> 16), k = (int)(e & 0xffffu);
+            ib = (int)(jbase + bl);
+            ia = sidx[k];
+            ok = mdp_shell_pair_ok(g, sx[k], sy[k], sz[k], ia, wb[bl], wb[32 + bl], wb[64 + bl], ib, rin2, rout2, shell_mode, exclude_same);
+        }
+        const unsigned bal = __ballot_sync(SG_FULL, ok);
+        if (ok) wst[nst + __popc(bal & lt)] = make_int2(ia, ib);
+        nst += __popc(bal);
+        if (nst > (unsigned)(SG_WSTAGE - 32)) {
+            warp_flush(list, count, capacity, frame, wst, nst, lane);
+            nst = 0;
+        }
+    }
     __syncwarp();
 }
 
 // grid = frames (strided); dynamic shared memory: sx, sy, sz [na] doubles, sidx [na], cell_of [na], start [ncell_max + 1],
-// fill [ncell_max]
-__global__ void __launch_bounds__(SG_THREADS) k_shell_grid(const double *__restrict__ xa, long long na, const double *__restrict__ xb,
-                                                           long long nb, const double *__restrict__ box, int nframes, double rin2,
-                                                           double rout2, int shell_mode, int exclude_same, int32_t *__restrict__ list,
-                                                           long long capacity, unsigned long long *__restrict__ count)
+// the halo copy of the cell ranges [(nc_max + 2)^3] (its first part doubles as the scatter cursors), then per warp: the B tile (96 doubles), the stage and the candidate queue
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_shell_grid(const double *__restrict__ xa, long long na, const double *__restrict__ xb,
+                                                        long long nb, const double *__restrict__ box, int nframes, double rin2,
+                                                        double rout2, int shell_mode, int exclude_same, int32_t *__restrict__ list,
+                                                        long long capacity, unsigned long long *__restrict__ count)
 {
     extern __shared__ __align__(16) unsigned char sg_smem[];
     constexpr int NCELL_MAX = SG_NC_MAX * SG_NC_MAX * SG_NC_MAX;
+    constexpr int HALO_MAX = (SG_NC_MAX + 2) * (SG_NC_MAX + 2) * (SG_NC_MAX + 2);
+    constexpr int WARPS = THREADS / 32;
     double *sx = reinterpret_cast<double *>(sg_smem);
     double *sy = sx + na;
     double *sz = sy + na;
     int *sidx = reinterpret_cast<int *>(sz + na);
     int *cell_of = sidx + na;
     int *start = cell_of + na;                  // [NCELL_MAX + 1]
-    int *fill = start + NCELL_MAX + 1;          // [NCELL_MAX]
+    uint32_t *halo = reinterpret_cast<uint32_t *>(start + NCELL_MAX + 1);   // [HALO_MAX]: the ranges the walk reads
+    int *fill = reinterpret_cast<int *>(halo);  // [NCELL_MAX] scatter cursors, dead before the halo copy is written
     const int tid = threadIdx.x;
     const double r = sqrt(rout2);
-    // per-warp staging behind the grid (dynamic shared memory, 8-byte aligned: everything before it is a multiple of 4 bytes)
-    __shared__ unsigned int nstage[SG_THREADS / 32], ncand[SG_THREADS / 32];
-    unsigned char *wbase = reinterpret_cast<unsigned char *>(fill + NCELL_MAX);
+    __shared__ ShellGrid g;
+    // per-warp buffers behind the grid (8-byte aligned: everything before them is a multiple of 4 bytes)
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(halo + HALO_MAX);
     wbase += (8 - (reinterpret_cast<uintptr_t>(wbase) & 7)) & 7;
     double *btile = reinterpret_cast<double *>(wbase);                                   // [warps][96]
-    int2 *stage = reinterpret_cast<int2 *>(btile + (SG_THREADS / 32) * 96);              // [warps][SG_WSTAGE]
-    unsigned int *candq = reinterpret_cast<unsigned int *>(stage + (SG_THREADS / 32) * SG_WSTAGE);   // [warps][SG_WQ]
-    if (tid < SG_THREADS / 32) {
-        nstage[tid] = 0u;
-        ncand[tid] = 0u;
-    }
+    int2 *stage = reinterpret_cast<int2 *>(btile + WARPS * 96);                          // [warps][SG_WSTAGE]
+    unsigned int *candq = reinterpret_cast<unsigned int *>(stage + WARPS * SG_WSTAGE);   // [warps][SG_WQ]
     for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
         const double *ax = xa + (long long)f * 3 * na, *ay = ax + na, *az = ay + na;
         const double *bx = xb + (long long)f * 3 * nb, *by = bx + nb, *bz = by + nb;
-        ShellGrid g;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            g.len[k] = box[f * 3 + k];
-            g.nc[k] = mdp_grid_cells(g.len[k], r);          // >= 3: checked on the host for every frame
-            g.inv_w[k] = (double)g.nc[k] / g.len[k];
-        }
-        mdp_grid_set_radius(g, r);
-        g.origin[0] = ax[0];
-        g.origin[1] = ay[0];
-        g.origin[2] = az[0];
-        const int ncell = g.nc[0] * g.nc[1] * g.nc[2];
         __syncthreads();                                     // the previous frame's grid is no longer read
-        for (int c = tid; c < ncell; c += SG_THREADS) fill[c] = 0;
+        if (tid == 0) {                                      // the frame's grid constants live in shared memory: 27 registers less
+            ShellGrid t;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                t.len[k] = box[f * 3 + k];
+                t.nc[k] = mdp_grid_cells(t.len[k], r);      // >= 3: checked on the host for every frame
+                t.inv_w[k] = (double)t.nc[k] / t.len[k];
+            }
+            mdp_grid_set_radius(t, r);
+            t.origin[0] = ax[0];
+            t.origin[1] = ay[0];
+            t.origin[2] = az[0];
+            g = t;
+        }
         __syncthreads();
-        for (int i = tid; i < (int)na; i += SG_THREADS) {
+        const int ncell = g.nc[0] * g.nc[1] * g.nc[2];
+        for (int c = tid; c < ncell; c += THREADS) fill[c] = 0;
+        __syncthreads();
+        for (int i = tid; i < (int)na; i += THREADS) {
             const int c = mdp_grid_cell(g, ax[i], ay[i], az[i]);
             cell_of[i] = c;
             atomicAdd(&fill[c], 1);
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_shell_grid(const double *__restr
             int inc = s;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, inc, d);
+                const int v = __shfl_up_sync(SG_FULL, inc, d);
                 if (tid >= d) inc += v;
             }
             int run = inc - s;
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_shell_grid(const double *__restr
             if (tid == 31) start[ncell] = inc;
         }
         __syncthreads();
-        for (int i = tid; i < (int)na; i += SG_THREADS) {
+        for (int i = tid; i < (int)na; i += THREADS) {
             const int c = cell_of[i];
             const int p = start[c] + atomicAdd(&fill[c], 1);
             sx[p] = ax[i];
@@ -149,18 +158,24 @@ __global__ void __launch_bounds__(SG_THREADS) k_shell_grid(const double *__restr
             sidx[p] = i;
         }
         __syncthreads();
+        for (int h = tid, nh = mdp_halo_cells(g); h < nh; h += THREADS) halo[h] = mdp_halo_entry(g, start, h);
+        __syncthreads();
         // Every warp streams its own tiles of 32 B points (coalesced), the next tile's coordinates already in flight.  Two
-        // phases per tile: (1) every lane walks the cells its point can have partners in and pushes (lane, slot) candidates
-        // into the warp's queue -- divergent, but a handful of integer instructions per step; (2) the queued candidates
-        // are evaluated 32 at a time, one per lane, with the reference's fp64 arithmetic -- dense.  (A first version
-        // evaluated inside the cell walk: 12 of 32 lanes active on average, 500 thread-instructions per B point.)
+        // phases per tile, both in CONVERGENT control flow:
+        //  (1) the cell walk.  Every lane has 1..27 cells to visit (shell_grid.h: 5.4 on average, at most 8 for the residence
+        //      shape), consecutive boxes of the halo grid; the warp loops to the LARGEST count among its lanes, lane l
+        //      visiting its c-th cell while c is below its own count.  Walked twice: once to count the lane's candidates (one
+        //      warp scan then gives every lane its place in the warp's candidate queue), once to write them.  A walk with
+        //      per-lane loop bounds serialises lane by lane (round 2a: 43 % of the issue slots used, the rest stalls), and a
+        //      ballot compaction per cell costs ~30 instructions per cell and round.
+        //  (2) the queued candidates are evaluated 32 at a time, one per lane, with the reference's fp64 arithmetic.
         {
             const int lane = tid & 31, w = tid >> 5;
+            const unsigned lt = (1u << lane) - 1u;
             int2 *wst = stage + w * SG_WSTAGE;
-            unsigned int *wn = &nstage[w];
             unsigned int *wq = candq + w * SG_WQ;
-            unsigned int *wqn = &ncand[w];
             double *wb = btile + w * 96;
+            unsigned int nst = 0;
             long long j = (long long)w * 32 + lane;
             double cx = 0.0, cy = 0.0, cz = 0.0;
             if (j < nb) {
@@ -168,8 +183,8 @@ __global__ void __launch_bounds__(SG_THREADS) k_shell_grid(const double *__restr
                 cy = by[j];
                 cz = bz[j];
             }
-            for (; j - lane < nb; j += SG_THREADS) {
-                const long long jn = j + SG_THREADS;
+            for (; j - lane < nb; j += THREADS) {
+                const long long jn = j + THREADS;
                 double nx = 0.0, ny = 0.0, nz = 0.0;
                 if (jn < nb) {
                     nx = bx[jn];
@@ -179,39 +194,74 @@ __global__ void __launch_bounds__(SG_THREADS) k_shell_grid(const double *__restr
                 wb[lane] = cx;
                 wb[32 + lane] = cy;
                 wb[64 + lane] = cz;
-                const ListEmit emit{list, count, capacity, f, (int)j, wst, wn};
-                if (j < nb)
-                    mdp_shell_candidates(g, start, cx, cy, cz, [&](int k) {
-                        const unsigned int p = atomicAdd(wqn, 1u);
-                        if (p < (unsigned)SG_WQ)
-                            wq[p] = ((unsigned)lane << 16) | (unsigned)k;
-                        else if (mdp_shell_pair_ok(g, sx[k], sy[k], sz[k], sidx[k], cx, cy, cz, (int)j, rin2, rout2, shell_mode, exclude_same))
-                            emit(sidx[k]);                            // queue full: settle it here
-                    });
-                __syncwarp();
-                const unsigned int nq = *wqn < (unsigned)SG_WQ ? *wqn : (unsigned)SG_WQ;
                 const long long jbase = j - lane;
-                for (unsigned int q0 = 0; q0 < nq; q0 += 32) {
-                    const unsigned int q = q0 + lane;
-                    if (q < nq) {
-                        const unsigned int e = wq[q];
-                        const int bl = (int)(e >> 16), k = (int)(e & 0xffffu);
-                        const int ib = (int)(jbase + bl);
-                        if (mdp_shell_pair_ok(g, sx[k], sy[k], sz[k], sidx[k], wb[bl], wb[32 + bl], wb[64 + bl], ib, rin2, rout2, shell_mode,
-                                              exclude_same))
-                            ListEmit{list, count, capacity, f, ib, wst, wn}(sidx[k]);
+                ShellWalk wk = mdp_shell_walk_begin(g, cx, cy, cz);
+                if (j >= nb) wk.tot = 0;
+                const int maxtot = __reduce_max_sync(SG_FULL, wk.tot);
+                // how many candidates each lane has (first walk), one scan over the warp: every lane knows where its entries go
+                int mine = 0;
+                {
+                    ShellWalk w1 = wk;
+                    for (int c = 0; c < maxtot; ++c) {
+                        unsigned int e = 0;
+                        if (c < w1.tot) e = halo[w1.cell];
+                        mdp_shell_walk_next(w1);
+                        mine += (int)(e >> 16);
                     }
-                    __syncwarp();
-                    if (*wn >= (unsigned)(SG_WSTAGE / 2)) warp_flush(list, count, capacity, f, wst, wn, lane);
                 }
-                __syncwarp();
-                if (lane == 0) *wqn = 0u;
-                __syncwarp();
+                int inc = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(SG_FULL, inc, d);
+                    if (lane >= d) inc += v;
+                }
+                unsigned int nq = (unsigned)__shfl_sync(SG_FULL, inc, 31);
+                if (nq <= (unsigned)SG_WQ) {
+                    // (second walk) the lane writes its entries behind those of the lanes below it
+                    unsigned int off = (unsigned)(inc - mine);
+                    const unsigned lanebits = (unsigned)lane << 16;
+                    for (int c = 0; c < maxtot; ++c) {
+                        unsigned int e = 0;
+                        if (c < wk.tot) e = halo[wk.cell];
+                        mdp_shell_walk_next(wk);
+                        const unsigned val = lanebits | (e & 0xffffu);
+                        const int cnt = (int)(e >> 16);
+                        if (cnt > 0) wq[off] = val;
+                        if (cnt > 1) wq[off + 1] = val + 1;
+                        if (cnt > 2) wq[off + 2] = val + 2;
+                        if (__builtin_expect(cnt > 3, 0))
+                            for (int u = 3; u < cnt; ++u) wq[off + u] = val + u;
+                        off += cnt;
+                    }
+                } else {
+                    // more candidates than the queue holds (dense A): cell by cell, ballot-compacted, draining when full
+                    nq = 0;
+                    for (int c = 0; c < maxtot; ++c) {
+                        unsigned int e = 0;
+                        if (c < wk.tot) e = halo[wk.cell];
+                        mdp_shell_walk_next(wk);
+                        const int s = (int)(e & 0xffffu), cnt = (int)(e >> 16);
+                        const int maxc = __reduce_max_sync(SG_FULL, cnt);
+                        for (int u = 0; u < maxc; ++u) {
+                            if (nq + 32u > (unsigned)SG_WQ) {            // uniform: settle what is queued, then go on
+                                shell_drain(g, sx, sy, sz, sidx, wb, wq, nq, jbase, rin2, rout2, shell_mode, exclude_same, list, count,
+                                            capacity, f, wst, nst, lane);
+                                nq = 0;
+                            }
+                            const bool has = u < cnt;
+                            const unsigned bal = __ballot_sync(SG_FULL, has);
+                            if (has) wq[nq + __popc(bal & lt)] = ((unsigned)lane << 16) | (unsigned)(s + u);
+                            nq += __popc(bal);
+                        }
+                    }
+                }
+                shell_drain(g, sx, sy, sz, sidx, wb, wq, nq, jbase, rin2, rout2, shell_mode, exclude_same, list, count, capacity, f, wst,
+                            nst, lane);
                 cx = nx;
                 cy = ny;
                 cz = nz;
             }
-            warp_flush(list, count, capacity, f, wst, wn, lane);
+            warp_flush(list, count, capacity, f, wst, nst, lane);
         }
     }
 }
@@ -235,8 +285,13 @@ int mdp_shell_search(mdp_ctx *ctx, int nframes, int64_t n_a, const double *xyz_a
     cudaStream_t st = (cudaStream_t)stream;
     MDP_CUDA(cudaSetDevice(ctx->device));
     constexpr size_t NCELL_MAX = (size_t)SG_NC_MAX * SG_NC_MAX * SG_NC_MAX;
-    constexpr size_t SG_WARP_BYTES = (SG_THREADS / 32) * (SG_WSTAGE * 8 + SG_WQ * 4 + 96 * 8);
-    const size_t smem = (size_t)n_a * (3 * 8 + 4 + 4) + (2 * NCELL_MAX + 1) * 4 + 8 + SG_WARP_BYTES;
+    // 1024 threads per CTA (32 warps hide the shared-memory latencies of the walk) when the grid leaves room, else 512
+    constexpr size_t HALO_MAX = (size_t)(SG_NC_MAX + 2) * (SG_NC_MAX + 2) * (SG_NC_MAX + 2);
+    const size_t grid_bytes = (size_t)n_a * (3 * 8 + 4 + 4) + (NCELL_MAX + 1 + HALO_MAX) * 4 + 8;
+    constexpr size_t SG_WARP_BYTES = SG_WSTAGE * 8 + SG_WQ * 4 + 96 * 8;
+    int threads = 1024;
+    if (grid_bytes + 32 * SG_WARP_BYTES + 1024 > ctx->smem_optin) threads = 512;
+    const size_t smem = grid_bytes + (size_t)(threads / 32) * SG_WARP_BYTES;
     if (smem + 1024 > ctx->smem_optin) return 1;
     int rc = ctx->arena_reserve(align256((size_t)nframes * 24) + 4096);
     if (rc) return rc;
@@ -248,12 +303,18 @@ int mdp_shell_search(mdp_ctx *ctx, int nframes, int64_t n_a, const double *xyz_a
     }
     MDP_CUDA(cudaMemcpyAsync(d_box, box, (size_t)nframes * 24, cudaMemcpyHostToDevice, st));
     MDP_CUDA(cudaMemsetAsync(count_out, 0, 8, st));
-    MDP_CUDA(cudaFuncSetAttribute((const void *)k_shell_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per_sm = std::max<int>(1, std::min<int>(4, (int)((size_t)220 * 1024 / (smem + 1024))));
+    const int per_sm = std::max<int>(1, std::min<int>(2048 / threads, (int)((size_t)220 * 1024 / (smem + 1024))));
     const unsigned grid = (unsigned)std::min<int64_t>(nframes, (int64_t)ctx->sm_count * per_sm);
     cudaEvent_t tk = ctx->timer_begin(0, st);
-    k_shell_grid<<<grid, SG_THREADS, smem, st>>>(xyz_a, n_a, xyz_b, n_b, d_box, nframes, rin2, rout2, shell_mode, exclude_same_index,
-                                                 list_out, capacity, (unsigned long long *)count_out);
+    if (threads == 1024) {
+        MDP_CUDA(cudaFuncSetAttribute((const void *)k_shell_grid<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_shell_grid<1024><<<grid, 1024, smem, st>>>(xyz_a, n_a, xyz_b, n_b, d_box, nframes, rin2, rout2, shell_mode, exclude_same_index,
+                                                     list_out, capacity, (unsigned long long *)count_out);
+    } else {
+        MDP_CUDA(cudaFuncSetAttribute((const void *)k_shell_grid<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_shell_grid<512><<<grid, 512, smem, st>>>(xyz_a, n_a, xyz_b, n_b, d_box, nframes, rin2, rout2, shell_mode, exclude_same_index,
+                                                   list_out, capacity, (unsigned long long *)count_out);
+    }
     ctx->timer_end(tk, st);
     MDP_LAUNCHED(ctx);
     return mdp_check_launch("k_shell_grid");

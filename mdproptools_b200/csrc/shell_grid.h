@@ -107,8 +107,8 @@ MDP_HD bool mdp_shell_accepts(double rsq, double rin2, double rout2, int shell_m
     return shell_mode ? (rsq > rin2 && rsq <= rout2) : (rsq < rout2);   // residence_time.py:102 / cluster_analysis.py:160
 }
 
-// Probe the grid with one B point: emit(ia) for every A point accepted.  cell_start[ncell + 1] and the A points sorted by
-// cell (sx, sy, sz, sidx = original index) describe the grid; ib is B's index (for exclude_same).
+// Probe the grid with one B point: emit(ia) for every A point accepted.  The halo copy of the cell ranges (below) and the
+// A points sorted by cell (sx, sy, sz, sidx = original index) describe the grid; ib is B's index (for exclude_same).
 //
 // Which neighbour cells can hold a partner is decided per axis from B's position INSIDE its cell: an A point in the cell
 // below is at least frac * w away (w = cell width), one in the cell above at least (1 - frac) * w, so the lower neighbour
@@ -116,31 +116,86 @@ MDP_HD bool mdp_shell_accepts(double rsq, double rin2, double rout2, int shell_m
 // orders of magnitude above the rounding of t and covers an A point that sits on a cell boundary and was rounded into the
 // neighbour).  With cells two to three radii wide (2 000 ions in a 126 A box: w = 7.9 A, r = 3 A) that is 5.4 cells per
 // point on average instead of 27.
+// the cells of axis k that can hold a partner of coordinate b: first (may be -1 or nc: wrap it with mdp_grid_wrap1) and
+// how many (1..3)
+MDP_HD void mdp_shell_axis_range(const ShellGrid &g, int k, double b, int &first, int &count)
+{
+    double frac;
+    const int c0 = mdp_grid_cell1f(b, g.origin[k], g.inv_w[k], g.nc[k], frac);
+    const int lo = frac <= g.rw[k] ? -1 : 0, hi = frac >= 1.0 - g.rw[k] ? 1 : 0;
+    first = c0 + lo;
+    count = hi - lo + 1;
+}
+
+MDP_HD int mdp_grid_wrap1(int c, int nc)          // c in [-1, nc + 1] -> [0, nc)
+{
+    return c < 0 ? c + nc : (c >= nc ? c - nc : c);
+}
+
+// The grid is read through a HALO copy: (nc + 2) cells per axis, entry (x', y', z') = the slot range of cell
+// (x' - 1, y' - 1, z' - 1) modulo nc, packed (count << 16 | first slot) (n_a <= 4096).  A point's up-to-27 cells are then
+// a box of consecutive halo indices -- no per-cell wrap, one load per cell.
+MDP_HD int mdp_halo_cells(const ShellGrid &g)
+{
+    return (g.nc[0] + 2) * (g.nc[1] + 2) * (g.nc[2] + 2);
+}
+
+MDP_HD uint32_t mdp_halo_entry(const ShellGrid &g, const int *cell_start, int idx)
+{
+    const int hx = g.nc[0] + 2, hy = g.nc[1] + 2;
+    const int x = idx % hx, y = (idx / hx) % hy, z = idx / (hx * hy);
+    const int cx = mdp_grid_wrap1(x - 1, g.nc[0]), cy = mdp_grid_wrap1(y - 1, g.nc[1]), cz = mdp_grid_wrap1(z - 1, g.nc[2]);
+    const int c = (cz * g.nc[1] + cy) * g.nc[0] + cx;
+    return ((uint32_t)(cell_start[c + 1] - cell_start[c]) << 16) | (uint32_t)cell_start[c];
+}
+
+// the walk of one B point over its cells: tot halo cells, visited in x-fastest order
+struct ShellWalk {
+    int cell;          // halo index of the cell to visit now
+    int n0, n1, tot;   // cells along x, along y, in total
+    int dx, dy;        // index step on an x carry (after the +1) and on a y carry
+    int ix, iy;
+};
+
+MDP_HD ShellWalk mdp_shell_walk_begin(const ShellGrid &g, double bx, double by, double bz)
+{
+    int fx, fy, fz, n2;
+    ShellWalk w;
+    mdp_shell_axis_range(g, 0, bx, fx, w.n0);
+    mdp_shell_axis_range(g, 1, by, fy, w.n1);
+    mdp_shell_axis_range(g, 2, bz, fz, n2);
+    const int hx = g.nc[0] + 2, hy = g.nc[1] + 2;
+    w.cell = ((fz + 1) * hy + (fy + 1)) * hx + (fx + 1);
+    w.tot = w.n0 * w.n1 * n2;
+    w.dx = hx - w.n0;
+    w.dy = hx * hy - w.n1 * hx;
+    w.ix = w.iy = 0;
+    return w;
+}
+
+MDP_HD void mdp_shell_walk_next(ShellWalk &w)
+{
+    w.cell += 1;
+    if (++w.ix == w.n0) {
+        w.ix = 0;
+        w.cell += w.dx;
+        if (++w.iy == w.n1) {
+            w.iy = 0;
+            w.cell += w.dy;
+        }
+    }
+}
+
 // cand(k) for every slot k of the sorted A arrays that lies in a cell B's point can have a partner in
 template <class Cand>
-MDP_HD void mdp_shell_candidates(const ShellGrid &g, const int *cell_start, double bx, double by, double bz, const Cand cand)
+MDP_HD void mdp_shell_candidates(const ShellGrid &g, const uint32_t *halo, double bx, double by, double bz, const Cand cand)
 {
-    int c0[3], lo[3], hi[3];
-    const double b[3] = {bx, by, bz};
-    for (int k = 0; k < 3; ++k) {
-        double frac;
-        c0[k] = mdp_grid_cell1f(b[k], g.origin[k], g.inv_w[k], g.nc[k], frac);
-        lo[k] = frac <= g.rw[k] ? -1 : 0;
-        hi[k] = frac >= 1.0 - g.rw[k] ? 1 : 0;
-    }
-    for (int oz = lo[2]; oz <= hi[2]; ++oz) {
-        int z = c0[2] + oz;
-        z = z < 0 ? z + g.nc[2] : (z >= g.nc[2] ? z - g.nc[2] : z);
-        for (int oy = lo[1]; oy <= hi[1]; ++oy) {
-            int y = c0[1] + oy;
-            y = y < 0 ? y + g.nc[1] : (y >= g.nc[1] ? y - g.nc[1] : y);
-            for (int ox = lo[0]; ox <= hi[0]; ++ox) {
-                int x = c0[0] + ox;
-                x = x < 0 ? x + g.nc[0] : (x >= g.nc[0] ? x - g.nc[0] : x);
-                const int c = (z * g.nc[1] + y) * g.nc[0] + x;
-                for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) cand(k);
-            }
-        }
+    ShellWalk w = mdp_shell_walk_begin(g, bx, by, bz);
+    for (int c = 0; c < w.tot; ++c) {
+        const uint32_t e = halo[w.cell];
+        const int s = (int)(e & 0xffffu), cnt = (int)(e >> 16);
+        for (int k = s; k < s + cnt; ++k) cand(k);
+        mdp_shell_walk_next(w);
     }
 }
 
@@ -167,10 +222,10 @@ struct ShellProbeCand {
 };
 
 template <class Emit>
-MDP_HD void mdp_shell_probe(const ShellGrid &g, const int *cell_start, const double *sx, const double *sy, const double *sz,
+MDP_HD void mdp_shell_probe(const ShellGrid &g, const uint32_t *halo, const double *sx, const double *sy, const double *sz,
                             const int *sidx, double bx, double by, double bz, int ib, double rin2, double rout2, int shell_mode,
                             int exclude_same, const Emit emit)
 {
-    mdp_shell_candidates(g, cell_start, bx, by, bz,
+    mdp_shell_candidates(g, halo, bx, by, bz,
                          ShellProbeCand<Emit>{g, sx, sy, sz, sidx, bx, by, bz, rin2, rout2, ib, shell_mode, exclude_same, emit});
 }

@@ -307,7 +307,7 @@ def xcorr_fft_enabled(T: int = XCORR_FFT_MIN_T) -> bool:
 
 def shell_grid_enabled() -> bool:
     """The small-set shell search (csrc/shell.cu) is the default for n_a <= 4096 central points against a set at least 8
-    times larger (round 2 on hardware, C5: 26 ms against 47 ms for the general engine's list mode, same entries);
+    times larger (round 2 on hardware, C5: 13.6 ms against 47 ms for the general engine's list mode, same entries);
     MDP_SHELL_GRID=0 selects the general engine."""
     import os
 

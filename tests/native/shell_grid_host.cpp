@@ -1,5 +1,5 @@
 // Host emulation of k_shell_grid (mdproptools_b200/csrc/shell.cu): the grid over A is built with the same cell function,
-// every B point probes it with the same mdp_shell_probe.  TEST INFRASTRUCTURE ONLY.  Built with -ffp-contract=off.
+// the halo copy with the same mdp_halo_entry, and every B point probes it with the same walk (mdp_shell_probe).  TEST INFRASTRUCTURE ONLY.  Built with -ffp-contract=off.
 #include <stdint.h>
 #include <vector>
 
@@ -45,8 +45,10 @@ extern "C" int emulate_shell_grid(const double *xa, const double *ya, const doub
         sz[p] = za[i];
         sidx[p] = i;
     }
+    std::vector<uint32_t> halo((size_t)mdp_halo_cells(g));
+    for (int h = 0; h < (int)halo.size(); ++h) halo[h] = mdp_halo_entry(g, start.data(), h);
     for (int j = 0; j < nb; ++j)
-        mdp_shell_probe(g, start.data(), sx.data(), sy.data(), sz.data(), sidx.data(), xb[j], yb[j], zb[j], j, rin2, rout2, shell_mode,
+        mdp_shell_probe(g, halo.data(), sx.data(), sy.data(), sz.data(), sidx.data(), xb[j], yb[j], zb[j], j, rin2, rout2, shell_mode,
                         exclude_same, Mark{out, nb, j});
     return 0;
 }

@@ -449,6 +449,20 @@ def test_shell_grid_search_equals_pair_list(ops, monkeypatch):
         assert len(ref) > 0 and ref == got, (r_in, r_out, mode)
     assert entries("1", 0.0, 9.0, 1) == entries("0", 0.0, 9.0, 1)               # 9 A > L/3: falls back to the engine
 
+    # dense A (31 points per cell, ~600 candidates per B point): every tile overflows the warp's candidate queue and
+    # takes the cell-by-cell path with intermediate drains
+    a = rng.uniform(0, 14.0, (1, 3, 2000))
+    b = rng.uniform(0, 14.0, (1, 3, 16000))
+
+    def packed(flag):
+        monkeypatch.setenv("MDP_SHELL_GRID", flag)
+        lst, _ = ops.pair_list(_dev(a), _dev(b), [(14.0, 14.0, 14.0)], 0.0, 9.0, 0)
+        l = lst.cpu().numpy().astype(np.int64)
+        return np.sort((l[:, 0] * 2000 + l[:, 1]) * 16000 + l[:, 2])
+
+    ref, got = packed("0"), packed("1")
+    assert len(ref) > 10 ** 6 and np.array_equal(ref, got)
+
 
 def test_survival_runs_kernel_equals_popcount_kernel(ops, monkeypatch):
     """mdp_survival_runs against mdp_bitmask_autocorr (itself pinned to the oracle) on the same neighbour lists: dense

@@ -378,7 +378,7 @@ def test_shell_grid_search_on_host(tmp_path):
 
 
 def test_fft_correlation_on_host(tmp_path):
-    """The FFT route of the unbiased correlation (csrc/fft_corr.h: Stockham radix-2 butterflies, both spectra from one
+    """The FFT route of the unbiased correlation (csrc/fft_corr.h: Stockham butterflies, three stages per pass, both spectra from one
     transform of a + i*b, second transform of the conjugated cross spectrum) against the oracle's long-double direct sum
     and the reference's numpy-FFT form: cross- and auto-correlation, lengths around powers of two, fewer lags than
     steps.  Tolerance: the north star's 1e-10 of max|C| (observed ~1e-15)."""
@@ -386,10 +386,17 @@ def test_fft_correlation_on_host(tmp_path):
     so = tmp_path / "fft_corr_host.so"
     src = os.path.join(ROOT, "tests", "native", "fft_corr_host.cpp")
     subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(so), src], check=True)
-    emu = ctypes.CDLL(str(so)).emulate_fft_xcorr
+    lib = ctypes.CDLL(str(so))
+    emu = lib.emulate_fft_xcorr
     emu.restype = ctypes.c_int
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
     rng = np.random.default_rng(51)
+    # three stages per pass (mdp_fft_radix_pass) are, bit for bit, three radix-2 stages: every log2 size up to 2^13,
+    # which covers every mix of radix-8, radix-4 and radix-2 passes
+    lib.fft_fused_vs_radix2.restype = ctypes.c_longlong
+    for p in range(1, 14):
+        re, im = rng.normal(0, 1, 1 << p), rng.normal(0, 1, 1 << p)
+        assert lib.fft_fused_vs_radix2(dp(re), dp(im), ctypes.c_int(p)) == 0, p
     worst = 0.0
     for T in (1, 2, 3, 7, 8, 9, 100, 255, 256, 257, 1000, 4097):
         for same in (False, True):

@@ -29,7 +29,7 @@ echo "ncu msd rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_shell_grid -s 1 -c 1 -f -o $OUT/prof_shell \
     python bench.py --steps 1 --warmup 1 --frames 4 --res-frames 1000 --skip-msd --skip-gk --skip-cpu --skip-triclinic --skip-clusters > $OUT/ncu_shell.log 2>&1
 echo "ncu shell rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fft_stage -s 5 -c 1 -f -o $OUT/prof_fft \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fft_pass -s 3 -c 1 -f -o $OUT/prof_fft \
     python bench.py --steps 1 --warmup 1 --frames 4 --skip-msd --skip-cpu --skip-residence --skip-triclinic --skip-clusters --gk-flux-frames 256 > $OUT/ncu_fft.log 2>&1
 echo "ncu fft rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_charge_flux -s 3 -c 1 -f -o $OUT/prof_flux \
