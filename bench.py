@@ -1105,8 +1105,9 @@ def bench_clusters_hydration(args, torch, dist, ops, ctx, dev, world, rank):
 
 def bench_rdf_from_files(torch, frames, nominal_pairs_per_frame, nfiles=32, copies=8):
     """The call a user of the reference makes: calc_atomic_rdf on LAMMPS dump FILES (C2 frames written as text with
-    LAMMPS' default %g, ids shuffled) -> page cache -> native parser (a batch of frames per call, one frame per host
-    thread) -> pinned SoA -> H2D on the copy stream -> pair engine -> D2H -> per-frame normalisation -> DataFrame."""
+    LAMMPS' default %g, ids shuffled) -> page cache -> pinned TEXT (reader threads) -> H2D on the copy stream -> device
+    parser (k_dump_rows) -> pair engine -> D2H -> per-frame normalisation -> DataFrame.  (MDP_DEVICE_PARSE=0: the host
+    parser, a batch of frames per call, one frame per host thread -> pinned SoA -> H2D.)"""
     import shutil
     import tempfile
     from mdproptools_b200.structural import rdf_cn
@@ -1147,6 +1148,7 @@ def bench_rdf_from_files(torch, frames, nominal_pairs_per_frame, nfiles=32, copi
                 "frames": T, "ms_per_frame": dt / T * 1e3, "text_MB_per_s": nbytes / dt / 1e6, "text_bytes": nbytes,
                 "g_full_max": float(df["g_full(r)"].max()),
                 "api": "rdf_cn.calc_atomic_rdf(filename=<dump files>) -- the reference's own entry point (rdf_cn.py:385)",
+                "parser": "device (k_dump_rows)" if os.environ.get("MDP_DEVICE_PARSE", "1") not in ("", "0") else "host",
                 "note": "text is %g (6 significant digits) as LAMMPS writes by default; files are read from the page cache"}
     finally:
         shutil.rmtree(d, ignore_errors=True)

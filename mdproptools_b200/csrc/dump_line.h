@@ -38,8 +38,8 @@ MDP_HD const char *mdp_token_end(const char *p, const char *end)
 }
 
 // Token at q (no leading blanks), scanned and converted in one pass.  Returns the end of the token when the exact fast
-// path applies (v holds the correctly rounded value), nullptr otherwise (v untouched): the token then has an exponent,
-// too many digits, no digit at all, or does not end at a blank / line end.
+// path applies (v holds the correctly rounded value), nullptr otherwise (v untouched): the token then has too many
+// digits, a decimal scale beyond 10^+-22, no digit at all, or does not end at a blank / line end.
 MDP_HD const char *mdp_parse_fast(const char *q, const char *le, double *v)
 {
     const char *p = q;
@@ -68,10 +68,29 @@ MDP_HD const char *mdp_parse_fast(const char *q, const char *le, double *v)
         sc = (int)(f0 - p);
         any = any || p > f0;
     }
-    // w cannot have wrapped while nd <= 19 (10^19 - 1 < 2^64)
-    if (any && nd <= 19 && w <= (1ull << 53) && sc >= -22 && (p == le || mdp_is_blank(*p) || *p == '\n')) {
+    if (any && p < le && (*p == 'e' || *p == 'E')) {     // decimal exponent (%g writes one below 1e-4: "1.23e-05")
+        const char *x = p + 1;
+        bool xneg = false;
+        if (x < le && (*x == '-' || *x == '+')) {
+            xneg = *x == '-';
+            ++x;
+        }
+        const char *x0 = x;
+        int ex = 0;
+        while (x < le && (unsigned)(*x - '0') < 10u && x - x0 < 4) {
+            ex = ex * 10 + (*x - '0');
+            ++x;
+        }
+        if (x == x0) return nullptr;                     // "1e" / "1e+": not a number the fast path knows
+        sc += xneg ? -ex : ex;
+        p = x;
+    }
+    // w cannot have wrapped while nd <= 19 (10^19 - 1 < 2^64).  Exact (Clinger): w and 10^|sc| are both doubles, so the
+    // one division or multiplication is the only rounding
+    if (any && nd <= 19 && w <= (1ull << 53) && sc >= -22 && sc <= 22 && (p == le || mdp_is_blank(*p) || *p == '\n')) {
         double d = (double)w;
-        if (sc) d = d / mdp_pow10(-sc);
+        if (sc < 0) d = d / mdp_pow10(-sc);
+        else if (sc > 0) d = d * mdp_pow10(sc);
         *v = neg ? -d : d;
         return p;
     }

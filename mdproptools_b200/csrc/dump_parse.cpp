@@ -397,16 +397,21 @@ extern "C" {
 int64_t mdp_dump_scan(const char *text, int64_t len, int64_t *offsets, int64_t max_frames)
 {
     if (!text || len <= 0) return 0;
+    // A frame starts at a line that begins with "ITEM: TIMESTEP".  Looking for the letter 'I' with memchr runs at memory
+    // speed over the atom rows (numbers; a row that does hold an 'I', say an element column, only costs a comparison) --
+    // a memchr per 30-byte line, as in round 1, cost three times the read of the file itself.
     int64_t n = 0;
-    const char *p = text, *end = text + len;
-    while (p < end) {
-        if (end - p >= 14 && memcmp(p, "ITEM: TIMESTEP", 14) == 0) {
-            if (offsets && n < max_frames) offsets[n] = (int64_t)(p - text);
+    const char *end = text + len;
+    for (const char *p = text; p < end;) {
+        const char *q = (const char *)memchr(p, 'I', (size_t)(end - p));
+        if (!q) break;
+        if ((q == text || q[-1] == '\n') && end - q >= 14 && memcmp(q, "ITEM: TIMESTEP", 14) == 0) {
+            if (offsets && n < max_frames) offsets[n] = (int64_t)(q - text);
             ++n;
+            p = q + 14;
+        } else {
+            p = q + 1;
         }
-        // jump to the next line that starts with 'I' cheaply: atom rows never start with 'I'
-        p = next_line(p, end);
-        while (p < end && *p != 'I') p = next_line(p, end);
     }
     return n;
 }

@@ -145,6 +145,55 @@ def _read_and_scan(fname: str):
         cap = n
 
 
+class TextFrame:
+    """One frame inside a text buffer shared by many files: byte offsets (frame start, first row, end) and the header."""
+    __slots__ = ("begin", "rows", "end", "timestep", "natoms", "box", "columns")
+
+    def __init__(self, begin, rows, end, timestep, natoms, box, columns):
+        self.begin, self.rows, self.end = begin, rows, end
+        self.timestep, self.natoms, self.box, self.columns = timestep, natoms, box, columns
+
+
+def read_text_frames(fname: str, view, addr: int, off: int, size: int):
+    """Reader-thread body of the text pipeline (io/pipeline.py): read ``fname`` straight into ``view[off:off + size]`` (a
+    pinned staging buffer whose first byte has address ``addr``), split it into frames (mdp_dump_scan) and read every
+    frame's header (mdp_dump_header).  The read and both native calls release the GIL.  Returns (bytes read, [TextFrame])
+    with offsets relative to the start of the staging buffer."""
+    got = 0
+    with open(fname, "rb", buffering=0) as fh:
+        while got < size:
+            n = fh.readinto(view[off + got:off + size])
+            if not n:
+                break
+            got += n
+    L = _lib.lib()
+    base = addr + off
+    cap = 64
+    while True:
+        offs = (ctypes.c_int64 * cap)()
+        n = int(L.mdp_dump_scan(ctypes.cast(ctypes.c_void_p(base), ctypes.c_char_p), got, offs, cap))
+        if n <= cap:
+            offs = list(offs[:max(n, 0)])
+            break
+        cap = n
+    frames = []
+    hdr = (ctypes.c_double * 16)()
+    cols = ctypes.create_string_buffer(4096)
+    ends = offs[1:] + [got]
+    for b0, e0 in zip(offs, ends):
+        _lib.check(L.mdp_dump_header(ctypes.cast(ctypes.c_void_p(base + b0), ctypes.c_char_p), e0 - b0, hdr, cols, 4096),
+                   "mdp_dump_header")
+        head = bytes(view[off + b0:off + min(e0, b0 + 4096)])
+        a = head.find(b"ITEM: ATOMS")
+        nl = head.find(b"\n", a) if a >= 0 else -1
+        if nl < 0:
+            raise RuntimeError(f"{fname}: no 'ITEM: ATOMS' line in the first 4096 bytes of a frame")
+        tric = hdr[11] != 0.0
+        box = Box([[hdr[2], hdr[3]], [hdr[4], hdr[5]], [hdr[6], hdr[7]]], [hdr[8], hdr[9], hdr[10]] if tric else None)
+        frames.append(TextFrame(off + b0, off + b0 + nl + 1, off + e0, int(hdr[0]), int(hdr[1]), box, cols.value.decode().split()))
+    return got, frames
+
+
 def _split_frames(buf: bytes):
     """Offsets of every line that starts with ``ITEM: TIMESTEP`` (bytes.find: memchr-speed, no per-line work)."""
     offs = [0] if buf.startswith(_FRAME_MARK) else []

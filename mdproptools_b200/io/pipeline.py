@@ -1,9 +1,13 @@
-"""Frame pipeline: dump text -> pinned SoA host buffers -> HBM on a side stream, overlapped with compute.
+"""Frame pipeline: dump text -> HBM, overlapped with compute.  Subsystem (a) of the north star.
 
-Subsystem (a) of the north star.  A reader thread parses frames with the native parser straight into a
-ring of pinned staging tensors ``[F, C, N]`` (ctypes releases the GIL while the C++ parser runs), the copy
-to the device is issued on a dedicated copy stream and the consumer only waits on the copy's event, so
-parsing, PCIe transfer and kernels of consecutive batches overlap.
+With a GPU (default): reader threads read the files straight into pinned TEXT buffers, the text is copied to the device
+on a copy stream and parsed there (csrc/dump_device.cu, the same exact number conversion as the host parser); the parsed
+``[F, C, N]`` columns are copied back into a pinned host tensor on a third stream for the consumers that look at ids and
+types on the host.  Reads of the next group of files, PCIe transfers, the parse kernel and the consumer's kernels overlap.
+
+Without a GPU, for .gz files, dumps without an id column, or with MDP_DEVICE_PARSE=0: a producer thread parses frames
+with the native host parser straight into a ring of pinned staging tensors ``[F, C, N]`` (ctypes releases the GIL while
+the C++ parser runs) and the copy to the device is issued on a dedicated copy stream.
 """
 from __future__ import annotations
 
@@ -34,6 +38,12 @@ class Batch:
     ready: object | None     # torch.cuda.Event recorded after the H2D copy
 
     def wait(self):
+        tr = getattr(self, "_trace", None)
+        if tr is not None:                                  # consumer timeline: its stream between two wait() calls
+            e = tr.event()
+            if tr.consumer_last is not None:
+                tr.gpu_span("consumer kernels", tr.consumer_last[0], tr.consumer_last[1], e)
+            tr.consumer_last = (self._trace_idx, e)
         if self.ready is not None:
             cur = torch.cuda.current_stream()
             cur.wait_event(self.ready)
@@ -45,6 +55,43 @@ class Batch:
 
     def col(self, name):
         return self.columns.index(name)
+
+
+class _Trace:
+    """Timeline of one pass of the text pipeline (MDP_PIPELINE_TRACE=<file>: one JSON line per pass is appended).  Host
+    intervals are perf_counter times, device intervals pairs of CUDA events on the stream that did the work; everything is
+    reported in milliseconds from the start of the pass.  Measurement aid only: nothing reads it back."""
+
+    def __init__(self, path):
+        import time
+        self.path, self.clock = path, time.perf_counter
+        self.t0 = self.clock()
+        self.base = torch.cuda.Event(enable_timing=True)
+        self.base.record()
+        self.host, self.gpu, self.lock = [], [], threading.Lock()
+
+    def span(self, name, idx, t_start):
+        with self.lock:
+            self.host.append((name, idx, (t_start - self.t0) * 1e3, (self.clock() - self.t0) * 1e3))
+
+    def event(self, stream=None):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream if stream is not None else torch.cuda.current_stream())
+        return e
+
+    def gpu_span(self, name, idx, e0, e1):
+        with self.lock:
+            self.gpu.append((name, idx, e0, e1))
+
+    def dump(self):
+        import json
+        torch.cuda.synchronize()
+        rows = [{"where": "host", "what": n, "batch": i, "t0_ms": round(a, 3), "t1_ms": round(b, 3)} for n, i, a, b in self.host]
+        rows += [{"where": "gpu", "what": n, "batch": i, "t0_ms": round(self.base.elapsed_time(a), 3),
+                  "t1_ms": round(self.base.elapsed_time(b), 3)} for n, i, a, b in self.gpu]
+        rows.sort(key=lambda r: r["t0_ms"])
+        with open(self.path, "a") as f:
+            f.write(json.dumps({"total_ms": round((self.clock() - self.t0) * 1e3, 3), "spans": rows}) + "\n")
 
 
 class _ProducerStopped(BaseException):
@@ -116,14 +163,17 @@ class FrameBatches:
         self.nthreads = nthreads
         self.prefetch = prefetch
         self.total_frames = None   # known once iteration has finished
-        # EXPERIMENTAL, off by default: ship the TEXT to the device and parse it there (csrc/dump_device.cu); frames the
-        # device parser refuses (numbers off the exact fast path, irregular ids) are re-parsed by the host parser
+        # Device parse (the default with a GPU, since round 2): the TEXT goes to the device and is parsed there
+        # (csrc/dump_device.cu) -- _produce_text below; frames the device parser refuses (numbers off the exact fast path,
+        # irregular ids) are re-parsed by the host parser, and trajectories it cannot take at all (no id column, .gz files)
+        # use the host pipeline.  MDP_DEVICE_PARSE=0 / device_parse=False select the host parser.
         if device_parse is None:
-            import os
-            device_parse = os.environ.get("MDP_DEVICE_PARSE", "0") not in ("", "0")
+            device_parse = _os.environ.get("MDP_DEVICE_PARSE", "1") not in ("", "0")
         self.device_parse = bool(device_parse) and self.to_device
         self.device_parsed_frames = 0
         self.host_reparsed_frames = 0
+        self._pool, self._pool_lock = [], threading.Lock()
+        self._trace = None
 
     def _produce(self, q: "queue.Queue"):
         try:
@@ -131,6 +181,11 @@ class FrameBatches:
 
             from .. import _lib
 
+            if self.device_parse:
+                plan = self._text_plan()
+                if plan is not None:
+                    self._produce_text(q, *plan)
+                    return
             copy_stream = torch.cuda.Stream(device=self.device) if self.to_device else None
             C = len(self.columns)
             pending = []                     # (trajectory index, frame text) of the batch being collected
@@ -154,14 +209,6 @@ class FrameBatches:
                 if buf is None or buf.shape[1:] != (C, cur_n) or buf.shape[0] < F:
                     buf = ring[slot] = torch.empty((max(F, cap), C, cur_n), dtype=torch.float64, pin_memory=self.cuda)
                 h = buf[:F]
-                if self.device_parse:
-                    got = self._flush_device([b for _, b in pending], [i for i, _ in pending], h, copy_stream)
-                    if got is not None:
-                        metas, dev, ev = got
-                        ring_ev[slot] = ev
-                        q.put(Batch(metas, self.columns, h, dev, ev))
-                        pending = []
-                        return
                 frames = _dump.parse_frames([b for _, b in pending], self.columns, h.numpy(), self.nthreads)
                 metas = [FrameMeta(idx, fr.timestep, fr.natoms, fr.box) for (idx, _), fr in zip(pending, frames)]
                 dev, ev = None, None
@@ -205,69 +252,240 @@ class FrameBatches:
             except _ProducerStopped:
                 pass
 
-    def _flush_device(self, bufs, indices, h, copy_stream):
-        """Device parse of one batch (EXPERIMENTAL): text -> pinned bytes -> H2D -> k_dump_rows -> D2H of the parsed SoA
-        into ``h`` (the consumers read types and ids on the host).  Returns (metas, dev, event), or None when the batch
-        does not qualify (no id column, too many columns) and the host parser should take it."""
-        import ctypes
+    # ---------------------------------------------------------------------------------------------------------------
+    # text pipeline: file -> pinned text (reader threads) -> HBM -> k_dump_rows -> [F, C, N] on the device (+ a copy on the
+    # host for the consumers that look at ids / types there)
+    # ---------------------------------------------------------------------------------------------------------------
+    def _text_plan(self):
+        """(files, file indices) of this rank when the device parser can take the trajectory, else None (host parser):
+        plain files whose first frame has an id column and every wanted column within the parser's limits."""
+        files = _dump.dump_files(self.pattern)
+        if not files or any(f.endswith(".gz") for f in files):
+            return None
+        import os
+        if max(os.path.getsize(f) for f in files) > (1 << 30):      # a file is staged (and shipped) whole
+            return None
+        with open(files[0], "rb") as fh:
+            head = fh.read(4096)
+        a = head.find(b"ITEM: ATOMS")
+        nl = head.find(b"\n", a) if a >= 0 else -1
+        if nl < 0 or self._colsel(head[a + 11:nl].decode().split()) is None:
+            return None
+        findex = list(range(len(files)))
+        if self.file_shard is not None:
+            findex = findex[self.file_shard[0]::self.file_shard[1]]
+        return [files[i] for i in findex], findex, len(files)
 
-        from .. import _lib, ops
-
-        cols = _dump.frame_columns(bufs[0])
+    def _colsel(self, cols):
+        """Output slot of every file column (-1: not wanted), or None when the device parser does not apply."""
         want = self.columns
         if "id" not in cols or any(w not in cols for w in want) or len(want) > 16:
             return None
         colsel = [want.index(c) if c in want else -1 for c in cols]
         if max([cols.index("id")] + [k for k, v in enumerate(colsel) if v >= 0]) >= 64:
             return None
-        F, C, n = h.shape
-        hdr = (ctypes.c_double * 16)()
-        metas, begin, end, off = [], [], [], 0
-        for idx, b in zip(indices, bufs):
-            _lib.check(_lib.lib().mdp_dump_header(b, len(b), hdr, None, 0), "mdp_dump_header")
-            tric = hdr[11] != 0.0
-            box = _dump.Box([[hdr[2], hdr[3]], [hdr[4], hdr[5]], [hdr[6], hdr[7]]], [hdr[8], hdr[9], hdr[10]] if tric else None)
-            metas.append(FrameMeta(idx, int(hdr[0]), int(hdr[1]), box))
-            a = b.find(b"ITEM: ATOMS")
-            begin.append(off + b.find(b"\n", a) + 1)
-            end.append(off + len(b))
-            off += len(b)
-        text = torch.empty((off,), dtype=torch.uint8, pin_memory=True)
-        tv = text.numpy()
-        pos = 0
-        for b in bufs:
-            tv[pos:pos + len(b)] = np.frombuffer(b, dtype=np.uint8)
-            pos += len(b)
-        device = self.device or torch.device("cuda", torch.cuda.current_device())
-        with torch.cuda.stream(copy_stream):
-            text_d = text.to(device, non_blocking=True)
-            begin_d = torch.tensor(begin, dtype=torch.int64).to(device)
-            end_d = torch.tensor(end, dtype=torch.int64).to(device)
-            dev = torch.empty((F, C, n), dtype=torch.float64, device=device)
-            seen = torch.empty((F, (n + 31) // 32), dtype=torch.int32, device=device)
-            status = torch.empty((F, 2), dtype=torch.int64, device=device)
-            ops.dump_parse_device(text_d, begin_d, end_d, max(e - b0 for b0, e in zip(begin, end)), n, len(cols), colsel,
-                                  cols.index("id"), dev, seen, status, stream=copy_stream)
-            st = status.cpu()                                   # synchronises the copy stream: the parse has finished
-            redo = [f for f in range(F) if int(st[f, 0]) != n or int(st[f, 1]) != 0]
-            good = [f for f in range(F) if f not in set(redo)]
-            if not redo:
-                h.copy_(dev, non_blocking=True)
-            else:
-                for f in good:
-                    h[f].copy_(dev[f], non_blocking=True)
-            for f in redo:                                      # nothing is approximated: the host parser decides
-                _dump.parse_frame(bufs[f], want, self.nthreads, out=h[f].numpy())
-                dev[f].copy_(h[f], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        copy_stream.synchronize()                               # h is complete before the batch is handed over
-        self.device_parsed_frames += len(good)
-        self.host_reparsed_frames += len(redo)
-        return metas, dev, ev
+        return colsel
+
+    def _host_buffer(self, F, C, n):
+        """A pinned [>= F, C, n] staging tensor from the pool (returned to it when the consumer asks for the next batch)."""
+        with self._pool_lock:
+            for k, b in enumerate(self._pool):
+                if b.shape[1:] == (C, n) and b.shape[0] >= F:
+                    return self._pool.pop(k)
+        return torch.empty((F, C, n), dtype=torch.float64, pin_memory=True)
+
+    def _produce_text(self, q, files, findex, nfiles_all):
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        from .. import ops
+
+        device = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        copy_stream, d2h_stream = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        want, C = self.columns, len(self.columns)
+        sizes = [os.path.getsize(f) for f in files]
+        readers = int(os.environ.get("MDP_READERS", max(4, min(16, (3 * (os.cpu_count() or 4)) // 4))))
+        # groups of consecutive files: one pinned text buffer, one H2D copy, (normally) one batch each.  Small groups keep
+        # the stages busy together: the first batch is ready after one group's reads, and while group k is parsed groups
+        # k+1 and k+2 are being read (64 MB of text = 20 C2 frames; MDP_TEXT_GROUP_MB for measurements)
+        group_bytes = min(self.max_batch_bytes, int(os.environ.get("MDP_TEXT_GROUP_MB", "64")) << 20)
+        groups, cur, cur_b = [], [], 0
+        for k, sz in enumerate(sizes):
+            if cur and (len(cur) >= self.max_batch_frames or cur_b + sz > group_bytes):
+                groups.append(cur)
+                cur, cur_b = [], 0
+            cur.append(k)
+            cur_b += sz
+        if cur:
+            groups.append(cur)
+        ahead = 2                                        # groups whose reads are in flight beyond the one being parsed
+        nring = self.prefetch + 4 + ahead
+        tring, tev = [None] * nring, [None] * nring      # pinned text buffers; the H2D copy that last read each of them
+        tr = self._trace
+        nbatch = [0]
+        sharded = self.file_shard is not None
+        state = {"next_index": 0}
+
+        with ThreadPoolExecutor(max_workers=max(1, readers)) as ex:
+
+            def submit(gi):
+                """Start reading the files of group gi into its text buffer."""
+                slot = gi % nring
+                if tev[slot] is not None:
+                    tev[slot].synchronize()
+                    tev[slot] = None
+                need = sum(sizes[k] for k in groups[gi])
+                t_sub = tr.clock() if tr is not None else 0.0
+                buf = tring[slot]
+                if buf is None or buf.numel() < need:
+                    buf = tring[slot] = torch.empty((max(need, 1),), dtype=torch.uint8, pin_memory=True)
+                view, addr, off, futs = memoryview(buf.numpy()), buf.data_ptr(), 0, []
+                for k in groups[gi]:
+                    futs.append(ex.submit(_dump.read_text_frames, files[k], view, addr, off, sizes[k]))
+                    off += sizes[k]
+                return slot, buf, view, futs, need, t_sub
+
+            def enqueue_run(run, cols, text_d, view):
+                """H2D is under way; parse one run of frames (equal atom count and columns) on the copy stream and start the
+                copy of the parsed columns back to the host."""
+                F, n = len(run), run[0][1].natoms
+                missing = [w for w in want if w not in cols]
+                if missing:
+                    raise KeyError(f"column(s) {missing} not in dump file (has {cols})")
+                h_full = self._host_buffer(F, C, n)
+                h = h_full[:F]
+                colsel = self._colsel(cols)
+                if colsel is None or n <= 0:                   # this run is not for the device parser: host parse, plain H2D
+                    _dump.parse_frames([bytes(view[fr.begin:fr.end]) for _, fr in run], want, h.numpy(), self.nthreads)
+                    with torch.cuda.stream(copy_stream):
+                        dev = h.to(device, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                    self.host_reparsed_frames += F
+                    return {"run": run, "h_full": h_full, "h": h, "dev": dev, "ev": ev, "st": None, "view": view}
+                begin = [fr.rows for _, fr in run]
+                end = [fr.end for _, fr in run]
+                st_h = torch.empty((F, 2), dtype=torch.int64, pin_memory=True)
+                with torch.cuda.stream(copy_stream):
+                    begin_d = torch.tensor(begin, dtype=torch.int64).to(device)
+                    end_d = torch.tensor(end, dtype=torch.int64).to(device)
+                    dev = torch.empty((F, C, n), dtype=torch.float64, device=device)
+                    seen = torch.empty((F, (n + 31) // 32), dtype=torch.int32, device=device)
+                    status = torch.empty((F, 2), dtype=torch.int64, device=device)
+                    e0 = tr.event(copy_stream) if tr is not None else None
+                    ops.dump_parse_device(text_d, begin_d, end_d, max(e - b for b, e in zip(begin, end)), n, len(cols), colsel,
+                                          cols.index("id"), dev, seen, status, stream=copy_stream)
+                    parsed = torch.cuda.Event(enable_timing=tr is not None)
+                    parsed.record(copy_stream)
+                    if tr is not None:
+                        tr.gpu_span("k_dump_rows", nbatch[0], e0, parsed)
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(parsed)
+                    e0 = tr.event(d2h_stream) if tr is not None else None
+                    st_h.copy_(status, non_blocking=True)
+                    h.copy_(dev, non_blocking=True)
+                    dev.record_stream(d2h_stream)
+                    status.record_stream(d2h_stream)
+                    ev = torch.cuda.Event(enable_timing=tr is not None)
+                    ev.record(d2h_stream)
+                    if tr is not None:
+                        tr.gpu_span("D2H parsed columns", nbatch[0], e0, ev)
+                nbatch[0] += 1
+                return {"run": run, "h_full": h_full, "h": h, "dev": dev, "ev": ev, "st": st_h, "view": view, "k": nbatch[0] - 1}
+
+            def enqueue(gi, sub):
+                slot, buf, view, futs, need, t_sub = sub
+                frames = []
+                for k, fut in zip(groups[gi], futs):
+                    _, frs = fut.result()
+                    if tr is not None and k == groups[gi][-1]:
+                        tr.span("file reads + header scans (reader threads)", gi, t_sub)
+                    if sharded:
+                        if len(frs) != 1:
+                            raise _dump.MultiFrameFile(files[k])
+                        frames.append((findex[k], frs[0]))
+                        continue
+                    for fr in frs:
+                        idx = state["next_index"]
+                        state["next_index"] += 1
+                        if self.frame_select is None or self.frame_select(idx):
+                            frames.append((idx, fr))
+                if not frames:
+                    return []
+                with torch.cuda.stream(copy_stream):
+                    e0 = tr.event(copy_stream) if tr is not None else None
+                    text_d = buf[:need].to(device, non_blocking=True)
+                    ev = torch.cuda.Event(enable_timing=tr is not None)
+                    ev.record(copy_stream)
+                    if tr is not None:
+                        tr.gpu_span("H2D text", gi, e0, ev)
+                tev[slot] = ev
+                recs, i = [], 0
+                while i < len(frames):
+                    n, cols = frames[i][1].natoms, frames[i][1].columns
+                    cap = max(1, min(self.max_batch_frames, self.max_batch_bytes // max(1, C * n * 8)))
+                    j = i
+                    while j < len(frames) and j - i < cap and frames[j][1].natoms == n and frames[j][1].columns == cols:
+                        j += 1
+                    recs.append(enqueue_run(frames[i:j], cols, text_d, view))
+                    i = j
+                return recs
+
+            def finalize(rec):
+                """Wait for the parse (this thread only), let the host parser redo what the device refused, hand over."""
+                run, h, dev, ev = rec["run"], rec["h"], rec["dev"], rec["ev"]
+                t_fin = tr.clock() if tr is not None else 0.0
+                if rec["st"] is not None:
+                    ev.synchronize()
+                    st = rec["st"].numpy()
+                    n = run[0][1].natoms
+                    redo = [f for f in range(len(run)) if int(st[f, 0]) != n or int(st[f, 1]) != 0]
+                    for f in redo:                               # nothing is approximated: the host parser decides
+                        fr = run[f][1]
+                        _dump.parse_frame(bytes(rec["view"][fr.begin:fr.end]), want, self.nthreads, out=h[f].numpy())
+                    if redo:
+                        with torch.cuda.stream(copy_stream):
+                            for f in redo:
+                                dev[f].copy_(h[f], non_blocking=True)
+                            ev = torch.cuda.Event()
+                            ev.record(copy_stream)
+                        ev.synchronize()
+                    self.device_parsed_frames += len(run) - len(redo)
+                    self.host_reparsed_frames += len(redo)
+                metas = [FrameMeta(idx, fr.timestep, fr.natoms, fr.box) for idx, fr in run]
+                batch = Batch(metas, self.columns, h, dev, ev)
+                batch._pool_buffer = rec["h_full"]
+                if tr is not None:
+                    batch._trace, batch._trace_idx = tr, rec.get("k", -1)
+                    tr.span("producer: wait for the parse, check status", rec.get("k", -1), t_fin)
+                    t_put = tr.clock()
+                q.put(batch)
+                if tr is not None:
+                    tr.span("producer: blocked handing over (consumer busy)", rec.get("k", -1), t_put)
+
+            subs, nsub, prev = {}, 0, []
+            try:
+                for gi in range(len(groups)):
+                    while nsub < len(groups) and nsub <= gi + ahead:     # reads of the next groups run while this one is parsed
+                        subs[nsub] = submit(nsub)
+                        nsub += 1
+                    cur = enqueue(gi, subs.pop(gi))                      # H2D + parse + D2H of this group: asynchronous
+                    for rec in prev:                                     # ... while the previous group is checked and handed over
+                        finalize(rec)
+                    prev = cur
+            except _dump.MultiFrameFile:
+                self.multi_frame_seen = True
+            for rec in prev:
+                finalize(rec)
+        self.total_frames = nfiles_all if sharded else state["next_index"]
+        q.put(None)
 
     def __iter__(self):
         q: "queue.Queue" = _StoppableQueue(self.prefetch)
+        import os
+        if self.device_parse and os.environ.get("MDP_PIPELINE_TRACE"):
+            self._trace = _Trace(os.environ["MDP_PIPELINE_TRACE"])
+            self._trace.consumer_last = None
         th = threading.Thread(target=self._produce, args=(q,), daemon=True)
         th.start()
         try:
@@ -278,12 +496,21 @@ class FrameBatches:
                 if isinstance(item, BaseException):
                     raise item
                 yield item
+                buf = getattr(item, "_pool_buffer", None)     # the consumer is done with this batch's host copy
+                if buf is not None:
+                    with self._pool_lock:
+                        self._pool.append(buf)
         finally:
             # the consumer may leave early (an exception in its loop body, a generator that is dropped): tell the producer to
             # stop, unblock its pending put, and wait for it -- otherwise the thread would sit in q.put() for ever, holding
             # the pinned staging ring, the device batches and the read-ahead pool
             q.stop()
             th.join()
+            if self._trace is not None:
+                tr, self._trace = self._trace, None
+                if tr.consumer_last is not None:
+                    tr.gpu_span("consumer kernels", tr.consumer_last[0], tr.consumer_last[1], tr.event())
+                tr.dump()
 
 
 class ArrayBatches:

@@ -89,21 +89,66 @@ def calc_atom_type_ids(ids, num_mols, num_atoms):
     return out
 
 
+def _same_values(a, b):
+    """a == b element for element.  Contiguous arrays of one dtype and shape are compared with one memcmp (ctypes releases
+    the GIL; 10^5 doubles take ~50 us, where ``np.array_equal`` builds a temporary and holds the GIL next to the pipeline's
+    reader threads)."""
+    if a is b:
+        return True
+    if a.shape != b.shape:
+        return False
+    if a.dtype == b.dtype and a.flags.c_contiguous and b.flags.c_contiguous:
+        import ctypes
+
+        return _memcmp()(ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(b.ctypes.data), ctypes.c_size_t(a.nbytes)) == 0
+    return bool(np.array_equal(a, b))
+
+
+def _memcmp():
+    import ctypes
+
+    fn = getattr(_memcmp, "fn", None)
+    if fn is None:
+        fn = ctypes.CDLL(None).memcmp
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        _memcmp.fn = fn
+    return fn
+
+
 class _TypeCache:
     """Per-frame host work that depends only on the frame's id/type column: the altered types, the {type: count} table and
-    the class of every atom.  Trajectories almost always repeat the same column frame after frame; one np.array_equal
-    (tens of microseconds for 10^5 atoms) then replaces ~1 ms of recomputation per frame, which is what the consumer
-    thread of the file pipeline spent next to a pair kernel that needs 0.1 ms per frame."""
+    the class of every atom.  Trajectories almost always repeat the same column frame after frame; one comparison (tens
+    of microseconds for 10^5 atoms) then replaces ~1 ms of recomputation per frame, which is what the consumer thread of
+    the file pipeline spent next to a pair kernel that needs 0.1 ms per frame."""
 
     def __init__(self):
         self.key = None
         self.val = None
+        self.src = None            # the object last asked about (an identical object needs no comparison at all)
 
     def get(self, column, make):
-        if self.key is None or self.key.shape != column.shape or not np.array_equal(self.key, column):
+        if column is self.src:
+            return self.val
+        if self.key is None or not _same_values(self.key, column):
             self.key = np.array(column, copy=True)
             self.val = make(column)
+        self.src = column if column.base is None else None      # (a view into a staging buffer is not an identity)
         return self.val
+
+
+class _DeviceCache:
+    """The class vector on the device: uploaded again only when the host vector is another object than last time (a
+    pageable H2D copy waits for the stream -- the consumer would stall behind its own kernels once per batch)."""
+
+    def __init__(self):
+        self.src, self.dev = None, None
+
+    def get(self, arr, device):
+        if arr is not self.src or self.dev is None or self.dev.device != device:
+            self.dev = torch.from_numpy(arr).to(device)
+            self.src = arr
+        return self.dev
 
 
 def _value_counts(typ):
@@ -392,7 +437,7 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
     batches = _frame_batches(filename, ["id", "type", "x", "y", "z"])
     counts, props = {}, {}
     device = torch.device("cuda", torch.cuda.current_device())   # a rank that receives no frames still joins the merge
-    tcache, ccache = _TypeCache(), _TypeCache()
+    tcache, ccache, dcache = _TypeCache(), _TypeCache(), _DeviceCache()
 
     def _typ_and_counts(col):
         typ_ = calc_atom_type_ids(col, num_mols, num_atoms_per_mol) if altered else np.array(col, copy=True)
@@ -403,7 +448,7 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
         device = dev.device
         F = len(batch.metas)
         host = batch.host.numpy()
-        cls = np.empty((F, host.shape[2]), dtype=np.int32)
+        cls_rows = []
         boxes = np.empty((F, 6 if flags else 3))
         same_cls, cls_first = True, None
         for k, meta in enumerate(batch.metas):
@@ -419,10 +464,11 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
             cls_k = ccache.get(typ, cmap.classes_of)
             same_cls = same_cls and (k == 0 or cls_k is cls_first)
             cls_first = cls_k if k == 0 else cls_first
-            cls[k] = cls_k
+            cls_rows.append(cls_k)
             boxes[k] = boxrow
         xyz = dev[:, 2:5, :].contiguous()
-        cls_d = torch.from_numpy(cls[0] if same_cls else cls).to(device)     # one [N] vector when the batch shares its classes
+        # one [N] vector when the batch shares its classes (and no upload at all when it is the previous batch's)
+        cls_d = dcache.get(cls_first, device) if same_cls else torch.from_numpy(np.stack(cls_rows)).to(device)
         hist = ops.pair_hist(xyz, cls_d, cmap.ncls, boxes, rcut2, edges, bin_size, flags=flags)
         red = ops.hist_reduce(hist, weights)                      # [F, 1+R, nb]
         for k, meta in enumerate(batch.metas):
@@ -437,14 +483,16 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
 
     rdf_full_sum = np.zeros(num_bins)
     rdf_part_sum = np.zeros((num_relations, num_bins))
+    den_cache = {}   # frames of one composition and volume share the divisors of _normalize_rdf (the NVT case: one entry)
     for idx in range(T):
         at, rho, rho_pairs, natoms = props[idx]
-        rdf_full = allc[idx, 0].astype(np.float64)
-        rdf_part = allc[idx, 1:].astype(np.float64)
-        rdf_full, rdf_part = _normalize_rdf(bin_size, rho_pairs, at, partial_relations, num_relations, num_bins, rdf_part,
-                                            rdf_full, natoms, rho)
-        rdf_full_sum += rdf_full
-        rdf_part_sum += rdf_part
+        key = (natoms, rho, np.asarray(rho_pairs).tobytes(), tuple(sorted(at.items())))
+        den = den_cache.get(key)
+        if den is None:
+            den = den_cache[key] = _rdf_denominators(bin_size, rho_pairs, at, partial_relations, num_relations, num_bins,
+                                                     natoms, rho)
+        rdf_full_sum += allc[idx, 0].astype(np.float64) / den[0]
+        rdf_part_sum += allc[idx, 1:].astype(np.float64) / den[1]
     rdf_full_sum = rdf_full_sum / T
     rdf_part_sum = rdf_part_sum / T
     return _save_rdf(radii, relation_matrix, path_or_buff, save_mode, rdf_part_sum, rdf_full_sum=rdf_full_sum)
@@ -480,7 +528,7 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
     batches = _frame_batches(filename, ["id", "type", "x", "y", "z"])
     counts, props = {}, {}
     device = torch.device("cuda", torch.cuda.current_device())   # a rank that receives no frames still joins the merge
-    tcache, ccache = _TypeCache(), _TypeCache()
+    tcache, ccache, dcache = _TypeCache(), _TypeCache(), _DeviceCache()
 
     def _typ_and_counts(col):
         typ_ = calc_atom_type_ids(col, num_mols, num_atoms_per_mol) if altered else np.array(col, copy=True)
@@ -491,7 +539,7 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
         device = dev.device
         F = len(batch.metas)
         host = batch.host.numpy()
-        cls = np.empty((F, host.shape[2]), dtype=np.int32)
+        cls_rows = []
         boxes = np.empty((F, 6 if flags else 3))
         same_cls, cls_first = True, None
         for k, meta in enumerate(batch.metas):
@@ -506,11 +554,11 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
             cls_k = ccache.get(typ, cmap.classes_of)
             same_cls = same_cls and (k == 0 or cls_k is cls_first)
             cls_first = cls_k if k == 0 else cls_first
-            cls[k] = cls_k
+            cls_rows.append(cls_k)
             boxes[k] = boxrow
         xyz = dev[:, 2:5, :].contiguous()
-        hist = ops.pair_hist(xyz, torch.from_numpy(cls[0] if same_cls else cls).to(device), cmap.ncls, boxes, rcut2_max, edges, 0.0,
-                             flags=flags)
+        cls_d = dcache.get(cls_first, device) if same_cls else torch.from_numpy(np.stack(cls_rows)).to(device)
+        hist = ops.pair_hist(xyz, cls_d, cmap.ncls, boxes, rcut2_max, edges, 0.0, flags=flags)
         red = ops.hist_reduce(hist, weights, cumulative=True)     # [F, R, nthr] cumulative over thresholds
         for k, meta in enumerate(batch.metas):
             counts[meta.index] = red[k]

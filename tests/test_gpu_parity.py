@@ -505,7 +505,7 @@ def test_device_dump_parser_matches_host_parser(sample_dir, tmp_path):
     rows = ["%d 1 %g %g %g" % (i + 1, 0.5 * i, 1.25 * i, 2.0 * i) for i in range(40)]
     body = "\n".join(rows) + "\n"
     head = "ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n40\nITEM: BOX BOUNDS pp pp pp\n0 9\n0 9\n0 9\nITEM: ATOMS id type x y z\n"
-    p.write_text(head % 0 + body + head % 10 + body.replace("1.25 ", "1.25e0 ", 1))
+    p.write_text(head % 0 + body + head % 10 + body.replace("1.25 ", "1.25e-40 ", 1))     # beyond the exact fast path: host re-parse
     ref = list(FrameBatches(str(p), ["id", "x", "y", "z"], device_parse=False))
     fb = FrameBatches(str(p), ["id", "x", "y", "z"], device_parse=True)
     got = list(fb)

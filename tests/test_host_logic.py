@@ -260,13 +260,16 @@ def test_device_parser_body_on_host(sample_dir, tmp_path):
 
     good = ((head % 4) + "1 1 0.5 1.5 2.5 a\n2 1 0.25 1 2 a\n3 2 7 8 9 a\n4 2 1 1 1 a\n").encode()
     cases = {
-        "exponent": (good.replace(b"0.25", b"2.5e-1"), 1),            # DPF_SLOW_TOKEN
+        "exponent beyond 10^22": (good.replace(b"0.25", b"2.5e-30"), 1),   # DPF_SLOW_TOKEN
         "digits": (good.replace(b"0.25", b"0.12345678901234567890123"), 1),
         "nan": (good.replace(b"0.25", b"nan"), 1),
         "short row": (good.replace(b"3 2 7 8 9 a", b"3 2 7"), 2),      # DPF_BAD_ROW
         "duplicate id": (good.replace(b"4 2 1 1 1", b"3 2 1 1 1"), 4),  # DPF_BAD_ID
         "id out of range": (good.replace(b"4 2 1 1 1", b"9 2 1 1 1"), 4),
     }
+    # exponents inside the exact range stay on the device (%g writes them for |x| < 1e-4)
+    out, status, _ = run([good.replace(b"0.25", b"2.5e-1"), good.replace(b"0.25", b"-1.25E-05")], ["id", "x", "y", "z"], False)
+    assert status.tolist() == [[4, 0], [4, 0]] and out[0, 1, 1] == 0.25 and out[1, 1, 1] == float("-1.25E-05")
     for name, (buf, flag) in cases.items():
         _, status, _ = run([good, buf], ["id", "x", "y", "z"], False)
         assert status[0].tolist() == [4, 0], name

@@ -1,9 +1,10 @@
 #!/bin/bash
-# file-based RDF entry point: batch size / reader thread sweep + a cProfile of one pass
+# file-based RDF entry point: device parser (text pipeline) against the host parser, batch size / reader thread sweep
 set -u
 cd "$(dirname "$0")/.."
+timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 600 -k "device_pars or frame_batches or golden" 2>&1 | tail -3
 python - <<'PY'
-import os, sys, time, shutil, tempfile, cProfile, pstats
+import os, sys, time, shutil, tempfile
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 import bench
@@ -23,18 +24,24 @@ for c in range(1, 8):
     for f in range(32):
         shutil.copy(os.path.join(d, f"dump.c2.{f}.dump"), os.path.join(d, f"dump.c2.{c * 32 + f}.dump"))
 pat = os.path.join(d, "dump.c2.*.dump")
+out = {}
 def run():
     t = time.perf_counter()
-    rdf_cn.calc_atomic_rdf(20, 0.05, 1, [39.9], [[1], [1]], pat, save_mode=False)
+    df = rdf_cn.calc_atomic_rdf(20, 0.05, 1, [39.9], [[1], [1]], pat, save_mode=False)
     torch.cuda.synchronize()
+    out["df"] = df
     return (time.perf_counter() - t) / 256 * 1e3
+os.environ["MDP_DEVICE_PARSE"] = "0"
 run()
-for mb in (64, 128, 256):
+print(f"host parser (default batch/readers): {min(run(), run()):.3f} ms/frame", flush=True)
+ref = out["df"].values.copy()
+os.environ["MDP_DEVICE_PARSE"] = "1"
+run()
+print("device parser result identical to host parser result:", bool(np.array_equal(ref, out["df"].values)))
+print(f"device parser (default batch/readers): {min(run(), run()):.3f} ms/frame", flush=True)
+for mb in (32, 64, 128, 256):
     for rd in (4, 8, 12):
         os.environ["MDP_BATCH_MB"] = str(mb); os.environ["MDP_READERS"] = str(rd)
-        print(f"batch {mb} MB readers {rd}: {min(run(), run()):.3f} ms/frame", flush=True)
-os.environ["MDP_BATCH_MB"] = "128"; os.environ["MDP_READERS"] = "8"
-pr = cProfile.Profile(); pr.enable(); run(); pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+        print(f"device parser, batch {mb} MB readers {rd}: {min(run(), run()):.3f} ms/frame", flush=True)
 shutil.rmtree(d)
 PY
