@@ -497,12 +497,12 @@ def run_gpu(args):
     rel = [[1], [1]]
     types = np.ones(N_ATOMS)
     for _ in range(2):
-        rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=16, frame_range=(lo, hi, T_total))
+        rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=128, frame_range=(lo, hi, T_total))
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 6))
     for _ in range(e2e_steps):
-        df_e2e = rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=16, frame_range=(lo, hi, T_total))
+        df_e2e = rdf_cn.calc_atomic_rdf_from_arrays(host, types, L, R_CUT, BIN, rel, batch_frames=128, frame_range=(lo, hi, T_total))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -540,17 +540,20 @@ def run_gpu(args):
     nominal_tflops = (F * N_ATOMS * (N_ATOMS - 1) // 2) * FLOPS_PER_PAIR * args.steps / (pair_ms * 1e-3) / 1e12
     frames_per_launch = F * args.steps / max(pair_n, 1)
     # what actually bounds k_pair_fast: instruction issue.  Warp instructions per 32 evaluated pairs from the committed ncu
-    # capture (profiles/r02a_k_pair_fast_meta.json) x this run's evaluated pairs / its kernel time, against 4 schedulers x
+    # capture (profiles/r*_k_pair_fast_meta.json) x this run's evaluated pairs / its kernel time, against 4 schedulers x
     # 148 SMs x 1 instruction per clock
     issue = None
     try:
-        meta = json.load(open(os.path.join(ROOT, "profiles", "r02a_k_pair_fast_meta.json")))
+        import glob
+        meta_path = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_pair_fast_meta.json")))[-1]      # the newest capture
+        meta = json.load(open(meta_path))
         wi = meta["warp_instr_per_32_pairs"] if not os.environ.get("MDP_PAIR_F64") else meta["all_fp64_kernel"]["warp_instr_per_32_pairs"]
         ips = evaluated_local / 32.0 * wi * args.steps / (pair_ms * 1e-3)
         ipk = 148 * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6
         issue = {"bound": "issue slots", "achieved": ips, "peak": ipk, "unit": "warp-instr/s", "frac": ips / ipk,
-                 "warp_instr_per_32_pairs": wi, "source": "instruction count per evaluated pair from profiles/r02a_k_pair_fast.txt "
-                 "(smsp__inst_executed.sum; issue slots 83.7 % busy under ncu), scaled to this run"}
+                 "warp_instr_per_32_pairs": wi, "source": f"instruction count per evaluated pair from profiles/{os.path.basename(meta_path)} "
+                 f"(smsp__inst_executed.sum of the committed ncu capture; issue slots {meta.get('issue_active_pct', 83.7)} % busy "
+                 "under ncu), scaled to this run"}
     except Exception:
         pass
     cpu_rate, cores, sample = cpu_rdf_sample(10.0) if not args.skip_cpu else (None, None, "skipped")
@@ -599,8 +602,12 @@ def run_gpu(args):
     if not args.skip_cpu:
         out["dump_parse"] = bench_dump_parse()
         out["rdf_from_files"] = bench_rdf_from_files(torch, frames, N_ATOMS * (N_ATOMS - 1) // 2)
+        c1 = bench_c1(torch)
+        if c1:
+            out["c1"] = c1
+            parity["c1_sha256"] = out["c1_sha256"] = all(c1["sha256_equals_reference"].values())
     _emit(json.dumps(out))
-    bad = [k for k in ("parity_frame0", "parity_frame0_triclinic", "nrank_equals_1rank")
+    bad = [k for k in ("parity_frame0", "parity_frame0_triclinic", "nrank_equals_1rank", "c1_sha256")
            if parity.get(k) is False]
     if bad:
         sys.stderr.write(f"PARITY FAILURE: {bad}\n")
@@ -1101,6 +1108,54 @@ def bench_clusters_hydration(args, torch, dist, ops, ctx, dev, world, rank):
                              "its time; the search of 2 000 points against 200 000 is dominated by sorting and culling the large set, "
                              "not by pair arithmetic -- the figure of merit is the time per frame"},
     }
+
+
+def bench_c1(torch):
+    """Config C1 (SURVEY 8d / BASELINE.md section 2): the reference's own example trajectory, all 101 frames of 10 479 atoms,
+    through the reference's entry points calc_atomic_rdf (486 s on one core there) and calc_atomic_cn (534 s).  The frames
+    are the git-ignored fixture tests/golden_large/c1_frames.tar.gz (oracle/make_c1_fixture.py); absent -> no leg.  The
+    DataFrames are checked against the survey's sha256 known answers of the unmodified reference."""
+    import hashlib
+    import shutil
+    import tarfile
+    import tempfile
+    from mdproptools_b200.structural import rdf_cn
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden_large", "c1_frames.tar.gz")
+    if not os.path.exists(path):
+        return None
+    d = tempfile.mkdtemp(prefix="mdp_c1_")
+    try:
+        with tarfile.open(path) as tf:
+            tf.extractall(d)
+        pat = os.path.join(d, "dump.nvt.*.dump")
+        mass = [16.0, 12.01, 1.008, 14.01, 32.06, 16.0, 12.01, 19.0, 24.305]
+        rel = [[9, 9, 9, 9], [1, 4, 6, 9]]
+        sha = lambda df: hashlib.sha256(np.ascontiguousarray(df.values, dtype=np.float64).tobytes()).hexdigest()
+
+        def best(fn):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                t = time.perf_counter()
+                df = fn()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t)
+            return min(ts), df
+
+        t_rdf, df_rdf = best(lambda: rdf_cn.calc_atomic_rdf(20, 0.05, 9, mass, rel, pat, save_mode=False))
+        t_cn, df_cn = best(lambda: rdf_cn.calc_atomic_cn([2.325, 4.375, 2.375, 13.0], 0.05, 9, mass, rel, pat, save_mode=False))
+        ok_rdf = sha(df_rdf) == "b418f238f5e58393edbe59e8419c8afe1053dada1af6959fa589ce88cfa9ccfc"
+        ok_cn = sha(df_cn) == "0ad5461c6508bf07e42aeb21004303b189fbf2a1ed756a2a01fc4ce1b488bb1e"
+        return {"metric": "c1_wall_seconds", "unit": "s", "higher_is_better": False, "frames": 101, "atoms": 10479,
+                "calc_atomic_rdf_s": t_rdf, "calc_atomic_cn_s": t_cn,
+                "published_reference_s": {"calc_atomic_rdf": 486.0, "calc_atomic_cn": 534.0,
+                                          "source": "BASELINE.md section 2: one core, numba, other hardware, incl. ~20 s JIT"},
+                "vs_published": {"calc_atomic_rdf": 486.0 / t_rdf, "calc_atomic_cn": 534.0 / t_cn},
+                "sha256_equals_reference": {"calc_atomic_rdf": ok_rdf, "calc_atomic_cn": ok_cn},
+                "api": "rdf_cn.calc_atomic_rdf / calc_atomic_cn(filename=<101 dump files>), warm (best of 3 after one pass)"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def bench_rdf_from_files(torch, frames, nominal_pairs_per_frame, nfiles=32, copies=8):

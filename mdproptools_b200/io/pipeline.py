@@ -524,10 +524,13 @@ class ArrayBatches:
             ab.done()
     """
 
-    def __init__(self, pos: torch.Tensor, batch_frames: int, device=None):
+    def __init__(self, pos: torch.Tensor, batch_frames: int, device=None, ramp: bool = True):
         self.pos = pos
         self.T = pos.shape[0]
         self.nb = max(1, min(int(batch_frames), self.T))
+        # ramp: the first batch is an eighth of batch_frames and the size doubles from batch to batch -- the kernels start
+        # after a short first copy, and the bulk of the trajectory still goes through in large batches (few launches)
+        self.first = max(1, self.nb // 8) if ramp else self.nb
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         shape = (self.nb,) + tuple(pos.shape[1:])
         self.bufs = [torch.empty(shape, dtype=pos.dtype, device=self.device) for _ in range(2 if self.T > self.nb else 1)]
@@ -536,9 +539,10 @@ class ArrayBatches:
         self.main = torch.cuda.current_stream(self.device)
         self._k = None
 
-    def _stage(self, f0, k):
-        f1 = min(self.T, f0 + self.nb)
-        k %= len(self.bufs)
+    def _stage(self, f0, i):
+        """Start the copy of batch number i (frames from f0 on) into buffer i % 2."""
+        f1 = min(self.T, f0 + min(self.nb, self.first << min(i, 30)))
+        k = i % len(self.bufs)
         with torch.cuda.stream(self.copy_stream):
             if self.consumed[k] is not None:
                 self.copy_stream.wait_event(self.consumed[k])
@@ -548,13 +552,13 @@ class ArrayBatches:
             x.copy_(self.pos[f0:f1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        return f0, f1, x, ev, k
+        return f0, f1, x, ev, k, i
 
     def __iter__(self):
         nxt = self._stage(0, 0)
         while nxt is not None:
-            f0, f1, x, ev, k = nxt
-            nxt = self._stage(f1, k + 1) if f1 < self.T else None
+            f0, f1, x, ev, k, i = nxt
+            nxt = self._stage(f1, i + 1) if f1 < self.T else None
             self.main.wait_event(ev)
             self._k = k
             yield f0, f1, x

@@ -15,7 +15,7 @@ d=json.load(open('gpurun_out/bench_full.json'))
 for k in ('value','ms_per_step','scaling','parity_frame0','parity_frame0_in_step_output','parity_frame0_triclinic','hist_sha256','gpu_launches','kernel_share'):
     print(k, d.get(k))
 print('roofline', d['roofline']['achieved'], d['roofline']['frac']); print('e2e', d['e2e']); print('cpu', d['cpu_baseline'])
-for leg in ('rdf_triclinic','msd','green_kubo','residence','clusters_hydration','dump_parse','rdf_from_files'):
+for leg in ('rdf_triclinic','msd','green_kubo','residence','clusters_hydration','dump_parse','rdf_from_files','c1'):
     v=d.get(leg)
     if not v: print(leg, None); continue
     print(leg, {k:(v[k] if not isinstance(v[k],dict) else {kk:vv for kk,vv in v[k].items() if kk in ('achieved','frac','bound','value')}) for k in v if k not in ('config','note','api')})

@@ -35,4 +35,8 @@ echo "ncu fft rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_charge_flux -s 3 -c 1 -f -o $OUT/prof_flux \
     python bench.py --steps 1 --warmup 1 --frames 4 --skip-msd --skip-cpu --skip-residence --skip-triclinic --skip-clusters --gk-flux-frames 2048 --gk-steps 20000 > $OUT/ncu_flux.log 2>&1
 echo "ncu flux rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dump_rows -s 2 -c 1 -f -o $OUT/prof_dump \
+    python bench.py --steps 1 --warmup 1 --frames 4 --skip-msd --skip-gk --skip-residence --skip-triclinic --skip-clusters > $OUT/ncu_dump.log 2>&1
+echo "ncu dump rows rc=$?"
+bash tools/gpu_files_trace.sh > $OUT/trace.log 2>&1; echo "files timeline rc=$?"; head -12 $OUT/files_timeline.txt
 echo "== done $(date -u)"
