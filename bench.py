@@ -601,7 +601,12 @@ def run_gpu(args):
         out["clusters_hydration"] = c5s
     if not args.skip_cpu:
         out["dump_parse"] = bench_dump_parse()
-        out["rdf_from_files"] = bench_rdf_from_files(torch, frames, N_ATOMS * (N_ATOMS - 1) // 2)
+    if not args.skip_cpu or args.files_leg:
+        # the first 32 frames of the walk on EVERY rank (not the rank's block): all ranks then see the same files, the file
+        # reads are sharded over them, and the DataFrame (df_sha256) must not depend on the number of ranks
+        del frames
+        out["rdf_from_files"] = bench_rdf_from_files(torch, make_frames(32, SEED, "cuda"), N_ATOMS * (N_ATOMS - 1) // 2,
+                                                     copies=args.files_copies)
         c1 = bench_c1(torch)
         if c1:
             out["c1"] = c1
@@ -1093,8 +1098,22 @@ def bench_clusters_hydration(args, torch, dist, ops, ctx, dev, world, rank):
     hyd_entries, oriented, cl_entries, cl_members, evaluated = (int(v) for v in c.tolist())
     nominal = T * ncat * (n + nwat)
     peaks = measured_peaks()
-    pk = peaks.get("fp64_unfused_tflops_sustained") or 148 * 64 * 1.965e9 / 1e12
-    ach = evaluated * FLOPS_PER_PAIR / (cs * 1e-3) / 1e12 * (1.0 if world == 1 else 1.0 / world)
+    if ops.shell_grid_enabled():
+        # both searches run in k_shell_grid (csrc/shell.cu): every coordinate of both sets is read once per frame
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        alg = T * ((ncat + nwat) + (ncat + n)) * 24 / world
+        gbs = alg / ((hs + cs) * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                "note": "the two neighbour searches (cation x water O, cation x all atoms; k_shell_grid + list allocation) only, "
+                        "per GPU: algorithmic bytes = 24 B per atom and frame of both sets over their CUDA-event time; the kernel "
+                        "is issue-bound (cell walk + exact fp64 test per candidate), HBM is the floor it is compared with"}
+    else:
+        pk = peaks.get("fp64_unfused_tflops_sustained") or 148 * 64 * 1.965e9 / 1e12
+        ach = evaluated * FLOPS_PER_PAIR / (cs * 1e-3) / 1e12 * (1.0 if world == 1 else 1.0 / world)
+        roof = {"bound": "fp64", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
+                "note": "the cation x all-atom search (k_pair in list mode, all-fp64) only: evaluated pairs x 11 unfused flops over "
+                        "its time; the search of 2 000 points against 200 000 is dominated by sorting and culling the large set, "
+                        "not by pair arithmetic -- the figure of merit is the time per frame"}
     return {
         "metric": "cluster_hydration_pair_evals_per_s", "value": nominal / (total_ms * 1e-3), "unit": "pair-evals/s", "scaling": "strong",
         "config": {"workload": f"C5: {n} atoms ({ncat} cations, {nan} anions x 5, {nwat} waters x 3) x {T} frames, 126 A box; per frame "
@@ -1103,10 +1122,7 @@ def bench_clusters_hydration(args, torch, dist, ops, ctx, dev, world, rank):
         "ms_per_step": total_ms, "hydration_search_ms": hs, "hydration_epilogue_ms": he, "cluster_search_ms": cs,
         "cluster_epilogue_ms": ce, "hydration_entries": hyd_entries, "oriented_waters": oriented, "cluster_entries": cl_entries,
         "cluster_member_molecules": cl_members,
-        "roofline": {"bound": "fp64", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
-                     "note": "the cation x all-atom search (k_pair in list mode, all-fp64) only: evaluated pairs x 11 unfused flops over "
-                             "its time; the search of 2 000 points against 200 000 is dominated by sorting and culling the large set, "
-                             "not by pair arithmetic -- the figure of merit is the time per frame"},
+        "roofline": roof,
     }
 
 
@@ -1202,6 +1218,7 @@ def bench_rdf_from_files(torch, frames, nominal_pairs_per_frame, nfiles=32, copi
         return {"metric": "rdf_pair_evals_per_s", "value": nominal_pairs_per_frame * T / dt, "unit": "pair-evals/s",
                 "frames": T, "ms_per_frame": dt / T * 1e3, "text_MB_per_s": nbytes / dt / 1e6, "text_bytes": nbytes,
                 "g_full_max": float(df["g_full(r)"].max()),
+                "df_sha256": __import__("hashlib").sha256(np.ascontiguousarray(df.values, dtype=np.float64).tobytes()).hexdigest(),
                 "api": "rdf_cn.calc_atomic_rdf(filename=<dump files>) -- the reference's own entry point (rdf_cn.py:385)",
                 "parser": "device (k_dump_rows)" if os.environ.get("MDP_DEVICE_PARSE", "1") not in ("", "0") else "host",
                 "note": "text is %g (6 significant digits) as LAMMPS writes by default; files are read from the page cache"}
@@ -1273,6 +1290,8 @@ def main():
     ap.add_argument("--msd-frames", type=int, default=MSD_FRAMES)
     ap.add_argument("--skip-msd", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--files-leg", action="store_true", help="run the file-based legs (rdf_from_files, c1) even with --skip-cpu")
+    ap.add_argument("--files-copies", type=int, default=8, help="rdf_from_files reads 32 x this many dump files")
     ap.add_argument("--skip-triclinic", action="store_true")
     ap.add_argument("--skip-msd-window", action="store_true")
     ap.add_argument("--msd-window", type=int, default=512)

@@ -887,8 +887,9 @@ def test_c1_full_diffusion_kat(c1_dir, tmp_path):
 # ------------------------------------------------------------------------------------------------
 def test_nrank_equals_1rank_under_nccl(tmp_path):
     """bench.py at reduced sizes on 1 GPU and under torchrun on 2 (and 4) GPUs: the same RDF histograms (sha256 of all
-    per-frame integer histograms), the same residence survival counts (sha256), the same MSD to 1e-12 -- frames, atoms and
-    central atoms are only re-distributed, never re-computed differently."""
+    per-frame integer histograms), the same residence survival counts (sha256), the same MSD to 1e-12, the same DataFrame
+    from dump files whose reads are sharded over the ranks -- frames, atoms and central atoms are only re-distributed,
+    never re-computed differently."""
     import json
     import subprocess
     import sys
@@ -898,7 +899,8 @@ def test_nrank_equals_1rank_under_nccl(tmp_path):
         pytest.skip("needs at least 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     small = ["--steps", "2", "--warmup", "1", "--frames", "24", "--msd-atoms", "400000", "--msd-frames", "200", "--gk-steps", "20000",
-             "--gk-flux-frames", "1000", "--res-frames", "400", "--c5-frames", "100", "--skip-cpu", "--skip-msd-window"]
+             "--gk-flux-frames", "1000", "--res-frames", "400", "--c5-frames", "100", "--skip-cpu", "--skip-msd-window",
+             "--files-leg", "--files-copies", "2"]
 
     def run(n):
         cmd = ([sys.executable, "bench.py", "--gpus", "1"] if n == 1 else
@@ -919,6 +921,10 @@ def test_nrank_equals_1rank_under_nccl(tmp_path):
         assert abs(many["msd"]["msd_last_frame"] / one["msd"]["msd_last_frame"] - 1) < 1e-12   # fp64 all-reduce order only
         a, b = many["green_kubo"]["charge_flux"]["abs_flux_sum"], one["green_kubo"]["charge_flux"]["abs_flux_sum"]
         assert abs(a / b - 1) < 1e-12
+        # the reference's entry point on files, reads sharded over the ranks, text parsed on each rank's device
+        assert many["rdf_from_files"]["df_sha256"] == one["rdf_from_files"]["df_sha256"]
+        if "c1" in one:
+            assert many.get("c1_sha256") is True and one.get("c1_sha256") is True
 
 
 # ------------------------------------------------------------------------------------------------
