@@ -530,10 +530,11 @@ class ArrayBatches:
         self.nb = max(1, min(int(batch_frames), self.T))
         # ramp: the first batch is an eighth of batch_frames and the size doubles from batch to batch -- the kernels start
         # after a short first copy, and the bulk of the trajectory still goes through in large batches (few launches)
-        self.first = max(1, self.nb // 8) if ramp else self.nb
+        self.first = max(1, int(batch_frames) // 8) if ramp else self.nb
+        self.first = min(self.first, self.nb)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         shape = (self.nb,) + tuple(pos.shape[1:])
-        self.bufs = [torch.empty(shape, dtype=pos.dtype, device=self.device) for _ in range(2 if self.T > self.nb else 1)]
+        self.bufs = [torch.empty(shape, dtype=pos.dtype, device=self.device) for _ in range(2 if self.T > self.first else 1)]
         self.consumed = [None] * len(self.bufs)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.main = torch.cuda.current_stream(self.device)
