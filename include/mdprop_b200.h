@@ -171,7 +171,7 @@ int mdp_cluster_members(mdp_ctx *ctx, int nframes, int64_t n_central, int64_t n_
                         const int32_t *mol_seg_off, const int32_t *mol_of_atom, double force_constant, double max_force,
                         int64_t m, const int32_t *list, int64_t *seg_off, uint32_t *mol_out, int32_t *mol_count, void *stream);
 
-/* EXPERIMENTAL, opt-in (MDP_SHELL_GRID=1): the entries mdp_pair_list returns (same arguments, orthogonal cell, no rsq
+/* The Python layer's default for small central sets (MDP_SHELL_GRID=0 selects mdp_pair_list): the entries mdp_pair_list returns (same arguments, orthogonal cell, no rsq
  * output), found through a cell grid over a SMALL set A (n_a <= 4096) held in shared memory while B is streamed once
  * (csrc/shell_grid.h).  Returns 0, or 1 when the grid does not apply (n_a too large, or the outer radius exceeds a third
  * of a box length in some frame): the caller then uses mdp_pair_list. */
@@ -232,7 +232,8 @@ int mdp_charge_flux(mdp_ctx *ctx, int nframes, int64_t n, const double *vel, con
  * nlags <= T lags are produced (out row stride = nlags). */
 int mdp_xcorr_unbiased(mdp_ctx *ctx, int nchan, int64_t T, const double *a, const double *b, int64_t nlags,
                        double *out, void *stream);
-/* EXPERIMENTAL, opt-in (MDP_XCORR_FFT=1): the same correlation through a radix-2 Stockham FFT in fp64 (csrc/fft_corr.h) --
+/* The Python layer's default from 2048 steps on (MDP_XCORR_FFT=0 selects the direct sum): the same correlation through a
+ * Stockham FFT in fp64, three radix-2 stages per pass (csrc/fft_corr.h) --
  * N log N instead of T^2/2, for the 10^6..10^7-step series of a viscosity run; agrees with mdp_xcorr_unbiased to the
  * round-off of an FFT (~1e-15 of max|C| times log2 N), which is how the reference computes it.  Same arguments. */
 int mdp_xcorr_fft(mdp_ctx *ctx, int nchan, int64_t T, const double *a, const double *b, int64_t nlags, double *out,
@@ -251,7 +252,7 @@ int mdp_bitmask_fill(mdp_ctx *ctx, int64_t nentries, const int32_t *list, int64_
 int mdp_bitmask_autocorr(mdp_ctx *ctx, int64_t npairs, int nwords, int64_t T, const uint64_t *masks,
                          uint64_t *cnt_out, void *stream);
 
-/* EXPERIMENTAL, opt-in (MDP_SURVIVAL_RUNS=1): the same counts as mdp_bitmask_autocorr -- cnt_out accumulates, bit for bit
+/* The Python layer's default (MDP_SURVIVAL_RUNS=0 selects mdp_bitmask_autocorr): the same counts as mdp_bitmask_autocorr -- cnt_out accumulates, bit for bit
  * the same integers -- from the RUNS of each pair's bitmask: a pair with k runs costs 4*k(k+1)/2 integer updates of a
  * second-difference array instead of T^2/128 word operations (csrc/survival_runs.h).  T is limited by the shared-memory
  * array (about 25 000 frames). */
@@ -295,7 +296,7 @@ int mdp_dump_parse(const char *text, int64_t len, const char *const *want, int n
 int mdp_dump_parse_batch(int nframes, const char *const *texts, const int64_t *lens, const char *const *want, int nwant,
                          double *out, int64_t frame_stride, int64_t out_stride, double *headers_out, int nthreads);
 
-/* EXPERIMENTAL, opt-in (FrameBatches(device_parse=True)); the default pipeline parses on the host.
+/* The file pipeline's default with a GPU (io/pipeline.py; MDP_DEVICE_PARSE=0 selects the host parser above).
  * Device-side parse of the atom rows of nframes frames whose bytes are already in device memory: rows are placed by id
  * (out[f][slot][id-1]) with the exact fast path the host parser uses (dump_line.h).  begin/end = DEVICE int64 [nframes]:
  * byte offsets into text of the first row / one past the last row of each frame; longest = max(end - begin);

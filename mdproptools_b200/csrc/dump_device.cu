@@ -1,5 +1,5 @@
-// dump_device.cu -- device-side parser of LAMMPS dump atom rows (EXPERIMENTAL, opt-in: FrameBatches(device_parse=True) /
-// MDP_DEVICE_PARSE=1; the default pipeline uses the host parser of dump_parse.cpp).
+// dump_device.cu -- device-side parser of LAMMPS dump atom rows (the file pipeline's default since round 2b:
+// io/pipeline.py ships the TEXT; MDP_DEVICE_PARSE=0 / FrameBatches(device_parse=False) select the host parser).
 //
 // Why: the text of a dump is no larger than the SoA doubles parsed from it (about 30 B per "id type x y z" row in %g
 // against 40 B), so shipping the TEXT over PCIe costs no more than shipping the parsed columns, and the conversion --

@@ -52,8 +52,12 @@ def owner_of_rows(idx: torch.Tensor, n: int, w: int | None = None) -> torch.Tens
     w = world_size() if w is None else w
     base, rem = divmod(n, w)
     cut = rem * (base + 1)
-    idx = idx.to(torch.int64)
-    return torch.where(idx < cut, idx // (base + 1), rem + (idx - cut) // max(base, 1))
+    if idx.dtype != torch.int32 or n >= (1 << 31):           # (int32 indices stay int32: half the bytes per pass)
+        idx = idx.to(torch.int64)
+    if rem == 0:
+        return torch.div(idx, max(base, 1), rounding_mode="floor")
+    return torch.where(idx < cut, torch.div(idx, base + 1, rounding_mode="floor"),
+                       rem + torch.div(idx - cut, max(base, 1), rounding_mode="floor"))
 
 
 def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
@@ -112,10 +116,11 @@ def exchange_rows(rows: torch.Tensor, dest: torch.Tensor) -> torch.Tensor:
         return rows
     w, me = d.get_world_size(), d.get_rank()
     rows = rows.contiguous()
-    dest = dest.to(torch.int64)
-    order = torch.argsort(dest, stable=True)
+    # stable sort by destination: 8-bit keys (one radix pass instead of the eight of an int64 sort)
+    key = dest.to(torch.uint8) if w <= 255 else dest.to(torch.int64)
+    order = torch.argsort(key, stable=True)
     srt = rows.index_select(0, order)
-    send = torch.bincount(dest, minlength=w)
+    send = torch.bincount(key if w <= 255 else dest.to(torch.int64), minlength=w).to(torch.int64)
     if d.get_backend() == "nccl":
         recv = torch.empty_like(send)
         d.all_to_all_single(recv, send)

@@ -390,7 +390,7 @@ def axis_density(coord, key, surface_key, target_keys, dist_from_interface, bin_
 
 
 def dump_parse_device(text, begin, end, longest, natoms, ncols, colsel, id_col, out, seen, status, stream=None):
-    """mdp_dump_parse_device (EXPERIMENTAL, opt-in): text uint8 [bytes], begin/end int64 [F] byte offsets of each frame's
+    """mdp_dump_parse_device (the file pipeline's parser, io/pipeline.py): text uint8 [bytes], begin/end int64 [F] byte offsets of each frame's
     rows, out float64 [F, nwant, N], seen int32 [F, ceil(N/32)] scratch, status int64 [F, 2] = (rows parsed, flags) --
     all on the device.  Enqueued on ``stream`` (default: the current stream); the caller checks ``status``."""
     F, nwant, stride = out.shape
