@@ -527,6 +527,13 @@ def run_gpu(args):
     res = None if args.skip_residence else bench_residence(args, torch, dist, ops, ctx, dev, world, rank)
     c5s = None if args.skip_clusters else bench_clusters_hydration(args, torch, dist, ops, ctx, dev, world, rank)
 
+    # --files-leg at N > 1: the file-based entry points run HERE, under the process group, on every rank (each rank writes
+    # the same files into a directory of its own; the reads are sharded over the ranks and the per-frame histograms
+    # all-gathered) -- what tests/test_gpu_parity.py::test_nrank_equals_1rank_under_nccl compares with the 1-rank result
+    files_early = None
+    if world > 1 and args.files_leg:
+        files_early = (bench_rdf_from_files(torch, make_frames(32, SEED, "cuda"), N_ATOMS * (N_ATOMS - 1) // 2,
+                                            copies=args.files_copies), bench_c1(torch))
     # every rank leaves the process group here: what follows on rank 0 (CPU baselines, host parser, the file-based leg)
     # is single-process work and must not meet a collective whose peers are gone
     if world > 1:
@@ -612,9 +619,13 @@ def run_gpu(args):
         # the first 32 frames of the walk on EVERY rank (not the rank's block): all ranks then see the same files, the file
         # reads are sharded over them, and the DataFrame (df_sha256) must not depend on the number of ranks
         del frames
-        out["rdf_from_files"] = bench_rdf_from_files(torch, make_frames(32, SEED, "cuda"), N_ATOMS * (N_ATOMS - 1) // 2,
-                                                     copies=args.files_copies)
-        c1 = bench_c1(torch)
+        if files_early is not None:
+            out["rdf_from_files"], c1 = files_early
+            out["rdf_from_files"]["ranks"] = world
+        else:
+            out["rdf_from_files"] = bench_rdf_from_files(torch, make_frames(32, SEED, "cuda"), N_ATOMS * (N_ATOMS - 1) // 2,
+                                                         copies=args.files_copies)
+            c1 = bench_c1(torch)
         if c1:
             out["c1"] = c1
             parity["c1_sha256"] = out["c1_sha256"] = all(c1["sha256_equals_reference"].values())

@@ -153,7 +153,11 @@ class FrameBatches:
         self.max_batch_frames = int(max_batch_frames)
         self.cuda = torch.cuda.is_available()
         self.to_device = to_device and self.cuda
-        self.device = device
+        # the device is fixed HERE, in the caller's thread: torch's current device is per thread, and the producer thread
+        # would otherwise start on device 0 whatever the caller (rank r of a multi-GPU job) has selected
+        self.device = torch.device(device) if device is not None else None
+        if self.to_device and (self.device is None or (self.device.type == "cuda" and self.device.index is None)):
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.frame_select = frame_select
         # file_shard=(rank, world): this rank READS only every world-th file (one frame per file assumed and checked: a file
         # with another number of frames sets multi_frame_seen and ends the iteration; the caller then falls back to
@@ -181,6 +185,8 @@ class FrameBatches:
 
             from .. import _lib
 
+            if self.to_device:
+                torch.cuda.set_device(self.device)
             if self.device_parse:
                 plan = self._text_plan()
                 if plan is not None:

@@ -922,7 +922,7 @@ def test_nrank_equals_1rank_under_nccl(tmp_path):
         a, b = many["green_kubo"]["charge_flux"]["abs_flux_sum"], one["green_kubo"]["charge_flux"]["abs_flux_sum"]
         assert abs(a / b - 1) < 1e-12
         # the reference's entry point on files, reads sharded over the ranks, text parsed on each rank's device
-        assert many["rdf_from_files"]["df_sha256"] == one["rdf_from_files"]["df_sha256"]
+        assert many["rdf_from_files"]["df_sha256"] == one["rdf_from_files"]["df_sha256"] and many["rdf_from_files"]["ranks"] == n
         if "c1" in one:
             assert many.get("c1_sha256") is True and one.get("c1_sha256") is True
 
