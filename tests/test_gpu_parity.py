@@ -927,6 +927,43 @@ def test_nrank_equals_1rank_under_nccl(tmp_path):
             assert many.get("c1_sha256") is True and one.get("c1_sha256") is True
 
 
+def test_api_nrank_equals_1rank_under_nccl(sample_dir, mini_dir, water_dir, slab_dir, visc_dir, tmp_path, request):
+    """Every file-based public entry point (RDF/CN atomic, molecular, intermolecular; clusters with their .xyz files;
+    hydration; number density; residence time; MSD all-atom and COM; charge flux and its correlations; viscosity; C1 at full
+    length when the fixture is there) in one process and under torchrun on 2 GPUs, on the golden fixtures: results from
+    integer counts must be identical, fp64 reductions whose order depends on the rank count equal to 1e-12
+    (tests/nccl_api_worker.py).  The single-process results are what the golden tests pin to the reference."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    c1_path = os.path.join(root, "tests", "golden_large", "c1_frames.tar.gz")
+    fixtures = [sample_dir, mini_dir, water_dir, slab_dir, visc_dir]
+    if os.path.exists(c1_path):
+        fixtures.append(request.getfixturevalue("c1_dir"))
+    res = {}
+    for n in (1, 2):
+        out = tmp_path / f"n{n}"
+        out.mkdir()
+        cmd = ([sys.executable] if n == 1 else
+               [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                "--master-port", str(29561 + n)]) + [os.path.join(root, "tests", "nccl_api_worker.py"), str(out)] + fixtures
+        r = subprocess.run(cmd, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-3000:]
+        res[n] = np.load(out / "results.npz")
+    assert sorted(res[1].files) == sorted(res[2].files) and len(res[1].files) >= 20
+    for k in res[1].files:
+        a, b = res[1][k], res[2][k]
+        assert a.shape == b.shape, k
+        if k.startswith("x_"):
+            assert np.array_equal(a, b), k
+        else:
+            scale = np.abs(a).max() + 1e-300
+            assert np.max(np.abs(a - b)) <= 1e-12 * scale, (k, float(np.max(np.abs(a - b)) / scale))
+
+
 # ------------------------------------------------------------------------------------------------
 # device epilogues of the cutoff searches (csrc/epilogue.cu) against numpy restatements of the reference's host code
 # ------------------------------------------------------------------------------------------------

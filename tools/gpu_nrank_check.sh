@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 OUT=gpurun_out
 mkdir -p $OUT
 N=${1:-2}
-timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 1000 -k "nrank" > $OUT/pytest_nrank.log 2>&1; echo "pytest nrank rc=$?"
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 1000 -k "nrank" > $OUT/pytest_nrank.log 2>&1; echo "pytest nrank rc=$?"
 tail -8 $OUT/pytest_nrank.log
 for n in 1 $N; do
   if [ $n = 1 ]; then
