@@ -1,14 +1,12 @@
 #!/bin/bash
-# Why is the rdf_from_files leg slower inside the full bench.py than alone?  Timeline of the leg's passes, with the CPU legs.
+# Timeline of the rdf_from_files leg inside the FULL default bench.py run (all legs before it), against the leg alone.
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-free -g | head -2
-for mode in cpu passive; do
-  if [ $mode = passive ]; then export OMP_WAIT_POLICY=PASSIVE KMP_BLOCKTIME=0 GOMP_SPINCOUNT=0; fi
+for mode in all alone; do
   rm -f gpurun_out/bench_files_trace_$mode.json
-  ARGS="--frames 64 --skip-msd --skip-gk --skip-residence --skip-clusters --skip-triclinic"
-  MDP_PIPELINE_TRACE=gpurun_out/bench_files_trace_$mode.json timeout 900 python bench.py --steps 2 --warmup 3 $ARGS > gpurun_out/bench_files_dbg_$mode.json 2> gpurun_out/bench_files_dbg_$mode.err
+  if [ $mode = alone ]; then ARGS="--frames 64 --skip-msd --skip-gk --skip-residence --skip-clusters --skip-triclinic --skip-cpu --files-leg"; else ARGS=""; fi
+  MDP_PIPELINE_TRACE=gpurun_out/bench_files_trace_$mode.json timeout 900 python bench.py --steps 8 --warmup 3 $ARGS > gpurun_out/bench_files_dbg_$mode.json 2> gpurun_out/bench_files_dbg_$mode.err
   echo "== $mode rc=$?"
   python - <<PY
 import json
