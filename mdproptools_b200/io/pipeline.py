@@ -94,6 +94,37 @@ class _Trace:
             f.write(json.dumps({"total_ms": round((self.clock() - self.t0) * 1e3, 3), "spans": rows}) + "\n")
 
 
+class _PinnedPool:
+    """Process-wide pool of pinned staging buffers (flat uint8 tensors).  cudaHostAlloc costs ~0.2 ms per MB: a pass over a
+    trajectory that allocated its text ring and host batches afresh spent more time pinning memory than reading files
+    (measured: passes of 0.5 s next to passes of 0.08 s, depending on when Python had freed the previous pass's buffers).
+    Buffers come back when a pass ends / the consumer moves on; at most ``cap`` bytes are kept."""
+
+    GRAIN = 16 << 20
+
+    def __init__(self, cap=6 << 30):
+        self.cap, self.free, self.lock = cap, [], threading.Lock()
+
+    def take(self, nbytes):
+        need = max(1, -(-int(nbytes) // self.GRAIN)) * self.GRAIN
+        with self.lock:
+            best = None
+            for k, b in enumerate(self.free):
+                if b.numel() >= need and (best is None or b.numel() < self.free[best].numel()):
+                    best = k
+            if best is not None and self.free[best].numel() <= 4 * need:
+                return self.free.pop(best)
+        return torch.empty((need,), dtype=torch.uint8, pin_memory=True)
+
+    def give(self, buf):
+        with self.lock:
+            if sum(b.numel() for b in self.free) + buf.numel() <= self.cap:
+                self.free.append(buf)
+
+
+_POOL = _PinnedPool()
+
+
 class _ProducerStopped(BaseException):
     """Raised inside the producer thread when the consumer has gone away."""
 
@@ -176,7 +207,6 @@ class FrameBatches:
         self.device_parse = bool(device_parse) and self.to_device
         self.device_parsed_frames = 0
         self.host_reparsed_frames = 0
-        self._pool, self._pool_lock = [], threading.Lock()
         self._trace = None
 
     def _produce(self, q: "queue.Queue"):
@@ -292,13 +322,12 @@ class FrameBatches:
             return None
         return colsel
 
-    def _host_buffer(self, F, C, n):
-        """A pinned [>= F, C, n] staging tensor from the pool (returned to it when the consumer asks for the next batch)."""
-        with self._pool_lock:
-            for k, b in enumerate(self._pool):
-                if b.shape[1:] == (C, n) and b.shape[0] >= F:
-                    return self._pool.pop(k)
-        return torch.empty((F, C, n), dtype=torch.float64, pin_memory=True)
+    @staticmethod
+    def _host_buffer(F, C, n):
+        """(pool buffer, pinned [F, C, n] float64 view of it); the buffer goes back to the pool when the consumer asks for
+        the next batch."""
+        raw = _POOL.take(F * C * n * 8)
+        return raw, raw[: F * C * n * 8].view(torch.float64).view(F, C, n)
 
     def _produce_text(self, q, files, findex, nfiles_all):
         import os
@@ -344,7 +373,9 @@ class FrameBatches:
                 t_sub = tr.clock() if tr is not None else 0.0
                 buf = tring[slot]
                 if buf is None or buf.numel() < need:
-                    buf = tring[slot] = torch.empty((max(need, 1),), dtype=torch.uint8, pin_memory=True)
+                    if buf is not None:
+                        _POOL.give(buf)
+                    buf = tring[slot] = _POOL.take(need)
                 view, addr, off, futs = memoryview(buf.numpy()), buf.data_ptr(), 0, []
                 for k in groups[gi]:
                     futs.append(ex.submit(_dump.read_text_frames, files[k], view, addr, off, sizes[k]))
@@ -358,8 +389,7 @@ class FrameBatches:
                 missing = [w for w in want if w not in cols]
                 if missing:
                     raise KeyError(f"column(s) {missing} not in dump file (has {cols})")
-                h_full = self._host_buffer(F, C, n)
-                h = h_full[:F]
+                h_full, h = self._host_buffer(F, C, n)
                 colsel = self._colsel(cols)
                 if colsel is None or n <= 0:                   # this run is not for the device parser: host parse, plain H2D
                     _dump.parse_frames([bytes(view[fr.begin:fr.end]) for _, fr in run], want, h.numpy(), self.nthreads)
@@ -471,6 +501,7 @@ class FrameBatches:
 
             subs, nsub, prev = {}, 0, []
             try:
+              try:
                 for gi in range(len(groups)):
                     while nsub < len(groups) and nsub <= gi + ahead:     # reads of the next groups run while this one is parsed
                         subs[nsub] = submit(nsub)
@@ -479,10 +510,22 @@ class FrameBatches:
                     for rec in prev:                                     # ... while the previous group is checked and handed over
                         finalize(rec)
                     prev = cur
-            except _dump.MultiFrameFile:
+              except _dump.MultiFrameFile:
                 self.multi_frame_seen = True
-            for rec in prev:
+              for rec in prev:
                 finalize(rec)
+            finally:
+                # the text buffers go back to the pool once nothing reads them any more (reads in flight, H2D copies)
+                for sub in subs.values():
+                    for fut in sub[3]:
+                        fut.cancel()
+                ex.shutdown(wait=True)
+                copy_stream.synchronize()
+                d2h_stream.synchronize()
+                for k, buf in enumerate(tring):
+                    if buf is not None:
+                        _POOL.give(buf)
+                        tring[k] = None
         self.total_frames = nfiles_all if sharded else state["next_index"]
         q.put(None)
 
@@ -504,8 +547,8 @@ class FrameBatches:
                 yield item
                 buf = getattr(item, "_pool_buffer", None)     # the consumer is done with this batch's host copy
                 if buf is not None:
-                    with self._pool_lock:
-                        self._pool.append(buf)
+                    item._pool_buffer = None
+                    _POOL.give(buf)
         finally:
             # the consumer may leave early (an exception in its loop body, a generator that is dropped): tell the producer to
             # stop, unblock its pending put, and wait for it -- otherwise the thread would sit in q.put() for ever, holding
