@@ -2,7 +2,6 @@
 # file-based RDF entry point: device parser (text pipeline) against the host parser, batch size / reader thread sweep
 set -u
 cd "$(dirname "$0")/.."
-timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 600 -k "device_pars or frame_batches or golden" 2>&1 | tail -3
 python - <<'PY'
 import os, sys, time, shutil, tempfile
 sys.path.insert(0, os.getcwd())
@@ -40,8 +39,9 @@ run()
 print("device parser result identical to host parser result:", bool(np.array_equal(ref, out["df"].values)))
 print(f"device parser (default batch/readers): {min(run(), run()):.3f} ms/frame", flush=True)
 for mb in (32, 64, 128, 256):
-    for rd in (4, 8, 12):
-        os.environ["MDP_BATCH_MB"] = str(mb); os.environ["MDP_READERS"] = str(rd)
-        print(f"device parser, batch {mb} MB readers {rd}: {min(run(), run()):.3f} ms/frame", flush=True)
+    for rd in (8, 12, 16):
+        os.environ["MDP_TEXT_GROUP_MB"] = str(mb); os.environ["MDP_READERS"] = str(rd)
+        run()
+        print(f"device parser, text groups of {mb} MB, readers {rd}: {min(run(), run(), run()):.3f} ms/frame", flush=True)
 shutil.rmtree(d)
 PY
