@@ -350,6 +350,26 @@ def _frame_box(box, flags):
     return lengths, lengths
 
 
+class _PropsCache:
+    """_frame_box + _calc_props of a frame, remembered for the next frames with the same box, atom count and type table
+    (every frame of an NVT trajectory): ~0.1 ms of small numpy calls per frame otherwise -- as much as the pair kernel
+    itself needs for a 10^5-atom frame.  The checks of _calc_props run (and raise) on the first frame of each kind."""
+
+    def __init__(self, flags, num_types, mass, partial_relations, col, num_atoms_per_mol):
+        self.args = (num_types, mass, partial_relations, col, num_atoms_per_mol)
+        self.flags, self.key, self.val = flags, None, None
+
+    def get(self, meta, at):
+        b = meta.box
+        key = (meta.natoms, id(at), tuple(map(tuple, b.bounds)), None if b.tilt is None else tuple(b.tilt))
+        if key != self.key:
+            lengths, boxrow = _frame_box(b, self.flags)
+            num_types, mass, rel, col, napm = self.args
+            rho, rho_pairs = _calc_props(lengths, meta.natoms, at, at, num_types, mass, rel, col, napm)
+            self.key, self.val = key, (at, boxrow, rho, rho_pairs)           # (holding `at` keeps its id unique)
+        return self.val[1:]
+
+
 # ------------------------------------------------------------------------------------------------
 # frame iteration shared by all entry points
 # ------------------------------------------------------------------------------------------------
@@ -438,6 +458,7 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
     counts, props = {}, {}
     device = torch.device("cuda", torch.cuda.current_device())   # a rank that receives no frames still joins the merge
     tcache, ccache, dcache = _TypeCache(), _TypeCache(), _DeviceCache()
+    pcache = _PropsCache(flags, num_types, mass, partial_relations, "id" if altered else "type", num_atoms_per_mol)
 
     def _typ_and_counts(col):
         typ_ = calc_atom_type_ids(col, num_mols, num_atoms_per_mol) if altered else np.array(col, copy=True)
@@ -454,9 +475,7 @@ def calc_atomic_rdf(r_cut, bin_size, num_types, mass, partial_relations, filenam
         for k, meta in enumerate(batch.metas):
             _log("The timestep of the current file is: " + str(meta.timestep))
             typ, at = tcache.get(host[k, 0] if altered else host[k, 1], _typ_and_counts)
-            lengths, boxrow = _frame_box(meta.box, flags)
-            rho, rho_pairs = _calc_props(lengths, meta.natoms, at, at, num_types, mass, partial_relations,
-                                         "id" if altered else "type", num_atoms_per_mol)
+            boxrow, rho, rho_pairs = pcache.get(meta, at)
             props[meta.index] = (at, rho, rho_pairs, meta.natoms)
             if cmap is None:
                 cmap = _ClassMap(named, present_types=at.keys())
@@ -529,6 +548,7 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
     counts, props = {}, {}
     device = torch.device("cuda", torch.cuda.current_device())   # a rank that receives no frames still joins the merge
     tcache, ccache, dcache = _TypeCache(), _TypeCache(), _DeviceCache()
+    pcache = _PropsCache(flags, num_types, mass, partial_relations, "id" if altered else "type", num_atoms_per_mol)
 
     def _typ_and_counts(col):
         typ_ = calc_atom_type_ids(col, num_mols, num_atoms_per_mol) if altered else np.array(col, copy=True)
@@ -544,9 +564,7 @@ def calc_atomic_cn(r_cut, bin_size, num_types, mass, partial_relations, filename
         same_cls, cls_first = True, None
         for k, meta in enumerate(batch.metas):
             typ, at = tcache.get(host[k, 0] if altered else host[k, 1], _typ_and_counts)
-            lengths, boxrow = _frame_box(meta.box, flags)
-            _calc_props(lengths, meta.natoms, at, at, num_types, mass, partial_relations, "id" if altered else "type",
-                        num_atoms_per_mol)
+            boxrow = pcache.get(meta, at)[0]
             props[meta.index] = at
             if cmap is None:
                 cmap = _ClassMap(named, present_types=at.keys())
