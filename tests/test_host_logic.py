@@ -593,6 +593,70 @@ def test_shard_ranges_cover_everything():
             assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
 
 
+def test_owner_of_rows_agrees_with_shard_range():
+    """The rank a central atom's rows are sent to (dist.owner_of_rows, int32 and int64 indices) is the rank whose
+    shard_range block holds it -- the residence-time exchange relies on it."""
+    import torch
+    from mdproptools_b200 import dist
+    for n in (1, 7, 8, 16, 101, 2000):
+        for w in (1, 2, 3, 8):
+            want = np.empty(n, dtype=np.int64)
+            for k in range(w):
+                lo, hi = dist.shard_range(n, k, w)
+                want[lo:hi] = k
+            for dt in (torch.int32, torch.int64):
+                got = dist.owner_of_rows(torch.arange(n, dtype=dt), n, w)
+                assert got.tolist() == want.tolist(), (n, w, dt)
+
+
+def test_per_frame_host_caches():
+    """The caches that keep the consumer thread of the file pipeline off the critical path: _same_values (memcmp of
+    contiguous arrays, element comparison otherwise), _TypeCache (recompute only when the column changes; an identical
+    object needs no comparison), _PropsCache (box / density work once per kind of frame, consistency error on the first)."""
+    from mdproptools_b200.io.dump import Box
+    from mdproptools_b200.io.pipeline import FrameMeta
+    from mdproptools_b200.structural import rdf_cn as R
+    a = np.arange(10, dtype=np.float64)
+    assert R._same_values(a, a.copy()) and not R._same_values(a, a + 1) and not R._same_values(a, a[:5])
+    assert R._same_values(a[::2], a[::2].copy()) and not R._same_values(a[::2], a[1::2])       # non-contiguous: element-wise
+    calls = []
+    tc = R._TypeCache()
+    make = lambda col: (calls.append(1), col.sum())[1]
+    buf = np.stack([a, a, a + 1])
+    assert tc.get(buf[0], make) == 45 and tc.get(buf[1], make) == 45 and len(calls) == 1     # equal rows of a staging buffer
+    assert tc.get(buf[2], make) == 55 and len(calls) == 2
+    obj = a.copy()
+    assert tc.get(obj, make) == 45 and tc.get(obj, make) == 45 and len(calls) == 3           # the same object again: no compare
+    at = {1: 6, 2: 4}
+    box = Box([[0.0, 10.0], [0.0, 10.0], [0.0, 10.0]], None)
+    pc = R._PropsCache(0, 2, [1.0, 2.0], [[1], [2]], "type", None)
+    row, rho, rho_pairs = pc.get(FrameMeta(0, 0, 10, box), at)
+    want_rho, want_pairs = R._calc_props((10.0, 10.0, 10.0), 10, at, at, 2, [1.0, 2.0], [[1], [2]], "type", None)
+    assert row == (10.0, 10.0, 10.0) and rho == want_rho and np.array_equal(rho_pairs, want_pairs)
+    assert pc.get(FrameMeta(1, 5, 10, Box([[0.0, 10.0], [0.0, 10.0], [0.0, 10.0]], None)), at)[1] == rho      # same kind of frame
+    row2, rho2, _ = pc.get(FrameMeta(2, 9, 10, Box([[0.0, 20.0], [0.0, 10.0], [0.0, 10.0]], None)), at)
+    assert row2 == (20.0, 10.0, 10.0) and rho2 == rho / 2
+    with pytest.raises(ValueError, match="Consistency check failed"):
+        R._PropsCache(0, 3, [1.0, 2.0, 3.0], [[1], [2]], "type", None).get(FrameMeta(0, 0, 10, box), at)
+
+
+@pytest.mark.gpu
+def test_pinned_pool_reuses_buffers():
+    from mdproptools_b200.io.pipeline import _PinnedPool
+    import torch
+    pool = _PinnedPool(cap=64 << 20)
+    b = pool.take(1000)
+    assert b.numel() == _PinnedPool.GRAIN and b.is_pinned()
+    pool.give(b)
+    assert pool.take(5 << 20) is b                       # reused: large enough and not wastefully large
+    pool.give(b)
+    c = pool.take(40 << 20)
+    assert c is not b and c.numel() == 48 << 20
+    pool.give(c)
+    pool.give(torch.empty(1))                            # beyond the cap nothing more is kept
+    assert sum(x.numel() for x in pool.free) <= 64 << 20
+
+
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
