@@ -68,7 +68,7 @@ MDP_HD void mdp_parse_chunk(const DevParseParams &p, int f, long long chunk, con
                 double v;
                 const char *te = mdp_parse_fast(q, lend, &v);
                 if (!te) {
-                    flags |= DPF_SLOW_TOKEN;   // exponent, too many digits, inf/nan, malformed: the host parser decides
+                    flags |= DPF_SLOW_TOKEN;   // too many digits, scale beyond 10^+-22, inf/nan, malformed: the host parser decides
                     ok = false;
                     break;
                 }

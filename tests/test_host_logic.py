@@ -194,7 +194,7 @@ def _atoms_section(buf: bytes):
 
 
 def test_device_parser_body_on_host(sample_dir, tmp_path):
-    """The body of the (opt-in) device dump parser, mdp_parse_chunk of csrc/dump_rows.h, run on the host for every
+    """The body of the device dump parser, mdp_parse_chunk of csrc/dump_rows.h, run on the host for every
     (frame, chunk) in both orders against the host parser: real sample frames (20 columns, 8 wanted), generated frames
     with row lengths around the 64-byte chunk size, CRLF and blank lines; and its refusals -- tokens off the exact fast
     path, short rows, duplicate / out-of-range ids, a wrong row count -- which the caller answers with the host parser."""
