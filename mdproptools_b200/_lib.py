@@ -128,6 +128,7 @@ class Context:
     """One mdp_ctx per (process, device)."""
 
     _instances: dict[int, "Context"] = {}
+    _lock = threading.Lock()         # the file pipeline's producer thread and the caller may both ask first
 
     def __init__(self, device: int):
         h = c_void_p()
@@ -145,7 +146,10 @@ class Context:
             device = torch.cuda.current_device()
         ctx = cls._instances.get(device)
         if ctx is None:
-            ctx = cls._instances[device] = Context(device)
+            with cls._lock:
+                ctx = cls._instances.get(device)
+                if ctx is None:
+                    ctx = cls._instances[device] = Context(device)
         return ctx
 
     def launch_count(self) -> int:
