@@ -51,6 +51,12 @@ constexpr int CTAS_PER_SM = 2;   // resident CTAs of the pair kernel per SM (reg
 // so that one 32-point chunk is a single contiguous 1 KB block and both halves are bank-conflict free.
 constexpr int GREC = 64;       // double2 per group
 constexpr int RING = 64;       // candidate ring of the pair kernel: entries per warp
+// Scratch words behind the shared histogram: single-row direct binning sends a miss of lane l to word nbins + l, PLUS ONE
+// when rsq >= edge[k + 1] -- which holds for the +inf padding points of a partial chunk against the +inf tail of the edge
+// table.  Lane 31 then reaches word nbins + 32: 33 words are needed (36 keeps what follows 16-byte aligned).  With 32,
+// that increment landed one word past the allocation: harmless while the total was not at an allocation boundary, an
+// illegal-address fault when it was (found by tools/gpu_fuzz_pair.py: one class, rectangular sets, 88 bins).
+constexpr int HIST_SCRATCH = 36 * 4;
 __host__ __device__ __forceinline__ int64_t rec_xy(int64_t pos) { return (pos >> 5) * GREC + (pos & 31); }
 __host__ __device__ __forceinline__ int64_t rec_zw(int64_t pos) { return (pos >> 5) * GREC + 32 + (pos & 31); }
 constexpr size_t REC_BYTES = 32;   // bytes per point
@@ -1575,15 +1581,15 @@ static int run_pair_call(mdp_ctx *ctx, const PairCall &c, cudaStream_t st)
         const size_t edge_bytes = edge_region_bytes(c.nbins);
         if (multicls) smem += (size_t)((ncp * 4 + 15) & ~15);
         const size_t cap = std::min<size_t>(ctx->smem_optin, (216 / CTAS_PER_SM) * 1024);   // keep CTAS_PER_SM CTAs per SM
-        MDP_REQUIRE(smem + hist_bytes + 128 + 16 <= ctx->smem_optin,
+        MDP_REQUIRE(smem + hist_bytes + HIST_SCRATCH + 16 <= ctx->smem_optin,
                     "pair: histogram of %d rows x %d bins does not fit in shared memory (%zu B needed); "
                     "reduce the number of distinct classes or bins per call",
                     nrows, c.nbins, smem + hist_bytes);
-        if (smem + hist_bytes + 128 + 16 + edge_bytes <= cap) {
+        if (smem + hist_bytes + HIST_SCRATCH + 16 + edge_bytes <= cap) {
             edges_in_smem = 1;
             smem += edge_bytes;
         }
-        smem += hist_bytes + 128 + 16;   // + one scratch word per lane (direct binning sends misses there) + the guard counter
+        smem += hist_bytes + HIST_SCRATCH + 16;   // + the scratch words direct binning sends misses to + the guard counter
     }
 
     // sub-batching over frames so that scratch stays bounded
