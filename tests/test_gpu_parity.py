@@ -1128,6 +1128,22 @@ def test_pair_engine_fuzz_fast_equals_f64():
     assert cases == 400 and bad == 0
 
 
+def test_other_kernels_fuzz():
+    """The first 60 cases per component of tools/gpu_fuzz_misc.py with seed 5: shell-grid search == the general engine's list
+    (wrapped, unwrapped, dense corners, central atoms among the partners), run-based survival counts == popcount kernel ==
+    oracle, FFT correlation == direct sum to 1e-10, text pipeline + device parser == host parser bit for bit (random column
+    orders, number spellings, CRLF, blank lines, several frames per file), per-atom MSD == oracle bit for bit.  A 30 s per
+    component run (35 000 cases, no mismatch) is recorded in profiles/r02b_fuzz_misc.txt."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gpu_fuzz_misc", os.path.join(root, "tools", "gpu_fuzz_misc.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    report = mod.main(budget=60.0, seed=5, max_cases=60)
+    assert sorted(report) == ["fft", "msd", "parser", "shell", "survival"]
+    assert all(n == 60 and bad == 0 for n, bad in report.values()), report
+
+
 def Context_stats():
     from mdproptools_b200._lib import Context
     import torch
