@@ -499,21 +499,26 @@ class FrameBatches:
                 if tr is not None:
                     tr.span("producer: blocked handing over (consumer busy)", rec.get("k", -1), t_put)
 
-            subs, nsub, prev = {}, 0, []
+            subs = {}
+
+            def run_groups():
+                nsub, prev = 0, []
+                try:
+                    for gi in range(len(groups)):
+                        while nsub < len(groups) and nsub <= gi + ahead:     # reads of the next groups run while this one is parsed
+                            subs[nsub] = submit(nsub)
+                            nsub += 1
+                        cur = enqueue(gi, subs.pop(gi))                      # H2D + parse + D2H of this group: asynchronous
+                        for rec in prev:                                     # ... while the previous group is checked and handed over
+                            finalize(rec)
+                        prev = cur
+                except _dump.MultiFrameFile:
+                    self.multi_frame_seen = True
+                for rec in prev:
+                    finalize(rec)
+
             try:
-              try:
-                for gi in range(len(groups)):
-                    while nsub < len(groups) and nsub <= gi + ahead:     # reads of the next groups run while this one is parsed
-                        subs[nsub] = submit(nsub)
-                        nsub += 1
-                    cur = enqueue(gi, subs.pop(gi))                      # H2D + parse + D2H of this group: asynchronous
-                    for rec in prev:                                     # ... while the previous group is checked and handed over
-                        finalize(rec)
-                    prev = cur
-              except _dump.MultiFrameFile:
-                self.multi_frame_seen = True
-              for rec in prev:
-                finalize(rec)
+                run_groups()
             finally:
                 # the text buffers go back to the pool once nothing reads them any more (reads in flight, H2D copies)
                 for sub in subs.values():
