@@ -55,7 +55,7 @@ constexpr int RING = 64;       // candidate ring of the pair kernel: entries per
 // when rsq >= edge[k + 1] -- which holds for the +inf padding points of a partial chunk against the +inf tail of the edge
 // table.  Lane 31 then reaches word nbins + 32: 33 words are needed (36 keeps what follows 16-byte aligned).  With 32,
 // that increment landed one word past the allocation: harmless while the total was not at an allocation boundary, an
-// illegal-address fault when it was (found by tools/gpu_fuzz_pair.py: one class, rectangular sets, 88 bins).
+// illegal-address fault when it was (found by tests/fuzz/fuzz_pair.py: one class, rectangular sets, 88 bins).
 constexpr int HIST_SCRATCH = 36 * 4;
 __host__ __device__ __forceinline__ int64_t rec_xy(int64_t pos) { return (pos >> 5) * GREC + (pos & 31); }
 __host__ __device__ __forceinline__ int64_t rec_zw(int64_t pos) { return (pos >> 5) * GREC + 32 + (pos & 31); }

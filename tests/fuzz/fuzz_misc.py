@@ -7,7 +7,7 @@
   parser    text -> HBM -> k_dump_rows (FrameBatches)         vs  the host parser, bit for bit (random spellings, CRLF, blanks)
   msd       k_msd_single per-atom values                      vs  the oracle, bit for bit
 
-    python tools/gpu_fuzz_misc.py [seconds per component] [seed]
+    python tests/fuzz/fuzz_misc.py [seconds per component] [seed]
 """
 import os
 import sys
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -4,7 +4,7 @@ API uses -- symmetric and rectangular histograms with 1..3 classes (both pair ke
 coordination numbers through the table-bin mode, neighbour lists in both shell modes (orthogonal and triclinic).
 Sizes are kept small enough for the oracle's O(N^2) loops.
 
-    python tools/gpu_fuzz_oracle.py [seconds per component] [seed]
+    python tests/fuzz/fuzz_oracle.py [seconds per component] [seed]
 """
 import os
 import sys
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

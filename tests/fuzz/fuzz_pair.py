@@ -4,7 +4,7 @@ all-fp64 kernel k_pair for EVERY geometry -- random atom counts, boxes (orthogon
 class counts, point distributions (uniform, clustered, simple-cubic lattice = thousands of pairs exactly on bin edges,
 unwrapped, far from the origin), symmetric and rectangular sets.  Every 10th case is also checked against the oracle.
 
-    python tools/gpu_fuzz_pair.py [seconds] [seed]          # prints one line per failure and a summary; exit 1 on failure
+    python tests/fuzz/fuzz_pair.py [seconds] [seed]          # prints one line per failure and a summary; exit 1 on failure
 """
 import os
 import sys
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

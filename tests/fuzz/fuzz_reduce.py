@@ -10,7 +10,7 @@
   msd_interval interval MSD                                                  vs  the oracle (1e-13)
   cumtrapz     cumulative trapezoid                                          vs  the oracle (1e-12 of max)
 
-    python tools/gpu_fuzz_reduce.py [seconds per component] [seed]
+    python tests/fuzz/fuzz_reduce.py [seconds per component] [seed]
 """
 import os
 import sys
@@ -18,7 +18,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -1114,14 +1114,14 @@ def test_pair_fast_equals_f64_kernel_and_oracle(ops, case):
 
 
 def test_pair_engine_fuzz_fast_equals_f64():
-    """The first 400 cases of tools/gpu_fuzz_pair.py with seed 1 (random sizes, boxes incl. triclinic, cutoffs, bin widths,
+    """The first 400 cases of tests/fuzz/fuzz_pair.py with seed 1 (random sizes, boxes incl. triclinic, cutoffs, bin widths,
     classes, distributions incl. lattices with thousands of pairs exactly on bin edges, symmetric and rectangular sets):
     k_pair_fast == k_pair bit for bit, every 10th case also == the oracle.  Case 118 of this sequence is the one that
     found the one-word overrun of the all-fp64 kernel's scratch area (an illegal-address fault before the fix); a 240 s
     run of the tool (139 220 cases, 2.3e12 pairs) is recorded in profiles/r02b_fuzz_pair.txt."""
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("gpu_fuzz_pair", os.path.join(root, "tools", "gpu_fuzz_pair.py"))
+    spec = importlib.util.spec_from_file_location("fuzz_pair", os.path.join(root, "tests", "fuzz", "fuzz_pair.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     cases, bad = mod.main(budget=120.0, seed=1, max_cases=400)
@@ -1129,14 +1129,14 @@ def test_pair_engine_fuzz_fast_equals_f64():
 
 
 def test_other_kernels_fuzz():
-    """The first 60 cases per component of tools/gpu_fuzz_misc.py with seed 5: shell-grid search == the general engine's list
+    """The first 60 cases per component of tests/fuzz/fuzz_misc.py with seed 5: shell-grid search == the general engine's list
     (wrapped, unwrapped, dense corners, central atoms among the partners), run-based survival counts == popcount kernel ==
     oracle, FFT correlation == direct sum to 1e-10, text pipeline + device parser == host parser bit for bit (random column
     orders, number spellings, CRLF, blank lines, several frames per file), per-atom MSD == oracle bit for bit.  A 30 s per
     component run (35 000 cases, no mismatch) is recorded in profiles/r02b_fuzz_misc.txt."""
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("gpu_fuzz_misc", os.path.join(root, "tools", "gpu_fuzz_misc.py"))
+    spec = importlib.util.spec_from_file_location("fuzz_misc", os.path.join(root, "tests", "fuzz", "fuzz_misc.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     report = mod.main(budget=60.0, seed=5, max_cases=60)
@@ -1145,14 +1145,14 @@ def test_other_kernels_fuzz():
 
 
 def test_pair_engine_fuzz_against_the_oracle():
-    """The first 150 cases per component of tools/gpu_fuzz_oracle.py with seed 9, each against the oracle's O(N^2) loops:
+    """The first 150 cases per component of tests/fuzz/fuzz_oracle.py with seed 9, each against the oracle's O(N^2) loops:
     symmetric and rectangular histograms (1..3 classes, both pair kernels, orthogonal and triclinic image, wrapped /
     unwrapped / clustered / lattice points), coordination numbers through the table-bin mode, neighbour lists in shell
     mode (orthogonal and triclinic, same-set exclusion).  A 30 s per component run (159 000 cases, no mismatch) is
     recorded in profiles/r02b_fuzz_oracle.txt."""
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("gpu_fuzz_oracle", os.path.join(root, "tools", "gpu_fuzz_oracle.py"))
+    spec = importlib.util.spec_from_file_location("fuzz_oracle", os.path.join(root, "tests", "fuzz", "fuzz_oracle.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     report = mod.main(budget=60.0, seed=9, max_cases=150)
@@ -1161,13 +1161,13 @@ def test_pair_engine_fuzz_against_the_oracle():
 
 
 def test_reductions_and_epilogues_fuzz():
-    """The first 40 cases per component of tools/gpu_fuzz_reduce.py with seed 3: list grouping, distinct pair keys, hydration
+    """The first 40 cases per component of tests/fuzz/fuzz_reduce.py with seed 3: list grouping, distinct pair keys, hydration
     cosines and counters (bit for bit), cluster membership, segment centres of mass (bit for bit), windowed and interval
     MSD, cumulative trapezoid -- against numpy / the oracle over random sizes around the tile and warp boundaries.  A 15 s
     per component run (43 800 cases, no mismatch) is recorded in profiles/r02b_fuzz_reduce.txt."""
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("gpu_fuzz_reduce", os.path.join(root, "tools", "gpu_fuzz_reduce.py"))
+    spec = importlib.util.spec_from_file_location("fuzz_reduce", os.path.join(root, "tests", "fuzz", "fuzz_reduce.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     report = mod.main(budget=60.0, seed=3, max_cases=40)
