@@ -31,7 +31,7 @@ import time
 # OpenMP workers (the oracle's CPU legs, torch's CPU ops) must SLEEP when they have nothing to do: with the default
 # spin-waiting the idle workers of an earlier parallel region keep every core busy while the file pipeline's reader
 # threads need them -- measured on the 16-core B200 host: rdf_from_files 1.0 ms/frame with spinning workers, 0.28 ms/frame
-# without (tools/gpu_bench_files_dbg.sh).  Must be set before the OpenMP runtimes load, i.e. before numpy / torch.
+# without (MDP_PIPELINE_TRACE timelines of the leg).  Must be set before the OpenMP runtimes load, i.e. before numpy / torch.
 for _k, _v in (("OMP_WAIT_POLICY", "PASSIVE"), ("GOMP_SPINCOUNT", "0"), ("KMP_BLOCKTIME", "0")):
     os.environ.setdefault(_k, _v)
 
