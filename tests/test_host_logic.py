@@ -593,6 +593,17 @@ def test_shard_ranges_cover_everything():
             assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
 
 
+def test_gpu_side_test_tools_compile():
+    """The randomised cross-checks (tests/fuzz/) and the NCCL worker only run on a GPU box; a syntax error in them should
+    not wait for one."""
+    import glob
+    import py_compile
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "fuzz", "*.py"))) + [os.path.join(ROOT, "tests", "nccl_api_worker.py")]
+    assert len(files) == 5
+    for f in files:
+        py_compile.compile(f, doraise=True, cfile=os.devnull)
+
+
 def test_owner_of_rows_agrees_with_shard_range():
     """The rank a central atom's rows are sent to (dist.owner_of_rows, int32 and int64 indices) is the rank whose
     shard_range block holds it -- the residence-time exchange relies on it."""
