@@ -593,6 +593,40 @@ def test_shard_ranges_cover_everything():
             assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
 
 
+def test_read_text_frames_offsets_and_headers(tmp_path):
+    """The reader-thread body of the text pipeline (io/dump.py: read_text_frames): a file is read into the middle of a
+    staging buffer; frame starts, first-row offsets, ends, headers (orthogonal and triclinic, LF and CRLF) and column
+    lists of a multi-frame file must describe exactly the text the host parser would be given."""
+    from mdproptools_b200.io import dump as D
+    rng = np.random.default_rng(3)
+    for eol in ("\n", "\r\n"):
+        p = tmp_path / ("t%d.dump" % len(eol))
+        frames = []
+        with open(p, "w", newline="") as f:
+            for k, (n, tri) in enumerate([(5, False), (9, True), (1, False)]):
+                head = f"ITEM: TIMESTEP{eol}{k * 7}{eol}ITEM: NUMBER OF ATOMS{eol}{n}{eol}"
+                head += (f"ITEM: BOX BOUNDS xy xz yz pp pp pp{eol}0 10 1.5{eol}0 11 -0.5{eol}0 12 0.25{eol}" if tri else
+                         f"ITEM: BOX BOUNDS pp pp pp{eol}0 10{eol}-1 11{eol}0.5 12{eol}")
+                head += f"ITEM: ATOMS id type x y z{eol}"
+                rows = "".join("%d 1 %g %g %g%s" % (i + 1, *rng.uniform(0, 9, 3), eol) for i in rng.permutation(n))
+                f.write(head + rows)
+                frames.append((head, rows, n, k * 7, tri))
+        size = os.path.getsize(p)
+        buf = np.zeros(size + 100, dtype=np.uint8)
+        got, frs = D.read_text_frames(str(p), memoryview(buf), buf.ctypes.data, 37, size)
+        assert got == size and len(frs) == 3
+        text = bytes(buf[37:37 + size])
+        assert text == open(p, "rb").read()
+        off = 37
+        for fr, (head, rows, n, ts, tri) in zip(frs, frames):
+            assert (fr.begin, fr.rows, fr.end) == (off, off + len(head), off + len(head) + len(rows))
+            assert (fr.timestep, fr.natoms, fr.columns) == (ts, n, ["id", "type", "x", "y", "z"])
+            assert (fr.box.tilt is not None) == tri
+            ref = D.parse_frame(bytes(buf[fr.begin:fr.end]), ["id", "x"])
+            assert ref.natoms == n and ref.box.bounds == fr.box.bounds and ref.box.tilt == fr.box.tilt
+            off = fr.end
+
+
 def test_gpu_side_test_tools_compile():
     """The randomised cross-checks (tests/fuzz/) and the NCCL worker only run on a GPU box; a syntax error in them should
     not wait for one."""
