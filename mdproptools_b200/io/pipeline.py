@@ -125,6 +125,21 @@ class _PinnedPool:
 _POOL = _PinnedPool()
 
 
+def _file_groups(sizes, max_files, max_bytes):
+    """Consecutive files in groups of at most ``max_files`` files and ``max_bytes`` bytes (a file larger than that is a
+    group of its own): lists of indices into ``sizes``, in order, covering every file once."""
+    groups, cur, cur_b = [], [], 0
+    for k, sz in enumerate(sizes):
+        if cur and (len(cur) >= max_files or cur_b + sz > max_bytes):
+            groups.append(cur)
+            cur, cur_b = [], 0
+        cur.append(k)
+        cur_b += sz
+    if cur:
+        groups.append(cur)
+    return groups
+
+
 class _ProducerStopped(BaseException):
     """Raised inside the producer thread when the consumer has gone away."""
 
@@ -344,15 +359,7 @@ class FrameBatches:
         # the stages busy together: the first batch is ready after one group's reads, and while group k is parsed groups
         # k+1 and k+2 are being read (64 MB of text = 20 C2 frames; MDP_TEXT_GROUP_MB for measurements)
         group_bytes = min(self.max_batch_bytes, int(os.environ.get("MDP_TEXT_GROUP_MB", "64")) << 20)
-        groups, cur, cur_b = [], [], 0
-        for k, sz in enumerate(sizes):
-            if cur and (len(cur) >= self.max_batch_frames or cur_b + sz > group_bytes):
-                groups.append(cur)
-                cur, cur_b = [], 0
-            cur.append(k)
-            cur_b += sz
-        if cur:
-            groups.append(cur)
+        groups = _file_groups(sizes, self.max_batch_frames, group_bytes)
         ahead = 2                                        # groups whose reads are in flight beyond the one being parsed
         nring = self.prefetch + 4 + ahead
         tring, tev = [None] * nring, [None] * nring      # pinned text buffers; the H2D copy that last read each of them

@@ -627,6 +627,21 @@ def test_read_text_frames_offsets_and_headers(tmp_path):
             off = fr.end
 
 
+def test_text_pipeline_file_groups():
+    from mdproptools_b200.io.pipeline import _file_groups
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        sizes = rng.integers(0, 100, int(rng.integers(0, 40))).tolist()
+        mf, mb = int(rng.integers(1, 9)), int(rng.integers(1, 300))
+        g = _file_groups(sizes, mf, mb)
+        assert [k for grp in g for k in grp] == list(range(len(sizes)))             # every file once, in order
+        for grp in g:
+            assert 1 <= len(grp) <= mf
+            assert len(grp) == 1 or sum(sizes[k] for k in grp) <= mb                # only a single oversized file may exceed
+        for a, b in zip(g, g[1:]):                                                  # greedy: the next file did not fit
+            assert len(a) == mf or sum(sizes[k] for k in a) + sizes[b[0]] > mb
+
+
 def test_gpu_side_test_tools_compile():
     """The randomised cross-checks (tests/fuzz/) and the NCCL worker only run on a GPU box; a syntax error in them should
     not wait for one."""
